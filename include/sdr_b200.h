@@ -1,0 +1,243 @@
+/*
+ * sdr_b200.h — C ABI of the B200-native IQ-sample DSP hot path.
+ *
+ * Drop-in boundary for the `Demod` pipeline of ccostes/rtl-sdr-rs's examples/simple_fm.rs and
+ * the `RtlSdr::read_sync` buffer surface that feeds it.  Every entry point names the reference
+ * interface it replaces (file:line relative to the reference root).  Plain pointers and sizes
+ * only: no C++/torch types cross this boundary.  All compute runs in hand-written CUDA kernels
+ * for sm_100a; there is NO CPU fallback — without a CUDA device every compute entry point
+ * returns SDR_E_CUDA.
+ *
+ * Conventions (reference: `Result<T, RtlsdrError>`, src/error.rs:40-53; panics in the example):
+ *   - `int`/`long` returns: >= 0 success (element counts where stated), < 0 an SDR_E_* code;
+ *     sdr_last_error() returns a thread-local message for the last failure.
+ *   - A handle is single-caller-at-a-time ("Send, not Sync", like `&mut self`); distinct handles
+ *     are independent (own CUDA stream).
+ *   - Host buffers are caller-owned.  *_dev variants take device pointers obtained from
+ *     sdr_dev_alloc() (16-byte aligned, with head/tail room the kernels may read) and are
+ *     asynchronous on the handle's stream until sdr_*_sync().
+ *   - Complex<i32> is {re:i32, im:i32} => interleaved int32_t pairs; complex f32 => float pairs.
+ */
+#ifndef SDR_B200_H
+#define SDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDR_B200_ABI_VERSION 1
+
+/* ---- errors ------------------------------------------------------------------------------ */
+enum {
+    SDR_OK = 0,
+    SDR_E_ARG = -1,   /* null pointer / invalid parameter */
+    SDR_E_LEN = -2,   /* length the reference would panic on: len % 8 != 0 (rotate_90 indexes
+                         i+7, examples/simple_fm.rs:284-295) or < 2 lowpassed samples (:356) */
+    SDR_E_CAP = -3,   /* output capacity too small (never truncates) */
+    SDR_E_CUDA = -4,  /* CUDA runtime error / no device */
+    SDR_E_NCCL = -5,  /* NCCL error / library not loadable */
+    SDR_E_IO = -6,    /* source I/O error (reference: RtlsdrError::Usb, src/error.rs:42) */
+    SDR_E_STATE = -7  /* call not valid in the handle's current state */
+};
+const char *sdr_last_error(void);
+int sdr_abi_version(void);
+/* Number of visible CUDA devices (0 if none); never fails. */
+int sdr_device_count(void);
+/* Fills name (<= cap bytes), SM count and global-memory bytes of a device. */
+int sdr_device_info(int device, char *name, size_t cap, int *sm_count, uint64_t *mem_bytes);
+/* Total kernels launched by this library in this process (bench.py's gpu_launches claim). */
+uint64_t sdr_kernel_launch_count(void);
+
+/* ---- device / pinned memory ---------------------------------------------------------------- */
+void *sdr_dev_alloc(int device, size_t bytes);          /* 256-B aligned, 4 KiB head+tail room */
+void sdr_dev_free(int device, void *p);
+void *sdr_host_alloc(size_t bytes);                     /* pinned host memory */
+void sdr_host_free(void *p);
+int sdr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
+int sdr_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
+int sdr_dev_memset(int device, void *dst, int value, size_t bytes);
+/* Counter-based synthetic IQ on the device: byte i = mix64(seed, i>>3) >> 8*(i&7) (uniform). */
+int sdr_synth_fill_dev(int device, uint8_t *d_buf, size_t bytes, uint64_t seed, uint64_t byte_offset);
+int sdr_device_sync(int device);
+
+/* ============================================================================================
+ * 1. Reference-exact integer path: `Demod` (examples/simple_fm.rs:232-427)
+ * ========================================================================================== */
+
+/* DemodConfig, examples/simple_fm.rs:179-185, field for field. */
+typedef struct {
+    uint32_t rate_in, rate_out, rate_resample, downsample, output_scale;
+} sdr_demod_config;
+
+/* RadioConfig, examples/simple_fm.rs:173-176. */
+typedef struct {
+    uint32_t capture_freq, capture_rate;
+} sdr_radio_config;
+
+/* The five carried fields of struct Demod, examples/simple_fm.rs:234-238. */
+typedef struct {
+    uint64_t prev_index;
+    int32_t now_lpr, prev_lpr_index;
+    int32_t lp_now_re, lp_now_im;
+    int32_t demod_pre_re, demod_pre_im;
+} sdr_demod_state;
+
+typedef struct sdr_demod sdr_demod;
+
+/* optimal_settings(freq, rate), examples/simple_fm.rs:189-214 (host arithmetic, no device).
+ * sample_rate / rate_resample play the SAMPLE_RATE / RATE_RESAMPLE constants (:26-27). */
+int sdr_optimal_settings(uint32_t freq, uint32_t rate, uint32_t sample_rate, uint32_t rate_resample,
+                         sdr_radio_config *radio, sdr_demod_config *demod);
+
+/* Demod::new, :243-252.  Requires 1 <= downsample, 1 <= rate_resample <= rate_out < 2^31. */
+int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out);
+void sdr_demod_free(sdr_demod *d);
+int sdr_demod_get_state(const sdr_demod *d, sdr_demod_state *st);
+int sdr_demod_set_state(sdr_demod *d, const sdr_demod_state *st);
+/* Audio samples one demodulate(len) call will return from the current state (closed form). */
+long sdr_demod_out_len(const sdr_demod *d, size_t len);
+
+/* Demod::demodulate(&mut self, Vec<u8>) -> Vec<i16>, :256-269.  One reference call: the first
+ * discriminator sample uses the f64 atan2 against demod_pre (:359), state is carried.  Fused
+ * kernel: rotate_90 + (-127) + boxcar + discriminator + resampler in one launch. */
+long sdr_demod_demodulate(sdr_demod *d, const uint8_t *buf, size_t len, int16_t *out, size_t out_cap);
+/* n_bufs consecutive demodulate() calls of buf_len bytes each (the reader->processor stream of
+ * examples/simple_fm.rs:108-128,145-160) in one pipelined submission.  Bit-identical to calling
+ * sdr_demod_demodulate n_bufs times.  out_lens (optional, n_bufs entries) receives the per-call
+ * audio counts.  Returns total audio samples. */
+long sdr_demod_demodulate_batch(sdr_demod *d, const uint8_t *buf, size_t buf_len, size_t n_bufs,
+                                int16_t *out, size_t out_cap, uint32_t *out_lens);
+/* Same, device-resident input and output (asynchronous; sdr_demod_sync() to wait). */
+long sdr_demod_demodulate_batch_dev(sdr_demod *d, const uint8_t *d_buf, size_t buf_len, size_t n_bufs,
+                                    int16_t *d_out, size_t out_cap);
+int sdr_demod_sync(sdr_demod *d);
+/* Device time (ms, CUDA events on the handle's stream) of the kernels of the last *_dev or
+ * batch submission, and the number of kernels it launched. */
+int sdr_demod_last_timing(const sdr_demod *d, float *kernel_ms, uint32_t *n_launches);
+
+/* Stage entry points (stage-level parity against the reference's three known-answer tests). */
+/* Demod::rotate_90(Vec<u8>) -> Vec<u8>, scalar branch :276-299; in place, len % 8 == 0. */
+long sdr_rotate_90(sdr_demod *d, uint8_t *buf, size_t len);
+/* `buf.iter().map(|v| *v as i16 - 127)` :258 followed by buf_to_complex :441-450:
+ * u8[len] -> Complex<i32>[len/2]. */
+long sdr_buf_to_complex(sdr_demod *d, const uint8_t *buf, size_t len, int32_t *out_pairs, size_t cap_pairs);
+/* Demod::low_pass_complex, :337-352 (state: prev_index, lp_now). */
+long sdr_low_pass_complex(sdr_demod *d, const int32_t *iq_pairs, size_t n, int32_t *out_pairs, size_t cap_pairs);
+/* Demod::fm_demod, :355-367 (state: demod_pre). n < 2 => SDR_E_LEN. */
+long sdr_fm_demod(sdr_demod *d, const int32_t *iq_pairs, size_t n, int16_t *out, size_t cap);
+/* Demod::low_pass_real, :408-426 (state: now_lpr, prev_lpr_index). */
+long sdr_low_pass_real(sdr_demod *d, const int16_t *in, size_t n, int16_t *out, size_t cap);
+/* Demod::fast_atan2(y, x), :383-405, vectorised: out[i] = fast_atan2(y[i], x[i]). */
+long sdr_fast_atan2(sdr_demod *d, const int32_t *y, const int32_t *x, size_t n, int32_t *out);
+/* Demod::polar_discriminant (:370-374, fast=0) / polar_discriminant_fast (:377-380, fast=1):
+ * out[i] = f(a[i], b[i]) for Complex<i32> pairs. */
+long sdr_polar_discriminant(sdr_demod *d, const int32_t *a_pairs, const int32_t *b_pairs, size_t n,
+                            int fast, int32_t *out);
+
+/* ============================================================================================
+ * 2. f32 tap'd-FIR receiver (BASELINE.json configs 2-3; extension — no reference implementation,
+ *    parity against the f64 oracle).  Stage names follow north_star: low_pass / fm_demod / resample.
+ *      low_pass : y[m] = sum_{k<T} h[k] * (x[(m+1)D-1-k] - 127),  x[n<0] = 127   (complex f32)
+ *      fm_demod : d[m] = gain * atan2(Im(y[m] conj y[m-1]), Re(..)),  y[-1] = 0   (f32)
+ *      resample : a[i] = sum_p g[iM - pL] * d[p]   (rational L/M polyphase FIR, f32)
+ *    T=D, h=1 reduces low_pass to the reference boxcar (:337-352) without rotate_90.
+ * ========================================================================================== */
+typedef struct {
+    uint32_t n_taps;     /* T >= 1 */
+    uint32_t decim;      /* D >= 1 */
+    uint32_t n_taps2;    /* T2 (0 = no resample stage: audio = discriminator output) */
+    uint32_t up, down;   /* L, M of the resampler */
+    float gain;          /* discriminator gain; 0 => 16384/pi (the reference's i16 scale) */
+} sdr_fmrx_config;
+
+typedef struct sdr_fmrx sdr_fmrx;
+
+int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *taps2, int cuda_device,
+                 sdr_fmrx **out);
+void sdr_fmrx_free(sdr_fmrx *r);
+int sdr_fmrx_reset(sdr_fmrx *r);
+/* Counts a process() call of n_samples will produce from the current state. */
+int sdr_fmrx_out_lens(const sdr_fmrx *r, size_t n_samples, size_t *n_y, size_t *n_audio);
+/* Whole chain, host buffers, streaming state carried (history, y[m-1], discriminator tail).
+ * iq: 2*n_samples bytes.  y_pairs / demod may be NULL (then they are never written to HBM:
+ * the fused convert+FIR+demod kernel keeps y on chip).  Returns audio samples written. */
+long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y_pairs, size_t y_cap,
+                      float *demod, size_t demod_cap, float *audio, size_t audio_cap);
+/* Device-resident variant (asynchronous). */
+long sdr_fmrx_process_dev(sdr_fmrx *r, const uint8_t *d_iq, size_t n_samples, float *d_y_pairs,
+                          float *d_demod, float *d_audio, size_t audio_cap);
+/* Stage entry points (north_star names), host buffers, state carried per stage. */
+long sdr_fmrx_low_pass(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y_pairs, size_t cap_pairs);
+long sdr_fmrx_fm_demod(sdr_fmrx *r, const float *y_pairs, size_t n, float *out, size_t cap);
+long sdr_fmrx_resample(sdr_fmrx *r, const float *d, size_t n, float *out, size_t cap);
+int sdr_fmrx_sync(sdr_fmrx *r);
+/* Per-kernel device time of the last process*(): [0] fused convert+FIR(+demod), [1] resampler,
+ * [2] everything else; and launches.  Which kernel variant ran: 1 = specialised, 0 = generic. */
+int sdr_fmrx_last_timing(const sdr_fmrx *r, float ms[3], uint32_t *n_launches, int *specialised);
+
+/* ============================================================================================
+ * 3. Wideband channeliser (configs 4-5): per channel c an NCO mix by a 32-bit phase word
+ *    (theta_c(n) = 2*pi*((fw_c*n) mod 2^32)/2^32), the same decimating FIR, the discriminator.
+ *    Multi-GPU: channels are partitioned across ranks; the raw u8 slab is broadcast from rank 0
+ *    with one ncclBroadcast per slab and nothing else.
+ * ========================================================================================== */
+typedef struct {
+    uint32_t n_channels;
+    uint32_t n_taps, decim;
+    float gain;
+} sdr_chan_config;
+typedef struct sdr_chan sdr_chan;
+
+int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *freq_words,
+                 int cuda_device, sdr_chan **out);
+void sdr_chan_free(sdr_chan *c);
+int sdr_chan_reset(sdr_chan *c);
+/* Host buffers.  y_pairs: [C][M][2] or NULL; demod: [C][M].  M = outputs per channel (returned). */
+long sdr_chan_process(sdr_chan *c, const uint8_t *iq, size_t n_samples, float *y_pairs, float *demod,
+                      size_t cap_per_channel);
+long sdr_chan_process_dev(sdr_chan *c, const uint8_t *d_iq, size_t n_samples, float *d_y_pairs,
+                          float *d_demod, size_t cap_per_channel);
+int sdr_chan_sync(sdr_chan *c);
+int sdr_chan_last_timing(const sdr_chan *c, float *kernel_ms, uint32_t *n_launches);
+
+/* NCCL plumbing for the slab broadcast (libnccl is dlopen()ed lazily; absent => SDR_E_NCCL). */
+#define SDR_NCCL_ID_BYTES 128
+typedef struct sdr_comm sdr_comm;
+int sdr_comm_unique_id(uint8_t id[SDR_NCCL_ID_BYTES]);                  /* rank 0 */
+int sdr_comm_init(int cuda_device, int rank, int world, const uint8_t id[SDR_NCCL_ID_BYTES],
+                  sdr_comm **out);
+/* ncclBroadcast(d_buf, d_buf, bytes, ncclUint8, root) on the comm's own stream; returns after
+ * enqueue.  sdr_comm_wait_on(chan) makes the channeliser's stream wait for the last broadcast. */
+int sdr_comm_bcast_u8(sdr_comm *c, uint8_t *d_buf, size_t bytes, int root);
+int sdr_comm_chan_wait(sdr_comm *c, sdr_chan *ch);   /* chan stream waits for last bcast */
+int sdr_comm_wait_chan(sdr_comm *c, sdr_chan *ch);   /* bcast stream waits for chan's work */
+int sdr_comm_sync(sdr_comm *c);
+void sdr_comm_free(sdr_comm *c);
+
+/* ============================================================================================
+ * 4. Buffer source surface: RtlSdr::read_sync(&self, buf: &mut [u8]) -> Result<usize>
+ *    (src/lib.rs:153-155 -> src/rtlsdr.rs:409-411 -> src/device/mod.rs:141-143).  No USB here:
+ *    file and seeded-synthetic sources with the same caller-owned-buffer contract.
+ * ========================================================================================== */
+#define SDR_DEFAULT_BUF_LENGTH (16 * 16384)   /* DEFAULT_BUF_LENGTH, src/lib.rs:25 */
+typedef struct sdr_source sdr_source;
+int sdr_source_open_file(const char *path, int loop, sdr_source **out);
+int sdr_source_open_synth(uint64_t seed, uint64_t total_bytes /* 0 = endless */, sdr_source **out);
+/* Blocking; fills buf; returns bytes written (short count at end of data, like a short USB
+ * read, examples/simple_fm.rs:121-125) or SDR_E_IO. */
+long sdr_source_read_sync(sdr_source *s, uint8_t *buf, size_t len);
+/* Extension the reference only has as a TODO (src/lib.rs:147): librtlsdr-style async reads.
+ * Spawns the reader thread of examples/simple_fm.rs:89-132; cb runs on it for each full buffer
+ * (buf_num buffers of buf_len bytes are cycled); returns when the source ends or is cancelled. */
+typedef void (*sdr_read_async_cb)(const uint8_t *buf, size_t len, void *ctx);
+int sdr_source_read_async(sdr_source *s, sdr_read_async_cb cb, void *ctx, uint32_t buf_num, uint32_t buf_len);
+int sdr_source_cancel_async(sdr_source *s);
+void sdr_source_close(sdr_source *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDR_B200_H */

@@ -1,0 +1,888 @@
+// int_path.cu — reference-exact integer path of `Demod` (examples/simple_fm.rs:232-427) on sm_100a.
+//
+// The reference is a chain of sequential, stateful loops.  Every piece of its state is either a
+// pure function of the running sample count (prev_index :234, prev_lpr_index :236) or a partial
+// sum / last value at a cut (lp_now :237, demod_pre :238, now_lpr :235), so every output has a
+// closed-form window and the whole chain parallelises:
+//
+//   lowpassed w  = sum of samples [w*D - p0, (w+1)*D - p0)            (low_pass_complex :337-352)
+//   demod k      = disc(lp[k], lp[k-1]);  k first-in-call -> f64 atan2 (fm_demod :355-367)
+//   audio e      = (sum of demod [J(e-1), J(e))) / (fast/slow),
+//                  J(e) = ceil(((e+1)*fast - q0)/slow)                (low_pass_real :408-426)
+//
+// k_demod_fused does rotate_90 (:276-299) + `- 127` (:258) + all three stages for one tile of
+// audio outputs per CTA: the tile's raw bytes come in with one 1-D bulk async copy (TMA engine,
+// SASS UBLKCP) into shared memory, the intermediate streams never leave the SM, and only the i16
+// audio goes back to HBM (2.06 algorithmic bytes per complex input sample).
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sdr {
+
+struct IntState {   // the data-dependent part of struct Demod, device resident between chunks
+    int32_t lp_now_re, lp_now_im, demod_pre_re, demod_pre_im, now_lpr, pad0, pad1, pad2;
+};
+
+// (angle/PI*16384) as i32 for the eight exact octant directions and (0,0), evaluated once on the
+// host with the platform libm exactly like examples/simple_fm.rs:370-374 does (Rust's f64::atan2
+// is the platform libm).  Index: see octant_index().
+struct OctTable {
+    int32_t v[9];
+};
+
+struct FusedArgs {
+    const uint8_t *in;
+    int16_t *out;
+    const IntState *st_in;
+    IntState *st_out;
+    unsigned long long n_samples, Ltot, Etot;
+    uint32_t S, D, p0, q0, fast, slow;
+    int32_t div;
+    uint32_t EB, lp_cap, tile_cap;
+    OctTable oct;
+};
+
+// ---- device arithmetic, bit-exact with the reference's wrapping semantics ---------------------
+__device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+__device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+__device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+__device__ __forceinline__ int32_t tdiv(int32_t a, int32_t b) {
+    if (b == 0) return 0;                              // the reference would panic; same as oracle
+    if (a == INT32_MIN && b == -1) return INT32_MIN;
+    return a / b;
+}
+
+// Demod::fast_atan2, examples/simple_fm.rs:383-405 — the i64 product is wrapped to i32 BEFORE the divide.
+__device__ __forceinline__ int32_t d_fast_atan2(int32_t y, int32_t x) {
+    const int32_t pi4 = 1 << 12, pi34 = 3 * (1 << 12);
+    if (x == 0 && y == 0) return 0;
+    int32_t yabs = y < 0 ? wsub(0, y) : y;
+    int32_t angle;
+    if (x >= 0) {
+        int32_t num = (int32_t)(uint32_t)((long long)pi4 * (long long)wsub(x, yabs));
+        angle = wsub(pi4, tdiv(num, wadd(x, yabs)));
+    } else {
+        int32_t num = (int32_t)(uint32_t)((long long)pi4 * (long long)wadd(x, yabs));
+        angle = wsub(pi34, tdiv(num, wsub(yabs, x)));
+    }
+    return y < 0 ? wsub(0, angle) : angle;
+}
+
+// a * b.conj() for Complex<i32>, wrapping (examples/simple_fm.rs:371,378)
+__device__ __forceinline__ void d_cmul_conj(int2 a, int2 b, int32_t &cre, int32_t &cim) {
+    cre = wadd(wmul(a.x, b.x), wmul(a.y, b.y));
+    cim = wsub(wmul(a.y, b.x), wmul(a.x, b.y));
+}
+
+// Demod::polar_discriminant, :370-374.  Exact octant directions come from the host-libm table
+// (they are the only inputs whose f64 result sits exactly on an integer, where a 1-ulp
+// difference between libm implementations would change the truncated value).
+__device__ __forceinline__ int32_t d_polar_f64(int32_t cre, int32_t cim, const OctTable &oct) {
+    if (cre == 0 && cim == 0) return oct.v[8];
+    int64_t ax = cre < 0 ? -(int64_t)cre : cre, ay = cim < 0 ? -(int64_t)cim : cim;
+    if (cim == 0) return oct.v[cre > 0 ? 0 : 4];
+    if (cre == 0) return oct.v[cim > 0 ? 2 : 6];
+    if (ax == ay) return oct.v[cim > 0 ? (cre > 0 ? 1 : 3) : (cre > 0 ? 7 : 5)];
+    double angle = atan2((double)cim, (double)cre);
+    double v = angle / 3.14159265358979323846264338327950288 * 16384.0;
+    return (int32_t)v;   // truncation toward zero == Rust `as i32` in range
+}
+
+// One sample of rotate_90 (:285-295, "negation" is 255 - x) followed by `- 127` (:258):
+// centred (a, b) = (I-127, Q-127); a negated component is 128 - x = 1 - (x - 127).
+__device__ __forceinline__ void rot_acc(uint32_t iq16, int phase, int32_t &re, int32_t &im) {
+    int32_t a = (int32_t)(iq16 & 255u) - 127, b = (int32_t)(iq16 >> 8) - 127;
+    int32_t r, i;
+    switch (phase) {
+        case 0: r = a; i = b; break;            // [b0, b1]
+        case 1: r = 1 - b; i = a; break;        // [255-b3, b2]
+        case 2: r = 1 - a; i = 1 - b; break;    // [255-b4, 255-b5]
+        default: r = b; i = 1 - a; break;       // [b7, 255-b6]
+    }
+    re = wadd(re, r);
+    im = wadd(im, i);
+}
+
+// ================================================================================================
+// Fused kernel: one CTA per tile of EB audio outputs.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned long long sh_wlo, sh_jlo, sh_jhi, sh_e0;
+    __shared__ uint32_t sh_ne, sh_rb, sh_nlp, sh_tail_from, sh_ntail;
+    __shared__ int32_t sh_off0;
+
+    unsigned char *tile = smem;
+    int2 *lp = reinterpret_cast<int2 *>(smem + a.tile_cap);
+    int16_t *dm = reinterpret_cast<int16_t *>(smem + a.tile_cap + (size_t)a.lp_cap * 8);
+    uint8_t *flag = smem + a.tile_cap + (size_t)a.lp_cap * 10;
+
+    const int tid = threadIdx.x;
+    const bool last = blockIdx.x == gridDim.x - 1;
+    const IntState st = *a.st_in;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        const unsigned long long fast = a.fast, slow = a.slow;
+        unsigned long long e0 = (unsigned long long)blockIdx.x * a.EB;
+        unsigned long long e1 = e0 + a.EB < a.Etot ? e0 + a.EB : a.Etot;
+        if (e0 > a.Etot) e0 = a.Etot;
+        // J(e) = ceil(((e+1)*fast - q0)/slow), J(-1) = 0
+        unsigned long long jlo = e0 ? (e0 * fast - a.q0 + slow - 1) / slow : 0ull;
+        unsigned long long jhi = last ? a.Ltot : (e1 ? (e1 * fast - a.q0 + slow - 1) / slow : 0ull);
+        unsigned long long wlo = jlo ? jlo - 1 : 0ull;
+        // relative form: J(e0-1+u) = jlo + ceil((u*fast - rb)/slow) for u >= 1
+        uint32_t rb = e0 ? (uint32_t)(jlo * slow - (e0 * fast - a.q0)) : a.q0;
+        long long s_lo = (long long)(wlo * a.D) - (long long)a.p0;
+        if (s_lo < 0) s_lo = 0;
+        unsigned long long s_hi = last ? a.n_samples : jhi * a.D - a.p0;
+        unsigned long long b_lo = (2ull * (unsigned long long)s_lo) & ~15ull;
+        unsigned long long b_hi = (2ull * s_hi + 15ull) & ~15ull;
+        uint32_t bytes = (uint32_t)(b_hi - b_lo);
+        sh_wlo = wlo;
+        sh_jlo = jlo;
+        sh_jhi = jhi;
+        sh_e0 = e0;
+        sh_ne = (uint32_t)(e1 - e0);
+        sh_rb = rb;
+        sh_nlp = (uint32_t)(jhi - wlo);
+        sh_off0 = (int32_t)((long long)(wlo * a.D) - (long long)a.p0 - (long long)(b_lo >> 1));
+        // tail samples (after the last complete window) feed lp_now' — last CTA only
+        sh_tail_from = (uint32_t)((a.Ltot * a.D - a.p0) - (b_lo >> 1));
+        sh_ntail = (uint32_t)(a.n_samples - (a.Ltot * a.D - a.p0));
+        if (bytes) {
+            mbar_arrive_expect_tx(&bar, bytes);
+            bulk_g2s_stream(tile, a.in + b_lo, bytes, &bar);
+        } else {
+            mbar_arrive(&bar);
+        }
+    }
+    __syncthreads();
+    const unsigned long long wlo = sh_wlo, jlo = sh_jlo, jhi = sh_jhi;
+    const uint32_t nlp = sh_nlp;
+
+    // ---- first-of-call flags (while the bulk copy is in flight) --------------------------------
+    for (uint32_t i = tid; i < nlp; i += blockDim.x) flag[i] = 0;
+    __syncthreads();
+    if (jhi > jlo) {
+        // calls whose first window can lie in [jlo, jhi)
+        unsigned long long c_lo = ((jlo + 1) * a.D - a.p0 - 1) / a.S;
+        unsigned long long c_hi = (jhi * a.D - a.p0 - 1) / a.S;
+        for (unsigned long long c = c_lo + tid; c <= c_hi; c += blockDim.x) {
+            unsigned long long w = (c * a.S + a.p0) / a.D;
+            if (w >= jlo && w < jhi) flag[w - wlo] = 1;
+        }
+    }
+
+    // ---- phase 1: rotate_90 + centre + boxcar over D samples ------------------------------------
+    mbar_wait(&bar, 0);
+    const int32_t off0 = sh_off0;
+    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tile);
+    for (uint32_t i = tid; i < nlp; i += blockDim.x) {
+        int32_t base = off0 + (int32_t)(i * a.D);
+        int32_t re = 0, im = 0;
+        if (wlo + i == 0) {
+            re = st.lp_now_re;
+            im = st.lp_now_im;
+        }
+        for (uint32_t j = 0; j < a.D; j++) {
+            int32_t pos = base + (int32_t)j;
+            if (pos < 0) continue;   // only window 0 with p0 > 0: those samples are already in lp_now
+            rot_acc(t16[pos], pos & 3, re, im);
+        }
+        lp[i] = make_int2(re, im);
+    }
+    if (last && tid == 255) {
+        int32_t re = 0, im = 0;
+        for (uint32_t j = 0; j < sh_ntail; j++) {
+            uint32_t pos = sh_tail_from + j;
+            rot_acc(t16[pos], pos & 3, re, im);
+        }
+        a.st_out->lp_now_re = re;
+        a.st_out->lp_now_im = im;
+    }
+    __syncthreads();
+
+    // ---- phase 2: polar discriminator --------------------------------------------------------------
+    for (uint32_t i = tid; i < nlp; i += blockDim.x) {
+        unsigned long long k = wlo + i;
+        if (k < jlo) continue;   // the predecessor-only element
+        int2 cur = lp[i];
+        int2 prev = (k == 0) ? make_int2(st.demod_pre_re, st.demod_pre_im) : lp[i - 1];
+        int32_t cre, cim;
+        d_cmul_conj(cur, prev, cre, cim);
+        int32_t pcm = flag[i] ? d_polar_f64(cre, cim, a.oct) : d_fast_atan2(cim, cre);
+        dm[i] = (int16_t)(uint16_t)(uint32_t)pcm;
+    }
+    __syncthreads();
+
+    // ---- phase 3: fractional boxcar resampler ------------------------------------------------------
+    const uint32_t ne = sh_ne, rb = sh_rb;
+    const uint32_t dbase = (uint32_t)(jlo - wlo);   // dm index of demod sample jlo
+    for (uint32_t t = tid; t < ne; t += blockDim.x) {
+        uint32_t r0 = t ? (t * a.fast - rb + a.slow - 1) / a.slow : 0u;
+        uint32_t r1 = ((t + 1) * a.fast - rb + a.slow - 1) / a.slow;
+        int32_t sum = (sh_e0 + t == 0) ? st.now_lpr : 0;
+        for (uint32_t j = r0; j < r1; j++) sum = wadd(sum, (int32_t)dm[dbase + j]);
+        a.out[sh_e0 + t] = (int16_t)(uint16_t)(uint32_t)tdiv(sum, a.div);
+    }
+    if (last && tid == 0) {
+        uint32_t r0 = ne ? (ne * a.fast - rb + a.slow - 1) / a.slow : 0u;
+        int32_t sum = (a.Etot == 0) ? st.now_lpr : 0;
+        for (uint32_t j = dbase + r0; j < nlp; j++) sum = wadd(sum, (int32_t)dm[j]);
+        a.st_out->now_lpr = sum;
+        int2 lastlp = nlp ? lp[nlp - 1] : make_int2(st.demod_pre_re, st.demod_pre_im);
+        a.st_out->demod_pre_re = lastlp.x;
+        a.st_out->demod_pre_im = lastlp.y;
+    }
+}
+
+// ================================================================================================
+// Stage kernels (stage-level parity against the reference's known-answer tests)
+// ================================================================================================
+
+// Demod::rotate_90 scalar branch, :281-298: one 8-byte group per thread, two PRMTs.
+__global__ void k_rotate_90(uint2 *buf, size_t n_groups) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        uint2 w = buf[g];
+        uint2 o;
+        o.x = __byte_perm(w.x, ~w.x, 0x2710);   // [b0, b1, 255-b3, b2]
+        o.y = __byte_perm(w.y, ~w.y, 0x6354);   // [255-b4, 255-b5, b7, 255-b6]
+        buf[g] = o;
+    }
+}
+
+// `*val as i16 - 127` (:258) + buf_to_complex (:441-450): u8 pairs -> Complex<i32>
+__global__ void k_buf_to_complex(const uint16_t *in, size_t n_pairs, int2 *out) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+        uint32_t v = in[i];
+        out[i] = make_int2((int32_t)(v & 255u) - 127, (int32_t)(v >> 8) - 127);
+    }
+}
+
+// Demod::low_pass_complex, :337-352.  Thread w < L sums its window; thread L sums the tail into st.
+__global__ void k_low_pass_complex(const int2 *in, unsigned long long n, uint32_t D, uint32_t p0,
+                                   unsigned long long L, const IntState *st_in, IntState *st_out, int2 *out) {
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w <= L; w += stride) {
+        long long s0 = (long long)(w * D) - (long long)p0;
+        long long s1 = (w < L) ? s0 + D : (long long)n;
+        int32_t re = 0, im = 0;
+        if (w == 0) {
+            re = st_in->lp_now_re;
+            im = st_in->lp_now_im;
+        }
+        for (long long s = s0 < 0 ? 0 : s0; s < s1; s++) {
+            int2 v = in[s];
+            re = wadd(re, v.x);
+            im = wadd(im, v.y);
+        }
+        if (w < L) {
+            out[w] = make_int2(re, im);
+        } else {
+            st_out->lp_now_re = re;
+            st_out->lp_now_im = im;
+        }
+    }
+}
+
+// Demod::fm_demod, :355-367
+__global__ void k_fm_demod(const int2 *in, unsigned long long n, const IntState *st_in, IntState *st_out,
+                           OctTable oct, int16_t *out) {
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int2 cur = in[i];
+        int2 prev = i ? in[i - 1] : make_int2(st_in->demod_pre_re, st_in->demod_pre_im);
+        int32_t cre, cim;
+        d_cmul_conj(cur, prev, cre, cim);
+        int32_t pcm = i ? d_fast_atan2(cim, cre) : d_polar_f64(cre, cim, oct);
+        out[i] = (int16_t)(uint16_t)(uint32_t)pcm;
+        if (i == n - 1) {
+            st_out->demod_pre_re = cur.x;
+            st_out->demod_pre_im = cur.y;
+        }
+    }
+}
+
+// Demod::low_pass_real, :408-426.  Thread e < E emits output e; thread E sums the tail.
+__global__ void k_low_pass_real(const int16_t *in, unsigned long long n, uint32_t q0, uint32_t fast,
+                                uint32_t slow, int32_t div, unsigned long long E, const IntState *st_in,
+                                IntState *st_out, int16_t *out) {
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e <= E; e += stride) {
+        unsigned long long j0 = e ? (e * fast - q0 + slow - 1) / slow : 0ull;
+        unsigned long long j1 = (e < E) ? ((e + 1) * fast - q0 + slow - 1) / slow : n;
+        int32_t sum = (e == 0) ? st_in->now_lpr : 0;
+        for (unsigned long long j = j0; j < j1; j++) sum = wadd(sum, (int32_t)in[j]);
+        if (e < E)
+            out[e] = (int16_t)(uint16_t)(uint32_t)tdiv(sum, div);
+        else
+            st_out->now_lpr = sum;
+    }
+}
+
+__global__ void k_fast_atan2_v(const int32_t *y, const int32_t *x, size_t n, int32_t *out) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = d_fast_atan2(y[i], x[i]);
+}
+
+__global__ void k_polar_v(const int2 *a, const int2 *b, size_t n, int fast, OctTable oct, int32_t *out) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t cre, cim;
+        d_cmul_conj(a[i], b[i], cre, cim);
+        out[i] = fast ? d_fast_atan2(cim, cre) : d_polar_f64(cre, cim, oct);
+    }
+}
+
+}  // namespace sdr
+
+using namespace sdr;
+
+// ================================================================================================
+// Host side
+// ================================================================================================
+struct sdr_demod {
+    sdr_demod_config cfg{};
+    int device = 0;
+    sdr_demod_state st{};
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_t0 = nullptr, ev_t1 = nullptr;
+    DevBuf d_in[2], d_out[2], d_state, d_a, d_b, d_c;
+    PinBuf h_state;
+    OctTable oct{};
+    uint32_t EB = 0, lp_cap = 0, tile_cap = 0;
+    size_t smem_bytes = 0;
+    bool pending = false;      // async *_dev submission whose state has not been committed yet
+    int pending_slot = 0;
+    float last_ms = 0.f;
+    uint32_t last_launches = 0;
+    bool timing_valid = false;
+};
+
+namespace {
+
+constexpr size_t kChunkBytes = size_t(32) << 20;
+
+inline int grid_for(size_t n, int device, int per_block = 256) {
+    size_t b = (n + per_block - 1) / per_block;
+    size_t cap = (size_t)sm_count(device) * 16;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+
+void fill_oct_table(OctTable &t) {
+    // (angle / PI * (1 << 14) as f64) as i32 — examples/simple_fm.rs:372-373, platform libm
+    const double PI = 3.14159265358979323846264338327950288;
+    const int ys[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    const int xs[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    for (int i = 0; i < 8; i++) t.v[i] = (int32_t)(std::atan2((double)ys[i], (double)xs[i]) / PI * 16384.0);
+    t.v[8] = (int32_t)(std::atan2(0.0, 0.0) / PI * 16384.0);
+}
+
+void to_dev_state(const sdr_demod_state &s, IntState &d) {
+    memset(&d, 0, sizeof(d));
+    d.lp_now_re = s.lp_now_re;
+    d.lp_now_im = s.lp_now_im;
+    d.demod_pre_re = s.demod_pre_re;
+    d.demod_pre_im = s.demod_pre_im;
+    d.now_lpr = s.now_lpr;
+}
+
+// closed-form bookkeeping of a run of `n_bufs` calls of S samples from index state (p0, q0)
+struct Plan {
+    uint64_t n_samples, Ltot, Etot;
+    uint32_t p1, q1;
+};
+Plan make_plan(const sdr_demod_config &c, uint32_t p0, uint32_t q0, uint64_t S, uint64_t n_bufs) {
+    Plan p;
+    p.n_samples = S * n_bufs;
+    p.Ltot = (p0 + p.n_samples) / c.downsample;
+    p.p1 = (uint32_t)((p0 + p.n_samples) % c.downsample);
+    unsigned __int128 t = (unsigned __int128)p.Ltot * c.rate_resample + q0;
+    p.Etot = (uint64_t)(t / c.rate_out);
+    p.q1 = (uint32_t)(t % c.rate_out);
+    return p;
+}
+
+int validate_lens(const sdr_demod *d, size_t buf_len, size_t n_bufs) {
+    if (buf_len == 0 || n_bufs == 0) return fail(SDR_E_LEN, "empty buffer (the reference asserts >1 lowpassed samples, examples/simple_fm.rs:356)");
+    if (buf_len % 8 != 0)
+        return fail(SDR_E_LEN, "buffer length %zu is not a multiple of 8 (rotate_90 indexes i+7, examples/simple_fm.rs:284-295)", buf_len);
+    const uint64_t S = buf_len / 2, D = d->cfg.downsample;
+    uint64_t p = d->st.prev_index;
+    size_t lim = n_bufs < D ? n_bufs : (size_t)D;   // p_c is periodic with period <= D
+    for (size_t c = 0; c < lim; c++) {
+        if ((p + S) / D < 2)
+            return fail(SDR_E_LEN, "call %zu would produce %llu lowpassed samples; fm_demod asserts len > 1 (examples/simple_fm.rs:356)", c,
+                        (unsigned long long)((p + S) / D));
+        p = (p + S) % D;
+    }
+    return SDR_OK;
+}
+
+int commit_pending(sdr_demod *d) {
+    if (!d->pending) return SDR_OK;
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    const IntState *h = d->h_state.as<IntState>();
+    d->st.lp_now_re = h->lp_now_re;
+    d->st.lp_now_im = h->lp_now_im;
+    d->st.demod_pre_re = h->demod_pre_re;
+    d->st.demod_pre_im = h->demod_pre_im;
+    d->st.now_lpr = h->now_lpr;
+    d->pending = false;
+    if (d->timing_valid) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, d->ev_t0, d->ev_t1) == cudaSuccess) d->last_ms = ms;
+    }
+    return SDR_OK;
+}
+
+// Launch the fused kernel for one chunk that starts on a call boundary.
+int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls, uint32_t p0, uint32_t q0,
+                 const Plan &pl, const IntState *st_in, IntState *st_out, int16_t *d_out) {
+    FusedArgs a{};
+    a.in = d_in;
+    a.out = d_out;
+    a.st_in = st_in;
+    a.st_out = st_out;
+    a.n_samples = pl.n_samples;
+    a.Ltot = pl.Ltot;
+    a.Etot = pl.Etot;
+    a.S = (uint32_t)S;
+    a.D = d->cfg.downsample;
+    a.p0 = p0;
+    a.q0 = q0;
+    a.fast = d->cfg.rate_out;
+    a.slow = d->cfg.rate_resample;
+    a.div = (int32_t)(d->cfg.rate_out / d->cfg.rate_resample);
+    a.EB = d->EB;
+    a.lp_cap = d->lp_cap;
+    a.tile_cap = d->tile_cap;
+    a.oct = d->oct;
+    (void)n_calls;
+    uint64_t blocks = pl.Etot ? (pl.Etot + d->EB - 1) / d->EB : 1;
+    if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "batch too large for one launch");
+    k_demod_fused<<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
+    SDR_LAUNCH_CHECK();
+    d->last_launches++;
+    return SDR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdr_optimal_settings(uint32_t freq, uint32_t rate, uint32_t sample_rate, uint32_t rate_resample,
+                         sdr_radio_config *radio, sdr_demod_config *demod) {
+    if (rate == 0) return fail(SDR_E_ARG, "rate must be non-zero");
+    uint32_t downsample = (1000000u / rate) + 1u;           // examples/simple_fm.rs:190
+    uint32_t capture_rate = downsample * rate;               // :192
+    uint32_t capture_freq = freq + capture_rate / 4u;        // :195
+    uint32_t output_scale = (1u << 15) / (128u * downsample);  // :197
+    if (output_scale < 1u) output_scale = 1u;                // :198-200
+    if (radio) {
+        radio->capture_freq = capture_freq;
+        radio->capture_rate = capture_rate;
+    }
+    if (demod) {
+        demod->rate_in = sample_rate;                        // :207
+        demod->rate_out = sample_rate;                       // :208
+        demod->rate_resample = rate_resample;                // :209
+        demod->downsample = downsample;
+        demod->output_scale = output_scale;
+    }
+    return SDR_OK;
+}
+
+int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out) {
+    if (!cfg || !out) return fail(SDR_E_ARG, "sdr_demod_new: null argument");
+    if (cfg->downsample < 1) return fail(SDR_E_ARG, "downsample must be >= 1");
+    if (cfg->rate_resample < 1 || cfg->rate_resample > cfg->rate_out || cfg->rate_out >= (1u << 31))
+        return fail(SDR_E_ARG, "need 1 <= rate_resample <= rate_out < 2^31 (low_pass_real divides by rate_out/rate_resample, examples/simple_fm.rs:421)");
+    int rc = use_device(cuda_device);
+    if (rc) return rc;
+    sdr_demod *d = new sdr_demod();
+    d->cfg = *cfg;
+    d->device = cuda_device;
+    fill_oct_table(d->oct);
+    // tile geometry: ~16 KB of raw bytes per CTA
+    const uint64_t D = cfg->downsample, fast = cfg->rate_out, slow = cfg->rate_resample;
+    uint64_t n_lp_target = 8192 / D;
+    if (n_lp_target < 4) n_lp_target = 4;
+    if (n_lp_target > 2048) n_lp_target = 2048;
+    uint64_t EB = n_lp_target * slow / fast;
+    if (EB < 1) EB = 1;
+    if (EB > 1024) EB = 1024;
+    while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 32)) EB /= 2;
+    if ((EB + 1) * fast + slow >= (1ull << 32)) {
+        delete d;
+        return fail(SDR_E_ARG, "rate_out too large");
+    }
+    uint64_t per = (fast + slow - 1) / slow;
+    uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
+    uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 64;
+    uint64_t smem = tile_cap + ((lp_cap * 11 + 15) & ~15ull) + 16;
+    if (smem > 200 * 1024) {
+        delete d;
+        return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
+    }
+    d->EB = (uint32_t)EB;
+    d->lp_cap = (uint32_t)lp_cap;
+    d->tile_cap = (uint32_t)tile_cap;
+    d->smem_bytes = (size_t)smem;
+    cudaError_t e = cudaFuncSetAttribute(k_demod_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&d->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&d->ev_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&d->ev_t1);
+    if (e != cudaSuccess) {
+        sdr_demod_free(d);
+        return fail(SDR_E_CUDA, "sdr_demod_new: %s", cudaGetErrorString(e));
+    }
+    if ((rc = d->d_state.reserve(4 * sizeof(IntState))) || (rc = d->h_state.reserve(4 * sizeof(IntState)))) {
+        sdr_demod_free(d);
+        return rc;
+    }
+    *out = d;
+    return SDR_OK;
+}
+
+void sdr_demod_free(sdr_demod *d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        d->d_in[i].release();
+        d->d_out[i].release();
+        if (d->ev_h2d[i]) cudaEventDestroy(d->ev_h2d[i]);
+        if (d->ev_done[i]) cudaEventDestroy(d->ev_done[i]);
+    }
+    d->d_state.release();
+    d->d_a.release();
+    d->d_b.release();
+    d->d_c.release();
+    d->h_state.release();
+    if (d->ev_t0) cudaEventDestroy(d->ev_t0);
+    if (d->ev_t1) cudaEventDestroy(d->ev_t1);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    delete d;
+}
+
+int sdr_demod_get_state(const sdr_demod *d, sdr_demod_state *st) {
+    if (!d || !st) return fail(SDR_E_ARG, "null argument");
+    int rc = commit_pending(const_cast<sdr_demod *>(d));
+    if (rc) return rc;
+    *st = d->st;
+    return SDR_OK;
+}
+
+int sdr_demod_set_state(sdr_demod *d, const sdr_demod_state *st) {
+    if (!d || !st) return fail(SDR_E_ARG, "null argument");
+    int rc = commit_pending(d);
+    if (rc) return rc;
+    if (st->prev_index >= d->cfg.downsample) return fail(SDR_E_ARG, "prev_index must be < downsample");
+    if (st->prev_lpr_index < 0 || (uint32_t)st->prev_lpr_index >= d->cfg.rate_out)
+        return fail(SDR_E_ARG, "prev_lpr_index must be in [0, rate_out)");
+    d->st = *st;
+    return SDR_OK;
+}
+
+long sdr_demod_out_len(const sdr_demod *d, size_t len) {
+    if (!d) return fail(SDR_E_ARG, "null handle");
+    int rc = validate_lens(d, len, 1);
+    if (rc) return rc;
+    Plan p = make_plan(d->cfg, (uint32_t)d->st.prev_index, (uint32_t)d->st.prev_lpr_index, len / 2, 1);
+    return (long)p.Etot;
+}
+
+long sdr_demod_demodulate_batch(sdr_demod *d, const uint8_t *buf, size_t buf_len, size_t n_bufs, int16_t *out,
+                                size_t out_cap, uint32_t *out_lens) {
+    if (!d || !buf || !out) return fail(SDR_E_ARG, "sdr_demod_demodulate: null argument");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if ((rc = commit_pending(d))) return rc;
+    if ((rc = validate_lens(d, buf_len, n_bufs))) return rc;
+    const uint64_t S = buf_len / 2;
+    const uint32_t p0 = (uint32_t)d->st.prev_index, q0 = (uint32_t)d->st.prev_lpr_index;
+    Plan total = make_plan(d->cfg, p0, q0, S, n_bufs);
+    if (total.Etot > out_cap)
+        return fail(SDR_E_CAP, "output capacity %zu < %llu audio samples", out_cap, (unsigned long long)total.Etot);
+    if (out_lens) {
+        uint32_t p = p0, q = q0;
+        for (size_t c = 0; c < n_bufs; c++) {
+            Plan one = make_plan(d->cfg, p, q, S, 1);
+            out_lens[c] = (uint32_t)one.Etot;
+            p = one.p1;
+            q = one.q1;
+        }
+    }
+    size_t per_chunk = kChunkBytes / buf_len;
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > n_bufs) per_chunk = n_bufs;
+    const size_t chunk_bytes = per_chunk * buf_len;
+    const size_t chunk_out_cap = (size_t)(make_plan(d->cfg, 0, d->cfg.rate_out - 1, S, per_chunk).Etot + 2);
+    for (int i = 0; i < 2; i++) {
+        if ((rc = d->d_in[i].reserve(chunk_bytes + 64))) return rc;
+        if ((rc = d->d_out[i].reserve(chunk_out_cap * sizeof(int16_t)))) return rc;
+    }
+    IntState *dst = d->d_state.as<IntState>();
+    IntState hs;
+    to_dev_state(d->st, hs);
+    *d->h_state.as<IntState>() = hs;
+    SDR_CUDA_TRY(cudaMemcpyAsync(&dst[0], d->h_state.p, sizeof(IntState), cudaMemcpyHostToDevice, d->stream));
+    d->last_launches = 0;
+    d->timing_valid = false;
+
+    uint32_t p = p0, q = q0;
+    size_t done = 0, out_off = 0;
+    int chunk = 0;
+    while (done < n_bufs) {
+        const int slot = chunk & 1;
+        const size_t nb = (n_bufs - done < per_chunk) ? n_bufs - done : per_chunk;
+        Plan pl = make_plan(d->cfg, p, q, S, nb);
+        // the copy engine may not overwrite a slot until the kernel that read it has finished
+        if (chunk >= 2) SDR_CUDA_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_done[slot], 0));
+        SDR_CUDA_TRY(cudaMemcpyAsync(d->d_in[slot].p, buf + done * buf_len, nb * buf_len, cudaMemcpyHostToDevice,
+                                     d->copy_stream));
+        SDR_CUDA_TRY(cudaEventRecord(d->ev_h2d[slot], d->copy_stream));
+        SDR_CUDA_TRY(cudaStreamWaitEvent(d->stream, d->ev_h2d[slot], 0));
+        if ((rc = launch_fused(d, d->d_in[slot].as<uint8_t>(), S, nb, p, q, pl, &dst[chunk & 1], &dst[(chunk + 1) & 1],
+                               d->d_out[slot].as<int16_t>())))
+            return rc;
+        if (pl.Etot)
+            SDR_CUDA_TRY(cudaMemcpyAsync(out + out_off, d->d_out[slot].p, pl.Etot * sizeof(int16_t),
+                                         cudaMemcpyDeviceToHost, d->stream));
+        SDR_CUDA_TRY(cudaEventRecord(d->ev_done[slot], d->stream));
+        p = pl.p1;
+        q = pl.q1;
+        out_off += pl.Etot;
+        done += nb;
+        chunk++;
+    }
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->h_state.p, &dst[chunk & 1], sizeof(IntState), cudaMemcpyDeviceToHost, d->stream));
+    d->st.prev_index = p;
+    d->st.prev_lpr_index = (int32_t)q;
+    d->pending = true;
+    if ((rc = commit_pending(d))) return rc;
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->copy_stream));
+    return (long)total.Etot;
+}
+
+long sdr_demod_demodulate(sdr_demod *d, const uint8_t *buf, size_t len, int16_t *out, size_t out_cap) {
+    return sdr_demod_demodulate_batch(d, buf, len, 1, out, out_cap, nullptr);
+}
+
+long sdr_demod_demodulate_batch_dev(sdr_demod *d, const uint8_t *d_buf, size_t buf_len, size_t n_bufs,
+                                    int16_t *d_out, size_t out_cap) {
+    if (!d || !d_buf || !d_out) return fail(SDR_E_ARG, "sdr_demod_demodulate_batch_dev: null argument");
+    if (reinterpret_cast<uintptr_t>(d_buf) & 15) return fail(SDR_E_ARG, "device input must be 16-byte aligned (use sdr_dev_alloc)");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if ((rc = commit_pending(d))) return rc;
+    if ((rc = validate_lens(d, buf_len, n_bufs))) return rc;
+    const uint64_t S = buf_len / 2;
+    const uint32_t p0 = (uint32_t)d->st.prev_index, q0 = (uint32_t)d->st.prev_lpr_index;
+    Plan pl = make_plan(d->cfg, p0, q0, S, n_bufs);
+    if (pl.Etot > out_cap)
+        return fail(SDR_E_CAP, "output capacity %zu < %llu audio samples", out_cap, (unsigned long long)pl.Etot);
+    IntState *dst = d->d_state.as<IntState>();
+    IntState hs;
+    to_dev_state(d->st, hs);
+    *d->h_state.as<IntState>() = hs;
+    SDR_CUDA_TRY(cudaMemcpyAsync(&dst[0], d->h_state.p, sizeof(IntState), cudaMemcpyHostToDevice, d->stream));
+    d->last_launches = 0;
+    SDR_CUDA_TRY(cudaEventRecord(d->ev_t0, d->stream));
+    if ((rc = launch_fused(d, d_buf, S, n_bufs, p0, q0, pl, &dst[0], &dst[1], d_out))) return rc;
+    SDR_CUDA_TRY(cudaEventRecord(d->ev_t1, d->stream));
+    d->timing_valid = true;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->h_state.p, &dst[1], sizeof(IntState), cudaMemcpyDeviceToHost, d->stream));
+    d->st.prev_index = pl.p1;
+    d->st.prev_lpr_index = (int32_t)pl.q1;
+    d->pending = true;
+    return (long)pl.Etot;
+}
+
+int sdr_demod_sync(sdr_demod *d) {
+    if (!d) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if ((rc = commit_pending(d))) return rc;
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return SDR_OK;
+}
+
+int sdr_demod_last_timing(const sdr_demod *d, float *kernel_ms, uint32_t *n_launches) {
+    if (!d) return fail(SDR_E_ARG, "null handle");
+    if (kernel_ms) *kernel_ms = d->last_ms;
+    if (n_launches) *n_launches = d->last_launches;
+    return SDR_OK;
+}
+
+// ---- stage entry points ---------------------------------------------------------------------------
+
+long sdr_rotate_90(sdr_demod *d, uint8_t *buf, size_t len) {
+    if (!d || !buf) return fail(SDR_E_ARG, "null argument");
+    if (len % 8) return fail(SDR_E_LEN, "rotate_90 needs len %% 8 == 0 (examples/simple_fm.rs:284-295)");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if (len == 0) return 0;
+    if ((rc = d->d_a.reserve(len))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_a.p, buf, len, cudaMemcpyHostToDevice, d->stream));
+    k_rotate_90<<<grid_for(len / 8, d->device), 256, 0, d->stream>>>(d->d_a.as<uint2>(), len / 8);
+    SDR_LAUNCH_CHECK();
+    SDR_CUDA_TRY(cudaMemcpyAsync(buf, d->d_a.p, len, cudaMemcpyDeviceToHost, d->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return (long)len;
+}
+
+long sdr_buf_to_complex(sdr_demod *d, const uint8_t *buf, size_t len, int32_t *out_pairs, size_t cap_pairs) {
+    if (!d || !buf || !out_pairs) return fail(SDR_E_ARG, "null argument");
+    size_t n = len / 2;   // windows(2).step_by(2): a trailing odd byte is dropped (:441-450)
+    if (n > cap_pairs) return fail(SDR_E_CAP, "capacity %zu < %zu pairs", cap_pairs, n);
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if ((rc = d->d_a.reserve(len + 16)) || (rc = d->d_b.reserve(n * 8))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_a.p, buf, n * 2, cudaMemcpyHostToDevice, d->stream));
+    k_buf_to_complex<<<grid_for(n, d->device), 256, 0, d->stream>>>(d->d_a.as<uint16_t>(), n, d->d_b.as<int2>());
+    SDR_LAUNCH_CHECK();
+    SDR_CUDA_TRY(cudaMemcpyAsync(out_pairs, d->d_b.p, n * 8, cudaMemcpyDeviceToHost, d->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return (long)n;
+}
+
+static int upload_state(sdr_demod *d) {
+    IntState hs;
+    to_dev_state(d->st, hs);
+    d->h_state.as<IntState>()[0] = hs;
+    d->h_state.as<IntState>()[1] = hs;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_state.p, d->h_state.p, 2 * sizeof(IntState), cudaMemcpyHostToDevice, d->stream));
+    return SDR_OK;
+}
+static int download_state(sdr_demod *d, IntState *hs) {
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->h_state.p, d->d_state.as<IntState>() + 1, sizeof(IntState), cudaMemcpyDeviceToHost,
+                                 d->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    *hs = *d->h_state.as<IntState>();
+    return SDR_OK;
+}
+
+long sdr_low_pass_complex(sdr_demod *d, const int32_t *iq, size_t n, int32_t *out_pairs, size_t cap_pairs) {
+    if (!d || (!iq && n) || !out_pairs) return fail(SDR_E_ARG, "null argument");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if ((rc = commit_pending(d))) return rc;
+    const uint32_t D = d->cfg.downsample, p0 = (uint32_t)d->st.prev_index;
+    const uint64_t L = (p0 + (uint64_t)n) / D;
+    if (L > cap_pairs) return fail(SDR_E_CAP, "capacity %zu < %llu pairs", cap_pairs, (unsigned long long)L);
+    if (n == 0) return 0;
+    if ((rc = d->d_a.reserve(n * 8)) || (rc = d->d_b.reserve((L + 1) * 8))) return rc;
+    if ((rc = upload_state(d))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_a.p, iq, n * 8, cudaMemcpyHostToDevice, d->stream));
+    IntState *ds = d->d_state.as<IntState>();
+    k_low_pass_complex<<<grid_for(L + 1, d->device), 256, 0, d->stream>>>(d->d_a.as<int2>(), n, D, p0, L, ds, ds + 1,
+                                                                            d->d_b.as<int2>());
+    SDR_LAUNCH_CHECK();
+    if (L) SDR_CUDA_TRY(cudaMemcpyAsync(out_pairs, d->d_b.p, L * 8, cudaMemcpyDeviceToHost, d->stream));
+    IntState hs;
+    if ((rc = download_state(d, &hs))) return rc;
+    d->st.lp_now_re = hs.lp_now_re;
+    d->st.lp_now_im = hs.lp_now_im;
+    d->st.prev_index = (p0 + (uint64_t)n) % D;
+    return (long)L;
+}
+
+long sdr_fm_demod(sdr_demod *d, const int32_t *iq, size_t n, int16_t *out, size_t cap) {
+    if (!d || !iq || !out) return fail(SDR_E_ARG, "null argument");
+    if (n < 2) return fail(SDR_E_LEN, "fm_demod asserts buf.len() > 1 (examples/simple_fm.rs:356)");
+    if (n > cap) return fail(SDR_E_CAP, "capacity %zu < %zu", cap, n);
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if ((rc = commit_pending(d))) return rc;
+    if ((rc = d->d_a.reserve(n * 8)) || (rc = d->d_b.reserve(n * 2))) return rc;
+    if ((rc = upload_state(d))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_a.p, iq, n * 8, cudaMemcpyHostToDevice, d->stream));
+    IntState *ds = d->d_state.as<IntState>();
+    k_fm_demod<<<grid_for(n, d->device), 256, 0, d->stream>>>(d->d_a.as<int2>(), n, ds, ds + 1, d->oct, d->d_b.as<int16_t>());
+    SDR_LAUNCH_CHECK();
+    SDR_CUDA_TRY(cudaMemcpyAsync(out, d->d_b.p, n * 2, cudaMemcpyDeviceToHost, d->stream));
+    IntState hs;
+    if ((rc = download_state(d, &hs))) return rc;
+    d->st.demod_pre_re = hs.demod_pre_re;
+    d->st.demod_pre_im = hs.demod_pre_im;
+    return (long)n;
+}
+
+long sdr_low_pass_real(sdr_demod *d, const int16_t *in, size_t n, int16_t *out, size_t cap) {
+    if (!d || (!in && n) || !out) return fail(SDR_E_ARG, "null argument");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if ((rc = commit_pending(d))) return rc;
+    const uint32_t fast = d->cfg.rate_out, slow = d->cfg.rate_resample, q0 = (uint32_t)d->st.prev_lpr_index;
+    unsigned __int128 t = (unsigned __int128)n * slow + q0;
+    const uint64_t E = (uint64_t)(t / fast);
+    if (E > cap) return fail(SDR_E_CAP, "capacity %zu < %llu", cap, (unsigned long long)E);
+    if (n == 0) return 0;
+    if ((rc = d->d_a.reserve(n * 2)) || (rc = d->d_b.reserve((E + 1) * 2))) return rc;
+    if ((rc = upload_state(d))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_a.p, in, n * 2, cudaMemcpyHostToDevice, d->stream));
+    IntState *ds = d->d_state.as<IntState>();
+    k_low_pass_real<<<grid_for(E + 1, d->device), 256, 0, d->stream>>>(d->d_a.as<int16_t>(), n, q0, fast, slow,
+                                                                         (int32_t)(fast / slow), E, ds, ds + 1,
+                                                                         d->d_b.as<int16_t>());
+    SDR_LAUNCH_CHECK();
+    if (E) SDR_CUDA_TRY(cudaMemcpyAsync(out, d->d_b.p, E * 2, cudaMemcpyDeviceToHost, d->stream));
+    IntState hs;
+    if ((rc = download_state(d, &hs))) return rc;
+    d->st.now_lpr = hs.now_lpr;
+    d->st.prev_lpr_index = (int32_t)(uint32_t)(t % fast);
+    return (long)E;
+}
+
+long sdr_fast_atan2(sdr_demod *d, const int32_t *y, const int32_t *x, size_t n, int32_t *out) {
+    if (!d || !y || !x || !out) return fail(SDR_E_ARG, "null argument");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if ((rc = d->d_a.reserve(n * 4)) || (rc = d->d_b.reserve(n * 4)) || (rc = d->d_c.reserve(n * 4))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_a.p, y, n * 4, cudaMemcpyHostToDevice, d->stream));
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_b.p, x, n * 4, cudaMemcpyHostToDevice, d->stream));
+    k_fast_atan2_v<<<grid_for(n, d->device), 256, 0, d->stream>>>(d->d_a.as<int32_t>(), d->d_b.as<int32_t>(), n,
+                                                                    d->d_c.as<int32_t>());
+    SDR_LAUNCH_CHECK();
+    SDR_CUDA_TRY(cudaMemcpyAsync(out, d->d_c.p, n * 4, cudaMemcpyDeviceToHost, d->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return (long)n;
+}
+
+long sdr_polar_discriminant(sdr_demod *d, const int32_t *a, const int32_t *b, size_t n, int fast, int32_t *out) {
+    if (!d || !a || !b || !out) return fail(SDR_E_ARG, "null argument");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if ((rc = d->d_a.reserve(n * 8)) || (rc = d->d_b.reserve(n * 8)) || (rc = d->d_c.reserve(n * 4))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_a.p, a, n * 8, cudaMemcpyHostToDevice, d->stream));
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_b.p, b, n * 8, cudaMemcpyHostToDevice, d->stream));
+    k_polar_v<<<grid_for(n, d->device), 256, 0, d->stream>>>(d->d_a.as<int2>(), d->d_b.as<int2>(), n, fast, d->oct,
+                                                               d->d_c.as<int32_t>());
+    SDR_LAUNCH_CHECK();
+    SDR_CUDA_TRY(cudaMemcpyAsync(out, d->d_c.p, n * 4, cudaMemcpyDeviceToHost, d->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return (long)n;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/sdr_b200.h declares, the ctypes table covers exactly that set, and compute entry points fail
+LOUDLY (SDR_E_CUDA) instead of falling back to anything when no device is present."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import sdrpkg
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "sdr_b200.h"
+
+
+def declared_functions():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    text = re.sub(r"typedef\s+void\s*\(\*\w+\)\([^;]*\);", "", text)
+    return sorted(set(re.findall(r"\b(sdr_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def S():
+    return sdrpkg.load()
+
+
+def test_library_loads_and_exports_every_declared_symbol(S):
+    names = declared_functions()
+    assert len(names) >= 55
+    L = C.CDLL(str(S.LIB_PATH))
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, f"declared in include/sdr_b200.h but not exported: {missing}"
+    assert S.lib().sdr_abi_version() == 1
+
+
+def test_ctypes_table_matches_header(S):
+    from rtl_sdr_rs_b200 import _ffi
+    assert sorted(_ffi.SIGNATURES) == declared_functions()
+
+
+def test_header_cites_the_reference_interface_it_replaces():
+    text = HEADER.read_text()
+    for cite in ("src/lib.rs:153", ":256-269", "examples/simple_fm.rs:179", ":337-352", ":355-367",
+                 ":408-426", ":383-405", ":276-299", "src/error.rs"):
+        assert cite in text, cite
+
+
+def test_optimal_settings_is_host_arithmetic(S):
+    r, c = S.optimal_settings()            # examples/simple_fm.rs:189-214
+    assert (c.downsample, c.output_scale, r.capture_rate, r.capture_freq) == (6, 42, 1_020_000, 95_155_000)
+    r, c = S.optimal_settings(100_000_000, 2_400_000, 2_400_000, 48_000)
+    assert (c.downsample, c.output_scale) == (1, 256)
+
+
+def test_no_cpu_fallback_without_a_device(S):
+    if S.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(S.SdrError) as e:
+        S.Demod()
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+    with pytest.raises(S.SdrError):
+        S.DevBuffer(1024)
+
+
+def test_package_has_no_oracle_dependency():
+    """The product package must never import or link the oracle (parity would be void)."""
+    pkg = ROOT / "rtl-sdr-rs_b200"
+    for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")) + list(pkg.glob("host/*")):
+        if f.is_file():
+            t = f.read_text(errors="ignore")
+            assert "oracle_ffi" not in t and "liboracle" not in t and "sdr_oracle" not in t, f
+
+
+def test_source_read_sync_file_and_synth(S, tmp_path, golden_dir):
+    import oracle_ffi as O
+    head = golden_dir / "capture_head.bin"
+    src = S.Source.open_file(head)
+    buf = np.empty(262144, np.uint8)
+    total, first = 0, None
+    while True:
+        n = src.read_sync(buf)
+        if first is None:
+            first = buf[:16].copy()
+        total += n
+        if n < buf.size:           # short read == end of data (examples/simple_fm.rs:121-125)
+            break
+    assert total == head.stat().st_size and first.tolist() == np.fromfile(head, np.uint8, 16).tolist()
+    src.close()
+    syn = S.Source.open_synth(0xB2000001, total_bytes=1000)
+    b = np.empty(600, np.uint8)
+    assert syn.read_sync(b) == 600 and np.array_equal(b, O.synth_fill(600, 0xB2000001))
+    assert syn.read_sync(b) == 400 and np.array_equal(b[:400], O.synth_fill(400, 0xB2000001, 600))
+    assert syn.read_sync(b) == 0
+    with pytest.raises(S.SdrError):
+        S.Source.open_file(tmp_path / "does-not-exist.bin")
+
+
+def test_source_read_async_delivers_every_full_buffer_in_order(S):
+    import oracle_ffi as O
+    n_bufs, blen = 37, 4096
+    syn = S.Source.open_synth(42, total_bytes=n_bufs * blen + 100)   # trailing short read is dropped
+    got = []
+    syn.read_async(lambda a: got.append(a.copy()), buf_num=4, buf_len=blen)
+    assert len(got) == n_bufs
+    assert np.array_equal(np.concatenate(got), O.synth_fill(n_bufs * blen, 42))
+    # cancel from inside the callback stops delivery
+    syn2 = S.Source.open_synth(43)
+    seen = []
+
+    def cb(a):
+        seen.append(a[0])
+        if len(seen) == 5:
+            syn2.cancel()
+    syn2.read_async(cb, buf_num=3, buf_len=1024)
+    assert 5 <= len(seen) <= 8
