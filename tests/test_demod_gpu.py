@@ -224,7 +224,7 @@ def test_device_resident_batch_and_size_independent_properties(S):
     # device generator == oracle generator on a sample
     assert np.array_equal(d_in.download(np.uint8, 4096, offset=123 * 8), O.synth_fill(4096, seed, 123 * 8))
     d = S.Demod()
-    cap = d.out_len(BUF) * n_bufs + 64
+    cap = (d.out_len(BUF) + 1) * n_bufs + 64   # per-call counts alternate 4112/4113
     d_out = S.DevBuffer(cap * 2)
     n = d.demodulate_batch_dev(d_in, BUF, n_bufs, d_out, cap)
     d.sync()
