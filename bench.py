@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the IQ-sample DSP hot path (driver contract in the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic IQ that is ALREADY RESIDENT in HBM.
+
+  cfg2 (default; BASELINE.json configs[1]): single-channel 2.4 Msps-equivalent synthetic IQ, 127-tap
+        FIR decimate-by-75, fused convert+FIR+polar-discriminator kernel, 63-tap audio FIR at 32 kHz;
+        2^30 complex samples (2 GiB of u8) per GPU per step.
+  cfg3 (configs[2]): 20 Msps-equivalent, 255-tap FIR /100, FM demod, 200k->32k (4/25) resampler.
+  cfg1 (configs[0] semantics at scale): the reference-exact integer Demod (boxcar-6, fast_atan2,
+        170k->32k) over 8192 x 262144-byte buffers per step.
+
+N > 1 (launched by torchrun, one rank per GPU): every rank owns one time slice of the same synthetic
+stream (weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
+`--impl reference` times the CPU restatement of the same workload (oracle port; the reference itself is
+Rust and cannot be built in this image) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+SEED = 0xB2000001
+METRIC = "IQ Msamples/s through fused convert+FIR+demod kernel; achieved HBM GB/s vs B200 peak"
+
+
+def workload_spec(name: str) -> dict:
+    if name == "cfg2":
+        return dict(name="cfg2", T=127, D=75, T2=63, up=1, down=1, fs=2.4e6, n=1 << 30, dtype="f32",
+                    desc="single-channel 2.4 Msps-equivalent synthetic IQ, 127-tap FIR decimate-by-75, fused "
+                         "convert+FIR+FM-demod kernel, 63-tap audio FIR @32 kHz (BASELINE.json configs[1])")
+    if name == "cfg3":
+        return dict(name="cfg3", T=255, D=100, T2=127, up=4, down=25, fs=20e6, n=1 << 30, dtype="f32",
+                    desc="single-channel 20 Msps-equivalent synthetic IQ, 255-tap FIR decimate-by-100, fused "
+                         "convert+FIR+FM-demod kernel, 200k->32k (4/25) 127-tap resampler (BASELINE.json configs[2])")
+    if name == "cfg1":
+        return dict(name="cfg1", buf_len=262144, n_bufs=8192, n=8192 * 131072, dtype="i32",
+                    desc="reference-exact integer Demod (rotate_90, -127, boxcar-6, fast_atan2, 170k->32k), "
+                         "8192 x 262144-byte buffers per step (BASELINE.json configs[0] semantics at HBM scale)")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def taps_for(w: dict):
+    from sigutil import channel_taps, lowpass_taps
+    taps = channel_taps(w["T"], w["D"])
+    taps2 = lowpass_taps(w["T2"], 0.45 / max(w["up"], w["down"]), gain=w["up"])
+    return taps, taps2
+
+
+def alg_bytes_per_sample(w: dict) -> float:
+    """Algorithmic HBM bytes of the DOMINANT kernel per complex input sample."""
+    if w["name"] == "cfg1":
+        return 2.0 + 2.0 * (32000 / 170000) / 6        # u8 IQ in, i16 audio out
+    return 2.0 + 4.0 / w["D"]                          # u8 IQ in, f32 discriminator out
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()          # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in Path(self.path).read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2])), pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (cpu_baseline leg and --impl reference): the oracle port timed on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_run(w: dict, sample_samples: int, reps: int, threads: int):
+    """Returns (seconds per rep list, samples per rep).  This is the ONLY place bench.py executes oracle/."""
+    import ctypes as C
+    import oracle_ffi as O
+    L = O.lib()
+    if w["name"] == "cfg1":
+        buf_len = w["buf_len"]
+        n_bufs = max(threads, sample_samples * 2 // buf_len)
+        data = O.synth_fill(n_bufs * buf_len, SEED)
+        _, cfg = O.optimal_settings()
+        out = np.empty(n_bufs * 4200, np.int16)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = L.orc_demodulate_many_mt(C.byref(cfg), O._p(data, C.c_uint8), buf_len, n_bufs, O._p(out, C.c_int16),
+                                         out.size, threads)
+            times.append(time.perf_counter() - t0)
+            assert r > 0
+        return times, n_bufs * buf_len // 2
+    taps, taps2 = taps_for(w)
+    iq = O.synth_fill(2 * sample_samples, SEED)
+    audio = np.empty(sample_samples // w["D"] * w["up"] // w["down"] + 16, np.float32)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        na = L.orc_fx_process_f32_mt(O._p(iq, C.c_uint8), sample_samples, O._p(taps, C.c_float), taps.size, w["D"],
+                                     O._p(taps2, C.c_float), taps2.size, w["up"], w["down"], C.c_float(16384.0 / np.pi),
+                                     O._p(audio, C.c_float), audio.size, threads)
+        times.append(time.perf_counter() - t0)
+        assert na > 0
+    return times, sample_samples
+
+
+def cpu_baseline(w: dict, budget_s: float = 8.0) -> dict:
+    import oracle_ffi as O
+    threads = O.max_threads()
+    sample = 1 << 26
+    t, n = cpu_run(w, sample, 1, threads)          # warm-up / calibration
+    reps = int(max(2, min(200, budget_s / max(t[0], 1e-3))))
+    times, n = cpu_run(w, sample, reps, threads)
+    best = n / min(times) / 1e6
+    return {"value": round(n / statistics.median(times) / 1e6, 2), "best": round(best, 2), "unit": "Msamples/s",
+            "cores": threads, "kind": "port",
+            "sample": f"{reps} passes over {n} complex samples (seeded synthetic, same taps/config), "
+                      f"oracle port ({'ref-like integer Demod, one independent Demod per thread' if w['name'] == 'cfg1' else 'f32 FIR+atan2f+resampler'}), {threads} pthreads"}
+
+
+def run_reference_arm(args, w):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    import oracle_ffi as O
+    threads = O.max_threads()
+    sample = 1 << 26
+    times, n = cpu_run(w, sample, args.warmup + args.steps, threads)
+    times = times[args.warmup:]
+    total = sum(times)
+    value = n * len(times) / total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(times), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": {"workload": w["desc"], "note": "the reference (Rust) cannot be built in this image: this arm is the "
+                   "oracle's CPU restatement of the same workload on all host threads; each step is a bounded sample"},
+        "cpu_baseline": {"value": round(value, 2), "unit": "Msamples/s", "cores": threads, "kind": "port",
+                         "sample": f"each step = {n} complex samples of the workload"},
+        "e2e": {"value": round(value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--n-log2", type=int, default=0, help="override samples per GPU per step (profiling runs only)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = workload_spec(args.workload)
+    if args.n_log2:
+        w["n"] = 1 << args.n_log2
+        if w["name"] == "cfg1":
+            w["n_bufs"] = w["n"] // 131072
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+
+    rank, local_rank, world = dist_env()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+    device = local_rank
+
+    import sdrpkg
+    S = sdrpkg.load()
+    if S.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    info = S.device_info(device)
+    n = w["n"]
+    # each rank owns the time slice [rank*n, (rank+1)*n) of ONE synthetic stream
+    d_in = S.DevBuffer(2 * n, device)
+    S.synth_fill_dev(d_in, 2 * n, SEED, byte_offset=2 * n * rank)
+
+    if w["name"] == "cfg1":
+        h = S.Demod(device=device)
+        out_cap = (h.out_len(w["buf_len"]) + 1) * w["n_bufs"] + 64
+        d_out = S.DevBuffer(2 * out_cap, device)
+
+        def step():
+            return h.demodulate_batch_dev(d_in, w["buf_len"], w["n_bufs"], d_out, out_cap)
+    else:
+        taps, taps2 = taps_for(w)
+        h = S.FmRx(taps, w["D"], taps2, w["up"], w["down"], device=device)
+        h.seek(n * rank)
+        _, na = h.out_lens(n)
+        out_cap = na + 64
+        d_out = S.DevBuffer(4 * out_cap, device)
+
+        def step():
+            return h.process_dev(d_in, n, d_out, out_cap)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        h.sync()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if w["name"] != "cfg1":
+        h.timing_totals(reset=True)
+    launches0 = S.kernel_launch_count()
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    h.span_begin()
+    for _ in range(args.steps):
+        step()
+    total_ms = h.span_end()          # records the closing event and waits for it
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = S.kernel_launch_count() - launches0
+    if w["name"] == "cfg1":
+        kern_ms = total_ms / args.steps
+    else:
+        sums, calls = h.timing_totals()
+        kern_ms = sums[0] / max(calls, 1)
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6               # whole-job Msamples/s
+
+    # ---- end-to-end through the public C-ABI call with HOST buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        n_e = 1 << 27
+        hb = S.HostBuffer(2 * n_e)
+        src = S.Source.open_synth(SEED + 1 + rank)
+        assert src.read_sync(hb.array) == 2 * n_e
+        src.close()
+        e_steps = max(3, min(args.steps, 10))
+        if w["name"] == "cfg1":
+            he = S.Demod(device=device)
+            out_h = S.HostBuffer(2 * (n_e // 6 + 64), np.int16)
+            import ctypes as C
+            from rtl_sdr_rs_b200 import _ffi as F
+
+            def e_step():
+                return F.check(F.lib().sdr_demod_demodulate_batch(he._h, hb.ptr, w["buf_len"], 2 * n_e // w["buf_len"],
+                                                                  out_h.ptr, out_h.array.size, None))
+        else:
+            he = S.FmRx(taps, w["D"], taps2, w["up"], w["down"], device=device)
+            out_h = S.HostBuffer(4 * (n_e // w["D"] * w["up"] // w["down"] + 64), np.float32)
+            from rtl_sdr_rs_b200 import _ffi as F
+
+            def e_step():
+                return F.check(F.lib().sdr_fmrx_process(he._h, hb.ptr, n_e, None, 0, None, 0, out_h.ptr, out_h.array.size))
+        n_out_e = 0
+        for _ in range(2):
+            n_out_e = e_step()
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            n_out_e = e_step()          # synchronous: returns when the host output buffer is filled
+        e_s = time.perf_counter() - t0
+        if dist is not None:
+            import torch
+            t = torch.tensor([e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_s = float(t[0])
+        e2e = {"value": round(world * n_e * e_steps / e_s / 1e6, 2), "unit": "Msamples/s",
+               "h2d_bytes_per_step": 2 * n_e, "d2h_bytes_per_step": int(n_out_e) * (2 if w["name"] == "cfg1" else 4),
+               "steps": e_steps, "samples_per_step": n_e,
+               "api": "sdr_demod_demodulate_batch" if w["name"] == "cfg1" else "sdr_fmrx_process",
+               "note": "pinned host input -> chunked H2D overlapped with the kernels -> D2H of the audio, per step"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    bps = alg_bytes_per_sample(w)
+    achieved = bps * n / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / f"traffic_{w['name']}.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": {"workload": w["desc"], "samples_per_gpu_per_step": n, "input_bytes_per_gpu": 2 * n,
+                   "l2_policy": "input (2 GiB) is larger than L2 (126 MB); no flush needed",
+                   "sharding": "each rank owns one time slice of the same seeded stream; no data-path collective",
+                   "device": info["name"], "sm_count": info["sm_count"]},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "k_demod_fused" if w["name"] == "cfg1" else "k_fir_fast (fused convert+FIR+demod)",
+                     "kernel_ms": round(kern_ms, 4), "alg_bytes_per_sample": round(bps, 4),
+                     "kernel_share_of_step": round(kern_ms / ms_per_step, 4)},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(w)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -117,6 +117,10 @@ int sdr_demod_sync(sdr_demod *d);
 /* Device time (ms, CUDA events on the handle's stream) of the kernels of the last *_dev or
  * batch submission, and the number of kernels it launched. */
 int sdr_demod_last_timing(const sdr_demod *d, float *kernel_ms, uint32_t *n_launches);
+/* Device-time span on the handle's stream (CUDA events): begin records an event, end records a
+ * second one, waits for it and returns the elapsed milliseconds between the two. */
+int sdr_demod_span_begin(sdr_demod *d);
+int sdr_demod_span_end(sdr_demod *d, float *ms);
 
 /* Stage entry points (stage-level parity against the reference's three known-answer tests). */
 /* Demod::rotate_90(Vec<u8>) -> Vec<u8>, scalar branch :276-299; in place, len % 8 == 0. */
@@ -177,6 +181,14 @@ int sdr_fmrx_sync(sdr_fmrx *r);
 /* Per-kernel device time of the last process*(): [0] fused convert+FIR(+demod), [1] resampler,
  * [2] everything else; and launches.  Which kernel variant ran: 1 = specialised, 0 = generic. */
 int sdr_fmrx_last_timing(const sdr_fmrx *r, float ms[3], uint32_t *n_launches, int *specialised);
+/* Sums of the per-kernel device times ([0] fused FIR, [1] resampler, [2] rest) over all timed
+ * process*() calls since the last reset, harvested from a ring of CUDA events (no per-call sync). */
+int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, int reset);
+int sdr_fmrx_span_begin(sdr_fmrx *r);
+int sdr_fmrx_span_end(sdr_fmrx *r, float *ms);
+/* Reposition a fresh stream at global sample index n (history = mid-scale): lets a rank that owns
+ * the time slice [n, ...) of one stream prime its carry by first processing the samples before n. */
+int sdr_fmrx_seek(sdr_fmrx *r, uint64_t global_sample_index);
 
 /* ============================================================================================
  * 3. Wideband channeliser (configs 4-5): per channel c an NCO mix by a 32-bit phase word

@@ -82,6 +82,8 @@ SIGNATURES = {
     "sdr_demod_demodulate_batch_dev": (_l, [_vp, _vp, _sz, _sz, _vp, _sz]),
     "sdr_demod_sync": (_i, [_vp]),
     "sdr_demod_last_timing": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "sdr_demod_span_begin": (_i, [_vp]),
+    "sdr_demod_span_end": (_i, [_vp, C.POINTER(C.c_float)]),
     "sdr_rotate_90": (_l, [_vp, _vp, _sz]),
     "sdr_buf_to_complex": (_l, [_vp, _vp, _sz, _vp, _sz]),
     "sdr_low_pass_complex": (_l, [_vp, _vp, _sz, _vp, _sz]),
@@ -100,6 +102,10 @@ SIGNATURES = {
     "sdr_fmrx_resample": (_l, [_vp, _vp, _sz, _vp, _sz]),
     "sdr_fmrx_sync": (_i, [_vp]),
     "sdr_fmrx_last_timing": (_i, [_vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_uint32), C.POINTER(_i)]),
+    "sdr_fmrx_timing_totals": (_i, [_vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_uint64), _i]),
+    "sdr_fmrx_span_begin": (_i, [_vp]),
+    "sdr_fmrx_span_end": (_i, [_vp, C.POINTER(C.c_float)]),
+    "sdr_fmrx_seek": (_i, [_vp, C.c_uint64]),
     "sdr_chan_new": (_i, [C.POINTER(ChanConfig), _vp, _vp, _i, C.POINTER(_vp)]),
     "sdr_chan_free": (None, [_vp]),
     "sdr_chan_reset": (_i, [_vp]),

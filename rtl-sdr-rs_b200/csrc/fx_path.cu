@@ -1,0 +1,881 @@
+// fx_path.cu — f32 tap'd-FIR receiver (BASELINE.json configs 2-3) for sm_100a.
+//
+//   low_pass : y[m] = sum_{k<T} h[k] * (x[(m+1)D-1-k] - 127)          complex f32, x[n<0] = 127
+//   fm_demod : d[m] = gain * atan2(Im(y[m] conj y[m-1]), Re(..))       f32
+//   resample : a[i] = sum_p g[iM - pL] * d[p]                           rational L/M polyphase FIR
+//
+// Hot kernel: k_fir_fast<T,D,B,NT,ODD> — fused u8->f32 convert + decimating FIR + discriminator.
+// "Block-owner" polyphase form: the stream is cut into decimation blocks of D samples; a thread owns
+// B consecutive blocks, converts every byte exactly once (PRMT into the mantissa of 2^23, one FADD)
+// and feeds it to the ceil(T/D) outputs it contributes to with taps read straight from the kernel
+// parameter constant bank (FFMA R, R, c[0][k], R — no tap loads).  Per-(block,lag) partial sums are
+// combined in a fixed order, so results are independent of how the stream is tiled or chunked.
+// Each CTA's raw bytes arrive with one 1-D bulk async copy (TMA engine) and are read once from HBM:
+// 2 B in + 4/D B out per complex sample.  y never leaves the SM unless the caller asks for it.
+//
+// Fallback for arbitrary (T,D): k_fir_generic — one warp per output, lanes stride the taps,
+// warp-shuffle reduction.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sdr {
+
+constexpr float kMagic = 8388608.0f + 127.0f;   // 2^23 + centre: float(0x4B0000bb) - kMagic = bb - 127 exactly
+
+struct FirArgs {
+    const uint8_t *x;          // call input, 16-B aligned
+    const uint8_t *carry_end;  // one past the last carried byte (16-B aligned); carry holds the samples before x
+    long long n_samples;       // samples in x
+    long long n_out;           // outputs this call produces
+    uint32_t r;                // samples of the current decimation block already consumed before x
+    float gain;
+    float2 *y_out;             // optional [n_out]
+    float *d_out;              // optional [n_out]
+    float2 *last_y;            // y of the last output of the call (stage-level fm_demod state)
+};
+
+template <int T>
+struct Taps {
+    float h[T];
+};
+
+__device__ __forceinline__ float cvt_byte(uint32_t w, int which) {
+    // PRMT puts byte `which` of w into the low mantissa byte of 0x4B000000 (= 2^23)
+    uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7440u + which);
+    return __uint_as_float(bits) - kMagic;
+}
+
+// Accurate 2x2 determinant / dot (Kahan): a*b - c*d with one rounding error of the result.
+__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
+    float cd = c * d;
+    float err = fmaf(-c, d, cd);
+    float dop = fmaf(a, b, -cd);
+    return dop + err;
+}
+__device__ __forceinline__ float discriminate(float2 y, float2 p, float gain) {
+    float cre = diff_of_products(y.x, p.x, -y.y, p.y);   // y.re*p.re + y.im*p.im
+    float cim = diff_of_products(y.y, p.x, y.x, p.y);    // y.im*p.re - y.re*p.im
+    return gain * atan2f(cim, cre);
+}
+
+// Stage one CTA tile [s0, s1) (call-local sample indices, s0 may be negative = carry) into smem.
+// Returns the byte offset of sample s0 inside `tile`.  Executed by one thread.
+__device__ __forceinline__ uint32_t load_tile(unsigned char *tile, const FirArgs &a, long long s0, long long s1,
+                                              uint64_t *bar) {
+    const uint32_t soff = (uint32_t)((2 * s0) & 15);   // two's complement & 15 == positive mod 16
+    uint32_t total = 0;
+    long long x_lo = s0 > 0 ? s0 : 0;
+    uint32_t carry_bytes = 0, x_bytes = 0;
+    if (s0 < 0) {
+        long long c_hi = s1 < 0 ? s1 : 0;                       // carry part is [s0, c_hi)
+        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
+    }
+    if (s1 > 0) {
+        long long b_lo = (2 * x_lo) & ~15ll;
+        long long b_hi = (2 * s1 + 15) & ~15ll;
+        x_bytes = (uint32_t)(b_hi - b_lo);
+    }
+    total = carry_bytes + x_bytes;
+    mbar_arrive_expect_tx(bar, total);
+    if (carry_bytes) bulk_g2s(tile, a.carry_end + 2 * s0 - soff, carry_bytes, bar);
+    if (x_bytes) {
+        long long b_lo = (2 * x_lo) & ~15ll;
+        // smem position of x byte b_lo: soff + (b_lo - 2*s0)
+        bulk_g2s_stream(tile + soff + (b_lo - 2 * s0), a.x + b_lo, x_bytes, bar);
+    }
+    return soff;
+}
+
+// =================================================================================================
+// Specialised kernel
+// =================================================================================================
+template <int T, int D, int B, int NT>
+struct FastGeom {
+    static constexpr int Q = (T + D - 1) / D;           // lags: outputs a sample contributes to
+    static constexpr int NBLK = NT * B;                 // decimation blocks per CTA tile
+    static constexpr int HB0 = Q;                       // halo blocks: y[m-1] of the first owned output complete
+    static constexpr int HB = (((NBLK - HB0) * D) % 2 == 0) ? HB0 : HB0 + 1;   // keep the 4-byte phase CTA-uniform
+    static constexpr int OUT = NBLK - HB;               // outputs owned per CTA
+    static constexpr int TILE_BYTES = NBLK * D * 2;
+    static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32;
+    static constexpr int SM_PART = NBLK * Q * 8;        // float2 partial per (block, lag)
+    static constexpr int SM_Y = NBLK * 8;
+    static constexpr int SMEM = SM_TILE + SM_PART + SM_Y;
+    static_assert((B * D) % 2 == 0, "thread span must be a whole number of 32-bit words");
+    static_assert(OUT > HB, "tile too small");
+};
+
+template <int T, int D, int B, int NT, bool ODD>
+__global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_constant__ Taps<T> taps) {
+    using G = FastGeom<T, D, B, NT>;
+    constexpr int Q = G::Q;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t sh_soff;
+    unsigned char *tile = smem;
+    float2 *part = reinterpret_cast<float2 *>(smem + G::SM_TILE);
+    float2 *ysm = reinterpret_cast<float2 *>(smem + G::SM_TILE + G::SM_PART);
+
+    const int tid = threadIdx.x;
+    const long long out0 = (long long)blockIdx.x * G::OUT;          // first owned output (call-local)
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        // tile = blocks [out0 - HB, out0 - HB + NBLK); block b covers samples [b*D - r, (b+1)*D - r)
+        long long s0 = (out0 - G::HB) * D - (long long)a.r;
+        long long last_out = out0 + G::OUT < a.n_out ? out0 + G::OUT : a.n_out;   // exclusive
+        long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
+        sh_soff = load_tile(tile, a, s0, s1, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    // ---- convert once, accumulate per (block, lag) ----------------------------------------------
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile) + (sh_soff >> 2) + tid * (B * D / 2);
+    float accr[B][Q], acci[B][Q];
+#pragma unroll
+    for (int b = 0; b < B; b++)
+#pragma unroll
+        for (int q = 0; q < Q; q++) accr[b][q] = acci[b][q] = 0.f;
+
+    constexpr int NW = B * D / 2 + (ODD ? 1 : 0);
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        const uint32_t word = w32[w];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int j = 2 * w + half - (ODD ? 1 : 0);   // sample index inside the thread's span
+            if (j < 0 || j >= B * D) continue;
+            const float xr = cvt_byte(word, 2 * half), xi = cvt_byte(word, 2 * half + 1);
+            const int bb = j / D, jj = j % D;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const int k = q * D + (D - 1 - jj);
+                if (k < T) {
+                    accr[bb][q] = fmaf(taps.h[k], xr, accr[bb][q]);
+                    acci[bb][q] = fmaf(taps.h[k], xi, acci[bb][q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < B; b++)
+#pragma unroll
+        for (int q = 0; q < Q; q++) part[(tid * B + b) * Q + q] = make_float2(accr[b][q], acci[b][q]);
+    __syncthreads();
+
+    // ---- combine partials oldest block first: y[g] = P[g-Q+1][Q-1] + ... + P[g][0] -----------------
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        const int g = tid + u * NT;
+        float yr = 0.f, yi = 0.f;
+        if (g >= Q - 1) {
+#pragma unroll
+            for (int q = Q - 1; q >= 0; q--) {
+                float2 p = part[(g - q) * Q + q];
+                yr += p.x;
+                yi += p.y;
+            }
+        }
+        ysm[g] = make_float2(yr, yi);
+    }
+    __syncthreads();
+
+    // ---- discriminator + stores ----------------------------------------------------------------------
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        const int g = tid + u * NT;
+        if (g < G::HB) continue;
+        const long long i = out0 + (g - G::HB);
+        if (i >= a.n_out) continue;
+        const float2 y = ysm[g];
+        if (a.y_out) a.y_out[i] = y;
+        if (a.d_out) a.d_out[i] = discriminate(y, ysm[g - 1], a.gain);
+        if (i == a.n_out - 1) *a.last_y = y;
+    }
+}
+
+// =================================================================================================
+// Generic kernel: one warp per output, lanes stride the taps, butterfly reduction.
+// =================================================================================================
+struct GenArgs {
+    FirArgs f;
+    const float *taps;   // [T] in global memory
+    int T, D, OPC;       // OPC = outputs owned per CTA
+    uint32_t sm_tile;    // bytes reserved for the tile
+};
+
+__global__ void __launch_bounds__(128) k_fir_generic(const GenArgs g) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t sh_soff;
+    unsigned char *tile = smem;
+    float *htap = reinterpret_cast<float *>(smem + g.sm_tile);
+    float2 *ysm = reinterpret_cast<float2 *>(smem + g.sm_tile + (size_t)((g.T + 3) & ~3) * 4);
+    const FirArgs &a = g.f;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long out0 = (long long)blockIdx.x * g.OPC;
+    long long n_here = a.n_out - out0 < g.OPC ? a.n_out - out0 : g.OPC;
+    // local output l in [0, n_here] is call-local output out0 - 1 + l (l = 0 is the predecessor for the discriminator)
+    const long long s0 = out0 * g.D - (long long)a.r - g.T;   // first sample of output out0-1
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        long long s1 = (out0 + n_here) * g.D - (long long)a.r;
+        sh_soff = load_tile(tile, a, s0, s1, &bar);
+    }
+    for (int k = tid; k < g.T; k += blockDim.x) htap[k] = g.taps[k];
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tile + sh_soff);
+    for (long long l = warp; l <= n_here; l += 4) {
+        // newest sample of this output, relative to s0
+        const int newest = (int)((out0 - 1 + l + 1) * g.D - 1 - (long long)a.r - s0);
+        float ar = 0.f, ai = 0.f;
+        for (int k = lane; k < g.T; k += 32) {
+            uint32_t v = t16[newest - k];
+            float h = htap[k];
+            ar = fmaf(h, (float)(int)(v & 255u) - 127.f, ar);
+            ai = fmaf(h, (float)(int)(v >> 8) - 127.f, ai);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, o);
+            ai += __shfl_xor_sync(0xffffffffu, ai, o);
+        }
+        if (lane == 0) ysm[l] = make_float2(ar, ai);
+    }
+    __syncthreads();
+    for (long long l = 1 + tid; l <= n_here; l += blockDim.x) {
+        const long long i = out0 + l - 1;
+        const float2 y = ysm[l];
+        if (a.y_out) a.y_out[i] = y;
+        if (a.d_out) a.d_out[i] = discriminate(y, ysm[l - 1], a.gain);
+        if (i == a.n_out - 1) *a.last_y = y;
+    }
+}
+
+// =================================================================================================
+// Small kernels: carry update, stage-level discriminator, resampler
+// =================================================================================================
+
+// new_carry = last cs samples of (old_carry ++ x[0..n)); both carries hold exactly cs samples (u16 each).
+__global__ void k_update_carry(const uint16_t *old_carry, const uint16_t *x, long long n, int cs, uint16_t *new_carry) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cs; i += gridDim.x * blockDim.x) {
+        long long p = n - cs + i;
+        new_carry[i] = p >= 0 ? x[p] : old_carry[cs + p];
+    }
+}
+
+// Discriminator history: dbuf = [hist (h2) | new d (n)]; move the last h2 values to the front.
+__global__ void k_shift_hist(float *dbuf, long long n, int h2) {
+    extern __shared__ float tmp[];
+    for (int i = threadIdx.x; i < h2; i += blockDim.x) tmp[i] = dbuf[n + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < h2; i += blockDim.x) dbuf[i] = tmp[i];
+}
+
+__global__ void k_fm_demod_f32(const float2 *y, long long n, float2 *prev_state, float gain, float *out) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    const float2 prev0 = *prev_state;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = discriminate(y[i], i ? y[i - 1] : prev0, gain);
+}
+__global__ void k_store_prev(const float2 *y, long long n, float2 *prev_state) {
+    if (n > 0) *prev_state = y[n - 1];
+}
+
+// a[i] = sum_p g[iM - pL] d[p]; dbuf[h2 + (p - P0)] = d[p]; outputs i in [i0, i0 + n_out)
+__global__ void k_resample(const float *dbuf, int h2, unsigned long long P0, const float *g, int T2,
+                           unsigned long long L, unsigned long long M, unsigned long long i0, long long n_out,
+                           float *out) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride) {
+        unsigned long long t = (i0 + o) * M;
+        unsigned long long p = t / L;
+        int k = (int)(t - p * L);
+        float acc = 0.f;
+        // local index of d[p]
+        long long li = (long long)p - (long long)P0 + h2;
+        while (k < T2 && li >= 0) {
+            acc = fmaf(g[k], dbuf[li], acc);
+            k += (int)L;
+            li--;
+        }
+        out[o] = acc;
+    }
+}
+
+}  // namespace sdr
+
+using namespace sdr;
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+namespace {
+
+struct FastVariant {
+    int T, D;
+    int out_per_cta, hb, smem, nt;
+    void (*launch)(const FirArgs &, const float *taps, bool odd, int grid, int smem, cudaStream_t);
+    cudaError_t (*prepare)(int smem);
+};
+
+template <int T, int D, int B, int NT>
+void launch_fast(const FirArgs &a, const float *taps, bool odd, int grid, int smem, cudaStream_t st) {
+    Taps<T> t;
+    memcpy(t.h, taps, sizeof(float) * T);
+    if (odd)
+        k_fir_fast<T, D, B, NT, true><<<grid, NT, smem, st>>>(a, t);
+    else
+        k_fir_fast<T, D, B, NT, false><<<grid, NT, smem, st>>>(a, t);
+}
+template <int T, int D, int B, int NT>
+cudaError_t prepare_fast(int smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+template <int T, int D, int B, int NT>
+FastVariant make_variant() {
+    using G = FastGeom<T, D, B, NT>;
+    return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, &launch_fast<T, D, B, NT>, &prepare_fast<T, D, B, NT>};
+}
+
+// Specialised (taps, decimation) shapes: BASELINE.json configs[1] (127, /75) and configs[2] (255, /100),
+// plus the reference's own boxcar shape (6, /6) used by the cross-path tests.
+const FastVariant *find_variant(uint32_t T, uint32_t D) {
+    static const FastVariant table[] = {
+        make_variant<127, 75, 2, 128>(),
+        make_variant<255, 100, 1, 256>(),
+        make_variant<6, 6, 4, 128>(),
+    };
+    if (getenv("SDR_FORCE_GENERIC")) return nullptr;
+    for (const auto &v : table)
+        if ((uint32_t)v.T == T && (uint32_t)v.D == D) return &v;
+    return nullptr;
+}
+
+constexpr size_t kFxChunkSamples = size_t(16) << 20;   // 32 MiB of IQ per pipelined chunk (host API)
+
+}  // namespace
+
+struct sdr_fmrx {
+    sdr_fmrx_config cfg{};
+    int device = 0;
+    std::vector<float> taps, taps2;
+    float gain = 0.f;
+    const FastVariant *fast = nullptr;
+    // generic geometry
+    int gen_opc = 0;
+    uint32_t gen_sm_tile = 0, gen_smem = 0;
+    // carry: last `cs` samples of the stream (ping-pong), right-aligned so carry_end is 16-B aligned
+    int cs = 0;
+    DevBuf d_carry[2];
+    int carry_cur = 0;
+    int h2 = 0;              // discriminator history length kept for the resampler
+    DevBuf d_taps, d_taps2, d_state;
+    DevBuf d_x[2], d_dbuf, d_audio[2], d_y[2], d_tmp;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    static constexpr int kRing = 64;   // per-call kernel timings are harvested lazily from this ring
+    cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_ring[kRing][4]{}, ev_s[2]{};
+    cudaEvent_t *ev_t = ev_ring[0];
+    bool ring_used[kRing]{};
+    uint64_t ring_next = 0, sum_calls = 0;
+    double sum_ms[3] = {0, 0, 0};
+    // closed-form stream position
+    uint64_t n_in = 0, n_y = 0, n_a = 0;
+    // stage-level resampler position (sdr_fmrx_resample keeps its own history in d_dbuf as well)
+    float last_ms[3] = {0, 0, 0};
+    uint32_t last_launches = 0;
+    bool timing_pending = false;
+};
+
+namespace {
+
+int fx_reset_device_state(sdr_fmrx *r) {
+    for (int i = 0; i < 2; i++) SDR_CUDA_TRY(cudaMemsetAsync(r->d_carry[i].p, 127, (size_t)r->cs * 2, r->stream));
+    SDR_CUDA_TRY(cudaMemsetAsync(r->d_state.p, 0, 64, r->stream));
+    SDR_CUDA_TRY(cudaMemsetAsync(r->d_dbuf.p, 0, r->d_dbuf.cap, r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    r->carry_cur = 0;
+    r->n_in = r->n_y = r->n_a = 0;
+    return SDR_OK;
+}
+
+inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+struct CallPlan {
+    uint64_t n_y, n_a, a0;   // FIR outputs, audio outputs, first audio index
+    uint32_t r;
+};
+CallPlan plan_call(const sdr_fmrx *r, uint64_t n_in0, uint64_t n_y0, size_t n) {
+    CallPlan p;
+    const uint64_t D = r->cfg.decim;
+    p.r = (uint32_t)(n_in0 % D);
+    p.n_y = (n_in0 + n) / D - n_in0 / D;
+    if (r->cfg.n_taps2) {
+        const uint64_t L = r->cfg.up, M = r->cfg.down;
+        p.a0 = ceil_div(n_y0 * L, M);
+        p.n_a = ceil_div((n_y0 + p.n_y) * L, M) - p.a0;
+    } else {
+        p.a0 = n_y0;
+        p.n_a = p.n_y;
+    }
+    return p;
+}
+
+int ensure_dbuf(sdr_fmrx *r, size_t n_y) {
+    size_t need = ((size_t)r->h2 + n_y + 8) * sizeof(float);
+    if (need <= r->d_dbuf.cap) return SDR_OK;
+    // grow while preserving the history at the front
+    DevBuf nb;
+    int rc = nb.reserve(need * 2);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaMemsetAsync(nb.p, 0, nb.cap, r->stream));
+    if (r->d_dbuf.p)
+        SDR_CUDA_TRY(cudaMemcpyAsync(nb.p, r->d_dbuf.p, (size_t)r->h2 * sizeof(float), cudaMemcpyDeviceToDevice, r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    r->d_dbuf.release();
+    r->d_dbuf = nb;
+    return SDR_OK;
+}
+
+// Launch FIR(+demod) for one call-chunk whose input is resident at d_x.  d_demod_target: where the
+// discriminator output goes (nullptr = none).
+int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint64_t n_out, float2 *d_y, float *d_d) {
+    if (n_out == 0) return SDR_OK;
+    FirArgs a{};
+    a.x = d_x;
+    a.carry_end = r->d_carry[r->carry_cur].as<uint8_t>() + (size_t)r->cs * 2;
+    a.n_samples = (long long)n;
+    a.n_out = (long long)n_out;
+    a.r = rphase;
+    a.gain = r->gain;
+    a.y_out = d_y;
+    a.d_out = d_d;
+    a.last_y = r->d_state.as<float2>();
+    if (r->fast) {
+        const FastVariant *v = r->fast;
+        uint64_t grid = ceil_div(n_out, (uint64_t)v->out_per_cta);
+        if (grid > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
+        bool odd = (((uint64_t)v->hb * r->cfg.decim + rphase) & 1) != 0;
+        v->launch(a, r->taps.data(), odd, (int)grid, v->smem, r->stream);
+    } else {
+        GenArgs g{};
+        g.f = a;
+        g.taps = r->d_taps.as<float>();
+        g.T = (int)r->cfg.n_taps;
+        g.D = (int)r->cfg.decim;
+        g.OPC = r->gen_opc;
+        g.sm_tile = r->gen_sm_tile;
+        uint64_t grid = ceil_div(n_out, (uint64_t)g.OPC);
+        if (grid > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
+        k_fir_generic<<<(int)grid, 128, r->gen_smem, r->stream>>>(g);
+    }
+    SDR_LAUNCH_CHECK();
+    r->last_launches++;
+    return SDR_OK;
+}
+
+int launch_carry_update(sdr_fmrx *r, const uint8_t *d_x, size_t n) {
+    if (n == 0) return SDR_OK;
+    int nxt = r->carry_cur ^ 1;
+    int blocks = (r->cs + 255) / 256;
+    k_update_carry<<<blocks, 256, 0, r->stream>>>(r->d_carry[r->carry_cur].as<uint16_t>(),
+                                                  reinterpret_cast<const uint16_t *>(d_x), (long long)n, r->cs,
+                                                  r->d_carry[nxt].as<uint16_t>());
+    SDR_LAUNCH_CHECK();
+    r->last_launches++;
+    r->carry_cur = nxt;
+    return SDR_OK;
+}
+
+int launch_resample(sdr_fmrx *r, uint64_t P0, uint64_t n_new, uint64_t a0, uint64_t n_a, float *d_audio) {
+    // dbuf = [hist h2 | d[P0 .. P0+n_new)]
+    if (n_a) {
+        int blocks = (int)std::min<uint64_t>(ceil_div(n_a, 256), (uint64_t)sm_count(r->device) * 16);
+        k_resample<<<blocks, 256, 0, r->stream>>>(r->d_dbuf.as<float>(), r->h2, P0, r->d_taps2.as<float>(),
+                                                   (int)r->cfg.n_taps2, r->cfg.up, r->cfg.down, a0, (long long)n_a, d_audio);
+        SDR_LAUNCH_CHECK();
+        r->last_launches++;
+    }
+    if (n_new) {
+        k_shift_hist<<<1, 256, (size_t)r->h2 * sizeof(float), r->stream>>>(r->d_dbuf.as<float>(), (long long)n_new, r->h2);
+        SDR_LAUNCH_CHECK();
+        r->last_launches++;
+    }
+    return SDR_OK;
+}
+
+void harvest_slot(sdr_fmrx *r, int slot) {
+    if (!r->ring_used[slot]) return;
+    r->ring_used[slot] = false;
+    if (cudaEventSynchronize(r->ev_ring[slot][3]) != cudaSuccess) return;
+    for (int i = 0; i < 3; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r->ev_ring[slot][i], r->ev_ring[slot][i + 1]) == cudaSuccess) {
+            r->last_ms[i] = ms;
+            r->sum_ms[i] += ms;
+        }
+    }
+    r->sum_calls++;
+}
+
+// Harvest every outstanding timing slot in submission order (the last one harvested is the latest call).
+void collect_timing(sdr_fmrx *r) {
+    r->timing_pending = false;
+    for (uint64_t k = r->ring_next >= sdr_fmrx::kRing ? r->ring_next - sdr_fmrx::kRing : 0; k < r->ring_next; k++)
+        harvest_slot(r, (int)(k % sdr_fmrx::kRing));
+}
+
+// Claim the next ring slot for a timed call.
+void next_timing_slot(sdr_fmrx *r) {
+    int slot = (int)(r->ring_next % sdr_fmrx::kRing);
+    harvest_slot(r, slot);
+    r->ev_t = r->ev_ring[slot];
+    r->ring_used[slot] = true;
+    r->ring_next++;
+}
+
+// One chunk, everything resident.  d_demod / d_y optional; d_audio required when the chain has a tail.
+int run_chunk(sdr_fmrx *r, const uint8_t *d_x, size_t n, float2 *d_y, float *d_demod, float *d_audio,
+              const CallPlan &pl, bool timed) {
+    int rc;
+    const bool has_res = r->cfg.n_taps2 != 0;
+    if ((rc = ensure_dbuf(r, pl.n_y))) return rc;
+    float *dnew = r->d_dbuf.as<float>() + r->h2;
+    // without a resample stage the discriminator output IS the audio
+    float *d_target = has_res ? dnew : (d_audio ? d_audio : dnew);
+    if (timed) {
+        next_timing_slot(r);
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_t[0], r->stream));
+    }
+    if ((rc = launch_fir(r, d_x, n, pl.r, pl.n_y, d_y, d_target))) return rc;
+    if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[1], r->stream));
+    if (has_res) {
+        if ((rc = launch_resample(r, r->n_y, pl.n_y, pl.a0, pl.n_a, d_audio))) return rc;
+    }
+    if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], r->stream));
+    if (d_demod && d_demod != d_target && pl.n_y)
+        SDR_CUDA_TRY(cudaMemcpyAsync(d_demod, d_target, pl.n_y * sizeof(float), cudaMemcpyDeviceToDevice, r->stream));
+    if ((rc = launch_carry_update(r, d_x, n))) return rc;
+    if (timed) {
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_t[3], r->stream));
+        r->timing_pending = true;
+    }
+    r->n_in += n;
+    r->n_y += pl.n_y;
+    r->n_a += pl.n_a;
+    return SDR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *taps2, int cuda_device, sdr_fmrx **out) {
+    if (!cfg || !taps || !out) return fail(SDR_E_ARG, "sdr_fmrx_new: null argument");
+    if (cfg->n_taps < 1 || cfg->decim < 1) return fail(SDR_E_ARG, "need n_taps >= 1 and decim >= 1");
+    if (cfg->n_taps2 && (!taps2 || cfg->up < 1 || cfg->down < 1)) return fail(SDR_E_ARG, "resampler needs taps2, up >= 1, down >= 1");
+    if (cfg->n_taps > (1u << 20) || cfg->decim > (1u << 20)) return fail(SDR_E_ARG, "n_taps/decim too large");
+    int rc = use_device(cuda_device);
+    if (rc) return rc;
+    sdr_fmrx *r = new sdr_fmrx();
+    r->cfg = *cfg;
+    r->device = cuda_device;
+    r->taps.assign(taps, taps + cfg->n_taps);
+    if (cfg->n_taps2) r->taps2.assign(taps2, taps2 + cfg->n_taps2);
+    r->gain = cfg->gain != 0.f ? cfg->gain : (float)(16384.0 / 3.14159265358979323846);
+    r->fast = find_variant(cfg->n_taps, cfg->decim);
+    const uint64_t T = cfg->n_taps, D = cfg->decim;
+    // generic geometry: ~32 KB of raw bytes per CTA
+    uint64_t opc = (16384 > T ? (16384 - T) : 0) / D;
+    if (opc < 1) opc = 1;
+    if (opc > 64) opc = 64;
+    r->gen_opc = (int)opc;
+    uint64_t gen_tile = (((opc + 1) * D + T) * 2 + 15 + 32) & ~15ull;
+    r->gen_sm_tile = (uint32_t)gen_tile;
+    uint64_t gen_smem = gen_tile + ((T + 3) & ~3ull) * 4 + (opc + 2) * 8;
+    r->gen_smem = (uint32_t)gen_smem;
+    if (gen_smem > 200 * 1024) {
+        delete r;
+        return fail(SDR_E_ARG, "n_taps/decim too large for the shared-memory tile (%llu bytes)", (unsigned long long)gen_smem);
+    }
+    // carry holds enough history for either kernel: T + D (generic), (HB+1)*D (fast); multiple of 8 samples
+    uint64_t cs = T + D + 8;
+    if (r->fast && (uint64_t)(r->fast->hb + 1) * D + 8 > cs) cs = (uint64_t)(r->fast->hb + 1) * D + 8;
+    cs = (cs + 7) & ~7ull;
+    r->cs = (int)cs;
+    r->h2 = cfg->n_taps2 ? (int)(cfg->n_taps2 / cfg->up + 2) : 0;
+    cudaError_t e = cudaFuncSetAttribute(k_fir_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem);
+    if (e == cudaSuccess && r->fast) e = r->fast->prepare(r->fast->smem);
+    if (e == cudaSuccess && r->h2 * sizeof(float) > 48 * 1024)
+        e = cudaFuncSetAttribute(k_shift_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(r->h2 * sizeof(float)));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&r->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_done[i], cudaEventDisableTiming);
+    }
+    for (int k = 0; k < sdr_fmrx::kRing && e == cudaSuccess; k++)
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&r->ev_ring[k][i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&r->ev_s[i]);
+    if (e != cudaSuccess) {
+        sdr_fmrx_free(r);
+        return fail(SDR_E_CUDA, "sdr_fmrx_new: %s", cudaGetErrorString(e));
+    }
+    if ((rc = r->d_carry[0].reserve(cs * 2)) || (rc = r->d_carry[1].reserve(cs * 2)) || (rc = r->d_state.reserve(64)) ||
+        (rc = r->d_taps.reserve(T * 4)) || (rc = r->d_taps2.reserve(cfg->n_taps2 ? cfg->n_taps2 * 4 : 4)) ||
+        (rc = r->d_dbuf.reserve(((size_t)r->h2 + 4096) * sizeof(float)))) {
+        sdr_fmrx_free(r);
+        return rc;
+    }
+    e = cudaMemcpy(r->d_taps.p, taps, T * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && cfg->n_taps2) e = cudaMemcpy(r->d_taps2.p, taps2, cfg->n_taps2 * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sdr_fmrx_free(r);
+        return fail(SDR_E_CUDA, "sdr_fmrx_new: %s", cudaGetErrorString(e));
+    }
+    if ((rc = fx_reset_device_state(r))) {
+        sdr_fmrx_free(r);
+        return rc;
+    }
+    *out = r;
+    return SDR_OK;
+}
+
+void sdr_fmrx_free(sdr_fmrx *r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    if (r->copy_stream) cudaStreamSynchronize(r->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        r->d_carry[i].release();
+        r->d_x[i].release();
+        r->d_audio[i].release();
+        r->d_y[i].release();
+        if (r->ev_h2d[i]) cudaEventDestroy(r->ev_h2d[i]);
+        if (r->ev_done[i]) cudaEventDestroy(r->ev_done[i]);
+    }
+    for (int k = 0; k < sdr_fmrx::kRing; k++)
+        for (int i = 0; i < 4; i++)
+            if (r->ev_ring[k][i]) cudaEventDestroy(r->ev_ring[k][i]);
+    for (int i = 0; i < 2; i++)
+        if (r->ev_s[i]) cudaEventDestroy(r->ev_s[i]);
+    r->d_taps.release();
+    r->d_taps2.release();
+    r->d_state.release();
+    r->d_dbuf.release();
+    r->d_tmp.release();
+    if (r->stream) cudaStreamDestroy(r->stream);
+    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    delete r;
+}
+
+int sdr_fmrx_reset(sdr_fmrx *r) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    return fx_reset_device_state(r);
+}
+
+int sdr_fmrx_out_lens(const sdr_fmrx *r, size_t n_samples, size_t *n_y, size_t *n_audio) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    CallPlan p = plan_call(r, r->n_in, r->n_y, n_samples);
+    if (n_y) *n_y = (size_t)p.n_y;
+    if (n_audio) *n_audio = (size_t)p.n_a;
+    return SDR_OK;
+}
+
+long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y_pairs, size_t y_cap, float *demod,
+                      size_t demod_cap, float *audio, size_t audio_cap) {
+    if (!r || (!iq && n_samples)) return fail(SDR_E_ARG, "sdr_fmrx_process: null argument");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    CallPlan total = plan_call(r, r->n_in, r->n_y, n_samples);
+    if (y_pairs && total.n_y > y_cap) return fail(SDR_E_CAP, "y capacity %zu < %llu", y_cap, (unsigned long long)total.n_y);
+    if (demod && total.n_y > demod_cap) return fail(SDR_E_CAP, "demod capacity %zu < %llu", demod_cap, (unsigned long long)total.n_y);
+    if (!audio && total.n_a) return fail(SDR_E_ARG, "audio buffer required");
+    if (total.n_a > audio_cap) return fail(SDR_E_CAP, "audio capacity %zu < %llu", audio_cap, (unsigned long long)total.n_a);
+    r->last_launches = 0;
+    // chunk on a multiple of 8 samples so that every chunk starts 16-byte aligned in the caller's buffer
+    const size_t chunk = kFxChunkSamples;
+    size_t done = 0, y_off = 0, a_off = 0;
+    int ci = 0;
+    while (done < n_samples) {
+        const int slot = ci & 1;
+        const size_t n = std::min(chunk, n_samples - done);
+        CallPlan pl = plan_call(r, r->n_in, r->n_y, n);
+        if ((rc = r->d_x[slot].reserve(std::min(chunk, n_samples) * 2 + 64))) return rc;
+        const size_t max_y = std::min(chunk, n_samples) / r->cfg.decim + 8;
+        const size_t max_a = r->cfg.n_taps2 ? (size_t)ceil_div((uint64_t)max_y * r->cfg.up, r->cfg.down) + 8 : max_y;
+        if ((rc = r->d_audio[slot].reserve(max_a * 4))) return rc;
+        if (y_pairs && (rc = r->d_y[slot].reserve((chunk / r->cfg.decim + 8) * 8))) return rc;
+        if (demod && (rc = r->d_tmp.reserve((chunk / r->cfg.decim + 8) * 4 * 2))) return rc;
+        if (ci >= 2) SDR_CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_done[slot], 0));
+        SDR_CUDA_TRY(cudaMemcpyAsync(r->d_x[slot].p, iq + done * 2, n * 2, cudaMemcpyHostToDevice, r->copy_stream));
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_h2d[slot], r->copy_stream));
+        SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_h2d[slot], 0));
+        float *d_dem = demod ? r->d_tmp.as<float>() + (size_t)slot * (chunk / r->cfg.decim + 8) : nullptr;
+        if ((rc = run_chunk(r, r->d_x[slot].as<uint8_t>(), n, y_pairs ? r->d_y[slot].as<float2>() : nullptr, d_dem,
+                            r->d_audio[slot].as<float>(), pl, done + n >= n_samples)))
+            return rc;
+        if (y_pairs && pl.n_y)
+            SDR_CUDA_TRY(cudaMemcpyAsync(y_pairs + 2 * y_off, r->d_y[slot].p, pl.n_y * 8, cudaMemcpyDeviceToHost, r->stream));
+        if (demod && pl.n_y)
+            SDR_CUDA_TRY(cudaMemcpyAsync(demod + y_off, d_dem, pl.n_y * 4, cudaMemcpyDeviceToHost, r->stream));
+        if (pl.n_a)
+            SDR_CUDA_TRY(cudaMemcpyAsync(audio + a_off, r->d_audio[slot].p, pl.n_a * 4, cudaMemcpyDeviceToHost, r->stream));
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_done[slot], r->stream));
+        done += n;
+        y_off += pl.n_y;
+        a_off += pl.n_a;
+        ci++;
+    }
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
+    collect_timing(r);
+    return (long)total.n_a;
+}
+
+long sdr_fmrx_process_dev(sdr_fmrx *r, const uint8_t *d_iq, size_t n_samples, float *d_y_pairs, float *d_demod,
+                          float *d_audio, size_t audio_cap) {
+    if (!r || (!d_iq && n_samples)) return fail(SDR_E_ARG, "sdr_fmrx_process_dev: null argument");
+    if (reinterpret_cast<uintptr_t>(d_iq) & 15) return fail(SDR_E_ARG, "device input must be 16-byte aligned (use sdr_dev_alloc)");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    CallPlan pl = plan_call(r, r->n_in, r->n_y, n_samples);
+    if (!d_audio && pl.n_a) return fail(SDR_E_ARG, "audio buffer required");
+    if (pl.n_a > audio_cap) return fail(SDR_E_CAP, "audio capacity %zu < %llu", audio_cap, (unsigned long long)pl.n_a);
+    r->last_launches = 0;
+    if ((rc = run_chunk(r, d_iq, n_samples, reinterpret_cast<float2 *>(d_y_pairs), d_demod, d_audio, pl, true))) return rc;
+    return (long)pl.n_a;
+}
+
+long sdr_fmrx_low_pass(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y_pairs, size_t cap_pairs) {
+    if (!r || (!iq && n_samples) || !y_pairs) return fail(SDR_E_ARG, "sdr_fmrx_low_pass: null argument");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    CallPlan pl = plan_call(r, r->n_in, r->n_y, n_samples);
+    if (pl.n_y > cap_pairs) return fail(SDR_E_CAP, "capacity %zu < %llu pairs", cap_pairs, (unsigned long long)pl.n_y);
+    if (n_samples == 0) return 0;
+    if ((rc = r->d_x[0].reserve(n_samples * 2 + 64)) || (rc = r->d_y[0].reserve((pl.n_y + 8) * 8))) return rc;
+    r->last_launches = 0;
+    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_x[0].p, iq, n_samples * 2, cudaMemcpyHostToDevice, r->stream));
+    if ((rc = launch_fir(r, r->d_x[0].as<uint8_t>(), n_samples, pl.r, pl.n_y, r->d_y[0].as<float2>(), nullptr))) return rc;
+    if ((rc = launch_carry_update(r, r->d_x[0].as<uint8_t>(), n_samples))) return rc;
+    if (pl.n_y) SDR_CUDA_TRY(cudaMemcpyAsync(y_pairs, r->d_y[0].p, pl.n_y * 8, cudaMemcpyDeviceToHost, r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    r->n_in += n_samples;
+    // n_y (the discriminator/resampler stream position) is advanced by the stages that consume y
+    return (long)pl.n_y;
+}
+
+long sdr_fmrx_fm_demod(sdr_fmrx *r, const float *y_pairs, size_t n, float *out, size_t cap) {
+    if (!r || (!y_pairs && n) || !out) return fail(SDR_E_ARG, "sdr_fmrx_fm_demod: null argument");
+    if (n > cap) return fail(SDR_E_CAP, "capacity %zu < %zu", cap, n);
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if ((rc = r->d_y[0].reserve(n * 8)) || (rc = r->d_tmp.reserve(n * 4))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_y[0].p, y_pairs, n * 8, cudaMemcpyHostToDevice, r->stream));
+    int blocks = (int)std::min<uint64_t>(ceil_div(n, 256), (uint64_t)sm_count(r->device) * 16);
+    k_fm_demod_f32<<<blocks, 256, 0, r->stream>>>(r->d_y[0].as<float2>(), (long long)n, r->d_state.as<float2>(), r->gain,
+                                                  r->d_tmp.as<float>());
+    SDR_LAUNCH_CHECK();
+    k_store_prev<<<1, 1, 0, r->stream>>>(r->d_y[0].as<float2>(), (long long)n, r->d_state.as<float2>());
+    SDR_LAUNCH_CHECK();
+    SDR_CUDA_TRY(cudaMemcpyAsync(out, r->d_tmp.p, n * 4, cudaMemcpyDeviceToHost, r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    return (long)n;
+}
+
+long sdr_fmrx_resample(sdr_fmrx *r, const float *d, size_t n, float *out, size_t cap) {
+    if (!r || (!d && n) || !out) return fail(SDR_E_ARG, "sdr_fmrx_resample: null argument");
+    if (!r->cfg.n_taps2) return fail(SDR_E_STATE, "handle was created without a resample stage");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    const uint64_t L = r->cfg.up, M = r->cfg.down;
+    uint64_t a0 = ceil_div(r->n_y * L, M), n_a = ceil_div((r->n_y + n) * L, M) - a0;
+    if (n_a > cap) return fail(SDR_E_CAP, "capacity %zu < %llu", cap, (unsigned long long)n_a);
+    if (n == 0) return 0;
+    if ((rc = ensure_dbuf(r, n)) || (rc = r->d_audio[0].reserve((n_a + 8) * 4))) return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_dbuf.as<float>() + r->h2, d, n * 4, cudaMemcpyHostToDevice, r->stream));
+    if ((rc = launch_resample(r, r->n_y, n, a0, n_a, r->d_audio[0].as<float>()))) return rc;
+    if (n_a) SDR_CUDA_TRY(cudaMemcpyAsync(out, r->d_audio[0].p, n_a * 4, cudaMemcpyDeviceToHost, r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    r->n_y += n;
+    r->n_a += n_a;
+    return (long)n_a;
+}
+
+int sdr_fmrx_sync(sdr_fmrx *r) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    collect_timing(r);
+    return SDR_OK;
+}
+
+int sdr_fmrx_span_begin(sdr_fmrx *r) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaEventRecord(r->ev_s[0], r->stream));
+    return SDR_OK;
+}
+
+int sdr_fmrx_span_end(sdr_fmrx *r, float *ms) {
+    if (!r || !ms) return fail(SDR_E_ARG, "null argument");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaEventRecord(r->ev_s[1], r->stream));
+    SDR_CUDA_TRY(cudaEventSynchronize(r->ev_s[1]));
+    SDR_CUDA_TRY(cudaEventElapsedTime(ms, r->ev_s[0], r->ev_s[1]));
+    collect_timing(r);
+    return SDR_OK;
+}
+
+int sdr_fmrx_seek(sdr_fmrx *r, uint64_t global_sample_index) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    if ((rc = fx_reset_device_state(r))) return rc;
+    r->n_in = global_sample_index;
+    r->n_y = global_sample_index / r->cfg.decim;
+    r->n_a = r->cfg.n_taps2 ? ceil_div(r->n_y * r->cfg.up, r->cfg.down) : r->n_y;
+    return SDR_OK;
+}
+
+int sdr_fmrx_last_timing(const sdr_fmrx *r, float ms[3], uint32_t *n_launches, int *specialised) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    if (ms)
+        for (int i = 0; i < 3; i++) ms[i] = r->last_ms[i];
+    if (n_launches) *n_launches = r->last_launches;
+    if (specialised) *specialised = r->fast ? 1 : 0;
+    return SDR_OK;
+}
+
+int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, int reset) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    collect_timing(r);
+    if (sums_ms)
+        for (int i = 0; i < 3; i++) sums_ms[i] = r->sum_ms[i];
+    if (n_calls) *n_calls = r->sum_calls;
+    if (reset) {
+        r->sum_ms[0] = r->sum_ms[1] = r->sum_ms[2] = 0.0;
+        r->sum_calls = 0;
+    }
+    return SDR_OK;
+}
+
+}  // extern "C"

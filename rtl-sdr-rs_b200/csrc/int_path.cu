@@ -354,7 +354,7 @@ struct sdr_demod {
     int device = 0;
     sdr_demod_state st{};
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_t0 = nullptr, ev_t1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
     DevBuf d_in[2], d_out[2], d_state, d_a, d_b, d_c;
     PinBuf h_state;
     OctTable oct{};
@@ -547,6 +547,8 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     }
     if (e == cudaSuccess) e = cudaEventCreate(&d->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&d->ev_t1);
+    if (e == cudaSuccess) e = cudaEventCreate(&d->ev_s0);
+    if (e == cudaSuccess) e = cudaEventCreate(&d->ev_s1);
     if (e != cudaSuccess) {
         sdr_demod_free(d);
         return fail(SDR_E_CUDA, "sdr_demod_new: %s", cudaGetErrorString(e));
@@ -577,6 +579,8 @@ void sdr_demod_free(sdr_demod *d) {
     d->h_state.release();
     if (d->ev_t0) cudaEventDestroy(d->ev_t0);
     if (d->ev_t1) cudaEventDestroy(d->ev_t1);
+    if (d->ev_s0) cudaEventDestroy(d->ev_s0);
+    if (d->ev_s1) cudaEventDestroy(d->ev_s1);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     delete d;
@@ -729,6 +733,24 @@ int sdr_demod_last_timing(const sdr_demod *d, float *kernel_ms, uint32_t *n_laun
     if (!d) return fail(SDR_E_ARG, "null handle");
     if (kernel_ms) *kernel_ms = d->last_ms;
     if (n_launches) *n_launches = d->last_launches;
+    return SDR_OK;
+}
+
+int sdr_demod_span_begin(sdr_demod *d) {
+    if (!d) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaEventRecord(d->ev_s0, d->stream));
+    return SDR_OK;
+}
+
+int sdr_demod_span_end(sdr_demod *d, float *ms) {
+    if (!d || !ms) return fail(SDR_E_ARG, "null argument");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaEventRecord(d->ev_s1, d->stream));
+    SDR_CUDA_TRY(cudaEventSynchronize(d->ev_s1));
+    SDR_CUDA_TRY(cudaEventElapsedTime(ms, d->ev_s0, d->ev_s1));
     return SDR_OK;
 }
 

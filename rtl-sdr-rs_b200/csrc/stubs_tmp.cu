@@ -3,17 +3,6 @@
 using sdr::fail;
 #define NI return fail(SDR_E_STATE, "%s: not implemented yet", __func__)
 extern "C" {
-int sdr_fmrx_new(const sdr_fmrx_config *, const float *, const float *, int, sdr_fmrx **) { NI; }
-void sdr_fmrx_free(sdr_fmrx *) {}
-int sdr_fmrx_reset(sdr_fmrx *) { NI; }
-int sdr_fmrx_out_lens(const sdr_fmrx *, size_t, size_t *, size_t *) { NI; }
-long sdr_fmrx_process(sdr_fmrx *, const uint8_t *, size_t, float *, size_t, float *, size_t, float *, size_t) { NI; }
-long sdr_fmrx_process_dev(sdr_fmrx *, const uint8_t *, size_t, float *, float *, float *, size_t) { NI; }
-long sdr_fmrx_low_pass(sdr_fmrx *, const uint8_t *, size_t, float *, size_t) { NI; }
-long sdr_fmrx_fm_demod(sdr_fmrx *, const float *, size_t, float *, size_t) { NI; }
-long sdr_fmrx_resample(sdr_fmrx *, const float *, size_t, float *, size_t) { NI; }
-int sdr_fmrx_sync(sdr_fmrx *) { NI; }
-int sdr_fmrx_last_timing(const sdr_fmrx *, float *, uint32_t *, int *) { NI; }
 int sdr_chan_new(const sdr_chan_config *, const float *, const uint32_t *, int, sdr_chan **) { NI; }
 void sdr_chan_free(sdr_chan *) {}
 int sdr_chan_reset(sdr_chan *) { NI; }

@@ -134,3 +134,11 @@ class Demod:
     def set_state(self, prev_index=0, now_lpr=0, prev_lpr_index=0, lp_now=(0, 0), demod_pre=(0, 0)):
         s = F.DemodState(prev_index, now_lpr, prev_lpr_index, lp_now[0], lp_now[1], demod_pre[0], demod_pre[1])
         F.check(F.lib().sdr_demod_set_state(self._h, C.byref(s)))
+
+    def span_begin(self):
+        F.check(F.lib().sdr_demod_span_begin(self._h))
+
+    def span_end(self) -> float:
+        ms = C.c_float(0)
+        F.check(F.lib().sdr_demod_span_end(self._h, C.byref(ms)))
+        return ms.value

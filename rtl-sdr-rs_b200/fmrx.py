@@ -88,3 +88,20 @@ class FmRx:
         n, spec = C.c_uint32(0), C.c_int(0)
         F.check(F.lib().sdr_fmrx_last_timing(self._h, C.byref(ms), C.byref(n), C.byref(spec)))
         return list(ms), n.value, spec.value
+
+    def span_begin(self):
+        F.check(F.lib().sdr_fmrx_span_begin(self._h))
+
+    def span_end(self) -> float:
+        ms = C.c_float(0)
+        F.check(F.lib().sdr_fmrx_span_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def seek(self, global_sample_index: int):
+        F.check(F.lib().sdr_fmrx_seek(self._h, global_sample_index))
+
+    def timing_totals(self, reset: bool = False):
+        sums = (C.c_double * 3)()
+        n = C.c_uint64(0)
+        F.check(F.lib().sdr_fmrx_timing_totals(self._h, C.byref(sums), C.byref(n), int(reset)))
+        return list(sums), n.value

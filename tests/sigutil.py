@@ -1,0 +1,67 @@
+"""Shared test/bench helpers: tap design, the seeded synthetic FM parity signal, tolerances."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def lowpass_taps(n_taps: int, cutoff_cyc_per_sample: float, gain: float = 1.0) -> np.ndarray:
+    """Hamming-windowed sinc designed in f64, rounded to f32 (the taps are DATA shared bit-for-bit by
+    the oracle and the CUDA path)."""
+    k = np.arange(n_taps, dtype=np.float64) - (n_taps - 1) / 2.0
+    h = 2.0 * cutoff_cyc_per_sample * np.sinc(2.0 * cutoff_cyc_per_sample * k)
+    h *= np.hamming(n_taps)
+    h *= gain / h.sum()
+    return h.astype(np.float32)
+
+
+def channel_taps(n_taps: int, decim: int) -> np.ndarray:
+    """The configs' channel filter: cutoff 0.4 * fs_out (SURVEY §8d cfg 2)."""
+    return lowpass_taps(n_taps, 0.4 / decim)
+
+
+def fm_test_signal(n: int, fs: float, seed: int = 0xB2000001, f_dev: float = 75e3, f_mod: float = 1e3,
+                   f_c: float = 0.0, amp: float = 100.0, noise: float = 8.0) -> np.ndarray:
+    """u8 interleaved IQ: 127.5 + amp*exp(j*phi[n]) + N(0, noise^2), phi' = 2*pi*(f_c + f_dev*sin(2*pi*f_mod*t))/fs."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / fs
+    inst = f_c + f_dev * np.sin(2 * np.pi * f_mod * t)
+    phi = 2 * np.pi * np.cumsum(inst) / fs
+    i = 127.5 + amp * np.cos(phi) + rng.normal(0, noise, n)
+    q = 127.5 + amp * np.sin(phi) + rng.normal(0, noise, n)
+    out = np.empty(2 * n, np.uint8)
+    out[0::2] = np.clip(np.rint(i), 0, 255).astype(np.uint8)
+    out[1::2] = np.clip(np.rint(q), 0, 255).astype(np.uint8)
+    return out
+
+
+def rel_err(got: np.ndarray, ref: np.ndarray) -> float:
+    """Norm-wise relative error max|got-ref| / max|ref|."""
+    ref = np.asarray(ref, np.float64)
+    return float(np.max(np.abs(np.asarray(got, np.float64) - ref)) / max(np.max(np.abs(ref)), 1e-300))
+
+
+def assert_close(got, ref, rtol=1e-5, what=""):
+    """The f32-path bar of BASELINE.json's north_star: within 1e-5 relative.  Element-wise
+    |got-ref| <= rtol*|ref| + rtol*rms(ref) (the rms term covers elements that cancel to ~0)."""
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    if ref.size == 0:
+        return
+    rms = float(np.sqrt(np.mean(ref * ref)))
+    err = np.abs(got - ref)
+    tol = rtol * np.abs(ref) + rtol * rms
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{ref.size} outside 1e-5 rel; worst err {err.max():.3e} (rms {rms:.3e})"
+
+
+def assert_angle_close(got, ref, full_scale: float, rtol=1e-5, what=""):
+    """Discriminator outputs live on a circle of circumference 2*full_scale (full_scale == gain*pi)."""
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    d = got - ref
+    d = (d + full_scale) % (2 * full_scale) - full_scale
+    tol = rtol * np.abs(ref) + rtol * full_scale
+    bad = np.abs(d) > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{ref.size} outside 1e-5 rel; worst {np.abs(d).max():.3e} of {full_scale}"
