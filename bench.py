@@ -52,7 +52,119 @@ def workload_spec(name: str) -> dict:
         return dict(name="cfg1", buf_len=262144, n_bufs=8192, n=8192 * 131072, dtype="i32",
                     desc="reference-exact integer Demod (rotate_90, -127, boxcar-6, fast_atan2, 170k->32k), "
                          "8192 x 262144-byte buffers per step (BASELINE.json configs[0] semantics at HBM scale)")
+    if name == "chan":
+        return dict(name="chan", T=255, D=100, C=64, fs=20e6, n=1 << 28, slab=1 << 25, dtype="f32",
+                    desc="wideband channeliser, 64 channels per GPU (per-channel 32-bit NCO folded into 255-tap complex "
+                         "taps, decimate-by-100, FM demod), 20 Msps-equivalent synthetic IQ; N>1: 64*N channels, raw u8 "
+                         "slabs (64 MiB) broadcast from rank 0 with one ncclBroadcast each (BASELINE.json configs[3]/[4])")
     raise SystemExit(f"unknown workload {name}")
+
+
+def run_chan(args, w):
+    """Channeliser bench (FP32-FMA-bound, not HBM-bound): rank r owns channels [64r, 64r+64) of 64*N; every
+    rank needs the whole raw stream, which rank 0 broadcasts slab by slab on its own stream while the
+    previous slab is being channelised."""
+    rank, local_rank, world = dist_env()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+    device = local_rank
+    import sdrpkg
+    from sigutil import channel_taps
+    S = sdrpkg.load()
+    info = S.device_info(device)
+    C, T, D, n, slab = w["C"], w["T"], w["D"], w["n"], w["slab"]
+    c_tot = C * world
+    taps = channel_taps(T, D)
+    offs = (np.arange(c_tot) - (c_tot - 1) / 2.0) * (w["fs"] / c_tot)
+    fw_all = (np.round(offs / w["fs"] * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
+    ch = S.Channeliser(taps, D, fw_all[rank * C:(rank + 1) * C], device=device)
+    d_in = S.DevBuffer(2 * n, device)
+    if rank == 0:
+        S.synth_fill_dev(d_in, 2 * n, SEED)
+    cap = slab // D + 1
+    d_dem = S.DevBuffer(4 * C * cap, device)
+    comm = None
+    if world > 1:
+        import torch
+        uid = [S.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = S.Comm(device, rank, world, uid[0])
+    n_slabs = n // slab
+
+    def step():
+        for s in range(n_slabs):
+            if comm is not None:
+                comm.wait_chan(ch)                      # slab memory is reused every step
+                comm.bcast_u8(d_in, 2 * slab, 0, offset=2 * slab * s)
+                comm.chan_wait(ch)
+            from rtl_sdr_rs_b200 import _ffi as F
+            F.check(F.lib().sdr_chan_process_dev(ch._h, d_in.at(2 * slab * s), slab, None, d_dem.ptr, cap))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        ch.sync()
+        if comm is not None:
+            comm.sync()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = S.kernel_launch_count()
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    kern_ms = 0.0
+    for _ in range(args.steps):
+        step()
+    ch.sync()
+    if comm is not None:
+        comm.sync()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    kern_ms = ch.last_timing()[0]                       # device time of the last slab's k_chan_fir launch
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = S.kernel_launch_count() - launches0
+    if dist is not None:
+        import torch
+        t = torch.tensor([wall_ms, kern_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_ms, kern_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+    if rank == 0:
+        ms_per_step = wall_ms / args.steps
+        fma_per_sample = 4.0 * C * T / D                # complex tap x complex sample = 4 FMAs
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fma_peak = info["sm_count"] * 128 * sm_mhz * 1e6 / 1e12          # TFMA/s at the observed clock
+        ach = fma_per_sample * slab / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": "channel-Msamples/s (input Msamples/s x channels) through the channeliser", "workload": "chan",
+            "value": round(c_tot * n / (ms_per_step * 1e-3) / 1e6, 1), "unit": "channel-Msamples/s",
+            "input_msamples_per_s": round(n / (ms_per_step * 1e-3) / 1e6, 1), "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "channels_total": c_tot, "samples_per_step": n, "slab_samples": slab,
+                       "timing": "host wall clock around K steps bracketed by stream syncs (multi-stream pipeline), max over ranks",
+                       "device": info["name"]},
+            "roofline": {"bound": "fp32-fma (CUDA cores; no tensor cores by north_star)", "achieved": round(ach, 2),
+                         "peak": round(fma_peak, 2), "unit": "TFMA/s", "frac": round(ach / fma_peak, 4),
+                         "kernel": "k_chan_fir", "kernel_ms_per_slab": round(kern_ms, 4),
+                         "hbm_gbs": round((2.0 + C * 12.0 / D) * slab / (kern_ms * 1e-3) / 1e9, 1),
+                         "note": "peak = SMs x 128 FMA/clk x observed SM clock"},
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
 
 
 def taps_for(w: dict):
@@ -217,7 +329,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1", "chan"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -229,6 +341,10 @@ def main():
         w["n"] = 1 << args.n_log2
         if w["name"] == "cfg1":
             w["n_bufs"] = w["n"] // 131072
+    if w["name"] == "chan":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference is defined for cfg1/cfg2/cfg3")
+        return run_chan(args, w)
     if args.impl == "reference":
         return run_reference_arm(args, w)
 

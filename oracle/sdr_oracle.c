@@ -398,7 +398,8 @@ size_t orc_fx_fm_demod(orc_fx *s, const double *y, size_t n, double *out) {
         double ar = y[2 * i], ai = y[2 * i + 1];
         double cre = ar * s->prev_re + ai * s->prev_im;
         double cim = ai * s->prev_re - ar * s->prev_im;
-        out[i] = s->gain * atan2(cim, cre);
+        /* zero predecessor (stream start) gives 0 by definition (never +-pi from a signed zero) */
+        out[i] = (cre == 0.0 && cim == 0.0) ? 0.0 : s->gain * atan2(cim, cre);
         s->prev_re = ar;
         s->prev_im = ai;
     }
@@ -480,7 +481,7 @@ size_t orc_fx_channelise(const uint8_t *iq, size_t n, const float *taps, uint32_
             }
             if (d_out) {
                 double cre = ar * pr + ai * pi_, cim = ai * pr - ar * pi_;
-                d_out[(size_t)c * M + m] = gain * atan2(cim, cre);
+                d_out[(size_t)c * M + m] = (cre == 0.0 && cim == 0.0) ? 0.0 : gain * atan2(cim, cre);
             }
             pr = ar;
             pi_ = ai;
@@ -532,7 +533,7 @@ static void orc_f32_disc(long lo, long hi, int tid, void *p) {
     for (long m = lo; m < hi; m++) {
         float pr = m ? c->yr[m - 1] : 0.f, pi_ = m ? c->yi[m - 1] : 0.f;
         float cre = c->yr[m] * pr + c->yi[m] * pi_, cim = c->yi[m] * pr - c->yr[m] * pi_;
-        c->d[m] = c->gain * atan2f(cim, cre);
+        c->d[m] = (cre == 0.f && cim == 0.f) ? 0.f : c->gain * atan2f(cim, cre);
     }
 }
 static void orc_f32_res(long lo, long hi, int tid, void *p) {

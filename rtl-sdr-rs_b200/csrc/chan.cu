@@ -1,0 +1,658 @@
+// chan.cu — wideband channeliser (BASELINE.json configs 4-5) for sm_100a, and the NCCL slab broadcast.
+//
+// Per channel c:  y_c[m] = sum_k h[k] * xc[n_m - k] * e^{-j theta_c(n_m - k)},   n_m = (m+1)D - 1,
+//                 theta_c(n) = 2*pi * ((fw_c * n) mod 2^32) / 2^32              (32-bit phase NCO)
+// Folding the NCO into the taps (exact, because the phase arithmetic is modular):
+//                 y_c[m] = e^{-j theta_c(n_m)} * sum_k g_c[k] * xc[n_m - k],    g_c[k] = h[k] e^{+j theta_c(k)}
+// so the inner loop has no sincos: it is C*T complex MACs per output column on CUDA cores
+// (~4*C*T/D FMAs per input sample: FP32-FMA-bound, not HBM-bound).
+//
+// k_chan_fir: persistent CTAs (one per SM).  The 64 channels' folded taps stay resident in shared
+// memory ([k][channel], 130 KB for T=255); raw bytes of the next output tile arrive with a bulk
+// async copy while the current tile computes; bytes are converted to f32 once per tile.  A lane owns
+// 2 channels x MR outputs (register tile), taps come in as one LDS.128 per tap (2 channels), samples
+// as warp-broadcast loads, so shared-memory wavefronts stay at ~50% of the FMA issue time.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sdr {
+
+constexpr int kChanGroup = 64;   // channels per CTA (lane <-> 2 channels)
+constexpr int kChanWarps = 8;
+
+struct ChanArgs {
+    const uint8_t *x;
+    const uint8_t *carry_end;
+    long long n_samples, n_out;
+    uint32_t r;                   // samples of the current decimation block consumed before x
+    uint32_t n0_lo;               // low 32 bits of the global index of x[0]
+    const float2 *gtaps;          // [groups][T4][64]
+    const uint32_t *fw;           // [groups*64]
+    float2 *y_out;                // [C_pad][cap]
+    long long cap;
+    int T4, D, pad;               // taps padded to a multiple of 4; pad: xs origin shift (alignment)
+    int n_tiles;
+    uint32_t sm_taps, sm_xs, sm_xb;   // byte sizes of the smem regions
+};
+
+__device__ __forceinline__ void cis_phase(uint32_t phase, float &c, float &s) {
+    // e^{+j 2 pi phase/2^32}: split so both sincospif arguments are exact in f32
+    float hi = (float)(phase >> 16) * (1.0f / 32768.0f);              // 2*phase_hi/2^16, exact
+    float lo = (float)(phase & 0xffffu) * (1.0f / 2147483648.0f);     // 2*phase_lo/2^32, exact
+    float ch, sh, cl, sl;
+    sincospif(hi, &sh, &ch);
+    sincospif(lo, &sl, &cl);
+    c = ch * cl - sh * sl;
+    s = sh * cl + ch * sl;
+}
+
+// Stage one tile's raw bytes: samples [s0, s1) (call-local; negative = carry) -> xb.  One thread.
+__device__ __forceinline__ uint32_t chan_load_tile(unsigned char *xb, const ChanArgs &a, long long s0, long long s1,
+                                                   uint64_t *bar) {
+    const uint32_t soff = (uint32_t)((2 * s0) & 15);
+    uint32_t carry_bytes = 0, x_bytes = 0;
+    long long x_lo = s0 > 0 ? s0 : 0;
+    if (s0 < 0) {
+        long long c_hi = s1 < 0 ? s1 : 0;
+        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
+    }
+    long long b_lo = (2 * x_lo) & ~15ll;
+    if (s1 > 0) x_bytes = (uint32_t)(((2 * s1 + 15) & ~15ll) - b_lo);
+    mbar_arrive_expect_tx(bar, carry_bytes + x_bytes);
+    if (carry_bytes) bulk_g2s(xb, a.carry_end + 2 * s0 - soff, carry_bytes, bar);
+    if (x_bytes) bulk_g2s(xb + soff + (b_lo - 2 * s0), a.x + b_lo, x_bytes, bar);
+    return soff;
+}
+
+template <int MR, bool ALIGNED>
+__global__ void __launch_bounds__(kChanWarps * 32, 1) k_chan_fir(const ChanArgs a) {
+    constexpr int MT = kChanWarps * MR;   // outputs per tile
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t sh_soff[2];
+    float2 *gt = reinterpret_cast<float2 *>(smem);                       // [T4][64]
+    float2 *xs = reinterpret_cast<float2 *>(smem + a.sm_taps);           // converted samples / y staging
+    unsigned char *xb0 = smem + a.sm_taps + a.sm_xs;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = blockIdx.y;
+    const int T4 = a.T4, D = a.D;
+    const int NS = MT * D + T4 - 1 + a.pad;      // samples per tile (incl. history)
+
+    // resident folded taps for this channel group
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(a.gtaps + (size_t)group * T4 * kChanGroup);
+        float4 *dst = reinterpret_cast<float4 *>(gt);
+        for (int i = tid; i < T4 * kChanGroup / 2; i += blockDim.x) dst[i] = src[i];
+    }
+    const uint32_t fw0 = a.fw[group * kChanGroup + 2 * lane], fw1 = a.fw[group * kChanGroup + 2 * lane + 1];
+
+    auto tile_s0 = [&](int tile) { return (long long)tile * MT * D - (long long)a.r - (T4 - 1) - a.pad; };
+    auto issue = [&](int tile, int buf) {
+        long long s0 = tile_s0(tile);
+        long long n_here = a.n_out - (long long)tile * MT < MT ? a.n_out - (long long)tile * MT : MT;
+        long long s1 = ((long long)tile * MT + n_here) * D - (long long)a.r;
+        sh_soff[buf] = chan_load_tile(xb0 + (size_t)buf * a.sm_xb, a, s0, s1, &bar[buf]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+        if ((int)blockIdx.x < a.n_tiles) issue(blockIdx.x, 0);
+    }
+    __syncthreads();
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, it++) {
+        const int buf = it & 1;
+        // prefetch the next tile's bytes into the other buffer (its previous contents were consumed
+        // before the __syncthreads that ended the previous iteration's conversion phase)
+        if (tid == 0 && tile + (int)gridDim.x < a.n_tiles) issue(tile + gridDim.x, buf ^ 1);
+        mbar_wait(&bar[buf], (it >> 1) & 1);
+        // ---- convert u8 -> centred f32 once per tile ---------------------------------------------
+        {
+            const uint16_t *t16 = reinterpret_cast<const uint16_t *>(xb0 + (size_t)buf * a.sm_xb + sh_soff[buf]);
+            for (int j = tid; j < NS; j += blockDim.x) {
+                uint32_t v = t16[j];
+                uint32_t bi = __byte_perm(v, 0x4B000000u, 0x7440u), bq = __byte_perm(v, 0x4B000000u, 0x7441u);
+                xs[j] = make_float2(__uint_as_float(bi) - 8388735.0f, __uint_as_float(bq) - 8388735.0f);
+            }
+        }
+        __syncthreads();
+
+        // ---- register-tiled complex MAC: lane = 2 channels, warp = MR outputs ------------------------
+        float ar0[MR], ai0[MR], ar1[MR], ai1[MR];
+#pragma unroll
+        for (int o = 0; o < MR; o++) ar0[o] = ai0[o] = ar1[o] = ai1[o] = 0.f;
+        // newest sample of output o (tile-local) sits at xs[(o+1)*D + T4 - 2 + pad]
+        const int base0 = (warp * MR + 1) * D + T4 - 2 + a.pad;
+        const float4 *g4 = reinterpret_cast<const float4 *>(gt) + lane;   // [k][32 lanes] float4 = 2 channels
+        for (int k0 = 0; k0 < T4; k0 += 4) {
+            float4 g[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) g[kk] = g4[(k0 + kk) * 32];
+#pragma unroll
+            for (int o = 0; o < MR; o++) {
+                const int j = base0 + o * D - k0;   // sample for tap k0; taps k0+1.. use j-1..
+                float2 x[4];
+                if (ALIGNED) {
+                    // j is odd: (j-1, j) and (j-3, j-2) are 16-byte aligned pairs
+                    float4 p = *reinterpret_cast<const float4 *>(&xs[j - 1]);
+                    float4 q = *reinterpret_cast<const float4 *>(&xs[j - 3]);
+                    x[0] = make_float2(p.z, p.w);
+                    x[1] = make_float2(p.x, p.y);
+                    x[2] = make_float2(q.z, q.w);
+                    x[3] = make_float2(q.x, q.y);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) x[kk] = xs[j - kk];
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    // (gr + j gi) * (xr + j xi)
+                    ar0[o] = fmaf(g[kk].x, x[kk].x, ar0[o]);
+                    ar0[o] = fmaf(-g[kk].y, x[kk].y, ar0[o]);
+                    ai0[o] = fmaf(g[kk].x, x[kk].y, ai0[o]);
+                    ai0[o] = fmaf(g[kk].y, x[kk].x, ai0[o]);
+                    ar1[o] = fmaf(g[kk].z, x[kk].x, ar1[o]);
+                    ar1[o] = fmaf(-g[kk].w, x[kk].y, ar1[o]);
+                    ai1[o] = fmaf(g[kk].z, x[kk].y, ai1[o]);
+                    ai1[o] = fmaf(g[kk].w, x[kk].x, ai1[o]);
+                }
+            }
+        }
+        __syncthreads();   // everyone is done reading xs: reuse it to transpose the y tile
+
+        // ---- de-rotate by the NCO phase at n_m and stage [channel][output] ------------------------------
+        float2 *ys = xs;   // [64][MT]
+#pragma unroll
+        for (int o = 0; o < MR; o++) {
+            const long long i = (long long)tile * MT + warp * MR + o;            // call-local output index
+            const uint32_t nm = a.n0_lo + (uint32_t)((i + 1) * D - 1) - a.r;     // global n_m mod 2^32
+            float c, s;
+            cis_phase(fw0 * nm, c, s);   // e^{+j theta}; we need e^{-j theta}: (yr + j yi)(c - j s)
+            ys[(2 * lane) * MT + warp * MR + o] = make_float2(ar0[o] * c + ai0[o] * s, ai0[o] * c - ar0[o] * s);
+            cis_phase(fw1 * nm, c, s);
+            ys[(2 * lane + 1) * MT + warp * MR + o] = make_float2(ar1[o] * c + ai1[o] * s, ai1[o] * c - ar1[o] * s);
+        }
+        __syncthreads();
+        {
+            const long long i0 = (long long)tile * MT;
+            const int n_here = (int)(a.n_out - i0 < MT ? a.n_out - i0 : MT);
+            for (int e = tid; e < kChanGroup * MT; e += blockDim.x) {
+                const int c = e / MT, o = e % MT;
+                if (o < n_here) a.y_out[(size_t)(group * kChanGroup + c) * a.cap + i0 + o] = ys[e];
+            }
+        }
+        __syncthreads();   // xs free for the next tile's conversion
+    }
+}
+
+// Folded taps: g[group][k][c] = h[k] * e^{+j theta_c(k)} (double precision, setup only).
+__global__ void k_chan_fold_taps(const float *h, int T, int T4, const uint32_t *fw, int C, int C_pad, float2 *g) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = C_pad * T4;
+    if (idx >= total) return;
+    int group = idx / (T4 * kChanGroup), rem = idx % (T4 * kChanGroup);
+    int k = rem / kChanGroup, cl = rem % kChanGroup, c = group * kChanGroup + cl;
+    float2 v = make_float2(0.f, 0.f);
+    if (c < C && k < T) {
+        uint32_t ph = fw[c] * (uint32_t)k;
+        double s, co;
+        sincospi(2.0 * ((double)ph / 4294967296.0), &s, &co);
+        v = make_float2((float)((double)h[k] * co), (float)((double)h[k] * s));
+    }
+    g[idx] = v;
+}
+
+__device__ __forceinline__ float chan_dop(float a, float b, float c, float d) {
+    float cd = c * d;
+    float err = fmaf(-c, d, cd);
+    return fmaf(a, b, -cd) + err;
+}
+
+// Discriminator over [C][cap]; prev[c] carries y_c[m-1] across calls.
+__global__ void k_chan_demod(const float2 *y, long long n_out, long long cap, int C, float2 *prev, float gain, float *d) {
+    const int c = blockIdx.y;
+    if (c >= C) return;
+    const float2 *yc = y + (size_t)c * cap;
+    const float2 p0 = prev[c];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
+        float2 a = yc[i], b = i ? yc[i - 1] : p0;
+        float cre = chan_dop(a.x, b.x, -a.y, b.y), cim = chan_dop(a.y, b.x, a.x, b.y);
+        d[(size_t)c * cap + i] = (cre == 0.f && cim == 0.f) ? 0.f : gain * atan2f(cim, cre);
+    }
+}
+__global__ void k_chan_store_prev(const float2 *y, long long n_out, long long cap, int C, float2 *prev) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C && n_out > 0) prev[c] = y[(size_t)c * cap + n_out - 1];
+}
+
+__global__ void k_chan_update_carry(const uint16_t *old_carry, const uint16_t *x, long long n, int cs, uint16_t *new_carry) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cs; i += gridDim.x * blockDim.x) {
+        long long p = n - cs + i;
+        new_carry[i] = p >= 0 ? x[p] : old_carry[cs + p];
+    }
+}
+
+}  // namespace sdr
+
+using namespace sdr;
+
+struct sdr_chan {
+    sdr_chan_config cfg{};
+    int device = 0;
+    int C_pad = 0, groups = 0, T4 = 0, pad = 0, mr = 0;
+    bool aligned = false;
+    uint32_t sm_taps = 0, sm_xs = 0, sm_xb = 0;
+    size_t smem = 0;
+    int cs = 0, carry_cur = 0;
+    float gain = 0.f;
+    uint64_t n_in = 0;
+    DevBuf d_carry[2], d_taps, d_gt, d_fw, d_prev, d_x, d_y, d_d;
+    size_t y_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3]{};
+    float last_ms = 0.f;
+    uint32_t last_launches = 0;
+    bool timing_pending = false;
+};
+
+namespace {
+
+using ChanKernel = void (*)(const ChanArgs);
+ChanKernel pick_kernel(int mr, bool aligned) {
+    switch (mr) {
+        case 8: return aligned ? k_chan_fir<8, true> : k_chan_fir<8, false>;
+        case 4: return aligned ? k_chan_fir<4, true> : k_chan_fir<4, false>;
+        case 2: return aligned ? k_chan_fir<2, true> : k_chan_fir<2, false>;
+        default: return aligned ? k_chan_fir<1, true> : k_chan_fir<1, false>;
+    }
+}
+
+int chan_reset_state(sdr_chan *c) {
+    for (int i = 0; i < 2; i++) SDR_CUDA_TRY(cudaMemsetAsync(c->d_carry[i].p, 127, (size_t)c->cs * 2, c->stream));
+    SDR_CUDA_TRY(cudaMemsetAsync(c->d_prev.p, 0, (size_t)c->C_pad * 8, c->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->carry_cur = 0;
+    c->n_in = 0;
+    return SDR_OK;
+}
+
+// y (and demod) for one call whose input is resident; d_y / d_d are [C][cap].
+int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d, size_t cap, uint64_t n_out) {
+    const int D = (int)c->cfg.decim;
+    c->last_launches = 0;
+    SDR_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    if (n_out) {
+        const int MT = kChanWarps * c->mr;
+        ChanArgs a{};
+        a.x = d_x;
+        a.carry_end = c->d_carry[c->carry_cur].as<uint8_t>() + (size_t)c->cs * 2;
+        a.n_samples = (long long)n;
+        a.n_out = (long long)n_out;
+        a.r = (uint32_t)(c->n_in % D);
+        a.n0_lo = (uint32_t)c->n_in;
+        a.gtaps = c->d_gt.as<float2>();
+        a.fw = c->d_fw.as<uint32_t>();
+        a.y_out = d_y;
+        a.cap = (long long)cap;
+        a.T4 = c->T4;
+        a.D = D;
+        a.pad = c->pad;
+        uint64_t tiles = (n_out + MT - 1) / MT;
+        if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
+        a.n_tiles = (int)tiles;
+        a.sm_taps = c->sm_taps;
+        a.sm_xs = c->sm_xs;
+        a.sm_xb = c->sm_xb;
+        int ctas = std::max(1, sm_count(c->device) / c->groups);
+        if ((uint64_t)ctas > tiles) ctas = (int)tiles;
+        dim3 grid(ctas, c->groups);
+        pick_kernel(c->mr, c->aligned)<<<grid, kChanWarps * 32, c->smem, c->stream>>>(a);
+        SDR_LAUNCH_CHECK();
+        c->last_launches++;
+    }
+    SDR_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (n_out && d_d) {
+        dim3 grid((unsigned)std::min<uint64_t>((n_out + 255) / 256, 64), c->cfg.n_channels);
+        k_chan_demod<<<grid, 256, 0, c->stream>>>(d_y, (long long)n_out, (long long)cap, (int)c->cfg.n_channels,
+                                                  c->d_prev.as<float2>(), c->gain, d_d);
+        SDR_LAUNCH_CHECK();
+        c->last_launches++;
+    }
+    if (n_out) {
+        k_chan_store_prev<<<(c->cfg.n_channels + 127) / 128, 128, 0, c->stream>>>(d_y, (long long)n_out, (long long)cap,
+                                                                                  (int)c->cfg.n_channels, c->d_prev.as<float2>());
+        SDR_LAUNCH_CHECK();
+        c->last_launches++;
+    }
+    if (n) {
+        int nxt = c->carry_cur ^ 1;
+        k_chan_update_carry<<<(c->cs + 255) / 256, 256, 0, c->stream>>>(c->d_carry[c->carry_cur].as<uint16_t>(),
+                                                                        reinterpret_cast<const uint16_t *>(d_x), (long long)n,
+                                                                        c->cs, c->d_carry[nxt].as<uint16_t>());
+        SDR_LAUNCH_CHECK();
+        c->last_launches++;
+        c->carry_cur = nxt;
+    }
+    SDR_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    c->timing_pending = true;
+    c->n_in += n;
+    return SDR_OK;
+}
+
+void chan_collect(sdr_chan *c) {
+    if (!c->timing_pending) return;
+    c->timing_pending = false;
+    float ms = 0.f;
+    if (cudaEventSynchronize(c->ev[2]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess)
+        c->last_ms = ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *freq_words, int cuda_device, sdr_chan **out) {
+    if (!cfg || !taps || !freq_words || !out) return fail(SDR_E_ARG, "sdr_chan_new: null argument");
+    if (cfg->n_channels < 1 || cfg->n_taps < 1 || cfg->decim < 1) return fail(SDR_E_ARG, "need n_channels, n_taps, decim >= 1");
+    int rc = use_device(cuda_device);
+    if (rc) return rc;
+    sdr_chan *c = new sdr_chan();
+    c->cfg = *cfg;
+    c->device = cuda_device;
+    c->gain = cfg->gain != 0.f ? cfg->gain : (float)(16384.0 / 3.14159265358979323846);
+    c->groups = (int)((cfg->n_channels + kChanGroup - 1) / kChanGroup);
+    c->C_pad = c->groups * kChanGroup;
+    c->T4 = (int)((cfg->n_taps + 3) & ~3u);
+    const int D = (int)cfg->decim, T4 = c->T4;
+    c->aligned = (D % 2 == 0);
+    // aligned mode wants the newest sample index (o+1)*D + T4 - 2 + pad odd; D even, T4 even => pad = 1
+    c->pad = c->aligned ? 1 : 0;
+    c->sm_taps = (uint32_t)((size_t)T4 * kChanGroup * 8);
+    // pick the largest MR whose tile fits beside the resident taps
+    const size_t budget = 225 * 1024;
+    c->mr = 0;
+    for (int mr : {8, 4, 2, 1}) {
+        size_t MT = (size_t)kChanWarps * mr;
+        size_t ns = MT * D + T4 - 1 + c->pad;
+        size_t xs = std::max(ns * 8, (size_t)kChanGroup * MT * 8);
+        xs = (xs + 15) & ~size_t(15);
+        size_t xb = ((ns * 2 + 15) & ~size_t(15)) + 32;
+        if (c->sm_taps + xs + 2 * xb <= budget) {
+            c->mr = mr;
+            c->sm_xs = (uint32_t)xs;
+            c->sm_xb = (uint32_t)xb;
+            c->smem = c->sm_taps + xs + 2 * xb;
+            break;
+        }
+    }
+    if (!c->mr) {
+        delete c;
+        return fail(SDR_E_ARG, "n_taps=%u / decim=%u do not fit the channeliser's shared-memory tile", cfg->n_taps, cfg->decim);
+    }
+    c->cs = (int)(((size_t)T4 + D + 16 + 7) & ~size_t(7));
+    cudaError_t e = cudaFuncSetAttribute(pick_kernel(c->mr, c->aligned), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess) {
+        sdr_chan_free(c);
+        return fail(SDR_E_CUDA, "sdr_chan_new: %s", cudaGetErrorString(e));
+    }
+    if ((rc = c->d_carry[0].reserve((size_t)c->cs * 2)) || (rc = c->d_carry[1].reserve((size_t)c->cs * 2)) ||
+        (rc = c->d_taps.reserve(cfg->n_taps * 4)) || (rc = c->d_fw.reserve((size_t)c->C_pad * 4)) ||
+        (rc = c->d_gt.reserve((size_t)c->C_pad * T4 * 8)) || (rc = c->d_prev.reserve((size_t)c->C_pad * 8))) {
+        sdr_chan_free(c);
+        return rc;
+    }
+    std::vector<uint32_t> fw(c->C_pad, 0u);
+    std::copy(freq_words, freq_words + cfg->n_channels, fw.begin());
+    e = cudaMemcpy(c->d_taps.p, taps, cfg->n_taps * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_fw.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sdr_chan_free(c);
+        return fail(SDR_E_CUDA, "sdr_chan_new: %s", cudaGetErrorString(e));
+    }
+    int total = c->C_pad * T4;
+    k_chan_fold_taps<<<(total + 255) / 256, 256, 0, c->stream>>>(c->d_taps.as<float>(), (int)cfg->n_taps, T4, c->d_fw.as<uint32_t>(),
+                                                                (int)cfg->n_channels, c->C_pad, c->d_gt.as<float2>());
+    if (cudaGetLastError() != cudaSuccess || (rc = chan_reset_state(c))) {
+        sdr_chan_free(c);
+        return rc ? rc : fail(SDR_E_CUDA, "sdr_chan_new: tap folding kernel failed");
+    }
+    count_launch();
+    *out = c;
+    return SDR_OK;
+}
+
+void sdr_chan_free(sdr_chan *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; i++) c->d_carry[i].release();
+    c->d_taps.release();
+    c->d_gt.release();
+    c->d_fw.release();
+    c->d_prev.release();
+    c->d_x.release();
+    c->d_y.release();
+    c->d_d.release();
+    for (int i = 0; i < 3; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int sdr_chan_reset(sdr_chan *c) {
+    if (!c) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    return chan_reset_state(c);
+}
+
+long sdr_chan_process(sdr_chan *c, const uint8_t *iq, size_t n_samples, float *y_pairs, float *demod, size_t cap) {
+    if (!c || (!iq && n_samples) || !demod) return fail(SDR_E_ARG, "sdr_chan_process: null argument");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    const uint64_t D = c->cfg.decim;
+    const uint64_t n_out = (c->n_in + n_samples) / D - c->n_in / D;
+    if (n_out > cap) return fail(SDR_E_CAP, "capacity %zu < %llu outputs per channel", cap, (unsigned long long)n_out);
+    if (n_samples == 0) return 0;
+    const size_t C = c->cfg.n_channels;
+    if ((rc = c->d_x.reserve(n_samples * 2 + 64)) || (rc = c->d_y.reserve((size_t)c->C_pad * (n_out + 1) * 8)) ||
+        (rc = c->d_d.reserve(C * (n_out + 1) * 4)))
+        return rc;
+    SDR_CUDA_TRY(cudaMemcpyAsync(c->d_x.p, iq, n_samples * 2, cudaMemcpyHostToDevice, c->stream));
+    const size_t dcap = n_out ? n_out : 1;
+    if ((rc = chan_run(c, c->d_x.as<uint8_t>(), n_samples, c->d_y.as<float2>(), c->d_d.as<float>(), dcap, n_out))) return rc;
+    if (n_out) {
+        if (y_pairs)
+            SDR_CUDA_TRY(cudaMemcpy2DAsync(y_pairs, cap * 8, c->d_y.p, dcap * 8, n_out * 8, C, cudaMemcpyDeviceToHost, c->stream));
+        SDR_CUDA_TRY(cudaMemcpy2DAsync(demod, cap * 4, c->d_d.p, dcap * 4, n_out * 4, C, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    chan_collect(c);
+    return (long)n_out;
+}
+
+long sdr_chan_process_dev(sdr_chan *c, const uint8_t *d_iq, size_t n_samples, float *d_y_pairs, float *d_demod, size_t cap) {
+    if (!c || (!d_iq && n_samples)) return fail(SDR_E_ARG, "sdr_chan_process_dev: null argument");
+    if (reinterpret_cast<uintptr_t>(d_iq) & 15) return fail(SDR_E_ARG, "device input must be 16-byte aligned (use sdr_dev_alloc)");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    const uint64_t D = c->cfg.decim;
+    const uint64_t n_out = (c->n_in + n_samples) / D - c->n_in / D;
+    if (n_out > cap) return fail(SDR_E_CAP, "capacity %zu < %llu outputs per channel", cap, (unsigned long long)n_out);
+    float2 *d_y = reinterpret_cast<float2 *>(d_y_pairs);
+    size_t ycap = cap;
+    if (!d_y) {   // caller does not want y: keep it in a library buffer with the caller's row stride
+        if (c->d_y.cap < (size_t)c->C_pad * cap * 8) SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));   // before a realloc
+        if ((rc = c->d_y.reserve((size_t)c->C_pad * cap * 8))) return rc;
+        d_y = c->d_y.as<float2>();
+    }
+    if ((rc = chan_run(c, d_iq, n_samples, d_y, d_demod, ycap, n_out))) return rc;
+    return (long)n_out;
+}
+
+int sdr_chan_sync(sdr_chan *c) {
+    if (!c) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    chan_collect(c);
+    return SDR_OK;
+}
+
+int sdr_chan_last_timing(const sdr_chan *c, float *kernel_ms, uint32_t *n_launches) {
+    if (!c) return fail(SDR_E_ARG, "null handle");
+    if (kernel_ms) *kernel_ms = c->last_ms;
+    if (n_launches) *n_launches = c->last_launches;
+    return SDR_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// NCCL plumbing: one ncclBroadcast(u8) per raw slab and nothing else.  libnccl is dlopen()ed lazily so
+// the library loads on boxes without NCCL and shares the copy a host process (e.g. torch) already loaded.
+// =================================================================================================
+namespace {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+constexpr int kNcclUint8 = 1;   // ncclUint8 / ncclChar group: ncclInt8=0, ncclUint8=1
+
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi &nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.h) break;
+    }
+    if (!api.h) return api;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+    api.Broadcast = (decltype(api.Broadcast))dlsym(api.h, "ncclBroadcast");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.GetErrorString;
+    return api;
+}
+
+int nccl_fail(const char *what, ncclResult_t r) {
+    return fail(SDR_E_NCCL, "%s failed: %s", what, nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+}
+
+}  // namespace
+
+struct sdr_comm {
+    int device = 0, rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_bcast = nullptr, ev_chan = nullptr;
+};
+
+extern "C" {
+
+int sdr_comm_unique_id(uint8_t id[SDR_NCCL_ID_BYTES]) {
+    if (!id) return fail(SDR_E_ARG, "null id");
+    if (!nccl().ok) return fail(SDR_E_NCCL, "libnccl.so.2 could not be loaded");
+    static_assert(sizeof(ncclUniqueId) == SDR_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    ncclResult_t r = nccl().GetUniqueId(&u);
+    if (r) return nccl_fail("ncclGetUniqueId", r);
+    memcpy(id, &u, sizeof(u));
+    return SDR_OK;
+}
+
+int sdr_comm_init(int cuda_device, int rank, int world, const uint8_t id[SDR_NCCL_ID_BYTES], sdr_comm **out) {
+    if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(SDR_E_ARG, "sdr_comm_init: bad argument");
+    if (!nccl().ok) return fail(SDR_E_NCCL, "libnccl.so.2 could not be loaded");
+    int rc = use_device(cuda_device);
+    if (rc) return rc;
+    sdr_comm *c = new sdr_comm();
+    c->device = cuda_device;
+    c->rank = rank;
+    c->world = world;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclResult_t r = nccl().CommInitRank(&c->comm, world, u, rank);
+    if (r) {
+        delete c;
+        return nccl_fail("ncclCommInitRank", r);
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_chan, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        sdr_comm_free(c);
+        return fail(SDR_E_CUDA, "sdr_comm_init: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return SDR_OK;
+}
+
+int sdr_comm_bcast_u8(sdr_comm *c, uint8_t *d_buf, size_t bytes, int root) {
+    if (!c || !d_buf) return fail(SDR_E_ARG, "sdr_comm_bcast_u8: null argument");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    ncclResult_t r = nccl().Broadcast(d_buf, d_buf, bytes, kNcclUint8, root, c->comm, c->stream);
+    if (r) return nccl_fail("ncclBroadcast", r);
+    SDR_CUDA_TRY(cudaEventRecord(c->ev_bcast, c->stream));
+    return SDR_OK;
+}
+
+int sdr_comm_chan_wait(sdr_comm *c, sdr_chan *ch) {
+    if (!c || !ch) return fail(SDR_E_ARG, "null argument");
+    SDR_CUDA_TRY(cudaStreamWaitEvent(ch->stream, c->ev_bcast, 0));
+    return SDR_OK;
+}
+
+int sdr_comm_wait_chan(sdr_comm *c, sdr_chan *ch) {
+    if (!c || !ch) return fail(SDR_E_ARG, "null argument");
+    SDR_CUDA_TRY(cudaEventRecord(c->ev_chan, ch->stream));
+    SDR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_chan, 0));
+    return SDR_OK;
+}
+
+int sdr_comm_sync(sdr_comm *c) {
+    if (!c) return fail(SDR_E_ARG, "null handle");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SDR_OK;
+}
+
+void sdr_comm_free(sdr_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
+    if (c->ev_chan) cudaEventDestroy(c->ev_chan);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+}  // extern "C"

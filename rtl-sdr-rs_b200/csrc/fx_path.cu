@@ -59,6 +59,7 @@ __device__ __forceinline__ float diff_of_products(float a, float b, float c, flo
 __device__ __forceinline__ float discriminate(float2 y, float2 p, float gain) {
     float cre = diff_of_products(y.x, p.x, -y.y, p.y);   // y.re*p.re + y.im*p.im
     float cim = diff_of_products(y.y, p.x, y.x, p.y);    // y.im*p.re - y.re*p.im
+    if (cre == 0.f && cim == 0.f) return 0.f;            // zero predecessor (stream start): 0 by definition, not +-pi
     return gain * atan2f(cim, cre);
 }
 
@@ -289,23 +290,78 @@ __global__ void k_store_prev(const float2 *y, long long n, float2 *prev_state) {
     if (n > 0) *prev_state = y[n - 1];
 }
 
-// a[i] = sum_p g[iM - pL] d[p]; dbuf[h2 + (p - P0)] = d[p]; outputs i in [i0, i0 + n_out)
-__global__ void k_resample(const float *dbuf, int h2, unsigned long long P0, const float *g, int T2,
-                           unsigned long long L, unsigned long long M, unsigned long long i0, long long n_out,
-                           float *out) {
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride) {
-        unsigned long long t = (i0 + o) * M;
-        unsigned long long p = t / L;
-        int k = (int)(t - p * L);
-        float acc = 0.f;
-        // local index of d[p]
-        long long li = (long long)p - (long long)P0 + h2;
-        while (k < T2 && li >= 0) {
-            acc = fmaf(g[k], dbuf[li], acc);
-            k += (int)L;
-            li--;
+// Resampler a[i] = sum_p g[iM - pL] d[p] in polyphase form: phase = (iM) mod L, p_i = (iM) div L,
+//   a[i] = sum_{j<J} gp[phase][j] * d[p_i - j],   gp[phase][j] = g[phase + jL] (zero padded), J = ceil(T2/L).
+// dbuf[h2 + (p - P0)] = d[p] (history of h2 >= J values in front); outputs i in [i0, i0 + n_out).
+
+// L = M = 1 (plain real FIR at the output rate): 8 outputs per thread, taps and a 16-float sliding
+// window per 8-tap chunk in registers: 64 FMAs per 6 shared-memory loads.
+constexpr int kFirR = 8, kFirThreads = 128, kFirOblk = kFirR * kFirThreads;
+__global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, int h2, const float *gp, int Jp,
+                                                             long long n_out, long long n_valid, float *out) {
+    extern __shared__ __align__(16) float fsm[];
+    float *taps = fsm;            // [Jp]
+    float *win = fsm + Jp;        // [kFirOblk + Jp]; win[idx] = dbuf[h2 + o0 - Jp + idx]
+    const long long o0 = (long long)blockIdx.x * kFirOblk;
+    for (int k = threadIdx.x; k < Jp; k += blockDim.x) taps[k] = gp[k];
+    const long long gbase = (long long)h2 + o0 - Jp;
+    for (int idx = threadIdx.x; idx < kFirOblk + Jp; idx += blockDim.x) {
+        long long gi = gbase + idx;
+        win[idx] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
+    }
+    __syncthreads();
+    float acc[kFirR];
+#pragma unroll
+    for (int r = 0; r < kFirR; r++) acc[r] = 0.f;
+    const int t8 = threadIdx.x * kFirR;
+    for (int j0 = 0; j0 < Jp; j0 += 8) {
+        float w[16], g[8];
+        const float4 *wp = reinterpret_cast<const float4 *>(win + Jp + t8 - j0 - 8);
+        const float4 *gq = reinterpret_cast<const float4 *>(taps + j0);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float4 v = wp[c];
+            w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
         }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            float4 v = gq[c];
+            g[4 * c] = v.x, g[4 * c + 1] = v.y, g[4 * c + 2] = v.z, g[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++)
+#pragma unroll
+            for (int r = 0; r < kFirR; r++) acc[r] = fmaf(g[jj], w[8 + r - jj], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kFirR; r++)
+        if (o0 + t8 + r < n_out) out[o0 + t8 + r] = acc[r];
+}
+
+// Generic rational L/M: one output per thread, polyphase taps in shared memory, 32-bit index math
+// relative to a per-CTA 64-bit base.
+__global__ void __launch_bounds__(256) k_resample_poly(const float *dbuf, int h2, unsigned long long P0, const float *gp,
+                                                       int J, uint32_t L, uint32_t M, unsigned long long i0,
+                                                       long long n_out, int taps_in_smem, float *out) {
+    extern __shared__ __align__(16) float fsm[];
+    const float *tp = gp;
+    if (taps_in_smem) {
+        for (int k = threadIdx.x; k < (int)(L * J); k += blockDim.x) fsm[k] = gp[k];
+        __syncthreads();
+        tp = fsm;
+    }
+    for (long long ob = (long long)blockIdx.x * 256; ob < n_out; ob += (long long)gridDim.x * 256) {
+        const unsigned long long t0 = (i0 + (unsigned long long)ob) * M;
+        const unsigned long long p0 = t0 / L;
+        const uint32_t ph0 = (uint32_t)(t0 - p0 * L);
+        const long long o = ob + threadIdx.x;
+        if (o >= n_out) continue;
+        const uint32_t trel = ph0 + threadIdx.x * M;
+        const uint32_t dp = trel / L, ph = trel - dp * L;
+        const float *x = dbuf + ((long long)(p0 - P0) + h2 + dp);
+        const float *g = tp + (size_t)ph * J;
+        float acc = 0.f;
+        for (int j = 0; j < J; j++) acc = fmaf(g[j], x[-j], acc);
         out[o] = acc;
     }
 }
@@ -379,6 +435,7 @@ struct sdr_fmrx {
     DevBuf d_carry[2];
     int carry_cur = 0;
     int h2 = 0;              // discriminator history length kept for the resampler
+    int J = 0, Jp = 0;       // polyphase taps per phase (J = ceil(T2/L)); Jp = J rounded up to 8
     DevBuf d_taps, d_taps2, d_state;
     DevBuf d_x[2], d_dbuf, d_audio[2], d_y[2], d_tmp;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -498,10 +555,21 @@ int launch_carry_update(sdr_fmrx *r, const uint8_t *d_x, size_t n) {
 
 int launch_resample(sdr_fmrx *r, uint64_t P0, uint64_t n_new, uint64_t a0, uint64_t n_a, float *d_audio) {
     // dbuf = [hist h2 | d[P0 .. P0+n_new)]
-    if (n_a) {
+    if (n_a && r->cfg.up == 1 && r->cfg.down == 1) {
+        uint64_t blocks = ceil_div(n_a, (uint64_t)kFirOblk);
+        if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
+        size_t sm = ((size_t)2 * r->Jp + kFirOblk) * sizeof(float);
+        k_fir_real_r8<<<(int)blocks, kFirThreads, sm, r->stream>>>(r->d_dbuf.as<float>(), r->h2, r->d_taps2.as<float>(), r->Jp,
+                                                                  (long long)n_a, (long long)(r->h2 + n_new), d_audio);
+        SDR_LAUNCH_CHECK();
+        r->last_launches++;
+    } else if (n_a) {
         int blocks = (int)std::min<uint64_t>(ceil_div(n_a, 256), (uint64_t)sm_count(r->device) * 16);
-        k_resample<<<blocks, 256, 0, r->stream>>>(r->d_dbuf.as<float>(), r->h2, P0, r->d_taps2.as<float>(),
-                                                   (int)r->cfg.n_taps2, r->cfg.up, r->cfg.down, a0, (long long)n_a, d_audio);
+        size_t tb = (size_t)r->cfg.up * r->J * sizeof(float);
+        int in_smem = tb <= 48 * 1024;
+        k_resample_poly<<<blocks, 256, in_smem ? tb : 0, r->stream>>>(r->d_dbuf.as<float>(), r->h2, P0, r->d_taps2.as<float>(),
+                                                                      r->J, r->cfg.up, r->cfg.down, a0, (long long)n_a, in_smem,
+                                                                      d_audio);
         SDR_LAUNCH_CHECK();
         r->last_launches++;
     }
@@ -612,7 +680,11 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
     if (r->fast && (uint64_t)(r->fast->hb + 1) * D + 8 > cs) cs = (uint64_t)(r->fast->hb + 1) * D + 8;
     cs = (cs + 7) & ~7ull;
     r->cs = (int)cs;
-    r->h2 = cfg->n_taps2 ? (int)(cfg->n_taps2 / cfg->up + 2) : 0;
+    if (cfg->n_taps2) {
+        r->J = (int)((cfg->n_taps2 + cfg->up - 1) / cfg->up);
+        r->Jp = (r->J + 7) & ~7;
+        r->h2 = r->Jp + 8;
+    }
     cudaError_t e = cudaFuncSetAttribute(k_fir_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem);
     if (e == cudaSuccess && r->fast) e = r->fast->prepare(r->fast->smem);
     if (e == cudaSuccess && r->h2 * sizeof(float) > 48 * 1024)
@@ -631,13 +703,25 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         return fail(SDR_E_CUDA, "sdr_fmrx_new: %s", cudaGetErrorString(e));
     }
     if ((rc = r->d_carry[0].reserve(cs * 2)) || (rc = r->d_carry[1].reserve(cs * 2)) || (rc = r->d_state.reserve(64)) ||
-        (rc = r->d_taps.reserve(T * 4)) || (rc = r->d_taps2.reserve(cfg->n_taps2 ? cfg->n_taps2 * 4 : 4)) ||
+        (rc = r->d_taps.reserve(T * 4)) || (rc = r->d_taps2.reserve(cfg->n_taps2 ? ((size_t)cfg->up * r->J + r->Jp + 8) * 4 : 4)) ||
         (rc = r->d_dbuf.reserve(((size_t)r->h2 + 4096) * sizeof(float)))) {
         sdr_fmrx_free(r);
         return rc;
     }
     e = cudaMemcpy(r->d_taps.p, taps, T * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && cfg->n_taps2) e = cudaMemcpy(r->d_taps2.p, taps2, cfg->n_taps2 * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && cfg->n_taps2) {
+        // polyphase layout gp[phase][j] = g[phase + j*L] (zero padded); for L = 1 this is g padded to Jp
+        std::vector<float> gp((size_t)cfg->up * r->J + r->Jp + 8, 0.f);
+        for (uint32_t ph = 0; ph < cfg->up; ph++)
+            for (int j = 0; j < r->J; j++) {
+                size_t k = ph + (size_t)j * cfg->up;
+                if (k < cfg->n_taps2) gp[(size_t)ph * r->J + j] = taps2[k];
+            }
+        e = cudaMemcpy(r->d_taps2.p, gp.data(), gp.size() * 4, cudaMemcpyHostToDevice);
+        size_t sm = ((size_t)2 * r->Jp + kFirOblk) * sizeof(float);
+        if (e == cudaSuccess && sm > 48 * 1024)
+            e = cudaFuncSetAttribute(k_fir_real_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    }
     if (e != cudaSuccess) {
         sdr_fmrx_free(r);
         return fail(SDR_E_CUDA, "sdr_fmrx_new: %s", cudaGetErrorString(e));

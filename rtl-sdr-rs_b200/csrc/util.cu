@@ -46,7 +46,10 @@ int DevBuf::reserve(size_t bytes) {
     size_t want = bytes + 2 * kDevRoom;
     void *q = nullptr;
     SDR_CUDA_TRY(cudaMalloc(&q, want));
+    // cudaMemset runs on the legacy stream, which the handles' non-blocking streams do NOT order against:
+    // wait for it, or it could land on top of data a handle stream copies into the new buffer.
     SDR_CUDA_TRY(cudaMemset(q, 127, want));
+    SDR_CUDA_TRY(cudaDeviceSynchronize());
     p = static_cast<char *>(q) + kDevRoom;
     cap = bytes;
     return SDR_OK;
@@ -139,6 +142,7 @@ void *sdr_dev_alloc(int device, size_t bytes) {
         return nullptr;
     }
     cudaMemset(q, 127, want);   // head/tail room reads as mid-scale (centred zero)
+    cudaDeviceSynchronize();    // the legacy-stream memset must not race with non-blocking handle streams
     return static_cast<char *>(q) + kDevRoom;
 }
 void sdr_dev_free(int device, void *p) {

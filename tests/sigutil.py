@@ -65,3 +65,33 @@ def assert_angle_close(got, ref, full_scale: float, rtol=1e-5, what=""):
     tol = rtol * np.abs(ref) + rtol * full_scale
     bad = np.abs(d) > tol
     assert not bad.any(), f"{what}: {int(bad.sum())}/{ref.size} outside 1e-5 rel; worst {np.abs(d).max():.3e} of {full_scale}"
+
+
+def disc_f64(y_pairs, gain, prev=(0.0, 0.0)):
+    """f64 polar discriminator of a complex stream given as (n,2) pairs (same definition as the oracle)."""
+    y = np.asarray(y_pairs, np.float64)
+    z = y[:, 0] + 1j * y[:, 1]
+    zp = np.concatenate([[complex(*prev)], z[:-1]])
+    c = z * np.conj(zp)
+    out = gain * np.arctan2(c.imag, c.real)
+    out[(c.real == 0) & (c.imag == 0)] = 0.0
+    return out
+
+
+def assert_demod_propagated(d_got, y_ref_pairs, d_ref, gain, rtol=1e-5, what=""):
+    """End-to-end discriminator check.  If y is within rtol (the f32 FIR bar), the angle between two
+    successive samples can move by at most dy[m]/|y[m]| + dy[m-1]/|y[m-1]| rad (first order); allow that
+    plus rtol of full scale.  Differences are taken on the circle."""
+    y = np.asarray(y_ref_pairs, np.float64)
+    mag = np.hypot(y[:, 0], y[:, 1])
+    rms = float(np.sqrt(np.mean(mag * mag))) if mag.size else 0.0
+    dy = rtol * mag + rtol * rms
+    rel = dy / np.maximum(mag, 1e-300)
+    relp = np.concatenate([[np.inf], rel[:-1]])
+    full = gain * np.pi
+    tol = gain * np.minimum(rel + relp, np.pi) + rtol * full
+    d = np.asarray(d_got, np.float64) - np.asarray(d_ref, np.float64)
+    d = (d + full) % (2 * full) - full
+    bad = np.abs(d) > tol
+    bad[0] = False if mag.size and not np.isfinite(relp[0]) else bad[0]
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{d.size} beyond the propagated 1e-5 bound; worst {np.abs(d).max():.3e}"

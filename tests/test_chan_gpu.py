@@ -1,0 +1,110 @@
+"""GPU parity tests of the wideband channeliser (sdr_chan_*) against the f64 oracle's DIRECT definition
+(mix by a 32-bit-phase NCO, then FIR/decimate, then discriminate).  Extension path: parity unpinned by the
+reference; bar = 1e-5 relative.  The kernel folds the NCO into per-channel complex taps, so this also
+checks that algebra."""
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+import sdrpkg
+from sigutil import assert_angle_close, assert_close, assert_demod_propagated, channel_taps, disc_f64, fm_test_signal
+
+pytestmark = pytest.mark.gpu
+GAIN = 16384.0 / np.pi
+
+
+@pytest.fixture(scope="module")
+def S():
+    m = sdrpkg.load()
+    if m.device_count() < 1:
+        pytest.fail("no CUDA device: the product path has no CPU fallback")
+    return m
+
+
+def freq_words(offsets_hz, fs):
+    return (np.round(np.asarray(offsets_hz, np.float64) / fs * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("C,T,D", [(64, 255, 100), (3, 31, 7), (130, 63, 20), (64, 127, 75), (8, 16, 4)])
+def test_channeliser_vs_direct_definition(S, C, T, D):
+    rng = np.random.default_rng(C * 100 + D)
+    fs = 20e6
+    taps = channel_taps(T, D)
+    fw = freq_words((np.arange(C) - (C - 1) / 2) * (fs / max(C, 2)) * 0.9, fs)
+    n = D * 150 + 37
+    iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+    ch = S.Channeliser(taps, D, fw)
+    y, d = ch.process(iq)
+    yo, do = O.channelise(iq, taps, D, fw)
+    assert y.shape == yo.shape and d.shape == do.shape == (C, n // D)
+    for c in range(C):
+        assert_close(y[c], yo[c], what=f"y ch{c}")
+        assert_angle_close(d[c], disc_f64(y[c], GAIN), GAIN * np.pi, what=f"demod stage ch{c}")
+        assert_demod_propagated(d[c], yo[c], do[c], GAIN, what=f"demod ch{c}")
+
+
+def test_streaming_chunks_are_bitwise_identical(S):
+    rng = np.random.default_rng(4)
+    C, T, D = 64, 255, 100
+    taps = channel_taps(T, D)
+    fw = freq_words((np.arange(C) - 31.5) * 200e3, 20e6)
+    n = D * 400 + 61
+    iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+    y1, d1 = S.Channeliser(taps, D, fw).process(iq)
+    ch = S.Channeliser(taps, D, fw)
+    parts = [ch.process(iq[2 * lo:2 * hi]) for lo, hi in ((0, 1), (1, 6777), (6777, 6800), (6800, n))]
+    y2 = np.concatenate([p[0] for p in parts], axis=1)
+    d2 = np.concatenate([p[1] for p in parts], axis=1)
+    assert np.array_equal(y1, y2) and np.array_equal(d1, d2)
+
+
+def test_zero_offset_channel_equals_single_channel_receiver(S):
+    """fw = 0: the channeliser's channel is the plain FIR of the f32 receiver (same taps, same input)."""
+    T, D = 255, 100
+    taps = channel_taps(T, D)
+    iq = fm_test_signal(D * 500, fs=20e6, f_dev=40e3)
+    y, d = S.Channeliser(taps, D, np.zeros(2, np.uint32)).process(iq)
+    y1, d1, _ = S.FmRx(taps, D).process(iq)
+    assert_close(y[0], y1, what="fw=0 channel vs FmRx")
+    assert np.array_equal(y[0], y[1])
+
+
+def test_fm_channels_are_recovered(S):
+    """Two FM carriers at +-1 MHz in a 20 Msps stream come out of their channels with the 1 kHz tone."""
+    fs, D, T = 20e6, 100, 255
+    n = D * 4000
+    a = fm_test_signal(n, fs, seed=1, f_c=1.0e6, f_dev=50e3, amp=50, noise=2).astype(np.float64) - 127.5
+    b = fm_test_signal(n, fs, seed=2, f_c=-1.0e6, f_dev=50e3, f_mod=2e3, amp=50, noise=2).astype(np.float64) - 127.5
+    iq = np.clip(np.rint(a + b + 127.5), 0, 255).astype(np.uint8)
+    taps = channel_taps(T, D)
+    _, d = S.Channeliser(taps, D, freq_words([1.0e6, -1.0e6, 3.0e6], fs)).process(iq, want_y=False)
+    spec = np.abs(np.fft.rfft(d[:, 200:] * np.hanning(d.shape[1] - 200), axis=1))
+    f = np.fft.rfftfreq(d.shape[1] - 200, D / fs)
+    assert abs(f[np.argmax(spec[0][1:]) + 1] - 1e3) < 150
+    assert abs(f[np.argmax(spec[1][1:]) + 1] - 2e3) < 150
+    assert spec[2].max() < 0.2 * spec[0].max()      # empty channel: no tone
+
+
+def test_device_resident_and_errors(S):
+    C, T, D = 64, 255, 100
+    taps = channel_taps(T, D)
+    fw = freq_words((np.arange(C) - 31.5) * 200e3, 20e6)
+    n = 1 << 22
+    d_iq = S.DevBuffer(2 * n)
+    S.synth_fill_dev(d_iq, 2 * n, 7)
+    ch = S.Channeliser(taps, D, fw)
+    cap = n // D + 1
+    d_d = S.DevBuffer(4 * C * cap)
+    m = ch.process_dev(d_iq, n, d_d, cap)
+    ch.sync()
+    ms, launches = ch.last_timing()
+    assert m == n // D and ms > 0 and launches == 4
+    d = d_d.download(np.float32, C * cap).reshape(C, cap)[:, :m]
+    _, d_host = S.Channeliser(taps, D, fw).process(O.synth_fill(2 * D * 300, 7), want_y=False)
+    assert np.array_equal(d[:, :300], d_host)
+    with pytest.raises(S.SdrError) as e:
+        ch.process_dev(d_iq, n, d_d, 10)
+    assert e.value.code == -3
+    with pytest.raises(S.SdrError):
+        S.Channeliser(taps, 0, fw)
+    d_iq.free(), d_d.free()
