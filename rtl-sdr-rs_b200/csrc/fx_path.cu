@@ -24,8 +24,6 @@
 
 namespace sdr {
 
-constexpr float kMagic = 8388608.0f + 127.0f;   // 2^23 + centre: float(0x4B0000bb) - kMagic = bb - 127 exactly
-
 struct FirArgs {
     const uint8_t *x;          // call input, 16-B aligned
     const uint8_t *carry_end;  // one past the last carried byte (16-B aligned); carry holds the samples before x
@@ -42,12 +40,6 @@ template <int T>
 struct Taps {
     float h[T];
 };
-
-__device__ __forceinline__ float cvt_byte(uint32_t w, int which) {
-    // PRMT puts byte `which` of w into the low mantissa byte of 0x4B000000 (= 2^23)
-    uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7440u + which);
-    return __uint_as_float(bits) - kMagic;
-}
 
 // Accurate 2x2 determinant / dot (Kahan): a*b - c*d with one rounding error of the result.
 __device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
@@ -94,26 +86,63 @@ __device__ __forceinline__ uint32_t load_tile(unsigned char *tile, const FirArgs
 // =================================================================================================
 // Specialised kernel
 // =================================================================================================
-template <int T, int D, int B, int NT>
+template <int T, int D, int B, int NT, int WB>
 struct FastGeom {
     static constexpr int Q = (T + D - 1) / D;           // lags: outputs a sample contributes to
     static constexpr int NBLK = NT * B;                 // decimation blocks per CTA tile
-    static constexpr int HB0 = Q;                       // halo blocks: y[m-1] of the first owned output complete
-    static constexpr int HB = (((NBLK - HB0) * D) % 2 == 0) ? HB0 : HB0 + 1;   // keep the 4-byte phase CTA-uniform
+    static constexpr int SPL = WB / 2;                  // samples per shared-memory load (LDS.32 / LDS.64)
+    // halo blocks: >= Q so that y[m-1] of the first owned output is complete, and such that the tile
+    // stride (OUT*D samples) is a whole number of load units, which keeps the load phase CTA-uniform
+    static constexpr int pick_hb() {
+        int hb = Q;
+        while (((NBLK - hb) * D) % SPL != 0) hb++;
+        return hb;
+    }
+    static constexpr int HB = pick_hb();
     static constexpr int OUT = NBLK - HB;               // outputs owned per CTA
     static constexpr int TILE_BYTES = NBLK * D * 2;
     static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32;
     static constexpr int SM_PART = NBLK * Q * 8;        // float2 partial per (block, lag)
     static constexpr int SM_Y = NBLK * 8;
     static constexpr int SMEM = SM_TILE + SM_PART + SM_Y;
-    static_assert((B * D) % 2 == 0, "thread span must be a whole number of 32-bit words");
+    static_assert(WB == 4 || WB == 8, "LDS.32 or LDS.64");
+    static_assert((B * D) % SPL == 0, "thread span must be a whole number of load units");
     static_assert(OUT > HB, "tile too small");
 };
 
-template <int T, int D, int B, int NT, bool ODD>
+// One PRMT builds the half2 (1024+I, 1024+Q) (fp16 0x64bb == 1024+bb exactly); the Blackwell
+// mixed-precision add (PTX add.rn.f32.f16, SASS FHADD) then yields the centred f32 sample in one
+// instruction per component: 3 instructions per complex sample, all exact.
+struct CvtConst {
+    float bias;        // -(1024 + 127)
+    uint32_t h1024;    // 0x64646464: fp16 exponent byte of 1024 for PRMT
+};
+__device__ __forceinline__ CvtConst cvt_consts() {
+    // Both constants are made opaque AND per-thread (tid >> 31 == 0) so that they live in ordinary vector
+    // registers: as literals / uniform values the compiler re-materialises them with one MOV per use
+    // (FHADD takes no immediate or uniform operand), which costs more than the conversion itself.
+    CvtConst c;
+    asm volatile(
+        "{\n"
+        ".reg .u32 t;\n"
+        "mov.u32 t, %%tid.x;\n"
+        "shr.u32 t, t, 31;\n"
+        "or.b32 %0, t, 0xC48FE000;\n"
+        "or.b32 %1, t, 0x64646464;\n"
+        "}\n"
+        : "=f"(c.bias), "=r"(c.h1024));
+    return c;
+}
+__device__ __forceinline__ void cvt_iq(uint32_t w, int half, const CvtConst &c, float &xr, float &xi) {
+    const uint32_t pair = __byte_perm(w, c.h1024, half ? 0x4342u : 0x4140u);
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(c.bias));
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(c.bias));
+}
+
+template <int T, int D, int B, int NT, int WB, int PH>
 __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_constant__ Taps<T> taps) {
-    using G = FastGeom<T, D, B, NT>;
-    constexpr int Q = G::Q;
+    using G = FastGeom<T, D, B, NT, WB>;
+    constexpr int Q = G::Q, SPL = G::SPL;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t sh_soff;
@@ -136,22 +165,32 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
     mbar_wait(&bar, 0);
 
     // ---- convert once, accumulate per (block, lag) ----------------------------------------------
-    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile) + (sh_soff >> 2) + tid * (B * D / 2);
+    // The thread's first sample sits PH samples into load unit (soff / WB) + tid * (B*D/SPL).
+    const unsigned char *ubase = tile + (size_t)((sh_soff / WB) + tid * (B * D / SPL)) * WB;
     float accr[B][Q], acci[B][Q];
 #pragma unroll
     for (int b = 0; b < B; b++)
 #pragma unroll
         for (int q = 0; q < Q; q++) accr[b][q] = acci[b][q] = 0.f;
 
-    constexpr int NW = B * D / 2 + (ODD ? 1 : 0);
+    constexpr int NU = (PH + B * D + SPL - 1) / SPL;
+    const CvtConst bias = cvt_consts();
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
-        const uint32_t word = w32[w];
+    for (int u = 0; u < NU; u++) {
+        uint32_t words[WB / 4];
+        if (WB == 8) {
+            const uint2 v = reinterpret_cast<const uint2 *>(ubase)[u];
+            words[0] = v.x;
+            words[WB / 4 - 1] = v.y;
+        } else {
+            words[0] = reinterpret_cast<const uint32_t *>(ubase)[u];
+        }
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int j = 2 * w + half - (ODD ? 1 : 0);   // sample index inside the thread's span
+        for (int i = 0; i < SPL; i++) {
+            const int j = u * SPL + i - PH;   // sample index inside the thread's span
             if (j < 0 || j >= B * D) continue;
-            const float xr = cvt_byte(word, 2 * half), xi = cvt_byte(word, 2 * half + 1);
+            float xr, xi;
+            cvt_iq(words[i >> 1], i & 1, bias, xr, xi);
             const int bb = j / D, jj = j % D;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
@@ -233,15 +272,17 @@ __global__ void __launch_bounds__(128) k_fir_generic(const GenArgs g) {
     __syncthreads();
     mbar_wait(&bar, 0);
     const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tile + sh_soff);
+    const CvtConst gbias = cvt_consts();
     for (long long l = warp; l <= n_here; l += 4) {
         // newest sample of this output, relative to s0
         const int newest = (int)((out0 - 1 + l + 1) * g.D - 1 - (long long)a.r - s0);
         float ar = 0.f, ai = 0.f;
         for (int k = lane; k < g.T; k += 32) {
-            uint32_t v = t16[newest - k];
-            float h = htap[k];
-            ar = fmaf(h, (float)(int)(v & 255u) - 127.f, ar);
-            ai = fmaf(h, (float)(int)(v >> 8) - 127.f, ai);
+            float xr, xi;
+            cvt_iq(t16[newest - k], 0, gbias, xr, xi);
+            const float h = htap[k];
+            ar = fmaf(h, xr, ar);
+            ai = fmaf(h, xi, ai);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -377,39 +418,53 @@ namespace {
 
 struct FastVariant {
     int T, D;
-    int out_per_cta, hb, smem, nt;
-    void (*launch)(const FirArgs &, const float *taps, bool odd, int grid, int smem, cudaStream_t);
+    int out_per_cta, hb, smem, nt, wb;
+    void (*launch)(const FirArgs &, const float *taps, int phase, int grid, int smem, cudaStream_t);
     cudaError_t (*prepare)(int smem);
 };
 
-template <int T, int D, int B, int NT>
-void launch_fast(const FirArgs &a, const float *taps, bool odd, int grid, int smem, cudaStream_t st) {
+template <int T, int D, int B, int NT, int WB, int PH>
+void launch_one(const FirArgs &a, const Taps<T> &t, int grid, int smem, cudaStream_t st) {
+    k_fir_fast<T, D, B, NT, WB, PH><<<grid, NT, smem, st>>>(a, t);
+}
+template <int T, int D, int B, int NT, int WB>
+void launch_fast(const FirArgs &a, const float *taps, int phase, int grid, int smem, cudaStream_t st) {
     Taps<T> t;
     memcpy(t.h, taps, sizeof(float) * T);
-    if (odd)
-        k_fir_fast<T, D, B, NT, true><<<grid, NT, smem, st>>>(a, t);
-    else
-        k_fir_fast<T, D, B, NT, false><<<grid, NT, smem, st>>>(a, t);
+    switch (phase) {
+        case 0: launch_one<T, D, B, NT, WB, 0>(a, t, grid, smem, st); break;
+        case 1: launch_one<T, D, B, NT, WB, 1>(a, t, grid, smem, st); break;
+        case 2: launch_one<T, D, B, NT, WB, (WB == 8 ? 2 : 0)>(a, t, grid, smem, st); break;
+        default: launch_one<T, D, B, NT, WB, (WB == 8 ? 3 : 1)>(a, t, grid, smem, st); break;
+    }
 }
-template <int T, int D, int B, int NT>
+template <int T, int D, int B, int NT, int WB>
 cudaError_t prepare_fast(int smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (WB == 8) {
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 2 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 3 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    return e;
 }
-template <int T, int D, int B, int NT>
+template <int T, int D, int B, int NT, int WB>
 FastVariant make_variant() {
-    using G = FastGeom<T, D, B, NT>;
-    return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, &launch_fast<T, D, B, NT>, &prepare_fast<T, D, B, NT>};
+    using G = FastGeom<T, D, B, NT, WB>;
+    return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, WB, &launch_fast<T, D, B, NT, WB>, &prepare_fast<T, D, B, NT, WB>};
 }
 
 // Specialised (taps, decimation) shapes: BASELINE.json configs[1] (127, /75) and configs[2] (255, /100),
-// plus the reference's own boxcar shape (6, /6) used by the cross-path tests.
+// plus the reference's own boxcar shape (6, /6) used by the cross-path tests.  D = 100 gives a 200-byte
+// thread stride, so 64-bit shared loads are aligned and bank-conflict free; D = 75 (300-byte stride) is
+// conflict free with 32-bit loads.
 const FastVariant *find_variant(uint32_t T, uint32_t D) {
     static const FastVariant table[] = {
-        make_variant<127, 75, 2, 128>(),
-        make_variant<255, 100, 1, 256>(),
-        make_variant<6, 6, 4, 128>(),
+        make_variant<127, 75, 2, 128, 4>(),
+        make_variant<255, 100, 1, 256, 8>(),
+        make_variant<6, 6, 4, 128, 4>(),
     };
     if (getenv("SDR_FORCE_GENERIC")) return nullptr;
     for (const auto &v : table)
@@ -521,8 +576,11 @@ int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint6
         const FastVariant *v = r->fast;
         uint64_t grid = ceil_div(n_out, (uint64_t)v->out_per_cta);
         if (grid > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
-        bool odd = (((uint64_t)v->hb * r->cfg.decim + rphase) & 1) != 0;
-        v->launch(a, r->taps.data(), odd, (int)grid, v->smem, r->stream);
+        // load phase of every tile: sample s0 = -(HB*D + r) sits at byte (2*s0 mod 16) of its 16-byte line
+        const long long s0 = -((long long)v->hb * r->cfg.decim + rphase);
+        const uint32_t soff = (uint32_t)((2 * s0) & 15);
+        const int phase = (int)((soff % (uint32_t)v->wb) / 2);
+        v->launch(a, r->taps.data(), phase, (int)grid, v->smem, r->stream);
     } else {
         GenArgs g{};
         g.f = a;

@@ -32,7 +32,13 @@ struct OctTable {
     int32_t v[9];
 };
 
+// n / d for n < 2^31 with a host-computed round-up magic (d = rate_resample is fixed per handle)
+struct UDiv {
+    uint32_t magic, shift;   // shift == 0xffffffff => d == 1
+};
+
 struct FusedArgs {
+    UDiv div_slow;
     const uint8_t *in;
     int16_t *out;
     const IntState *st_in;
@@ -60,11 +66,12 @@ __device__ __forceinline__ int32_t d_fast_atan2(int32_t y, int32_t x) {
     if (x == 0 && y == 0) return 0;
     int32_t yabs = y < 0 ? wsub(0, y) : y;
     int32_t angle;
+    // (pi4 as i64 * v as i64) as i32 with pi4 = 2^12 is exactly the low 32 bits of v << 12
     if (x >= 0) {
-        int32_t num = (int32_t)(uint32_t)((long long)pi4 * (long long)wsub(x, yabs));
+        int32_t num = (int32_t)((uint32_t)wsub(x, yabs) << 12);
         angle = wsub(pi4, tdiv(num, wadd(x, yabs)));
     } else {
-        int32_t num = (int32_t)(uint32_t)((long long)pi4 * (long long)wadd(x, yabs));
+        int32_t num = (int32_t)((uint32_t)wadd(x, yabs) << 12);
         angle = wsub(pi34, tdiv(num, wsub(yabs, x)));
     }
     return y < 0 ? wsub(0, angle) : angle;
@@ -103,6 +110,44 @@ __device__ __forceinline__ void rot_acc(uint32_t iq16, int phase, int32_t &re, i
     }
     re = wadd(re, r);
     im = wadd(im, i);
+}
+
+// u8 x s8 dot product of four byte lanes with 32-bit accumulate (SASS IDP.4A)
+__device__ __forceinline__ int32_t dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int32_t c) {
+    int32_t d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+// rotate_90 (:285-295) + `- 127` (:258) + boxcar over the tile samples [pos, end), two samples per
+// 32-bit word.  A word holds samples (n, n+1) with n even, so its rotation phase pair is n%4 in {0,2}:
+//   n%4==0: re += I0 - 127 + 128 - Q1,  im += Q0 - 127 + I1 - 127  -> coef re [+1,0,0,-1], im [0,+1,+1,0]
+//   n%4==2: re += 128 - I0 + Q1 - 127,  im += 128 - Q0 + 128 - I1  -> coef re [-1,0,0,+1], im [0,-1,-1,0]
+// (the "+1 asymmetry" of 255-x then -127 lives in the constants).  Odd window edges use half-word masks.
+__device__ __forceinline__ void boxcar_rot(const uint32_t *w32, int pos, int end, int32_t &re, int32_t &im) {
+    if (pos < end && (pos & 1)) {   // head: upper half of its word; phase 1 or 3
+        const uint32_t w = w32[pos >> 1];
+        const bool p2 = pos & 2;
+        re = dp4a_us(w, p2 ? 0x01000000u : 0xFF000000u, re) + (p2 ? -127 : 128);
+        im = dp4a_us(w, p2 ? 0x00FF0000u : 0x00010000u, im) + (p2 ? 128 : -127);
+        pos++;
+    }
+    for (; pos + 2 <= end; pos += 2) {
+        const uint32_t w = w32[pos >> 1];
+        const bool p2 = pos & 2;
+        re = dp4a_us(w, p2 ? 0x010000FFu : 0xFF000001u, re) + 1;
+        im = dp4a_us(w, p2 ? 0x00FFFF00u : 0x00010100u, im) + (p2 ? 256 : -254);
+    }
+    if (pos < end) {                // tail: lower half of its word; phase 0 or 2
+        const uint32_t w = w32[pos >> 1];
+        const bool p2 = pos & 2;
+        re = dp4a_us(w, p2 ? 0x000000FFu : 0x00000001u, re) + (p2 ? 128 : -127);
+        im = dp4a_us(w, p2 ? 0x0000FF00u : 0x00000100u, im) + (p2 ? 128 : -127);
+    }
+}
+
+__device__ __forceinline__ uint32_t udiv(uint32_t n, UDiv d) {
+    return d.shift == 0xffffffffu ? n : (__umulhi(n, d.magic) >> d.shift);
 }
 
 // ================================================================================================
@@ -181,7 +226,7 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
     // ---- phase 1: rotate_90 + centre + boxcar over D samples ------------------------------------
     mbar_wait(&bar, 0);
     const int32_t off0 = sh_off0;
-    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tile);
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
     for (uint32_t i = tid; i < nlp; i += blockDim.x) {
         int32_t base = off0 + (int32_t)(i * a.D);
         int32_t re = 0, im = 0;
@@ -189,19 +234,13 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
             re = st.lp_now_re;
             im = st.lp_now_im;
         }
-        for (uint32_t j = 0; j < a.D; j++) {
-            int32_t pos = base + (int32_t)j;
-            if (pos < 0) continue;   // only window 0 with p0 > 0: those samples are already in lp_now
-            rot_acc(t16[pos], pos & 3, re, im);
-        }
+        // base < 0 only for window 0 with p0 > 0: those samples are already in lp_now
+        boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)a.D, re, im);
         lp[i] = make_int2(re, im);
     }
     if (last && tid == 255) {
         int32_t re = 0, im = 0;
-        for (uint32_t j = 0; j < sh_ntail; j++) {
-            uint32_t pos = sh_tail_from + j;
-            rot_acc(t16[pos], pos & 3, re, im);
-        }
+        boxcar_rot(w32, (int)sh_tail_from, (int)(sh_tail_from + sh_ntail), re, im);
         a.st_out->lp_now_re = re;
         a.st_out->lp_now_im = im;
     }
@@ -224,14 +263,14 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
     const uint32_t ne = sh_ne, rb = sh_rb;
     const uint32_t dbase = (uint32_t)(jlo - wlo);   // dm index of demod sample jlo
     for (uint32_t t = tid; t < ne; t += blockDim.x) {
-        uint32_t r0 = t ? (t * a.fast - rb + a.slow - 1) / a.slow : 0u;
-        uint32_t r1 = ((t + 1) * a.fast - rb + a.slow - 1) / a.slow;
+        uint32_t r0 = t ? udiv(t * a.fast - rb + a.slow - 1, a.div_slow) : 0u;
+        uint32_t r1 = udiv((t + 1) * a.fast - rb + a.slow - 1, a.div_slow);
         int32_t sum = (sh_e0 + t == 0) ? st.now_lpr : 0;
         for (uint32_t j = r0; j < r1; j++) sum = wadd(sum, (int32_t)dm[dbase + j]);
         a.out[sh_e0 + t] = (int16_t)(uint16_t)(uint32_t)tdiv(sum, a.div);
     }
     if (last && tid == 0) {
-        uint32_t r0 = ne ? (ne * a.fast - rb + a.slow - 1) / a.slow : 0u;
+        uint32_t r0 = ne ? udiv(ne * a.fast - rb + a.slow - 1, a.div_slow) : 0u;
         int32_t sum = (a.Etot == 0) ? st.now_lpr : 0;
         for (uint32_t j = dbase + r0; j < nlp; j++) sum = wadd(sum, (int32_t)dm[j]);
         a.st_out->now_lpr = sum;
@@ -463,6 +502,17 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     a.fast = d->cfg.rate_out;
     a.slow = d->cfg.rate_resample;
     a.div = (int32_t)(d->cfg.rate_out / d->cfg.rate_resample);
+    {   // round-up magic for n / rate_resample, exact for n < 2^31 (Granlund-Montgomery)
+        const uint32_t dv = d->cfg.rate_resample;
+        if (dv == 1) {
+            a.div_slow = UDiv{0u, 0xffffffffu};
+        } else {
+            uint32_t s = 0;
+            while ((1ull << s) < dv) s++;                       // s = ceil(log2 dv) >= 1
+            uint64_t m = ((1ull << (31 + s)) / dv) + 1;          // < 2^32 because dv > 2^(s-1)
+            a.div_slow = UDiv{(uint32_t)m, s - 1};              // q = umulhi(n, m) >> (s-1)
+        }
+    }
     a.EB = d->EB;
     a.lp_cap = d->lp_cap;
     a.tile_cap = d->tile_cap;
@@ -521,8 +571,9 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     uint64_t EB = n_lp_target * slow / fast;
     if (EB < 1) EB = 1;
     if (EB > 1024) EB = 1024;
-    while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 32)) EB /= 2;
-    if ((EB + 1) * fast + slow >= (1ull << 32)) {
+    // the kernel's relative index math and its magic division need (EB+1)*fast + slow < 2^31
+    while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 31)) EB /= 2;
+    if ((EB + 1) * fast + slow >= (1ull << 31)) {
         delete d;
         return fail(SDR_E_ARG, "rate_out too large");
     }
