@@ -190,6 +190,22 @@ int sdr_fmrx_span_end(sdr_fmrx *r, float *ms);
  * the time slice [n, ...) of one stream prime its carry by first processing the samples before n. */
 int sdr_fmrx_seek(sdr_fmrx *r, uint64_t global_sample_index);
 
+/* ---- closed-form stream bookkeeping (pure host arithmetic: no device needed) -------------------
+ * The reference discovers these counts by running its loops (:337-352, :408-426); here they are
+ * formulas, so callers can size buffers up front and a multi-rank job can cut ONE stream into
+ * per-rank time slices that tile it exactly. */
+/* For a stream positioned at global sample n_in0: index of the first FIR output / audio sample a
+ * call of n_samples produces, and how many. */
+int sdr_fmrx_plan(const sdr_fmrx_config *cfg, uint64_t n_in0, size_t n_samples, uint64_t *y0, size_t *n_y,
+                  uint64_t *a0, size_t *n_audio);
+/* Integer Demod: lowpassed / audio counts of n_bufs calls of buf_len bytes from state `st` (NULL =
+ * fresh) and the index part of the state afterwards (prev_index, prev_lpr_index). */
+int sdr_demod_plan(const sdr_demod_config *cfg, const sdr_demod_state *st, size_t buf_len, size_t n_bufs,
+                   size_t *n_lowpassed, size_t *n_audio, sdr_demod_state *after);
+/* Contiguous slice [lo, hi) of a stream of `total` samples owned by `rank` of `world`, cut on
+ * multiples of `align` samples (the remainder goes to the last rank). */
+int sdr_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t align, uint64_t *lo, uint64_t *hi);
+
 /* ============================================================================================
  * 3. Wideband channeliser (configs 4-5): per channel c an NCO mix by a 32-bit phase word
  *    (theta_c(n) = 2*pi*((fw_c*n) mod 2^32)/2^32), the same decimating FIR, the discriminator.

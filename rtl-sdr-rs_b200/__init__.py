@@ -26,6 +26,9 @@ from ._ffi import (  # noqa: F401
     DevBuffer,
     HostBuffer,
     synth_fill_dev,
+    fmrx_plan,
+    demod_plan,
+    shard_range,
 )
 from .demod import Demod  # noqa: F401
 from .fmrx import FmRx  # noqa: F401

@@ -106,6 +106,11 @@ SIGNATURES = {
     "sdr_fmrx_span_begin": (_i, [_vp]),
     "sdr_fmrx_span_end": (_i, [_vp, C.POINTER(C.c_float)]),
     "sdr_fmrx_seek": (_i, [_vp, C.c_uint64]),
+    "sdr_fmrx_plan": (_i, [C.POINTER(FmrxConfig), C.c_uint64, _sz, C.POINTER(C.c_uint64), C.POINTER(_sz),
+                           C.POINTER(C.c_uint64), C.POINTER(_sz)]),
+    "sdr_demod_plan": (_i, [C.POINTER(DemodConfig), C.POINTER(DemodState), _sz, _sz, C.POINTER(_sz), C.POINTER(_sz),
+                            C.POINTER(DemodState)]),
+    "sdr_shard_range": (_i, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sdr_chan_new": (_i, [C.POINTER(ChanConfig), _vp, _vp, _i, C.POINTER(_vp)]),
     "sdr_chan_free": (None, [_vp]),
     "sdr_chan_reset": (_i, [_vp]),
@@ -247,3 +252,24 @@ class HostBuffer:
 
 def synth_fill_dev(buf: DevBuffer, nbytes: int, seed: int, byte_offset: int = 0, dst_offset: int = 0):
     check(lib().sdr_synth_fill_dev(buf.device, buf.at(dst_offset), nbytes, seed, byte_offset))
+
+
+def fmrx_plan(cfg: FmrxConfig, n_in0: int, n_samples: int):
+    """(y0, n_y, a0, n_audio) of a call at global sample n_in0 — pure host arithmetic."""
+    y0, a0, ny, na = C.c_uint64(0), C.c_uint64(0), C.c_size_t(0), C.c_size_t(0)
+    check(lib().sdr_fmrx_plan(C.byref(cfg), n_in0, n_samples, C.byref(y0), C.byref(ny), C.byref(a0), C.byref(na)))
+    return y0.value, ny.value, a0.value, na.value
+
+
+def demod_plan(cfg: DemodConfig, buf_len: int, n_bufs: int, state: DemodState | None = None):
+    """(n_lowpassed, n_audio, DemodState-after[index fields]) — pure host arithmetic."""
+    nl, na, after = C.c_size_t(0), C.c_size_t(0), DemodState()
+    check(lib().sdr_demod_plan(C.byref(cfg), C.byref(state) if state is not None else None, buf_len, n_bufs,
+                               C.byref(nl), C.byref(na), C.byref(after)))
+    return nl.value, na.value, after
+
+
+def shard_range(total: int, world: int, rank: int, align: int = 1):
+    lo, hi = C.c_uint64(0), C.c_uint64(0)
+    check(lib().sdr_shard_range(total, world, rank, align, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value

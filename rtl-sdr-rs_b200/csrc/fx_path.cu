@@ -338,17 +338,24 @@ __global__ void k_store_prev(const float2 *y, long long n, float2 *prev_state) {
 // L = M = 1 (plain real FIR at the output rate): 8 outputs per thread, taps and a 16-float sliding
 // window per 8-tap chunk in registers: 64 FMAs per 6 shared-memory loads.
 constexpr int kFirR = 8, kFirThreads = 128, kFirOblk = kFirR * kFirThreads;
+inline size_t fir_real_smem(int Jp) {   // taps + padded window (one pad chunk per 8 chunks)
+    return ((size_t)Jp + ((size_t)(kFirOblk + Jp) * 9) / 8 + 16) * sizeof(float);
+}
 __global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, int h2, const float *gp, int Jp,
                                                              long long n_out, long long n_valid, float *out) {
     extern __shared__ __align__(16) float fsm[];
     float *taps = fsm;            // [Jp]
-    float *win = fsm + Jp;        // [kFirOblk + Jp]; win[idx] = dbuf[h2 + o0 - Jp + idx]
+    // window: logical win[idx] = dbuf[h2 + o0 - Jp + idx], idx < kFirOblk + Jp, stored in 16-byte chunks
+    // with one pad chunk after every 8 (chunk c lives at c + c/8): lanes read chunks 2t+k, and the pad
+    // turns that stride-2 pattern into 8 distinct bank groups per quarter warp (conflict-free LDS.128).
+    float4 *win4 = reinterpret_cast<float4 *>(fsm + Jp);
+    float *win = fsm + Jp;
     const long long o0 = (long long)blockIdx.x * kFirOblk;
     for (int k = threadIdx.x; k < Jp; k += blockDim.x) taps[k] = gp[k];
     const long long gbase = (long long)h2 + o0 - Jp;
     for (int idx = threadIdx.x; idx < kFirOblk + Jp; idx += blockDim.x) {
         long long gi = gbase + idx;
-        win[idx] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
+        win[idx + (idx >> 5) * 4] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
     }
     __syncthreads();
     float acc[kFirR];
@@ -357,11 +364,11 @@ __global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, 
     const int t8 = threadIdx.x * kFirR;
     for (int j0 = 0; j0 < Jp; j0 += 8) {
         float w[16], g[8];
-        const float4 *wp = reinterpret_cast<const float4 *>(win + Jp + t8 - j0 - 8);
+        const int c0 = (Jp + t8 - j0 - 8) >> 2;   // first logical chunk (Jp, t8, j0 are multiples of 8)
         const float4 *gq = reinterpret_cast<const float4 *>(taps + j0);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            float4 v = wp[c];
+            float4 v = win4[(c0 + c) + ((c0 + c) >> 3)];
             w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
         }
 #pragma unroll
@@ -374,36 +381,61 @@ __global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, 
 #pragma unroll
             for (int r = 0; r < kFirR; r++) acc[r] = fmaf(g[jj], w[8 + r - jj], acc[r]);
     }
+    // 8 consecutive outputs per thread: two 16-byte stores when the row is whole and aligned
+    float *dst = out + o0 + t8;
+    if (o0 + t8 + kFirR <= n_out && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        reinterpret_cast<float4 *>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4 *>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
 #pragma unroll
-    for (int r = 0; r < kFirR; r++)
-        if (o0 + t8 + r < n_out) out[o0 + t8 + r] = acc[r];
+        for (int r = 0; r < kFirR; r++)
+            if (o0 + t8 + r < n_out) dst[r] = acc[r];
+    }
 }
 
 // Generic rational L/M: one output per thread, polyphase taps in shared memory, 32-bit index math
 // relative to a per-CTA 64-bit base.
 __global__ void __launch_bounds__(256) k_resample_poly(const float *dbuf, int h2, unsigned long long P0, const float *gp,
                                                        int J, uint32_t L, uint32_t M, unsigned long long i0,
-                                                       long long n_out, int taps_in_smem, float *out) {
+                                                       long long n_out, int taps_in_smem, int win_cap, long long n_valid,
+                                                       float *out) {
     extern __shared__ __align__(16) float fsm[];
     const float *tp = gp;
+    float *xw = fsm;                       // staged window of d (when win_cap > 0), after the taps
     if (taps_in_smem) {
         for (int k = threadIdx.x; k < (int)(L * J); k += blockDim.x) fsm[k] = gp[k];
-        __syncthreads();
         tp = fsm;
+        xw = fsm + ((L * J + 3) & ~3u);
     }
+    __syncthreads();
     for (long long ob = (long long)blockIdx.x * 256; ob < n_out; ob += (long long)gridDim.x * 256) {
         const unsigned long long t0 = (i0 + (unsigned long long)ob) * M;
         const unsigned long long p0 = t0 / L;
         const uint32_t ph0 = (uint32_t)(t0 - p0 * L);
         const long long o = ob + threadIdx.x;
-        if (o >= n_out) continue;
         const uint32_t trel = ph0 + threadIdx.x * M;
         const uint32_t dp = trel / L, ph = trel - dp * L;
-        const float *x = dbuf + ((long long)(p0 - P0) + h2 + dp);
+        const long long xbase = (long long)(p0 - P0) + h2;       // dbuf index of d[p0]
         const float *g = tp + (size_t)ph * J;
         float acc = 0.f;
-        for (int j = 0; j < J; j++) acc = fmaf(g[j], x[-j], acc);
-        out[o] = acc;
+        if (win_cap) {
+            // the 256 outputs of this tile read d[p0 - (J-1) .. p0 + (ph0 + 255*M)/L]: stage it once, coalesced
+            const int span = (int)((ph0 + 255u * M) / L) + J;
+            __syncthreads();               // previous tile's readers are done
+            for (int k = threadIdx.x; k < span; k += blockDim.x) {
+                const long long gi = xbase - (J - 1) + k;
+                xw[k] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
+            }
+            __syncthreads();
+            if (o < n_out) {
+                const float *x = xw + (J - 1) + dp;
+                for (int j = 0; j < J; j++) acc = fmaf(g[j], x[-j], acc);
+            }
+        } else if (o < n_out) {
+            const float *x = dbuf + (xbase + dp);
+            for (int j = 0; j < J; j++) acc = fmaf(g[j], x[-j], acc);
+        }
+        if (o < n_out) out[o] = acc;
     }
 }
 
@@ -418,7 +450,7 @@ namespace {
 
 struct FastVariant {
     int T, D;
-    int out_per_cta, hb, smem, nt, wb;
+    int out_per_cta, hb, smem, nt, wb, b;
     void (*launch)(const FirArgs &, const float *taps, int phase, int grid, int smem, cudaStream_t);
     cudaError_t (*prepare)(int smem);
 };
@@ -453,7 +485,7 @@ cudaError_t prepare_fast(int smem) {
 template <int T, int D, int B, int NT, int WB>
 FastVariant make_variant() {
     using G = FastGeom<T, D, B, NT, WB>;
-    return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, WB, &launch_fast<T, D, B, NT, WB>, &prepare_fast<T, D, B, NT, WB>};
+    return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, WB, B, &launch_fast<T, D, B, NT, WB>, &prepare_fast<T, D, B, NT, WB>};
 }
 
 // Specialised (taps, decimation) shapes: BASELINE.json configs[1] (127, /75) and configs[2] (255, /100),
@@ -461,15 +493,27 @@ FastVariant make_variant() {
 // thread stride, so 64-bit shared loads are aligned and bank-conflict free; D = 75 (300-byte stride) is
 // conflict free with 32-bit loads.
 const FastVariant *find_variant(uint32_t T, uint32_t D) {
+    // first entry of a shape = default CTA size; SDR_FIR_NT=<threads> selects another compiled size (tuning)
     static const FastVariant table[] = {
+        make_variant<127, 75, 2, 32, 4>(),     // 10 KB/CTA: many small CTAs overlap load and compute best
+        make_variant<127, 75, 2, 64, 4>(),
         make_variant<127, 75, 2, 128, 4>(),
-        make_variant<255, 100, 1, 256, 8>(),
+        make_variant<255, 100, 1, 160, 8>(),   // 37 KB/CTA -> 6 CTAs = 960 threads per SM (measured best)
+        make_variant<255, 100, 1, 128, 8>(),
+        make_variant<255, 100, 1, 192, 8>(),
+        make_variant<255, 100, 1, 64, 8>(),
         make_variant<6, 6, 4, 128, 4>(),
     };
     if (getenv("SDR_FORCE_GENERIC")) return nullptr;
+    const char *nt_env = getenv("SDR_FIR_NT"), *b_env = getenv("SDR_FIR_B");
+    const int want_nt = nt_env ? atoi(nt_env) : 0, want_b = b_env ? atoi(b_env) : 0;
+    const FastVariant *first = nullptr;
     for (const auto &v : table)
-        if ((uint32_t)v.T == T && (uint32_t)v.D == D) return &v;
-    return nullptr;
+        if ((uint32_t)v.T == T && (uint32_t)v.D == D) {
+            if (!first) first = &v;
+            if (want_nt && v.nt == want_nt && (!want_b || v.b == want_b)) return &v;
+        }
+    return first;
 }
 
 constexpr size_t kFxChunkSamples = size_t(16) << 20;   // 32 MiB of IQ per pipelined chunk (host API)
@@ -616,18 +660,22 @@ int launch_resample(sdr_fmrx *r, uint64_t P0, uint64_t n_new, uint64_t a0, uint6
     if (n_a && r->cfg.up == 1 && r->cfg.down == 1) {
         uint64_t blocks = ceil_div(n_a, (uint64_t)kFirOblk);
         if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
-        size_t sm = ((size_t)2 * r->Jp + kFirOblk) * sizeof(float);
+        size_t sm = fir_real_smem(r->Jp);
         k_fir_real_r8<<<(int)blocks, kFirThreads, sm, r->stream>>>(r->d_dbuf.as<float>(), r->h2, r->d_taps2.as<float>(), r->Jp,
                                                                   (long long)n_a, (long long)(r->h2 + n_new), d_audio);
         SDR_LAUNCH_CHECK();
         r->last_launches++;
     } else if (n_a) {
         int blocks = (int)std::min<uint64_t>(ceil_div(n_a, 256), (uint64_t)sm_count(r->device) * 16);
-        size_t tb = (size_t)r->cfg.up * r->J * sizeof(float);
-        int in_smem = tb <= 48 * 1024;
-        k_resample_poly<<<blocks, 256, in_smem ? tb : 0, r->stream>>>(r->d_dbuf.as<float>(), r->h2, P0, r->d_taps2.as<float>(),
-                                                                      r->J, r->cfg.up, r->cfg.down, a0, (long long)n_a, in_smem,
-                                                                      d_audio);
+        size_t tb = (((size_t)r->cfg.up * r->J + 3) & ~size_t(3)) * sizeof(float);
+        int in_smem = tb <= 32 * 1024;
+        // window of d one 256-output tile touches; staged in shared memory when it is small
+        size_t span = ((size_t)(r->cfg.up - 1) + 255ull * r->cfg.down) / r->cfg.up + r->J + 1;
+        int win_cap = (in_smem && span <= 3072) ? (int)span : 0;
+        size_t sm = (in_smem ? tb : 0) + (size_t)win_cap * sizeof(float);
+        k_resample_poly<<<blocks, 256, sm, r->stream>>>(r->d_dbuf.as<float>(), r->h2, P0, r->d_taps2.as<float>(), r->J,
+                                                        r->cfg.up, r->cfg.down, a0, (long long)n_a, in_smem, win_cap,
+                                                        (long long)(r->h2 + n_new), d_audio);
         SDR_LAUNCH_CHECK();
         r->last_launches++;
     }
@@ -776,7 +824,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
                 if (k < cfg->n_taps2) gp[(size_t)ph * r->J + j] = taps2[k];
             }
         e = cudaMemcpy(r->d_taps2.p, gp.data(), gp.size() * 4, cudaMemcpyHostToDevice);
-        size_t sm = ((size_t)2 * r->Jp + kFirOblk) * sizeof(float);
+        size_t sm = fir_real_smem(r->Jp);
         if (e == cudaSuccess && sm > 48 * 1024)
             e = cudaFuncSetAttribute(k_fir_real_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     }

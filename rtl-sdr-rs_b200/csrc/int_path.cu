@@ -37,8 +37,15 @@ struct UDiv {
     uint32_t magic, shift;   // shift == 0xffffffff => d == 1
 };
 
+// n / d for n < 2^63 (d fixed per handle / per batch): q = umul64hi(n, magic) >> shift
+struct UDiv64 {
+    unsigned long long magic;
+    uint32_t shift;   // 0xffffffff => d == 1
+};
+
 struct FusedArgs {
     UDiv div_slow;
+    UDiv64 d64_slow, d64_S, d64_D;
     const uint8_t *in;
     int16_t *out;
     const IntState *st_in;
@@ -146,6 +153,9 @@ __device__ __forceinline__ void boxcar_rot(const uint32_t *w32, int pos, int end
     }
 }
 
+__device__ __forceinline__ unsigned long long udiv64(unsigned long long n, UDiv64 d) {
+    return d.shift == 0xffffffffu ? n : (__umul64hi(n, d.magic) >> d.shift);
+}
 __device__ __forceinline__ uint32_t udiv(uint32_t n, UDiv d) {
     return d.shift == 0xffffffffu ? n : (__umulhi(n, d.magic) >> d.shift);
 }
@@ -156,7 +166,7 @@ __device__ __forceinline__ uint32_t udiv(uint32_t n, UDiv d) {
 __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned long long sh_wlo, sh_jlo, sh_jhi, sh_e0;
+    __shared__ unsigned long long sh_wlo, sh_jlo, sh_jhi, sh_e0, sh_clo, sh_chi;
     __shared__ uint32_t sh_ne, sh_rb, sh_nlp, sh_tail_from, sh_ntail;
     __shared__ int32_t sh_off0;
 
@@ -177,8 +187,8 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
         unsigned long long e1 = e0 + a.EB < a.Etot ? e0 + a.EB : a.Etot;
         if (e0 > a.Etot) e0 = a.Etot;
         // J(e) = ceil(((e+1)*fast - q0)/slow), J(-1) = 0
-        unsigned long long jlo = e0 ? (e0 * fast - a.q0 + slow - 1) / slow : 0ull;
-        unsigned long long jhi = last ? a.Ltot : (e1 ? (e1 * fast - a.q0 + slow - 1) / slow : 0ull);
+        unsigned long long jlo = e0 ? udiv64(e0 * fast - a.q0 + slow - 1, a.d64_slow) : 0ull;
+        unsigned long long jhi = last ? a.Ltot : (e1 ? udiv64(e1 * fast - a.q0 + slow - 1, a.d64_slow) : 0ull);
         unsigned long long wlo = jlo ? jlo - 1 : 0ull;
         // relative form: J(e0-1+u) = jlo + ceil((u*fast - rb)/slow) for u >= 1
         uint32_t rb = e0 ? (uint32_t)(jlo * slow - (e0 * fast - a.q0)) : a.q0;
@@ -205,6 +215,9 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
         } else {
             mbar_arrive(&bar);
         }
+        // calls whose first window can lie in [jlo, jhi): computed while the copy is in flight
+        sh_clo = jhi > jlo ? udiv64((jlo + 1) * a.D - a.p0 - 1, a.d64_S) : 1ull;
+        sh_chi = jhi > jlo ? udiv64(jhi * a.D - a.p0 - 1, a.d64_S) : 0ull;
     }
     __syncthreads();
     const unsigned long long wlo = sh_wlo, jlo = sh_jlo, jhi = sh_jhi;
@@ -213,12 +226,10 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
     // ---- first-of-call flags (while the bulk copy is in flight) --------------------------------
     for (uint32_t i = tid; i < nlp; i += blockDim.x) flag[i] = 0;
     __syncthreads();
-    if (jhi > jlo) {
-        // calls whose first window can lie in [jlo, jhi)
-        unsigned long long c_lo = ((jlo + 1) * a.D - a.p0 - 1) / a.S;
-        unsigned long long c_hi = (jhi * a.D - a.p0 - 1) / a.S;
-        for (unsigned long long c = c_lo + tid; c <= c_hi; c += blockDim.x) {
-            unsigned long long w = (c * a.S + a.p0) / a.D;
+    {
+        const unsigned long long c_hi = sh_chi;
+        for (unsigned long long c = sh_clo + tid; c <= c_hi; c += blockDim.x) {
+            unsigned long long w = udiv64(c * a.S + a.p0, a.d64_D);
             if (w >= jlo && w < jhi) flag[w - wlo] = 1;
         }
     }
@@ -513,6 +524,16 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
             a.div_slow = UDiv{(uint32_t)m, s - 1};              // q = umulhi(n, m) >> (s-1)
         }
     }
+    auto magic64 = [](uint64_t dv) {
+        if (dv <= 1) return UDiv64{0ull, 0xffffffffu};
+        uint32_t sh = 0;
+        while (sh < 63 && (1ull << sh) < dv) sh++;
+        unsigned __int128 m = (((unsigned __int128)1 << (63 + sh)) / dv) + 1;   // < 2^64 because dv > 2^(sh-1)
+        return UDiv64{(unsigned long long)m, sh - 1};
+    };
+    a.d64_slow = magic64(d->cfg.rate_resample);
+    a.d64_S = magic64(S);
+    a.d64_D = magic64(d->cfg.downsample);
     a.EB = d->EB;
     a.lp_cap = d->lp_cap;
     a.tile_cap = d->tile_cap;
