@@ -96,9 +96,10 @@ def run_chan(args, w):
     n_slabs = n // slab
 
     def step():
-        for s in range(n_slabs):
+        if comm is not None:
+            comm.wait_chan(ch)                          # the slab memory is reused every step: wait for the previous
+        for s in range(n_slabs):                        # step's channelising once, then broadcast(s+1) overlaps process(s)
             if comm is not None:
-                comm.wait_chan(ch)                      # slab memory is reused every step
                 comm.bcast_u8(d_in, 2 * slab, 0, offset=2 * slab * s)
                 comm.chan_wait(ch)
             from rtl_sdr_rs_b200 import _ffi as F

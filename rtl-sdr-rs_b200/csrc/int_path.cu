@@ -73,14 +73,13 @@ __device__ __forceinline__ int32_t d_fast_atan2(int32_t y, int32_t x) {
     if (x == 0 && y == 0) return 0;
     int32_t yabs = y < 0 ? wsub(0, y) : y;
     int32_t angle;
-    // (pi4 as i64 * v as i64) as i32 with pi4 = 2^12 is exactly the low 32 bits of v << 12
-    if (x >= 0) {
-        int32_t num = (int32_t)((uint32_t)wsub(x, yabs) << 12);
-        angle = wsub(pi4, tdiv(num, wadd(x, yabs)));
-    } else {
-        int32_t num = (int32_t)((uint32_t)wadd(x, yabs) << 12);
-        angle = wsub(pi34, tdiv(num, wsub(yabs, x)));
-    }
+    // (pi4 as i64 * v as i64) as i32 with pi4 = 2^12 is exactly the low 32 bits of v << 12.
+    // Both branches of :396-400 share ONE divide here (select operands first): a warp whose lanes see both
+    // signs of x would otherwise execute the ~28-instruction integer division twice.
+    const bool xpos = x >= 0;
+    const int32_t num = (int32_t)((uint32_t)(xpos ? wsub(x, yabs) : wadd(x, yabs)) << 12);
+    const int32_t den = xpos ? wadd(x, yabs) : wsub(yabs, x);
+    angle = wsub(xpos ? pi4 : pi34, tdiv(num, den));
     return y < 0 ? wsub(0, angle) : angle;
 }
 
@@ -132,19 +131,40 @@ __device__ __forceinline__ int32_t dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int
 //   n%4==2: re += 128 - I0 + Q1 - 127,  im += 128 - Q0 + 128 - I1  -> coef re [-1,0,0,+1], im [0,-1,-1,0]
 // (the "+1 asymmetry" of 255-x then -127 lives in the constants).  Odd window edges use half-word masks.
 __device__ __forceinline__ void boxcar_rot(const uint32_t *w32, int pos, int end, int32_t &re, int32_t &im) {
-    if (pos < end && (pos & 1)) {   // head: upper half of its word; phase 1 or 3
+    if (pos >= end) return;
+    if (pos & 1) {                  // head: upper half of its word; phase 1 or 3
         const uint32_t w = w32[pos >> 1];
         const bool p2 = pos & 2;
         re = dp4a_us(w, p2 ? 0x01000000u : 0xFF000000u, re) + (p2 ? -127 : 128);
         im = dp4a_us(w, p2 ? 0x00FF0000u : 0x00010000u, im) + (p2 ? 128 : -127);
         pos++;
     }
-    for (; pos + 2 <= end; pos += 2) {
-        const uint32_t w = w32[pos >> 1];
-        const bool p2 = pos & 2;
-        re = dp4a_us(w, p2 ? 0x010000FFu : 0xFF000001u, re) + 1;
-        im = dp4a_us(w, p2 ? 0x00FFFF00u : 0x00010100u, im) + (p2 ? 256 : -254);
+    // whole words: peel one so that the rest are (phase-0 word, phase-2 word) pairs with fixed coefficients
+    int wi = pos >> 1;
+    const int wend = end >> 1;            // exclusive: words fully inside the window
+    if (wi < wend && (wi & 1)) {          // a phase-2 word first
+        const uint32_t w = w32[wi];
+        re = dp4a_us(w, 0x010000FFu, re) + 1;
+        im = dp4a_us(w, 0x00FFFF00u, im) + 256;
+        wi++;
     }
+    int npairs = 0;
+    for (; wi + 2 <= wend; wi += 2, npairs++) {   // wi even: the pair is one aligned 8-byte load
+        const uint2 w = *reinterpret_cast<const uint2 *>(w32 + wi);
+        re = dp4a_us(w.x, 0xFF000001u, re);
+        im = dp4a_us(w.x, 0x00010100u, im);
+        re = dp4a_us(w.y, 0x010000FFu, re);
+        im = dp4a_us(w.y, 0x00FFFF00u, im);
+    }
+    re += 2 * npairs;                     // (+1) + (+1) per pair
+    im += 2 * npairs;                     // (-254) + (+256) per pair
+    if (wi < wend) {                      // a trailing phase-0 word
+        const uint32_t w = w32[wi];
+        re = dp4a_us(w, 0xFF000001u, re) + 1;
+        im = dp4a_us(w, 0x00010100u, im) - 254;
+        wi++;
+    }
+    pos = wi << 1;
     if (pos < end) {                // tail: lower half of its word; phase 0 or 2
         const uint32_t w = w32[pos >> 1];
         const bool p2 = pos & 2;
