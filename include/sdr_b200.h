@@ -122,6 +122,20 @@ int sdr_demod_last_timing(const sdr_demod *d, float *kernel_ms, uint32_t *n_laun
 int sdr_demod_span_begin(sdr_demod *d);
 int sdr_demod_span_end(sdr_demod *d, float *ms);
 
+/* Persistent ring: successive USB-sized buffers stream through ONE resident kernel — no relaunch per buffer.
+ * Mirrors the reader -> channel -> processor pair of examples/simple_fm.rs:55-60,108-128,145-160: the
+ * producer thread acquires the next pinned slot (blocks while all n_slots are in flight), fills it (read_sync
+ * straight into it) and commits it; the consumer thread collects the audio of the oldest buffer.  Output is
+ * bit-identical to one sdr_demod_demodulate(buf_len) call per buffer.  While a ring is open the Demod handle
+ * is owned by it, and nothing else may allocate or device-synchronise on that GPU (the ring kernel never
+ * retires until sdr_ring_close, which also hands the carried state back to the handle). */
+typedef struct sdr_ring sdr_ring;
+int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots /* 2..64 */, sdr_ring **out);
+int sdr_ring_acquire(sdr_ring *r, uint8_t **buf);                 /* producer */
+int sdr_ring_commit(sdr_ring *r);                                 /* producer: H2D copy + doorbell */
+long sdr_ring_collect(sdr_ring *r, int16_t *out, size_t cap);     /* consumer: audio of the oldest buffer */
+int sdr_ring_close(sdr_ring *r);
+
 /* Stage entry points (stage-level parity against the reference's three known-answer tests). */
 /* Demod::rotate_90(Vec<u8>) -> Vec<u8>, scalar branch :276-299; in place, len % 8 == 0. */
 long sdr_rotate_90(sdr_demod *d, uint8_t *buf, size_t len);
@@ -254,6 +268,12 @@ void sdr_comm_free(sdr_comm *c);
 typedef struct sdr_source sdr_source;
 int sdr_source_open_file(const char *path, int loop, sdr_source **out);
 int sdr_source_open_synth(uint64_t seed, uint64_t total_bytes /* 0 = endless */, sdr_source **out);
+/* rtl_tcp client: a dongle elsewhere feeds this box without USB.  Wire format of examples/rtl_tcp.rs: 12-byte
+ * greeting "RTL0" + tuner type + gain count (u32 BE, send_handshake :691-697), then raw u8 IQ; commands are
+ * 1 byte id + u32 BE parameter (command_loop :633-689: 0x01 frequency, 0x02 sample rate, ... 0x0e bias tee). */
+int sdr_source_open_rtl_tcp(const char *host, uint16_t port, sdr_source **out);
+int sdr_source_rtl_tcp_info(const sdr_source *s, uint32_t *tuner_type, uint32_t *gain_count);
+int sdr_source_rtl_tcp_command(sdr_source *s, uint8_t cmd, uint32_t param);
 /* Blocking; fills buf; returns bytes written (short count at end of data, like a short USB
  * read, examples/simple_fm.rs:121-125) or SDR_E_IO. */
 long sdr_source_read_sync(sdr_source *s, uint8_t *buf, size_t len);

@@ -30,7 +30,7 @@ from ._ffi import (  # noqa: F401
     demod_plan,
     shard_range,
 )
-from .demod import Demod  # noqa: F401
+from .demod import Demod, Ring  # noqa: F401
 from .fmrx import FmRx  # noqa: F401
 from .chan import Channeliser, Comm  # noqa: F401
 from .source import Source  # noqa: F401

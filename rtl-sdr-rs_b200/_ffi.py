@@ -84,6 +84,11 @@ SIGNATURES = {
     "sdr_demod_last_timing": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "sdr_demod_span_begin": (_i, [_vp]),
     "sdr_demod_span_end": (_i, [_vp, C.POINTER(C.c_float)]),
+    "sdr_demod_ring_open": (_i, [_vp, _sz, C.c_uint32, C.POINTER(_vp)]),
+    "sdr_ring_acquire": (_i, [_vp, C.POINTER(_vp)]),
+    "sdr_ring_commit": (_i, [_vp]),
+    "sdr_ring_collect": (_l, [_vp, _vp, _sz]),
+    "sdr_ring_close": (_i, [_vp]),
     "sdr_rotate_90": (_l, [_vp, _vp, _sz]),
     "sdr_buf_to_complex": (_l, [_vp, _vp, _sz, _vp, _sz]),
     "sdr_low_pass_complex": (_l, [_vp, _vp, _sz, _vp, _sz]),
@@ -127,6 +132,9 @@ SIGNATURES = {
     "sdr_comm_free": (None, [_vp]),
     "sdr_source_open_file": (_i, [C.c_char_p, _i, C.POINTER(_vp)]),
     "sdr_source_open_synth": (_i, [C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
+    "sdr_source_open_rtl_tcp": (_i, [C.c_char_p, C.c_uint16, C.POINTER(_vp)]),
+    "sdr_source_rtl_tcp_info": (_i, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "sdr_source_rtl_tcp_command": (_i, [_vp, C.c_uint8, C.c_uint32]),
     "sdr_source_read_sync": (_l, [_vp, _vp, _sz]),
     "sdr_source_read_async": (_i, [_vp, READ_ASYNC_CB, _vp, C.c_uint32, C.c_uint32]),
     "sdr_source_cancel_async": (_i, [_vp]),

@@ -15,6 +15,8 @@
 // SASS UBLKCP) into shared memory, the intermediate streams never leave the SM, and only the i16
 // audio goes back to HBM (2.06 algorithmic bytes per complex input sample).
 #include <cmath>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -44,7 +46,7 @@ struct UDiv64 {
 };
 
 struct FusedArgs {
-    UDiv div_slow;
+    UDiv div_slow, div_audio;
     UDiv64 d64_slow, d64_S, d64_D;
     const uint8_t *in;
     int16_t *out;
@@ -173,6 +175,73 @@ __device__ __forceinline__ void boxcar_rot(const uint32_t *w32, int pos, int end
     }
 }
 
+// Compile-time-D version for whole windows (DT even): straight-line code.  With the phase-0 coefficient
+// vectors C (phase-2 words use -C), half-word masks m_j for an odd start, and the per-sample constants
+// folded into K[pos & 3]:
+//     re = sgn * ( sum_{j even} dp4a(w_j, Cre & m_j) - sum_{j odd} dp4a(w_j, Cre & m_j) ) + Kre[pos & 3]
+// where w_j are the words the window touches and sgn = -1 iff the first word is a phase-2 word.
+template <int DT>
+struct BoxK {   // constants of a DT-sample window that starts at sample phase ph: sum of the per-sample constants
+    static constexpr int re(int ph) {
+        int k = 0;
+        for (int j = 0; j < DT; j++) {
+            const int p = (ph + j) & 3;
+            k += (p == 1 || p == 2) ? 128 : -127;   // phase 0: I-127, 1: 128-Q, 2: 128-I, 3: Q-127
+        }
+        return k;
+    }
+    static constexpr int im(int ph) {
+        int k = 0;
+        for (int j = 0; j < DT; j++) {
+            const int p = (ph + j) & 3;
+            k += (p == 2 || p == 3) ? 128 : -127;   // phase 0: Q-127, 1: I-127, 2: 128-Q, 3: 128-I
+        }
+        return k;
+    }
+};
+
+template <int DT>
+__device__ __forceinline__ void boxcar_rot_fixed(const uint32_t *w32, int pos, int32_t &re, int32_t &im) {
+    static_assert(DT >= 2 && DT % 2 == 0, "even window length");
+    constexpr uint32_t CRE = 0xFF000001u, CIM = 0x00010100u;   // phase-0 word: re [+1,0,0,-1], im [0,+1,+1,0]
+    constexpr int NWE = DT / 2;
+    const uint32_t *w = w32 + (pos >> 1);
+    int32_t er = 0, orr = 0, ei = 0, oi = 0;
+    if (!(pos & 1)) {
+#pragma unroll
+        for (int j = 0; j < NWE; j++) {
+            const uint32_t v = w[j];
+            if (j & 1) {
+                orr = dp4a_us(v, CRE, orr);
+                oi = dp4a_us(v, CIM, oi);
+            } else {
+                er = dp4a_us(v, CRE, er);
+                ei = dp4a_us(v, CIM, ei);
+            }
+        }
+    } else {   // head = upper half of w[0], tail = lower half of w[NWE]
+#pragma unroll
+        for (int j = 0; j <= NWE; j++) {
+            const uint32_t v = w[j];
+            const uint32_t m = j == 0 ? 0xFFFF0000u : (j == NWE ? 0x0000FFFFu : 0xFFFFFFFFu);
+            if (j & 1) {
+                orr = dp4a_us(v, CRE & m, orr);
+                oi = dp4a_us(v, CIM & m, oi);
+            } else {
+                er = dp4a_us(v, CRE & m, er);
+                ei = dp4a_us(v, CIM & m, ei);
+            }
+        }
+    }
+    const bool neg = (pos >> 1) & 1;   // first word is a phase-2 word
+    const int32_t sr = er - orr, si = ei - oi;
+    const int ph = pos & 3;
+    const int32_t kr = ph == 0 ? BoxK<DT>::re(0) : ph == 1 ? BoxK<DT>::re(1) : ph == 2 ? BoxK<DT>::re(2) : BoxK<DT>::re(3);
+    const int32_t ki = ph == 0 ? BoxK<DT>::im(0) : ph == 1 ? BoxK<DT>::im(1) : ph == 2 ? BoxK<DT>::im(2) : BoxK<DT>::im(3);
+    re = wadd(re, wadd(neg ? -sr : sr, kr));
+    im = wadd(im, wadd(neg ? -si : si, ki));
+}
+
 __device__ __forceinline__ unsigned long long udiv64(unsigned long long n, UDiv64 d) {
     return d.shift == 0xffffffffu ? n : (__umul64hi(n, d.magic) >> d.shift);
 }
@@ -183,7 +252,12 @@ __device__ __forceinline__ uint32_t udiv(uint32_t n, UDiv d) {
 // ================================================================================================
 // Fused kernel: one CTA per tile of EB audio outputs.
 // ================================================================================================
-__global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
+// One tile of EB audio outputs.  `first_use`: this CTA has not initialised its mbarrier yet; `parity`: phase
+// of the mbarrier for this use (a persistent CTA flips it per tile).  Ends with a __syncthreads so the
+// shared-memory tile can be reused.
+template <int DT>
+__device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t tile_idx, const uint32_t n_tiles,
+                                           const uint32_t parity, const bool first_use) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long sh_wlo, sh_jlo, sh_jhi, sh_e0, sh_clo, sh_chi;
@@ -196,14 +270,16 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
     uint8_t *flag = smem + a.tile_cap + (size_t)a.lp_cap * 10;
 
     const int tid = threadIdx.x;
-    const bool last = blockIdx.x == gridDim.x - 1;
+    const bool last = tile_idx == n_tiles - 1;
     const IntState st = *a.st_in;
 
     if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_barrier_init();
+        if (first_use) {
+            mbar_init(&bar, 1);
+            fence_barrier_init();
+        }
         const unsigned long long fast = a.fast, slow = a.slow;
-        unsigned long long e0 = (unsigned long long)blockIdx.x * a.EB;
+        unsigned long long e0 = (unsigned long long)tile_idx * a.EB;
         unsigned long long e1 = e0 + a.EB < a.Etot ? e0 + a.EB : a.Etot;
         if (e0 > a.Etot) e0 = a.Etot;
         // J(e) = ceil(((e+1)*fast - q0)/slow), J(-1) = 0
@@ -255,7 +331,7 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
     }
 
     // ---- phase 1: rotate_90 + centre + boxcar over D samples ------------------------------------
-    mbar_wait(&bar, 0);
+    mbar_wait(&bar, parity);
     const int32_t off0 = sh_off0;
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
     for (uint32_t i = tid; i < nlp; i += blockDim.x) {
@@ -266,7 +342,10 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
             im = st.lp_now_im;
         }
         // base < 0 only for window 0 with p0 > 0: those samples are already in lp_now
-        boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)a.D, re, im);
+        if (DT > 0 && base >= 0)
+            boxcar_rot_fixed<(DT > 0 ? DT : 2)>(w32, base, re, im);
+        else
+            boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)a.D, re, im);
         lp[i] = make_int2(re, im);
     }
     if (last && tid == 255) {
@@ -298,7 +377,10 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
         uint32_t r1 = udiv((t + 1) * a.fast - rb + a.slow - 1, a.div_slow);
         int32_t sum = (sh_e0 + t == 0) ? st.now_lpr : 0;
         for (uint32_t j = r0; j < r1; j++) sum = wadd(sum, (int32_t)dm[dbase + j]);
-        a.out[sh_e0 + t] = (int16_t)(uint16_t)(uint32_t)tdiv(sum, a.div);
+        // truncating sum / (fast/slow): |sum| < 2^31, divide the magnitude with the magic, restore the sign
+        const uint32_t mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
+        const uint32_t qm = mag >> 31 ? (uint32_t)((int64_t)mag / a.div) : udiv(mag, a.div_audio);
+        a.out[sh_e0 + t] = (int16_t)(uint16_t)(sum < 0 ? (uint32_t)0 - qm : qm);
     }
     if (last && tid == 0) {
         uint32_t r0 = ne ? udiv(ne * a.fast - rb + a.slow - 1, a.div_slow) : 0u;
@@ -308,6 +390,124 @@ __global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
         int2 lastlp = nlp ? lp[nlp - 1] : make_int2(st.demod_pre_re, st.demod_pre_im);
         a.st_out->demod_pre_re = lastlp.x;
         a.st_out->demod_pre_im = lastlp.y;
+    }
+    if (last) __threadfence();   // the state words are consumed by another CTA in ring mode
+    __syncthreads();   // the shared-memory tile (and the mbarrier phase) may now be reused
+}
+
+// One launch per batch of calls: one CTA per tile.
+// DT = compile-time downsample (0 = any): the reference's own setting, 6 (optimal_settings :189-190), is specialised.
+template <int DT>
+__global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
+    demod_tile<DT>(a, blockIdx.x, gridDim.x, 0, true);
+}
+
+// ================================================================================================
+// Persistent ring: successive USB-sized buffers stream through ONE resident kernel, no relaunch.
+//
+// The host copies buffer k into device slot k % n_slots and then (stream-ordered) writes the doorbell
+// seq_ready[slot] = k + 1.  Every CTA walks the buffers in order, spins on the doorbell, and takes the tiles
+// t = blockIdx.x, + gridDim.x, ... of that buffer (each buffer is exactly one reference demodulate() call).
+// The three data-dependent state words hop from the last tile of buffer k to tile 0 of buffer k+1 through
+// `state_gen` (release/acquire); the index state is closed-form in k.  The CTA that finishes a buffer's last
+// outstanding tile publishes seq_done[slot] = k + 1 in host-mapped memory, where the audio already is.
+// ================================================================================================
+struct RingCtl {                       // device memory
+    unsigned int seq_ready[64];        // doorbells, written by the copy engine
+    unsigned int done_tiles[64];       // tiles finished per slot
+    unsigned int stop;                 // host sets 1 to retire the kernel
+    unsigned int pad;
+    unsigned long long state_gen;      // buffers whose final state has been published
+    IntState states[66];               // states[k % (n_slots+1)] = state at the START of buffer k
+};
+
+struct RingArgs {
+    FusedArgs proto;                   // constants (config, magics, tile geometry); per-buffer fields are filled in
+    RingCtl *ctl;
+    volatile unsigned int *seq_done;   // host-mapped [n_slots]
+    const uint8_t *d_in;               // device slots [n_slots][buf_len]
+    int16_t *h_out;                    // host-mapped audio slots [n_slots][out_stride]
+    unsigned long long buf_len, out_stride;
+    unsigned int n_slots;
+    unsigned int p0, q0;               // index state at ring open
+    UDiv64 d64_fast;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) k_demod_ring(const RingArgs r) {
+    __shared__ FusedArgs sh_a;
+    __shared__ unsigned int sh_go, sh_ntiles;
+    const int tid = threadIdx.x;
+    const unsigned long long S = r.buf_len / 2, D = r.proto.D, fast = r.proto.fast, slow = r.proto.slow;
+    uint32_t uses = 0;
+    for (unsigned long long k = 0;; k++) {
+        const unsigned int slot = (unsigned int)(k % r.n_slots);
+        if (tid == 0) {
+            // wait for the doorbell of buffer k (or for stop)
+            unsigned int go = 2;
+            while (go == 2) {
+                if (ld_acquire_u32(&r.ctl->seq_ready[slot]) == (unsigned int)(k + 1)) go = 1;
+                else if (ld_acquire_u32(&r.ctl->stop)) go = 0;
+                else __nanosleep(100);
+            }
+            sh_go = go;
+            if (go) {
+                // closed-form index state at the start of buffer k
+                const unsigned long long n0 = r.p0 + k * S;
+                const unsigned long long Lstart = udiv64(n0, r.proto.d64_D);
+                const unsigned long long pk = n0 - Lstart * D;
+                const unsigned long long t0 = r.q0 + Lstart * slow;
+                const unsigned long long qk = t0 - udiv64(t0, r.d64_fast) * fast;
+                FusedArgs a = r.proto;
+                a.in = r.d_in + (size_t)slot * r.buf_len;
+                a.out = r.h_out + (size_t)slot * r.out_stride;
+                a.st_in = &r.ctl->states[k % (r.n_slots + 1)];
+                a.st_out = &r.ctl->states[(k + 1) % (r.n_slots + 1)];
+                a.n_samples = S;
+                a.p0 = (uint32_t)pk;
+                a.q0 = (uint32_t)qk;
+                a.Ltot = udiv64(pk + S, r.proto.d64_D);
+                a.Etot = udiv64(qk + a.Ltot * slow, r.d64_fast);
+                sh_a = a;
+                sh_ntiles = a.Etot ? (unsigned int)((a.Etot + a.EB - 1) / a.EB) : 1u;
+            }
+        }
+        __syncthreads();
+        if (!sh_go) return;
+        const unsigned int n_tiles = sh_ntiles;
+        for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            if (t == 0) {   // tile 0 consumes the state the previous buffer's last tile produced
+                if (tid == 0)
+                    while (ld_acquire_u64(&r.ctl->state_gen) < k) __nanosleep(50);
+                __syncthreads();
+            }
+            demod_tile<DT>(sh_a, t, n_tiles, uses & 1, uses == 0);
+            uses++;
+            if (tid == 0) {
+                if (t == n_tiles - 1) st_release_u64(&r.ctl->state_gen, k + 1);   // st_out written above (+ __syncthreads)
+                __threadfence_system();                                              // audio stores reach host memory
+                if (atomicAdd(&r.ctl->done_tiles[slot], 1u) == n_tiles - 1) {
+                    r.ctl->done_tiles[slot] = 0;
+                    __threadfence_system();
+                    r.seq_done[slot] = (unsigned int)(k + 1);
+                }
+            }
+        }
+        __syncthreads();   // sh_a is rewritten for the next buffer
     }
 }
 
@@ -435,6 +635,7 @@ struct sdr_demod {
     float last_ms = 0.f;
     uint32_t last_launches = 0;
     bool timing_valid = false;
+    bool ring_open = false;    // a persistent ring owns the handle until sdr_ring_close()
 };
 
 namespace {
@@ -499,6 +700,7 @@ int validate_lens(const sdr_demod *d, size_t buf_len, size_t n_bufs) {
 }
 
 int commit_pending(sdr_demod *d) {
+    if (d->ring_open) return fail(SDR_E_STATE, "handle is owned by an open ring (sdr_ring_close first)");
     if (!d->pending) return SDR_OK;
     SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
     const IntState *h = d->h_state.as<IntState>();
@@ -513,6 +715,22 @@ int commit_pending(sdr_demod *d) {
         if (cudaEventElapsedTime(&ms, d->ev_t0, d->ev_t1) == cudaSuccess) d->last_ms = ms;
     }
     return SDR_OK;
+}
+
+// Round-up magics (Granlund-Montgomery): q = umulhi(n, m) >> shift, exact for n < 2^31 (32-bit) / n < 2^63 (64-bit).
+UDiv magic32(uint32_t dv) {
+    if (dv <= 1) return UDiv{0u, 0xffffffffu};
+    uint32_t s = 0;
+    while ((1ull << s) < dv) s++;                       // s = ceil(log2 dv) >= 1
+    uint64_t m = ((1ull << (31 + s)) / dv) + 1;          // < 2^32 because dv > 2^(s-1)
+    return UDiv{(uint32_t)m, s - 1};
+}
+UDiv64 magic64(uint64_t dv) {
+    if (dv <= 1) return UDiv64{0ull, 0xffffffffu};
+    uint32_t sh = 0;
+    while (sh < 63 && (1ull << sh) < dv) sh++;
+    unsigned __int128 m = (((unsigned __int128)1 << (63 + sh)) / dv) + 1;   // < 2^64 because dv > 2^(sh-1)
+    return UDiv64{(unsigned long long)m, sh - 1};
 }
 
 // Launch the fused kernel for one chunk that starts on a call boundary.
@@ -533,24 +751,8 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     a.fast = d->cfg.rate_out;
     a.slow = d->cfg.rate_resample;
     a.div = (int32_t)(d->cfg.rate_out / d->cfg.rate_resample);
-    {   // round-up magic for n / rate_resample, exact for n < 2^31 (Granlund-Montgomery)
-        const uint32_t dv = d->cfg.rate_resample;
-        if (dv == 1) {
-            a.div_slow = UDiv{0u, 0xffffffffu};
-        } else {
-            uint32_t s = 0;
-            while ((1ull << s) < dv) s++;                       // s = ceil(log2 dv) >= 1
-            uint64_t m = ((1ull << (31 + s)) / dv) + 1;          // < 2^32 because dv > 2^(s-1)
-            a.div_slow = UDiv{(uint32_t)m, s - 1};              // q = umulhi(n, m) >> (s-1)
-        }
-    }
-    auto magic64 = [](uint64_t dv) {
-        if (dv <= 1) return UDiv64{0ull, 0xffffffffu};
-        uint32_t sh = 0;
-        while (sh < 63 && (1ull << sh) < dv) sh++;
-        unsigned __int128 m = (((unsigned __int128)1 << (63 + sh)) / dv) + 1;   // < 2^64 because dv > 2^(sh-1)
-        return UDiv64{(unsigned long long)m, sh - 1};
-    };
+    a.div_slow = magic32(d->cfg.rate_resample);
+    a.div_audio = magic32(d->cfg.rate_out / d->cfg.rate_resample);
     a.d64_slow = magic64(d->cfg.rate_resample);
     a.d64_S = magic64(S);
     a.d64_D = magic64(d->cfg.downsample);
@@ -561,7 +763,10 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     (void)n_calls;
     uint64_t blocks = pl.Etot ? (pl.Etot + d->EB - 1) / d->EB : 1;
     if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "batch too large for one launch");
-    k_demod_fused<<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
+    if (d->cfg.downsample == 6)
+        k_demod_fused<6><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
+    else
+        k_demod_fused<0><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
     SDR_LAUNCH_CHECK();
     d->last_launches++;
     return SDR_OK;
@@ -630,7 +835,8 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     d->lp_cap = (uint32_t)lp_cap;
     d->tile_cap = (uint32_t)tile_cap;
     d->smem_bytes = (size_t)smem;
-    cudaError_t e = cudaFuncSetAttribute(k_demod_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_demod_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
@@ -825,6 +1031,215 @@ int sdr_demod_last_timing(const sdr_demod *d, float *kernel_ms, uint32_t *n_laun
     if (!d) return fail(SDR_E_ARG, "null handle");
     if (kernel_ms) *kernel_ms = d->last_ms;
     if (n_launches) *n_launches = d->last_launches;
+    return SDR_OK;
+}
+
+
+// ---- persistent ring (host side) --------------------------------------------------------------------------
+struct sdr_ring {
+    sdr_demod *d = nullptr;
+    size_t buf_len = 0, out_stride = 0;
+    uint32_t n_slots = 0;
+    uint8_t *h_in = nullptr;              // pinned [n_slots][buf_len]
+    DevBuf d_in, d_ctl;
+    int16_t *h_out = nullptr, *h_out_dev = nullptr;              // host-mapped audio slots
+    volatile unsigned int *h_seq_done = nullptr;
+    unsigned int *h_seq_done_dev = nullptr;
+    unsigned int *h_doorbell = nullptr;   // pinned [n_slots] + stop word at [n_slots]
+    cudaStream_t ring_stream = nullptr, copy_stream = nullptr;
+    std::atomic<uint64_t> head{0}, tail{0};   // committed / collected buffers
+    bool acquired = false;
+    uint32_t p0 = 0, q0 = 0;
+};
+
+static void ring_release(sdr_ring *r) {
+    if (!r) return;
+    if (r->ring_stream) cudaStreamDestroy(r->ring_stream);
+    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    if (r->h_in) cudaFreeHost(r->h_in);
+    if (r->h_out) cudaFreeHost(r->h_out);
+    if (r->h_seq_done) cudaFreeHost((void *)r->h_seq_done);
+    if (r->h_doorbell) cudaFreeHost(r->h_doorbell);
+    r->d_in.release();
+    r->d_ctl.release();
+    if (r->d) r->d->ring_open = false;
+    delete r;
+}
+
+int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring **out) {
+    if (!d || !out) return fail(SDR_E_ARG, "sdr_demod_ring_open: null argument");
+    if (n_slots < 2 || n_slots > 64) return fail(SDR_E_ARG, "n_slots must be in [2, 64]");
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    if ((rc = commit_pending(d))) return rc;
+    if ((rc = validate_lens(d, buf_len, d->cfg.downsample))) return rc;   // every phase a buffer can start on
+    sdr_ring *r = new sdr_ring();
+    r->d = d;
+    r->buf_len = buf_len;
+    r->n_slots = n_slots;
+    const uint64_t S = buf_len / 2, D = d->cfg.downsample, fast = d->cfg.rate_out, slow = d->cfg.rate_resample;
+    r->out_stride = (size_t)((((S + D - 1) / D + 1) * slow + fast - 1) / fast + 8);
+    r->p0 = (uint32_t)d->st.prev_index;
+    r->q0 = (uint32_t)d->st.prev_lpr_index;
+    cudaError_t e = cudaHostAlloc((void **)&r->h_in, (size_t)n_slots * buf_len, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&r->h_out, (size_t)n_slots * r->out_stride * 2, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&r->h_out_dev, r->h_out, 0);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&r->h_seq_done, 64 * sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&r->h_seq_done_dev, (void *)r->h_seq_done, 0);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&r->h_doorbell, 72 * sizeof(unsigned int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->ring_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        ring_release(r);
+        return fail(SDR_E_CUDA, "sdr_demod_ring_open: %s", cudaGetErrorString(e));
+    }
+    if ((rc = r->d_in.reserve((size_t)n_slots * buf_len + 64)) || (rc = r->d_ctl.reserve(sizeof(RingCtl)))) {
+        ring_release(r);
+        return rc;
+    }
+    for (int i = 0; i < 64; i++) r->h_seq_done[i] = 0;
+    RingCtl *h_ctl = new RingCtl();
+    memset(h_ctl, 0, sizeof(RingCtl));
+    to_dev_state(d->st, h_ctl->states[0]);
+    e = cudaMemcpy(r->d_ctl.p, h_ctl, sizeof(RingCtl), cudaMemcpyHostToDevice);
+    delete h_ctl;
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        ring_release(r);
+        return fail(SDR_E_CUDA, "sdr_demod_ring_open: %s", cudaGetErrorString(e));
+    }
+    RingArgs a{};
+    Plan pl = make_plan(d->cfg, 0, 0, S, 1);
+    // constants of the per-buffer FusedArgs (launch_fused fills the same fields for the one-shot kernel)
+    FusedArgs &f = a.proto;
+    f.S = (uint32_t)S;
+    f.D = d->cfg.downsample;
+    f.fast = d->cfg.rate_out;
+    f.slow = d->cfg.rate_resample;
+    f.div = (int32_t)(d->cfg.rate_out / d->cfg.rate_resample);
+    f.div_slow = magic32(d->cfg.rate_resample);
+    f.div_audio = magic32(d->cfg.rate_out / d->cfg.rate_resample);
+    f.d64_slow = magic64(d->cfg.rate_resample);
+    f.d64_S = magic64(S);
+    f.d64_D = magic64(d->cfg.downsample);
+    f.EB = d->EB;
+    f.lp_cap = d->lp_cap;
+    f.tile_cap = d->tile_cap;
+    f.oct = d->oct;
+    a.ctl = r->d_ctl.as<RingCtl>();
+    a.seq_done = r->h_seq_done_dev;
+    a.d_in = r->d_in.as<uint8_t>();
+    a.h_out = r->h_out_dev;
+    a.buf_len = buf_len;
+    a.out_stride = r->out_stride;
+    a.n_slots = n_slots;
+    a.p0 = r->p0;
+    a.q0 = r->q0;
+    a.d64_fast = magic64(d->cfg.rate_out);
+    unsigned tiles = (unsigned)((pl.Etot + 1 + d->EB - 1) / d->EB + 1);
+    unsigned grid = std::max(1u, std::min(tiles, (unsigned)sm_count(d->device) / 2));
+    const bool d6 = d->cfg.downsample == 6;
+    e = d6 ? cudaFuncSetAttribute(k_demod_ring<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes)
+           : cudaFuncSetAttribute(k_demod_ring<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes);
+    if (e == cudaSuccess) {
+        if (d6)
+            k_demod_ring<6><<<grid, 256, d->smem_bytes, r->ring_stream>>>(a);
+        else
+            k_demod_ring<0><<<grid, 256, d->smem_bytes, r->ring_stream>>>(a);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        ring_release(r);
+        return fail(SDR_E_CUDA, "sdr_demod_ring_open: launch failed: %s", cudaGetErrorString(e));
+    }
+    count_launch();
+    d->ring_open = true;
+    *out = r;
+    return SDR_OK;
+}
+
+int sdr_ring_acquire(sdr_ring *r, uint8_t **buf) {
+    if (!r || !buf) return fail(SDR_E_ARG, "sdr_ring_acquire: null argument");
+    if (r->acquired) return fail(SDR_E_STATE, "a slot is already acquired (commit it first)");
+    while (r->head.load() - r->tail.load() >= r->n_slots) std::this_thread::yield();   // ring full: wait for collect()
+    *buf = r->h_in + (size_t)(r->head.load() % r->n_slots) * r->buf_len;
+    r->acquired = true;
+    return SDR_OK;
+}
+
+int sdr_ring_commit(sdr_ring *r) {
+    if (!r) return fail(SDR_E_ARG, "null ring");
+    if (!r->acquired) return fail(SDR_E_STATE, "no slot acquired");
+    int rc = use_device(r->d->device);
+    if (rc) return rc;
+    const uint64_t k = r->head.load();
+    const uint32_t slot = (uint32_t)(k % r->n_slots);
+    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_in.as<uint8_t>() + (size_t)slot * r->buf_len, r->h_in + (size_t)slot * r->buf_len,
+                                 r->buf_len, cudaMemcpyHostToDevice, r->copy_stream));
+    r->h_doorbell[slot] = (unsigned int)(k + 1);
+    SDR_CUDA_TRY(cudaMemcpyAsync(&r->d_ctl.as<RingCtl>()->seq_ready[slot], &r->h_doorbell[slot], sizeof(unsigned int),
+                                 cudaMemcpyHostToDevice, r->copy_stream));   // stream order: data first, then the doorbell
+    r->acquired = false;
+    r->head.store(k + 1);
+    return SDR_OK;
+}
+
+long sdr_ring_collect(sdr_ring *r, int16_t *out, size_t cap) {
+    if (!r || !out) return fail(SDR_E_ARG, "sdr_ring_collect: null argument");
+    const uint64_t k = r->tail.load();
+    if (k == r->head.load()) return fail(SDR_E_STATE, "nothing outstanding");
+    const uint32_t slot = (uint32_t)(k % r->n_slots);
+    // closed-form audio count of buffer k
+    const uint64_t S = r->buf_len / 2, D = r->d->cfg.downsample;
+    const uint64_t n0 = r->p0 + k * S, Lstart = n0 / D, pk = n0 % D;
+    const unsigned __int128 t0 = (unsigned __int128)Lstart * r->d->cfg.rate_resample + r->q0;
+    const uint32_t qk = (uint32_t)(t0 % r->d->cfg.rate_out);
+    Plan pl = make_plan(r->d->cfg, (uint32_t)pk, qk, S, 1);
+    if (pl.Etot > cap) return fail(SDR_E_CAP, "output capacity %zu < %llu audio samples", cap, (unsigned long long)pl.Etot);
+    uint64_t spins = 0;
+    while (r->h_seq_done[slot] != (unsigned int)(k + 1)) {
+        if ((++spins & 0xfff) == 0) {
+            cudaError_t e = cudaStreamQuery(r->ring_stream);
+            if (e != cudaErrorNotReady) {
+                (void)cudaGetLastError();
+                return fail(SDR_E_CUDA, "ring kernel is not running (%s)", cudaGetErrorString(e));
+            }
+            std::this_thread::yield();
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(out, r->h_out + (size_t)slot * r->out_stride, pl.Etot * sizeof(int16_t));
+    r->tail.store(k + 1);
+    return (long)pl.Etot;
+}
+
+int sdr_ring_close(sdr_ring *r) {
+    if (!r) return fail(SDR_E_ARG, "null ring");
+    sdr_demod *d = r->d;
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    r->h_doorbell[64] = 1;
+    cudaError_t e = cudaMemcpyAsync(&r->d_ctl.as<RingCtl>()->stop, &r->h_doorbell[64], sizeof(unsigned int),
+                                    cudaMemcpyHostToDevice, r->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->ring_stream);   // every committed buffer is processed before stop is seen
+    const uint64_t n = r->head.load();
+    IntState hs{};
+    if (e == cudaSuccess)
+        e = cudaMemcpy(&hs, &r->d_ctl.as<RingCtl>()->states[n % (r->n_slots + 1)], sizeof(IntState), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+        const uint64_t S = r->buf_len / 2;
+        Plan pl = make_plan(d->cfg, r->p0, r->q0, S, n);
+        d->st.prev_index = pl.p1;
+        d->st.prev_lpr_index = (int32_t)pl.q1;
+        d->st.lp_now_re = hs.lp_now_re;
+        d->st.lp_now_im = hs.lp_now_im;
+        d->st.demod_pre_re = hs.demod_pre_re;
+        d->st.demod_pre_im = hs.demod_pre_im;
+        d->st.now_lpr = hs.now_lpr;
+    }
+    ring_release(r);
+    if (e != cudaSuccess) return fail(SDR_E_CUDA, "sdr_ring_close: %s", cudaGetErrorString(e));
     return SDR_OK;
 }
 

@@ -5,6 +5,11 @@
 //     -> Sdr::read_sync  src/rtlsdr.rs:409-411 -> Device::bulk_transfer  src/device/mod.rs:141-143
 // and the reader-thread -> channel -> processor hand-off of examples/simple_fm.rs:55-60,108-128,145-156
 // (sdr_source_read_async; the reference only has a TODO for an async API, src/lib.rs:147).
+#include <arpa/inet.h>
+#include <netdb.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -23,8 +28,10 @@ int fail(int code, const char *fmt, ...);
 using sdr::fail;
 
 struct sdr_source {
-    enum Kind { FILE_SRC, SYNTH } kind = SYNTH;
+    enum Kind { FILE_SRC, SYNTH, RTL_TCP } kind = SYNTH;
     FILE *fp = nullptr;
+    int sock = -1;                          // rtl_tcp client socket
+    uint32_t tuner_type = 0, gain_count = 0;   // from the 12-byte "RTL0" greeting
     bool loop = false;
     uint64_t seed = 0, total = 0, pos = 0;   // synth: stream byte position
     std::atomic<bool> cancel{false};
@@ -40,6 +47,16 @@ inline uint64_t mix64(uint64_t seed, uint64_t idx) {
 }
 
 long read_once(sdr_source *s, uint8_t *buf, size_t len) {
+    if (s->kind == sdr_source::RTL_TCP) {
+        size_t got = 0;
+        while (got < len) {
+            ssize_t r = recv(s->sock, buf + got, len - got, 0);
+            if (r < 0) return fail(SDR_E_IO, "rtl_tcp recv failed");
+            if (r == 0) break;              // server closed: short count, like a short USB read
+            got += (size_t)r;
+        }
+        return (long)got;
+    }
     if (s->kind == sdr_source::FILE_SRC) {
         size_t got = 0;
         while (got < len) {
@@ -96,6 +113,67 @@ int sdr_source_open_synth(uint64_t seed, uint64_t total_bytes, sdr_source **out)
     s->seed = seed;
     s->total = total_bytes;
     *out = s;
+    return SDR_OK;
+}
+
+// rtl_tcp wire format (examples/rtl_tcp.rs): the server greets with 12 bytes "RTL0" + tuner type (u32 BE) +
+// gain count (u32 BE) (send_handshake, :691-697) and then streams raw interleaved u8 IQ; the client may send
+// 5-byte commands: 1 byte id + u32 big-endian parameter (command_loop, :633-689; 0x01 frequency, 0x02 sample
+// rate, 0x03 gain mode, 0x04 gain, 0x05 ppm, ... 0x0e bias tee).
+int sdr_source_open_rtl_tcp(const char *host, uint16_t port, sdr_source **out) {
+    if (!host || !out) return fail(SDR_E_ARG, "sdr_source_open_rtl_tcp: null argument");
+    addrinfo hints{}, *res = nullptr;
+    hints.ai_family = AF_UNSPEC;
+    hints.ai_socktype = SOCK_STREAM;
+    char portstr[16];
+    snprintf(portstr, sizeof(portstr), "%u", (unsigned)port);
+    if (getaddrinfo(host, portstr, &hints, &res) != 0 || !res) return fail(SDR_E_IO, "cannot resolve %s", host);
+    int fd = -1;
+    for (addrinfo *ai = res; ai; ai = ai->ai_next) {
+        fd = socket(ai->ai_family, ai->ai_socktype, ai->ai_protocol);
+        if (fd < 0) continue;
+        if (connect(fd, ai->ai_addr, ai->ai_addrlen) == 0) break;
+        close(fd);
+        fd = -1;
+    }
+    freeaddrinfo(res);
+    if (fd < 0) return fail(SDR_E_IO, "cannot connect to %s:%u", host, (unsigned)port);
+    uint8_t hdr[12];
+    size_t got = 0;
+    while (got < sizeof(hdr)) {
+        ssize_t r = recv(fd, hdr + got, sizeof(hdr) - got, 0);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    if (got != sizeof(hdr) || memcmp(hdr, "RTL0", 4) != 0) {
+        close(fd);
+        return fail(SDR_E_IO, "%s:%u did not send the rtl_tcp \"RTL0\" greeting", host, (unsigned)port);
+    }
+    sdr_source *s = new sdr_source();
+    s->kind = sdr_source::RTL_TCP;
+    s->sock = fd;
+    s->tuner_type = ((uint32_t)hdr[4] << 24) | ((uint32_t)hdr[5] << 16) | ((uint32_t)hdr[6] << 8) | hdr[7];
+    s->gain_count = ((uint32_t)hdr[8] << 24) | ((uint32_t)hdr[9] << 16) | ((uint32_t)hdr[10] << 8) | hdr[11];
+    *out = s;
+    return SDR_OK;
+}
+
+int sdr_source_rtl_tcp_info(const sdr_source *s, uint32_t *tuner_type, uint32_t *gain_count) {
+    if (!s || s->kind != sdr_source::RTL_TCP) return fail(SDR_E_STATE, "not an rtl_tcp source");
+    if (tuner_type) *tuner_type = s->tuner_type;
+    if (gain_count) *gain_count = s->gain_count;
+    return SDR_OK;
+}
+
+int sdr_source_rtl_tcp_command(sdr_source *s, uint8_t cmd, uint32_t param) {
+    if (!s || s->kind != sdr_source::RTL_TCP) return fail(SDR_E_STATE, "not an rtl_tcp source");
+    const uint8_t msg[5] = {cmd, (uint8_t)(param >> 24), (uint8_t)(param >> 16), (uint8_t)(param >> 8), (uint8_t)param};
+    size_t sent = 0;
+    while (sent < sizeof(msg)) {
+        ssize_t r = send(s->sock, msg + sent, sizeof(msg) - sent, MSG_NOSIGNAL);
+        if (r <= 0) return fail(SDR_E_IO, "rtl_tcp command send failed");
+        sent += (size_t)r;
+    }
     return SDR_OK;
 }
 
@@ -182,6 +260,7 @@ int sdr_source_cancel_async(sdr_source *s) {
 void sdr_source_close(sdr_source *s) {
     if (!s) return;
     if (s->fp) fclose(s->fp);
+    if (s->sock >= 0) close(s->sock);
     delete s;
 }
 

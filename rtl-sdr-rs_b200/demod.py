@@ -142,3 +142,43 @@ class Demod:
         ms = C.c_float(0)
         F.check(F.lib().sdr_demod_span_end(self._h, C.byref(ms)))
         return ms.value
+
+
+class Ring:
+    """Persistent-kernel ring over a Demod (sdr_demod_ring_*): buffers stream through one resident kernel."""
+
+    def __init__(self, demod: Demod, buf_len: int, n_slots: int = 8):
+        # While the ring kernel is resident, anything that device-synchronises (cudaFree of a handle that the
+        # garbage collector finalises, an allocation) would wait for it forever: finalise garbage first.
+        import gc
+        gc.collect()
+        self.demod, self.buf_len = demod, buf_len
+        h = C.c_void_p()
+        F.check(F.lib().sdr_demod_ring_open(demod._h, buf_len, n_slots, C.byref(h)))
+        self._h = h
+        self._cap = buf_len // 2 + 8
+
+    def submit(self, buf: np.ndarray):
+        """acquire the next pinned slot, copy `buf` into it, commit (H2D + doorbell, no kernel launch)."""
+        b = np.ascontiguousarray(buf, dtype=np.uint8)
+        assert b.size == self.buf_len
+        p = C.c_void_p()
+        F.check(F.lib().sdr_ring_acquire(self._h, C.byref(p)))
+        C.memmove(p, b.ctypes.data, b.size)
+        F.check(F.lib().sdr_ring_commit(self._h))
+
+    def collect(self) -> np.ndarray:
+        out = np.empty(self._cap, np.int16)
+        n = F.check(F.lib().sdr_ring_collect(self._h, F.ptr(out), out.size))
+        return out[:n].copy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            F.check(F.lib().sdr_ring_close(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

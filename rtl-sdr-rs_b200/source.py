@@ -25,6 +25,21 @@ class Source:
         F.check(F.lib().sdr_source_open_synth(seed, total_bytes, C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def open_rtl_tcp(cls, host: str, port: int = 1234) -> "Source":
+        """rtl_tcp client (wire format of examples/rtl_tcp.rs:633-697)."""
+        h = C.c_void_p()
+        F.check(F.lib().sdr_source_open_rtl_tcp(host.encode(), port, C.byref(h)))
+        return cls(h)
+
+    def rtl_tcp_info(self):
+        t, g = C.c_uint32(0), C.c_uint32(0)
+        F.check(F.lib().sdr_source_rtl_tcp_info(self._h, C.byref(t), C.byref(g)))
+        return t.value, g.value
+
+    def rtl_tcp_command(self, cmd: int, param: int):
+        F.check(F.lib().sdr_source_rtl_tcp_command(self._h, cmd, param & 0xFFFFFFFF))
+
     def read_sync(self, buf: np.ndarray) -> int:
         """read_sync(&self, buf: &mut [u8]) -> Result<usize>: fills the caller's buffer, returns bytes read."""
         assert buf.dtype == np.uint8 and buf.flags.c_contiguous

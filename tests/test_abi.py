@@ -114,3 +114,45 @@ def test_source_read_async_delivers_every_full_buffer_in_order(S):
             syn2.cancel()
     syn2.read_async(cb, buf_num=3, buf_len=1024)
     assert 5 <= len(seen) <= 8
+
+
+def test_source_rtl_tcp_wire_format(S):
+    """A local server speaking examples/rtl_tcp.rs's protocol: 12-byte RTL0 greeting, raw IQ, 5-byte BE commands."""
+    import socket
+    import struct
+    import threading
+    import oracle_ffi as O
+    payload = O.synth_fill(3 * 4096 + 100, 77).tobytes()
+    got_cmds = []
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    port = srv.getsockname()[1]
+
+    def serve():
+        c, _ = srv.accept()
+        c.sendall(b"RTL0" + struct.pack(">II", 5, 29))            # R820T, 29 gain steps (send_handshake :691-697)
+        for _ in range(2):
+            got_cmds.append(struct.unpack(">BI", c.recv(5, socket.MSG_WAITALL)))
+        c.sendall(payload)
+        c.close()
+    t = threading.Thread(target=serve, daemon=True)
+    t.start()
+    src = S.Source.open_rtl_tcp("127.0.0.1", port)
+    assert src.rtl_tcp_info() == (5, 29)
+    src.rtl_tcp_command(0x01, 94_900_000 + 255_000)               # set frequency (:658)
+    src.rtl_tcp_command(0x02, 1_020_000)                          # set sample rate (:659)
+    buf = np.empty(4096, np.uint8)
+    chunks = []
+    while True:
+        n = src.read_sync(buf)
+        chunks.append(buf[:n].copy())
+        if n < buf.size:
+            break
+    t.join(5)
+    assert b"".join(c.tobytes() for c in chunks) == payload
+    assert got_cmds == [(0x01, 95_155_000), (0x02, 1_020_000)]
+    src.close()
+    srv.close()
+    with pytest.raises(S.SdrError):
+        S.Source.open_rtl_tcp("127.0.0.1", 1)                     # nothing listens there
