@@ -427,7 +427,7 @@ struct RingArgs {
     volatile unsigned int *seq_done;   // host-mapped [n_slots]
     const uint8_t *d_in;               // device slots [n_slots][buf_len]
     int16_t *h_out;                    // host-mapped audio slots [n_slots][out_stride]
-    unsigned long long buf_len, out_stride;
+    unsigned long long buf_len, out_stride, slot_stride;
     unsigned int n_slots;
     unsigned int p0, q0;               // index state at ring open
     UDiv64 d64_fast;
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) k_demod_ring(const RingArgs r) {
                 const unsigned long long t0 = r.q0 + Lstart * slow;
                 const unsigned long long qk = t0 - udiv64(t0, r.d64_fast) * fast;
                 FusedArgs a = r.proto;
-                a.in = r.d_in + (size_t)slot * r.buf_len;
+                a.in = r.d_in + (size_t)slot * r.slot_stride;   // 16-byte aligned device slots (bulk-copy source)
                 a.out = r.h_out + (size_t)slot * r.out_stride;
                 a.st_in = &r.ctl->states[k % (r.n_slots + 1)];
                 a.st_out = &r.ctl->states[(k + 1) % (r.n_slots + 1)];
@@ -1038,7 +1038,7 @@ int sdr_demod_last_timing(const sdr_demod *d, float *kernel_ms, uint32_t *n_laun
 // ---- persistent ring (host side) --------------------------------------------------------------------------
 struct sdr_ring {
     sdr_demod *d = nullptr;
-    size_t buf_len = 0, out_stride = 0;
+    size_t buf_len = 0, out_stride = 0, slot_stride = 0;
     uint32_t n_slots = 0;
     uint8_t *h_in = nullptr;              // pinned [n_slots][buf_len]
     DevBuf d_in, d_ctl;
@@ -1076,6 +1076,7 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     sdr_ring *r = new sdr_ring();
     r->d = d;
     r->buf_len = buf_len;
+    r->slot_stride = (buf_len + 15) & ~size_t(15);
     r->n_slots = n_slots;
     const uint64_t S = buf_len / 2, D = d->cfg.downsample, fast = d->cfg.rate_out, slow = d->cfg.rate_resample;
     r->out_stride = (size_t)((((S + D - 1) / D + 1) * slow + fast - 1) / fast + 8);
@@ -1093,7 +1094,7 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
         ring_release(r);
         return fail(SDR_E_CUDA, "sdr_demod_ring_open: %s", cudaGetErrorString(e));
     }
-    if ((rc = r->d_in.reserve((size_t)n_slots * buf_len + 64)) || (rc = r->d_ctl.reserve(sizeof(RingCtl)))) {
+    if ((rc = r->d_in.reserve((size_t)n_slots * r->slot_stride + 64)) || (rc = r->d_ctl.reserve(sizeof(RingCtl)))) {
         ring_release(r);
         return rc;
     }
@@ -1131,6 +1132,7 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     a.d_in = r->d_in.as<uint8_t>();
     a.h_out = r->h_out_dev;
     a.buf_len = buf_len;
+    a.slot_stride = r->slot_stride;
     a.out_stride = r->out_stride;
     a.n_slots = n_slots;
     a.p0 = r->p0;
@@ -1174,7 +1176,7 @@ int sdr_ring_commit(sdr_ring *r) {
     if (rc) return rc;
     const uint64_t k = r->head.load();
     const uint32_t slot = (uint32_t)(k % r->n_slots);
-    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_in.as<uint8_t>() + (size_t)slot * r->buf_len, r->h_in + (size_t)slot * r->buf_len,
+    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_in.as<uint8_t>() + (size_t)slot * r->slot_stride, r->h_in + (size_t)slot * r->buf_len,
                                  r->buf_len, cudaMemcpyHostToDevice, r->copy_stream));
     r->h_doorbell[slot] = (unsigned int)(k + 1);
     SDR_CUDA_TRY(cudaMemcpyAsync(&r->d_ctl.as<RingCtl>()->seq_ready[slot], &r->h_doorbell[slot], sizeof(unsigned int),
