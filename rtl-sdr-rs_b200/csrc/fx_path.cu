@@ -133,6 +133,24 @@ __device__ __forceinline__ CvtConst cvt_consts() {
         : "=f"(c.bias), "=r"(c.h1024));
     return c;
 }
+// Packed FP32: Blackwell's FFMA2 (PTX fma.rn.f32x2) does the re and im lanes of one tap in ONE issue slot;
+// ptxas turns the duplicated tap {h, h} into a scalar-broadcast uniform operand (FFMA2 R, R.F32x2, UR.F32, R)
+// fed by one LDCU.128 per four taps.  Each half is an ordinary IEEE fma, so results are bit-identical to fmaf.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void fma_f32x2(unsigned long long &acc, float h, unsigned long long x) {
+    const unsigned long long hh = pack_f32x2(h, h);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(hh), "l"(x));
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
 __device__ __forceinline__ void cvt_iq(uint32_t w, int half, const CvtConst &c, float &xr, float &xi) {
     const uint32_t pair = __byte_perm(w, c.h1024, half ? 0x4342u : 0x4140u);
     asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(c.bias));
@@ -167,11 +185,11 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
     // ---- convert once, accumulate per (block, lag) ----------------------------------------------
     // The thread's first sample sits PH samples into load unit (soff / WB) + tid * (B*D/SPL).
     const unsigned char *ubase = tile + (size_t)((sh_soff / WB) + tid * (B * D / SPL)) * WB;
-    float accr[B][Q], acci[B][Q];
+    unsigned long long acc[B][Q];   // packed (re, im) accumulators
 #pragma unroll
     for (int b = 0; b < B; b++)
 #pragma unroll
-        for (int q = 0; q < Q; q++) accr[b][q] = acci[b][q] = 0.f;
+        for (int q = 0; q < Q; q++) acc[b][q] = 0ull;
 
     constexpr int NU = (PH + B * D + SPL - 1) / SPL;
     const CvtConst bias = cvt_consts();
@@ -191,21 +209,19 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
             if (j < 0 || j >= B * D) continue;
             float xr, xi;
             cvt_iq(words[i >> 1], i & 1, bias, xr, xi);
+            const unsigned long long x2 = pack_f32x2(xr, xi);
             const int bb = j / D, jj = j % D;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
                 const int k = q * D + (D - 1 - jj);
-                if (k < T) {
-                    accr[bb][q] = fmaf(taps.h[k], xr, accr[bb][q]);
-                    acci[bb][q] = fmaf(taps.h[k], xi, acci[bb][q]);
-                }
+                if (k < T) fma_f32x2(acc[bb][q], taps.h[k], x2);
             }
         }
     }
 #pragma unroll
     for (int b = 0; b < B; b++)
 #pragma unroll
-        for (int q = 0; q < Q; q++) part[(tid * B + b) * Q + q] = make_float2(accr[b][q], acci[b][q]);
+        for (int q = 0; q < Q; q++) part[(tid * B + b) * Q + q] = unpack_f32x2(acc[b][q]);
     __syncthreads();
 
     // ---- combine partials oldest block first: y[g] = P[g-Q+1][Q-1] + ... + P[g][0] -----------------

@@ -235,9 +235,14 @@ __device__ __forceinline__ void boxcar_rot_fixed(const uint32_t *w32, int pos, i
     }
     const bool neg = (pos >> 1) & 1;   // first word is a phase-2 word
     const int32_t sr = er - orr, si = ei - oi;
-    const int ph = pos & 3;
-    const int32_t kr = ph == 0 ? BoxK<DT>::re(0) : ph == 1 ? BoxK<DT>::re(1) : ph == 2 ? BoxK<DT>::re(2) : BoxK<DT>::re(3);
-    const int32_t ki = ph == 0 ? BoxK<DT>::im(0) : ph == 1 ? BoxK<DT>::im(1) : ph == 2 ? BoxK<DT>::im(2) : BoxK<DT>::im(3);
+    // K[pos & 3] from two packed 64-bit literals (4 x int16): one shift + sign-extend instead of a select tree
+    constexpr unsigned long long PK_RE = ((unsigned long long)(uint16_t)BoxK<DT>::re(0)) | ((unsigned long long)(uint16_t)BoxK<DT>::re(1) << 16) |
+                                         ((unsigned long long)(uint16_t)BoxK<DT>::re(2) << 32) | ((unsigned long long)(uint16_t)BoxK<DT>::re(3) << 48);
+    constexpr unsigned long long PK_IM = ((unsigned long long)(uint16_t)BoxK<DT>::im(0)) | ((unsigned long long)(uint16_t)BoxK<DT>::im(1) << 16) |
+                                         ((unsigned long long)(uint16_t)BoxK<DT>::im(2) << 32) | ((unsigned long long)(uint16_t)BoxK<DT>::im(3) << 48);
+    static_assert(DT * 128 < 32768, "window constants must fit int16");
+    const int sh = (pos & 3) * 16;
+    const int32_t kr = (int32_t)(int16_t)(PK_RE >> sh), ki = (int32_t)(int16_t)(PK_IM >> sh);
     re = wadd(re, wadd(neg ? -sr : sr, kr));
     im = wadd(im, wadd(neg ? -si : si, ki));
 }
@@ -267,7 +272,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     unsigned char *tile = smem;
     int2 *lp = reinterpret_cast<int2 *>(smem + a.tile_cap);
     int16_t *dm = reinterpret_cast<int16_t *>(smem + a.tile_cap + (size_t)a.lp_cap * 8);
-    uint8_t *flag = smem + a.tile_cap + (size_t)a.lp_cap * 10;
+    uint8_t *flag = smem + a.tile_cap + (((size_t)a.lp_cap * 10 + 15) & ~size_t(15));   // 16-byte aligned
 
     const int tid = threadIdx.x;
     const bool last = tile_idx == n_tiles - 1;
@@ -319,8 +324,16 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     const unsigned long long wlo = sh_wlo, jlo = sh_jlo, jhi = sh_jhi;
     const uint32_t nlp = sh_nlp;
 
+    // 32-bit forms of the per-element tests (the 64-bit bases are block-uniform)
+    const bool tile0 = wlo == 0;                      // this tile holds lowpassed window 0 / demod 0
+    const uint32_t skip = (uint32_t)(jlo - wlo);      // 1 if element 0 is only the predecessor of demod jlo
+    const uint32_t D = a.D, fast = a.fast, slow = a.slow;
+
     // ---- first-of-call flags (while the bulk copy is in flight) --------------------------------
-    for (uint32_t i = tid; i < nlp; i += blockDim.x) flag[i] = 0;
+    {
+        uint32_t *f32 = reinterpret_cast<uint32_t *>(flag);
+        for (uint32_t i = tid; i < (nlp + 3) / 4; i += blockDim.x) f32[i] = 0;
+    }
     __syncthreads();
     {
         const unsigned long long c_hi = sh_chi;
@@ -335,9 +348,9 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     const int32_t off0 = sh_off0;
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
     for (uint32_t i = tid; i < nlp; i += blockDim.x) {
-        int32_t base = off0 + (int32_t)(i * a.D);
+        int32_t base = off0 + (int32_t)(i * D);
         int32_t re = 0, im = 0;
-        if (wlo + i == 0) {
+        if (tile0 && i == 0) {
             re = st.lp_now_re;
             im = st.lp_now_im;
         }
@@ -345,7 +358,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
         if (DT > 0 && base >= 0)
             boxcar_rot_fixed<(DT > 0 ? DT : 2)>(w32, base, re, im);
         else
-            boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)a.D, re, im);
+            boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)D, re, im);
         lp[i] = make_int2(re, im);
     }
     if (last && tid == 255) {
@@ -358,10 +371,9 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
 
     // ---- phase 2: polar discriminator --------------------------------------------------------------
     for (uint32_t i = tid; i < nlp; i += blockDim.x) {
-        unsigned long long k = wlo + i;
-        if (k < jlo) continue;   // the predecessor-only element
+        if (i < skip) continue;   // the predecessor-only element
         int2 cur = lp[i];
-        int2 prev = (k == 0) ? make_int2(st.demod_pre_re, st.demod_pre_im) : lp[i - 1];
+        int2 prev = (tile0 && i == 0) ? make_int2(st.demod_pre_re, st.demod_pre_im) : lp[i - 1];
         int32_t cre, cim;
         d_cmul_conj(cur, prev, cre, cim);
         int32_t pcm = flag[i] ? d_polar_f64(cre, cim, a.oct) : d_fast_atan2(cim, cre);
@@ -372,10 +384,11 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     // ---- phase 3: fractional boxcar resampler ------------------------------------------------------
     const uint32_t ne = sh_ne, rb = sh_rb;
     const uint32_t dbase = (uint32_t)(jlo - wlo);   // dm index of demod sample jlo
+    const bool e0zero = sh_e0 == 0;
     for (uint32_t t = tid; t < ne; t += blockDim.x) {
-        uint32_t r0 = t ? udiv(t * a.fast - rb + a.slow - 1, a.div_slow) : 0u;
-        uint32_t r1 = udiv((t + 1) * a.fast - rb + a.slow - 1, a.div_slow);
-        int32_t sum = (sh_e0 + t == 0) ? st.now_lpr : 0;
+        uint32_t r0 = t ? udiv(t * fast - rb + slow - 1, a.div_slow) : 0u;
+        uint32_t r1 = udiv((t + 1) * fast - rb + slow - 1, a.div_slow);
+        int32_t sum = (e0zero && t == 0) ? st.now_lpr : 0;
         for (uint32_t j = r0; j < r1; j++) sum = wadd(sum, (int32_t)dm[dbase + j]);
         // truncating sum / (fast/slow): |sum| < 2^31, divide the magnitude with the magic, restore the sign
         const uint32_t mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
@@ -826,7 +839,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     uint64_t per = (fast + slow - 1) / slow;
     uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
     uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 64;
-    uint64_t smem = tile_cap + ((lp_cap * 11 + 15) & ~15ull) + 16;
+    uint64_t smem = tile_cap + ((lp_cap * 10 + 15) & ~15ull) + ((lp_cap + 19) & ~15ull) + 16;
     if (smem > 200 * 1024) {
         delete d;
         return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
