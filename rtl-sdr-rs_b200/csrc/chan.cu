@@ -69,22 +69,6 @@ __device__ __forceinline__ uint32_t chan_load_tile(unsigned char *xb, const Chan
     return soff;
 }
 
-// packed FP32 (Blackwell FFMA2): acc(re,im) += s * (x.lo, x.hi) with the scalar s broadcast to both lanes
-__device__ __forceinline__ unsigned long long c_pack(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void c_fma2(unsigned long long &acc, float s, unsigned long long x) {
-    const unsigned long long ss = c_pack(s, s);
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ss), "l"(x));
-}
-__device__ __forceinline__ float2 c_unpack(unsigned long long v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-
 template <int MR, bool ALIGNED>
 __global__ void __launch_bounds__(kChanWarps * 32, 1) k_chan_fir(const ChanArgs a) {
     constexpr int MT = kChanWarps * MR;   // outputs per tile
@@ -143,9 +127,9 @@ __global__ void __launch_bounds__(kChanWarps * 32, 1) k_chan_fir(const ChanArgs 
         __syncthreads();
 
         // ---- register-tiled complex MAC: lane = 2 channels, warp = MR outputs ------------------------
-        unsigned long long acc0[MR], acc1[MR];   // packed (re, im) per output, channels 2*lane and 2*lane+1
+        float ar0[MR], ai0[MR], ar1[MR], ai1[MR];
 #pragma unroll
-        for (int o = 0; o < MR; o++) acc0[o] = acc1[o] = 0ull;
+        for (int o = 0; o < MR; o++) ar0[o] = ai0[o] = ar1[o] = ai1[o] = 0.f;
         // newest sample of output o (tile-local) sits at xs[(o+1)*D + T4 - 2 + pad]
         const int base0 = (warp * MR + 1) * D + T4 - 2 + a.pad;
         const float4 *g4 = reinterpret_cast<const float4 *>(gt) + lane;   // [k][32 lanes] float4 = 2 channels
@@ -171,12 +155,15 @@ __global__ void __launch_bounds__(kChanWarps * 32, 1) k_chan_fir(const ChanArgs 
                 }
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) {
-                    // (gr + j gi)(xr + j xi) = gr*(xr, xi) + gi*(-xi, xr): two packed FMAs per channel
-                    const unsigned long long xs = c_pack(x[kk].x, x[kk].y), xq = c_pack(-x[kk].y, x[kk].x);
-                    c_fma2(acc0[o], g[kk].x, xs);
-                    c_fma2(acc0[o], g[kk].y, xq);
-                    c_fma2(acc1[o], g[kk].z, xs);
-                    c_fma2(acc1[o], g[kk].w, xq);
+                    // (gr + j gi) * (xr + j xi)
+                    ar0[o] = fmaf(g[kk].x, x[kk].x, ar0[o]);
+                    ar0[o] = fmaf(-g[kk].y, x[kk].y, ar0[o]);
+                    ai0[o] = fmaf(g[kk].x, x[kk].y, ai0[o]);
+                    ai0[o] = fmaf(g[kk].y, x[kk].x, ai0[o]);
+                    ar1[o] = fmaf(g[kk].z, x[kk].x, ar1[o]);
+                    ar1[o] = fmaf(-g[kk].w, x[kk].y, ar1[o]);
+                    ai1[o] = fmaf(g[kk].z, x[kk].y, ai1[o]);
+                    ai1[o] = fmaf(g[kk].w, x[kk].x, ai1[o]);
                 }
             }
         }
@@ -189,11 +176,10 @@ __global__ void __launch_bounds__(kChanWarps * 32, 1) k_chan_fir(const ChanArgs 
             const long long i = (long long)tile * MT + warp * MR + o;            // call-local output index
             const uint32_t nm = a.n0_lo + (uint32_t)((i + 1) * D - 1) - a.r;     // global n_m mod 2^32
             float c, s;
-            const float2 y0 = c_unpack(acc0[o]), y1 = c_unpack(acc1[o]);
             cis_phase(fw0 * nm, c, s);   // e^{+j theta}; we need e^{-j theta}: (yr + j yi)(c - j s)
-            ys[(2 * lane) * MT + warp * MR + o] = make_float2(y0.x * c + y0.y * s, y0.y * c - y0.x * s);
+            ys[(2 * lane) * MT + warp * MR + o] = make_float2(ar0[o] * c + ai0[o] * s, ai0[o] * c - ar0[o] * s);
             cis_phase(fw1 * nm, c, s);
-            ys[(2 * lane + 1) * MT + warp * MR + o] = make_float2(y1.x * c + y1.y * s, y1.y * c - y1.x * s);
+            ys[(2 * lane + 1) * MT + warp * MR + o] = make_float2(ar1[o] * c + ai1[o] * s, ai1[o] * c - ar1[o] * s);
         }
         __syncthreads();
         {

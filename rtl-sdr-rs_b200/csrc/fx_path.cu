@@ -368,10 +368,16 @@ __global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, 
     float *win = fsm + Jp;
     const long long o0 = (long long)blockIdx.x * kFirOblk;
     for (int k = threadIdx.x; k < Jp; k += blockDim.x) taps[k] = gp[k];
-    const long long gbase = (long long)h2 + o0 - Jp;
-    for (int idx = threadIdx.x; idx < kFirOblk + Jp; idx += blockDim.x) {
-        long long gi = gbase + idx;
-        win[idx + (idx >> 5) * 4] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
+    const long long gbase = (long long)h2 + o0 - Jp;   // h2 = Jp + 8, o0 % 1024 == 0: a multiple of 8 floats
+    const int n_chunks = (kFirOblk + Jp) / 4;
+    if ((gbase & 3) == 0 && gbase >= 0 && gbase + kFirOblk + Jp <= n_valid) {
+        const float4 *src = reinterpret_cast<const float4 *>(dbuf + gbase);   // whole tile valid: 16-byte loads
+        for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) win4[c + (c >> 3)] = src[c];
+    } else {
+        for (int idx = threadIdx.x; idx < kFirOblk + Jp; idx += blockDim.x) {
+            long long gi = gbase + idx;
+            win[idx + (idx >> 5) * 4] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
+        }
     }
     __syncthreads();
     float acc[kFirR];
