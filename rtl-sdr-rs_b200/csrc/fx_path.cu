@@ -4,14 +4,15 @@
 //   fm_demod : d[m] = gain * atan2(Im(y[m] conj y[m-1]), Re(..))       f32
 //   resample : a[i] = sum_p g[iM - pL] * d[p]                           rational L/M polyphase FIR
 //
-// Hot kernel: k_fir_fast<T,D,B,NT,ODD> — fused u8->f32 convert + decimating FIR + discriminator.
+// Hot kernel: k_fir_fast<T,D,B,NT,WB,PH> — fused u8->f32 convert + decimating FIR + discriminator.
 // "Block-owner" polyphase form: the stream is cut into decimation blocks of D samples; a thread owns
-// B consecutive blocks, converts every byte exactly once (PRMT into the mantissa of 2^23, one FADD)
-// and feeds it to the ceil(T/D) outputs it contributes to with taps read straight from the kernel
-// parameter constant bank (FFMA R, R, c[0][k], R — no tap loads).  Per-(block,lag) partial sums are
-// combined in a fixed order, so results are independent of how the stream is tiled or chunked.
-// Each CTA's raw bytes arrive with one 1-D bulk async copy (TMA engine) and are read once from HBM:
-// 2 B in + 4/D B out per complex sample.  y never leaves the SM unless the caller asks for it.
+// B consecutive blocks, converts every byte exactly once (one PRMT to a half2 (1024+I, 1024+Q), two
+// mixed-precision adds FHADD -> centred f32) and feeds the sample to the ceil(T/D) outputs it contributes
+// to with packed-FP32 FFMA2 (re and im lanes in one issue slot; the tap is a scalar-broadcast uniform
+// register loaded four at a time from the kernel-parameter constant bank — no per-thread tap loads).
+// Per-(block,lag) partial sums are combined in a fixed order, so results are independent of how the
+// stream is tiled or chunked.  Each CTA's raw bytes arrive with one 1-D bulk async copy (TMA engine) and
+// are read once from HBM: 2 B in + 4/D B out per complex sample.  y never leaves the SM unless asked for.
 //
 // Fallback for arbitrary (T,D): k_fir_generic — one warp per output, lanes stride the taps,
 // warp-shuffle reduction.
@@ -351,24 +352,25 @@ __global__ void k_store_prev(const float2 *y, long long n, float2 *prev_state) {
 //   a[i] = sum_{j<J} gp[phase][j] * d[p_i - j],   gp[phase][j] = g[phase + jL] (zero padded), J = ceil(T2/L).
 // dbuf[h2 + (p - P0)] = d[p] (history of h2 >= J values in front); outputs i in [i0, i0 + n_out).
 
-// L = M = 1 (plain real FIR at the output rate): 8 outputs per thread, taps and a 16-float sliding
-// window per 8-tap chunk in registers: 64 FMAs per 6 shared-memory loads.
-constexpr int kFirR = 8, kFirThreads = 128, kFirOblk = kFirR * kFirThreads;
+// L = M = 1 (plain real FIR at the output rate).  Register tile of kFirR = 16 outputs x 16 taps per step: a
+// 32-float sliding window (8 LDS.128) and 16 taps (4 broadcast LDS.128) feed 256 FMAs, which keeps shared-
+// memory wavefronts (36 per 256 warp-FMAs) under the FMA issue time — an 8x8 tile is shared-memory-bound.
+constexpr int kFirR = 16, kFirTC = 16, kFirThreads = 128, kFirOblk = kFirR * kFirThreads;
 inline size_t fir_real_smem(int Jp) {   // taps + padded window (one pad chunk per 8 chunks)
     return ((size_t)Jp + ((size_t)(kFirOblk + Jp) * 9) / 8 + 16) * sizeof(float);
 }
 __global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, int h2, const float *gp, int Jp,
                                                              long long n_out, long long n_valid, float *out) {
     extern __shared__ __align__(16) float fsm[];
-    float *taps = fsm;            // [Jp]
+    float *taps = fsm;            // [Jp], Jp a multiple of 16
     // window: logical win[idx] = dbuf[h2 + o0 - Jp + idx], idx < kFirOblk + Jp, stored in 16-byte chunks
-    // with one pad chunk after every 8 (chunk c lives at c + c/8): lanes read chunks 2t+k, and the pad
-    // turns that stride-2 pattern into 8 distinct bank groups per quarter warp (conflict-free LDS.128).
+    // with one pad chunk after every 8 (chunk c lives at c + c/8): lanes read chunks 4t+k, and the pad
+    // turns that stride-4 pattern into 8 distinct bank groups per quarter warp (conflict-free LDS.128).
     float4 *win4 = reinterpret_cast<float4 *>(fsm + Jp);
     float *win = fsm + Jp;
     const long long o0 = (long long)blockIdx.x * kFirOblk;
     for (int k = threadIdx.x; k < Jp; k += blockDim.x) taps[k] = gp[k];
-    const long long gbase = (long long)h2 + o0 - Jp;   // h2 = Jp + 8, o0 % 1024 == 0: a multiple of 8 floats
+    const long long gbase = (long long)h2 + o0 - Jp;   // h2 = Jp + 16, o0 % 2048 == 0: a multiple of 16 floats
     const int n_chunks = (kFirOblk + Jp) / 4;
     if ((gbase & 3) == 0 && gbase >= 0 && gbase + kFirOblk + Jp <= n_valid) {
         const float4 *src = reinterpret_cast<const float4 *>(dbuf + gbase);   // whole tile valid: 16-byte loads
@@ -383,67 +385,81 @@ __global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, 
     float acc[kFirR];
 #pragma unroll
     for (int r = 0; r < kFirR; r++) acc[r] = 0.f;
-    const int t8 = threadIdx.x * kFirR;
-    for (int j0 = 0; j0 < Jp; j0 += 8) {
-        float w[16], g[8];
-        const int c0 = (Jp + t8 - j0 - 8) >> 2;   // first logical chunk (Jp, t8, j0 are multiples of 8)
+    const int t0 = threadIdx.x * kFirR;
+    for (int j0 = 0; j0 < Jp; j0 += kFirTC) {
+        // outputs u = t0 + r (r < 16), taps j = j0 + jj (jj < 16): sample win[Jp + u - j]; the 32 floats
+        // w[c] = win[Jp + t0 - j0 - 16 + c] cover it: sample(r, jj) = w[16 + r - jj]
+        float w[kFirR + kFirTC], g[kFirTC];
+        const int c0 = (Jp + t0 - j0 - kFirTC) >> 2;   // first logical chunk (all terms are multiples of 16)
         const float4 *gq = reinterpret_cast<const float4 *>(taps + j0);
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < (kFirR + kFirTC) / 4; c++) {
             float4 v = win4[(c0 + c) + ((c0 + c) >> 3)];
             w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
         }
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
+        for (int c = 0; c < kFirTC / 4; c++) {
             float4 v = gq[c];
             g[4 * c] = v.x, g[4 * c + 1] = v.y, g[4 * c + 2] = v.z, g[4 * c + 3] = v.w;
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++)
+        for (int jj = 0; jj < kFirTC; jj++)
 #pragma unroll
-            for (int r = 0; r < kFirR; r++) acc[r] = fmaf(g[jj], w[8 + r - jj], acc[r]);
+            for (int r = 0; r < kFirR; r++) acc[r] = fmaf(g[jj], w[kFirTC + r - jj], acc[r]);
     }
-    // 8 consecutive outputs per thread: two 16-byte stores when the row is whole and aligned
-    float *dst = out + o0 + t8;
-    if (o0 + t8 + kFirR <= n_out && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        reinterpret_cast<float4 *>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        reinterpret_cast<float4 *>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    // 16 consecutive outputs per thread: four 16-byte stores when the row is whole and aligned
+    float *dst = out + o0 + t0;
+    if (o0 + t0 + kFirR <= n_out && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int c = 0; c < kFirR / 4; c++)
+            reinterpret_cast<float4 *>(dst)[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
     } else {
 #pragma unroll
         for (int r = 0; r < kFirR; r++)
-            if (o0 + t8 + r < n_out) dst[r] = acc[r];
+            if (o0 + t0 + r < n_out) dst[r] = acc[r];
     }
 }
 
-// Generic rational L/M: one output per thread, polyphase taps in shared memory, 32-bit index math
-// relative to a per-CTA 64-bit base.
+// Generic rational L/M: one output per thread, polyphase taps in shared memory (row stride Js = J|1 so the
+// L phases of a warp hit different banks), the d window of a 256-output tile staged once, 32-bit index
+// math relative to a per-tile 64-bit base computed by one thread.
 __global__ void __launch_bounds__(256) k_resample_poly(const float *dbuf, int h2, unsigned long long P0, const float *gp,
                                                        int J, uint32_t L, uint32_t M, unsigned long long i0,
                                                        long long n_out, int taps_in_smem, int win_cap, long long n_valid,
                                                        float *out) {
     extern __shared__ __align__(16) float fsm[];
+    __shared__ unsigned long long sh_p0;
+    __shared__ uint32_t sh_ph0;
+    const int Js = J | 1;
     const float *tp = gp;
+    int tstride = J;
     float *xw = fsm;                       // staged window of d (when win_cap > 0), after the taps
     if (taps_in_smem) {
-        for (int k = threadIdx.x; k < (int)(L * J); k += blockDim.x) fsm[k] = gp[k];
+        for (int k = threadIdx.x; k < (int)L * J; k += blockDim.x) fsm[(k / J) * Js + (k % J)] = gp[k];
         tp = fsm;
-        xw = fsm + ((L * J + 3) & ~3u);
+        tstride = Js;
+        xw = fsm + ((L * Js + 3) & ~3u);
     }
-    __syncthreads();
     for (long long ob = (long long)blockIdx.x * 256; ob < n_out; ob += (long long)gridDim.x * 256) {
-        const unsigned long long t0 = (i0 + (unsigned long long)ob) * M;
-        const unsigned long long p0 = t0 / L;
-        const uint32_t ph0 = (uint32_t)(t0 - p0 * L);
+        __syncthreads();                   // taps staged / previous tile's readers are done
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = (i0 + (unsigned long long)ob) * M;
+            const unsigned long long p0 = t0 / L;
+            sh_p0 = p0;
+            sh_ph0 = (uint32_t)(t0 - p0 * L);
+        }
+        __syncthreads();
+        const unsigned long long p0 = sh_p0;
+        const uint32_t ph0 = sh_ph0;
         const long long o = ob + threadIdx.x;
         const uint32_t trel = ph0 + threadIdx.x * M;
         const uint32_t dp = trel / L, ph = trel - dp * L;
         const long long xbase = (long long)(p0 - P0) + h2;       // dbuf index of d[p0]
-        const float *g = tp + (size_t)ph * J;
+        const float *g = tp + (size_t)ph * tstride;
         float acc = 0.f;
         if (win_cap) {
             // the 256 outputs of this tile read d[p0 - (J-1) .. p0 + (ph0 + 255*M)/L]: stage it once, coalesced
             const int span = (int)((ph0 + 255u * M) / L) + J;
-            __syncthreads();               // previous tile's readers are done
             for (int k = threadIdx.x; k < span; k += blockDim.x) {
                 const long long gi = xbase - (J - 1) + k;
                 xw[k] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
@@ -689,7 +705,7 @@ int launch_resample(sdr_fmrx *r, uint64_t P0, uint64_t n_new, uint64_t a0, uint6
         r->last_launches++;
     } else if (n_a) {
         int blocks = (int)std::min<uint64_t>(ceil_div(n_a, 256), (uint64_t)sm_count(r->device) * 16);
-        size_t tb = (((size_t)r->cfg.up * r->J + 3) & ~size_t(3)) * sizeof(float);
+        size_t tb = (((size_t)r->cfg.up * (r->J | 1) + 3) & ~size_t(3)) * sizeof(float);
         int in_smem = tb <= 32 * 1024;
         // window of d one 256-output tile touches; staged in shared memory when it is small
         size_t span = ((size_t)(r->cfg.up - 1) + 255ull * r->cfg.down) / r->cfg.up + r->J + 1;
@@ -810,8 +826,8 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
     r->cs = (int)cs;
     if (cfg->n_taps2) {
         r->J = (int)((cfg->n_taps2 + cfg->up - 1) / cfg->up);
-        r->Jp = (r->J + 7) & ~7;
-        r->h2 = r->Jp + 8;
+        r->Jp = (r->J + 15) & ~15;
+        r->h2 = r->Jp + 16;
     }
     cudaError_t e = cudaFuncSetAttribute(k_fir_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem);
     if (e == cudaSuccess && r->fast) e = r->fast->prepare(r->fast->smem);
@@ -831,7 +847,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         return fail(SDR_E_CUDA, "sdr_fmrx_new: %s", cudaGetErrorString(e));
     }
     if ((rc = r->d_carry[0].reserve(cs * 2)) || (rc = r->d_carry[1].reserve(cs * 2)) || (rc = r->d_state.reserve(64)) ||
-        (rc = r->d_taps.reserve(T * 4)) || (rc = r->d_taps2.reserve(cfg->n_taps2 ? ((size_t)cfg->up * r->J + r->Jp + 8) * 4 : 4)) ||
+        (rc = r->d_taps.reserve(T * 4)) || (rc = r->d_taps2.reserve(cfg->n_taps2 ? ((size_t)cfg->up * r->J + r->Jp + 16) * 4 : 4)) ||
         (rc = r->d_dbuf.reserve(((size_t)r->h2 + 4096) * sizeof(float)))) {
         sdr_fmrx_free(r);
         return rc;
@@ -839,7 +855,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
     e = cudaMemcpy(r->d_taps.p, taps, T * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && cfg->n_taps2) {
         // polyphase layout gp[phase][j] = g[phase + j*L] (zero padded); for L = 1 this is g padded to Jp
-        std::vector<float> gp((size_t)cfg->up * r->J + r->Jp + 8, 0.f);
+        std::vector<float> gp((size_t)cfg->up * r->J + r->Jp + 16, 0.f);
         for (uint32_t ph = 0; ph < cfg->up; ph++)
             for (int j = 0; j < r->J; j++) {
                 size_t k = ph + (size_t)j * cfg->up;
