@@ -105,21 +105,6 @@ __device__ __forceinline__ int32_t d_polar_f64(int32_t cre, int32_t cim, const O
     return (int32_t)v;   // truncation toward zero == Rust `as i32` in range
 }
 
-// One sample of rotate_90 (:285-295, "negation" is 255 - x) followed by `- 127` (:258):
-// centred (a, b) = (I-127, Q-127); a negated component is 128 - x = 1 - (x - 127).
-__device__ __forceinline__ void rot_acc(uint32_t iq16, int phase, int32_t &re, int32_t &im) {
-    int32_t a = (int32_t)(iq16 & 255u) - 127, b = (int32_t)(iq16 >> 8) - 127;
-    int32_t r, i;
-    switch (phase) {
-        case 0: r = a; i = b; break;            // [b0, b1]
-        case 1: r = 1 - b; i = a; break;        // [255-b3, b2]
-        case 2: r = 1 - a; i = 1 - b; break;    // [255-b4, 255-b5]
-        default: r = b; i = 1 - a; break;       // [b7, 255-b6]
-    }
-    re = wadd(re, r);
-    im = wadd(im, i);
-}
-
 // u8 x s8 dot product of four byte lanes with 32-bit accumulate (SASS IDP.4A)
 __device__ __forceinline__ int32_t dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int32_t c) {
     int32_t d;
