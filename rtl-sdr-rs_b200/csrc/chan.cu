@@ -69,6 +69,22 @@ __device__ __forceinline__ uint32_t chan_load_tile(unsigned char *xb, const Chan
     return soff;
 }
 
+// packed FP32 (Blackwell FFMA2): acc(lo,hi) += s * (x.lo, x.hi), scalar s broadcast to both lanes
+__device__ __forceinline__ unsigned long long c_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void c_fma2(unsigned long long &acc, float s, unsigned long long x) {
+    const unsigned long long ss = c_pack(s, s);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ss), "l"(x));
+}
+__device__ __forceinline__ float2 c_unpack(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
 template <int W, int MR, bool ALIGNED>
 __global__ void __launch_bounds__(W * 32, 1) k_chan_fir(const ChanArgs a) {
     constexpr int MT = W * MR;   // outputs per tile: W warps x MR outputs
@@ -194,6 +210,93 @@ __global__ void __launch_bounds__(W * 32, 1) k_chan_fir(const ChanArgs a) {
     }
 }
 
+// =================================================================================================
+// k_chan_fir_u — the fast channeliser kernel (n_taps <= 255): lanes own OUTPUTS, taps are UNIFORM.
+//
+// k_chan_fir above is limited by shared-memory wavefronts (every warp re-reads the 130 KB tap table) and
+// reaches ~53 % of the FP32 peak.  Here a lane owns one output column and CH = 16 channels live in its
+// registers; the folded taps of those 16 channels are a 32 KB __grid_constant__ kernel parameter, so for
+// tap k every lane needs the SAME 16 (gr, gi) pairs: they arrive as scalar-broadcast uniform registers
+// (LDCU.128 from the constant bank) inside packed FFMA2s — no shared-memory tap traffic at all.  The only
+// per-lane load is its own raw sample (one LDS.U16 + PRMT + 2 FHADD per tap, amortised over 32 FFMA2s).
+//   A_c += gr_c * (xr, xi);  B_c += gi_c * (xr, xi);   y_c = (A.re - B.im) + j (A.im + B.re)
+// (no negation / swap in the loop).  One launch per 16 channels; each re-reads the raw bytes (2 B/sample
+// against ~650 FMA/sample: irrelevant).
+// =================================================================================================
+constexpr int kChanUCh = 16, kChanUThreads = 128, kChanUMaxT = 255;
+struct TapsU {
+    float2 g[kChanUMaxT * kChanUCh];   // [k][channel]: (gr, gi) of the folded tap
+};
+struct ChanUArgs {
+    const uint8_t *x;
+    const uint8_t *carry_end;
+    const uint32_t *fw;      // [C_pad] NCO phase words
+    float2 *y_out;           // [C_pad][cap]
+    long long n_samples, n_out, cap;
+    uint32_t r, n0_lo;
+    int ch0, n_ch, T, D;     // first channel of this launch, channels that exist (< CH for the last group)
+};
+
+__global__ void __launch_bounds__(kChanUThreads) k_chan_fir_u(const ChanUArgs a, const __grid_constant__ TapsU taps) {
+    constexpr int CH = kChanUCh;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t sh_soff;
+    const int tid = threadIdx.x;
+    const long long out0 = (long long)blockIdx.x * kChanUThreads;
+    const long long n_here = a.n_out - out0 < kChanUThreads ? a.n_out - out0 : kChanUThreads;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        ChanArgs la{};   // chan_load_tile only needs x / carry_end
+        la.x = a.x;
+        la.carry_end = a.carry_end;
+        const long long s0 = out0 * a.D - (long long)a.r - (a.T - 1);
+        const long long s1 = (out0 + n_here) * a.D - (long long)a.r;
+        sh_soff = chan_load_tile(smem, la, s0, s1, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    // newest sample of output out0 + tid, relative to the tile's first sample s0
+    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(smem + sh_soff) + (tid + 1) * a.D + a.T - 2;
+    unsigned long long A[CH], B[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) A[c] = B[c] = 0ull;
+    // opaque per-thread conversion constants (see fx_path.cu: FHADD takes no immediate / uniform operand)
+    float bias;
+    uint32_t h1024;
+    asm volatile(
+        "{\n.reg .u32 t;\nmov.u32 t, %%tid.x;\nshr.u32 t, t, 31;\nor.b32 %0, t, 0xC48FE000;\nor.b32 %1, t, 0x64646464;\n}\n"
+        : "=f"(bias), "=r"(h1024));
+#pragma unroll 2
+    for (int k = 0; k < a.T; k++) {
+        const uint32_t pair = __byte_perm((uint32_t)t16[-k], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
+        float xr, xi;
+        asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(bias));
+        asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(bias));
+        const unsigned long long x2 = c_pack(xr, xi);
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const float2 g = taps.g[k * CH + c];
+            c_fma2(A[c], g.x, x2);
+            c_fma2(B[c], g.y, x2);
+        }
+    }
+    if (tid < n_here) {
+        const long long i = out0 + tid;
+        const uint32_t nm = a.n0_lo + (uint32_t)((i + 1) * a.D - 1) - a.r;   // global n_m mod 2^32
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            if (c >= a.n_ch) break;
+            const float2 pa = c_unpack(A[c]), pb = c_unpack(B[c]);
+            const float yr = pa.x - pb.y, yi = pa.y + pb.x;
+            float co, si;
+            cis_phase(a.fw[a.ch0 + c] * nm, co, si);   // e^{+j theta}; de-rotate with its conjugate
+            a.y_out[(size_t)(a.ch0 + c) * a.cap + i] = make_float2(yr * co + yi * si, yi * co - yr * si);
+        }
+    }
+}
+
 // Folded taps: g[group][k][c] = h[k] * e^{+j theta_c(k)} (double precision, setup only).
 __global__ void k_chan_fold_taps(const float *h, int T, int T4, const uint32_t *fw, int C, int C_pad, float2 *g) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,6 +353,9 @@ struct sdr_chan {
     int device = 0;
     int C_pad = 0, groups = 0, T4 = 0, pad = 0, mr = 0, warps = 8;
     bool aligned = false;
+    bool use_uniform = false;                  // k_chan_fir_u path (n_taps <= 255)
+    std::vector<TapsU> taps_u;                 // one 32 KB parameter blob per 16 channels
+    size_t smem_u = 0;
     uint32_t sm_taps = 0, sm_xs = 0, sm_xb = 0;
     size_t smem = 0;
     int cs = 0, carry_cur = 0;
@@ -299,7 +405,29 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
     const int D = (int)c->cfg.decim;
     c->last_launches = 0;
     SDR_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    if (n_out) {
+    if (n_out && c->use_uniform) {
+        ChanUArgs u{};
+        u.x = d_x;
+        u.carry_end = c->d_carry[c->carry_cur].as<uint8_t>() + (size_t)c->cs * 2;
+        u.fw = c->d_fw.as<uint32_t>();
+        u.y_out = d_y;
+        u.n_samples = (long long)n;
+        u.n_out = (long long)n_out;
+        u.cap = (long long)cap;
+        u.r = (uint32_t)(c->n_in % D);
+        u.n0_lo = (uint32_t)c->n_in;
+        u.T = (int)c->cfg.n_taps;
+        u.D = D;
+        const uint64_t tiles = (n_out + kChanUThreads - 1) / kChanUThreads;
+        if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
+        for (size_t g = 0; g < c->taps_u.size(); g++) {
+            u.ch0 = (int)g * kChanUCh;
+            u.n_ch = std::min<int>(kChanUCh, (int)c->cfg.n_channels - u.ch0);
+            k_chan_fir_u<<<(unsigned)tiles, kChanUThreads, c->smem_u, c->stream>>>(u, c->taps_u[g]);
+            SDR_LAUNCH_CHECK();
+            c->last_launches++;
+        }
+    } else if (n_out) {
         const int MT = c->warps * c->mr;
         ChanArgs a{};
         a.x = d_x;
@@ -431,6 +559,27 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
     if (e != cudaSuccess) {
         sdr_chan_free(c);
         return fail(SDR_E_CUDA, "sdr_chan_new: %s", cudaGetErrorString(e));
+    }
+    // uniform-tap kernel: folded taps g_c[k] = h[k] e^{+j theta_c(k)} as kernel-parameter blobs (setup, host f64)
+    const char *force_smem = getenv("SDR_CHAN_SMEM_TAPS");
+    if (cfg->n_taps <= (uint32_t)kChanUMaxT && !(force_smem && atoi(force_smem))) {
+        c->use_uniform = true;
+        const size_t n_groups = (cfg->n_channels + kChanUCh - 1) / kChanUCh;
+        c->taps_u.assign(n_groups, TapsU{});
+        for (uint32_t ch = 0; ch < cfg->n_channels; ch++)
+            for (uint32_t k = 0; k < cfg->n_taps; k++) {
+                const uint32_t ph = freq_words[ch] * k;   // mod 2^32
+                const double th = 2.0 * 3.14159265358979323846 * ((double)ph / 4294967296.0);
+                c->taps_u[ch / kChanUCh].g[(size_t)k * kChanUCh + ch % kChanUCh] =
+                    make_float2((float)((double)taps[k] * std::cos(th)), (float)((double)taps[k] * std::sin(th)));
+            }
+        c->smem_u = (((size_t)kChanUThreads * D + cfg->n_taps + 16) * 2 + 15 + 32) & ~size_t(15);
+        if (c->smem_u > 200 * 1024) c->use_uniform = false;
+        else e = cudaFuncSetAttribute(k_chan_fir_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_u);
+        if (e != cudaSuccess) {
+            sdr_chan_free(c);
+            return fail(SDR_E_CUDA, "sdr_chan_new: %s", cudaGetErrorString(e));
+        }
     }
     int total = c->C_pad * T4;
     k_chan_fold_taps<<<(total + 255) / 256, 256, 0, c->stream>>>(c->d_taps.as<float>(), (int)cfg->n_taps, T4, c->d_fw.as<uint32_t>(),
