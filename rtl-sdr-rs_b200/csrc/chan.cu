@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_chan_fir(const ChanArgs a) {
 // =================================================================================================
 constexpr int kChanUCh = 16, kChanUThreads = 128, kChanUMaxT = 255;
 struct TapsU {
-    float2 g[kChanUMaxT * kChanUCh];   // [k][channel]: (gr, gi) of the folded tap
+    float4 g[kChanUMaxT * kChanUCh / 2];   // [k][channel pair]: (gr0, gi0, gr1, gi1) — one LDCU.128 per two channels
 };
 struct ChanUArgs {
     const uint8_t *x;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kChanUThreads) k_chan_fir_u(const ChanUArgs a,
     asm volatile(
         "{\n.reg .u32 t;\nmov.u32 t, %%tid.x;\nshr.u32 t, t, 31;\nor.b32 %0, t, 0xC48FE000;\nor.b32 %1, t, 0x64646464;\n}\n"
         : "=f"(bias), "=r"(h1024));
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < a.T; k++) {
         const uint32_t pair = __byte_perm((uint32_t)t16[-k], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
         float xr, xi;
@@ -276,10 +276,12 @@ __global__ void __launch_bounds__(kChanUThreads) k_chan_fir_u(const ChanUArgs a,
         asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(bias));
         const unsigned long long x2 = c_pack(xr, xi);
 #pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const float2 g = taps.g[k * CH + c];
+        for (int c = 0; c < CH; c += 2) {
+            const float4 g = taps.g[k * (CH / 2) + c / 2];
             c_fma2(A[c], g.x, x2);
             c_fma2(B[c], g.y, x2);
+            c_fma2(A[c + 1], g.z, x2);
+            c_fma2(B[c + 1], g.w, x2);
         }
     }
     if (tid < n_here) {
@@ -290,8 +292,10 @@ __global__ void __launch_bounds__(kChanUThreads) k_chan_fir_u(const ChanUArgs a,
             if (c >= a.n_ch) break;
             const float2 pa = c_unpack(A[c]), pb = c_unpack(B[c]);
             const float yr = pa.x - pb.y, yi = pa.y + pb.x;
+            // e^{+j theta} from the top 24 phase bits (angle error <= 2 pi 2^-25: far inside the 1e-5 bar);
+            // de-rotate with its conjugate
             float co, si;
-            cis_phase(a.fw[a.ch0 + c] * nm, co, si);   // e^{+j theta}; de-rotate with its conjugate
+            sincospif((float)(int32_t)(a.fw[a.ch0 + c] * nm) * (1.0f / 2147483648.0f), &si, &co);
             a.y_out[(size_t)(a.ch0 + c) * a.cap + i] = make_float2(yr * co + yi * si, yi * co - yr * si);
         }
     }
@@ -570,8 +574,15 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
             for (uint32_t k = 0; k < cfg->n_taps; k++) {
                 const uint32_t ph = freq_words[ch] * k;   // mod 2^32
                 const double th = 2.0 * 3.14159265358979323846 * ((double)ph / 4294967296.0);
-                c->taps_u[ch / kChanUCh].g[(size_t)k * kChanUCh + ch % kChanUCh] =
-                    make_float2((float)((double)taps[k] * std::cos(th)), (float)((double)taps[k] * std::sin(th)));
+                float4 &q = c->taps_u[ch / kChanUCh].g[(size_t)k * (kChanUCh / 2) + (ch % kChanUCh) / 2];
+                const float gr = (float)((double)taps[k] * std::cos(th)), gi = (float)((double)taps[k] * std::sin(th));
+                if (ch & 1) {
+                    q.z = gr;
+                    q.w = gi;
+                } else {
+                    q.x = gr;
+                    q.y = gi;
+                }
             }
         c->smem_u = (((size_t)kChanUThreads * D + cfg->n_taps + 16) * 2 + 15 + 32) & ~size_t(15);
         if (c->smem_u > 200 * 1024) c->use_uniform = false;
