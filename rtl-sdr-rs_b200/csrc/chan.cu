@@ -223,9 +223,10 @@ __global__ void __launch_bounds__(W * 32, 1) k_chan_fir(const ChanArgs a) {
 // (no negation / swap in the loop).  One launch per 16 channels; each re-reads the raw bytes (2 B/sample
 // against ~650 FMA/sample: irrelevant).
 // =================================================================================================
-constexpr int kChanUCh = 16, kChanUThreads = 128, kChanUMaxT = 255;
+constexpr int kChanUCh = 8, kChanUMo = 2, kChanUThreads = 128, kChanUMaxT = 255;
+constexpr int kChanUOut = kChanUThreads * kChanUMo;   // outputs per CTA
 struct TapsU {
-    float4 g[kChanUMaxT * kChanUCh / 2];   // [k][channel pair]: (gr0, gi0, gr1, gi1) — one LDCU.128 per two channels
+    float2 g[kChanUMaxT * kChanUCh];   // [k][channel]: (gr, gi) of the folded tap
 };
 struct ChanUArgs {
     const uint8_t *x;
@@ -237,14 +238,16 @@ struct ChanUArgs {
     int ch0, n_ch, T, D;     // first channel of this launch, channels that exist (< CH for the last group)
 };
 
+// A lane owns kChanUMo outputs (tid and tid + 128 of the CTA's 256) x kChanUCh channels: every uniform tap
+// load (LDCU.64 of one (gr, gi)) feeds 2*MO FFMA2s, which keeps the constant/MIO queue below the FMA time.
 __global__ void __launch_bounds__(kChanUThreads) k_chan_fir_u(const ChanUArgs a, const __grid_constant__ TapsU taps) {
-    constexpr int CH = kChanUCh;
+    constexpr int CH = kChanUCh, MO = kChanUMo;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t sh_soff;
     const int tid = threadIdx.x;
-    const long long out0 = (long long)blockIdx.x * kChanUThreads;
-    const long long n_here = a.n_out - out0 < kChanUThreads ? a.n_out - out0 : kChanUThreads;
+    const long long out0 = (long long)blockIdx.x * kChanUOut;
+    const long long n_here = a.n_out - out0 < kChanUOut ? a.n_out - out0 : kChanUOut;
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
@@ -257,40 +260,52 @@ __global__ void __launch_bounds__(kChanUThreads) k_chan_fir_u(const ChanUArgs a,
     }
     __syncthreads();
     mbar_wait(&bar, 0);
-    // newest sample of output out0 + tid, relative to the tile's first sample s0
-    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(smem + sh_soff) + (tid + 1) * a.D + a.T - 2;
-    unsigned long long A[CH], B[CH];
+    // newest sample of output out0 + tid + 128*o, relative to the tile's first sample s0
+    const uint16_t *t16[MO];
 #pragma unroll
-    for (int c = 0; c < CH; c++) A[c] = B[c] = 0ull;
+    for (int o = 0; o < MO; o++)
+        t16[o] = reinterpret_cast<const uint16_t *>(smem + sh_soff) + (tid + o * kChanUThreads + 1) * a.D + a.T - 2;
+    unsigned long long A[MO][CH], B[MO][CH];
+#pragma unroll
+    for (int o = 0; o < MO; o++)
+#pragma unroll
+        for (int c = 0; c < CH; c++) A[o][c] = B[o][c] = 0ull;
     // opaque per-thread conversion constants (see fx_path.cu: FHADD takes no immediate / uniform operand)
     float bias;
     uint32_t h1024;
     asm volatile(
         "{\n.reg .u32 t;\nmov.u32 t, %%tid.x;\nshr.u32 t, t, 31;\nor.b32 %0, t, 0xC48FE000;\nor.b32 %1, t, 0x64646464;\n}\n"
         : "=f"(bias), "=r"(h1024));
-#pragma unroll 4
+#pragma unroll 2
     for (int k = 0; k < a.T; k++) {
-        const uint32_t pair = __byte_perm((uint32_t)t16[-k], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
-        float xr, xi;
-        asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(bias));
-        asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(bias));
-        const unsigned long long x2 = c_pack(xr, xi);
+        unsigned long long x2[MO];
 #pragma unroll
-        for (int c = 0; c < CH; c += 2) {
-            const float4 g = taps.g[k * (CH / 2) + c / 2];
-            c_fma2(A[c], g.x, x2);
-            c_fma2(B[c], g.y, x2);
-            c_fma2(A[c + 1], g.z, x2);
-            c_fma2(B[c + 1], g.w, x2);
+        for (int o = 0; o < MO; o++) {
+            const uint32_t pair = __byte_perm((uint32_t)t16[o][-k], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
+            float xr, xi;
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(bias));
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(bias));
+            x2[o] = c_pack(xr, xi);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const float2 g = taps.g[k * CH + c];
+#pragma unroll
+            for (int o = 0; o < MO; o++) {
+                c_fma2(A[o][c], g.x, x2[o]);
+                c_fma2(B[o][c], g.y, x2[o]);
+            }
         }
     }
-    if (tid < n_here) {
-        const long long i = out0 + tid;
+#pragma unroll
+    for (int o = 0; o < MO; o++) {
+        const long long i = out0 + tid + o * kChanUThreads;
+        if (i >= a.n_out) continue;
         const uint32_t nm = a.n0_lo + (uint32_t)((i + 1) * a.D - 1) - a.r;   // global n_m mod 2^32
 #pragma unroll
         for (int c = 0; c < CH; c++) {
             if (c >= a.n_ch) break;
-            const float2 pa = c_unpack(A[c]), pb = c_unpack(B[c]);
+            const float2 pa = c_unpack(A[o][c]), pb = c_unpack(B[o][c]);
             const float yr = pa.x - pb.y, yi = pa.y + pb.x;
             // e^{+j theta} from the top 24 phase bits (angle error <= 2 pi 2^-25: far inside the 1e-5 bar);
             // de-rotate with its conjugate
@@ -422,7 +437,7 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
         u.n0_lo = (uint32_t)c->n_in;
         u.T = (int)c->cfg.n_taps;
         u.D = D;
-        const uint64_t tiles = (n_out + kChanUThreads - 1) / kChanUThreads;
+        const uint64_t tiles = (n_out + kChanUOut - 1) / kChanUOut;
         if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
         for (size_t g = 0; g < c->taps_u.size(); g++) {
             u.ch0 = (int)g * kChanUCh;
@@ -574,17 +589,10 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
             for (uint32_t k = 0; k < cfg->n_taps; k++) {
                 const uint32_t ph = freq_words[ch] * k;   // mod 2^32
                 const double th = 2.0 * 3.14159265358979323846 * ((double)ph / 4294967296.0);
-                float4 &q = c->taps_u[ch / kChanUCh].g[(size_t)k * (kChanUCh / 2) + (ch % kChanUCh) / 2];
-                const float gr = (float)((double)taps[k] * std::cos(th)), gi = (float)((double)taps[k] * std::sin(th));
-                if (ch & 1) {
-                    q.z = gr;
-                    q.w = gi;
-                } else {
-                    q.x = gr;
-                    q.y = gi;
-                }
+                c->taps_u[ch / kChanUCh].g[(size_t)k * kChanUCh + ch % kChanUCh] =
+                    make_float2((float)((double)taps[k] * std::cos(th)), (float)((double)taps[k] * std::sin(th)));
             }
-        c->smem_u = (((size_t)kChanUThreads * D + cfg->n_taps + 16) * 2 + 15 + 32) & ~size_t(15);
+        c->smem_u = (((size_t)kChanUOut * D + cfg->n_taps + 16) * 2 + 15 + 32) & ~size_t(15);
         if (c->smem_u > 200 * 1024) c->use_uniform = false;
         else e = cudaFuncSetAttribute(k_chan_fir_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_u);
         if (e != cudaSuccess) {
