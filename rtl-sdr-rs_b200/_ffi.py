@@ -2,6 +2,8 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
+import pathlib
 from pathlib import Path
 
 import numpy as np
@@ -149,10 +151,11 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise SdrError(SDR_E_STATE, f"{LIB_PATH} is missing: build it with `make -C {PKG_DIR}` "
+    path = pathlib.Path(os.environ.get("SDR_B200_LIB", LIB_PATH))   # override: A/B builds of the same ABI
+    if not path.exists():
+        raise SdrError(SDR_E_STATE, f"{path} is missing: build it with `make -C {PKG_DIR}` "
                                     "(or __graft_entry__.build()); there is no CPU fallback")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
         fn.restype = res
