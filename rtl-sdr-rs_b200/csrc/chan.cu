@@ -373,7 +373,7 @@ struct sdr_chan {
     int C_pad = 0, groups = 0, T4 = 0, pad = 0, mr = 0, warps = 8;
     bool aligned = false;
     bool use_uniform = false;                  // k_chan_fir_u path (n_taps <= 255)
-    std::vector<TapsU> taps_u;                 // one 32 KB parameter blob per 16 channels
+    std::vector<TapsU> taps_u;                 // one 16 KB parameter blob per 8 channels
     size_t smem_u = 0;
     uint32_t sm_taps = 0, sm_xs = 0, sm_xb = 0;
     size_t smem = 0;
@@ -383,6 +383,11 @@ struct sdr_chan {
     DevBuf d_carry[2], d_taps, d_gt, d_fw, d_prev, d_x, d_y, d_d;
     size_t y_cap = 0;
     cudaStream_t stream = nullptr;
+    // the channel-group launches of one call are independent: groups 1.. go round-robin to side streams (fork / join
+    // on events) so that the partial last wave of one launch is filled by the next launch's first CTAs
+    static constexpr int kSide = 3;
+    cudaStream_t side[kSide]{};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSide]{};
     cudaEvent_t ev[3]{};
     float last_ms = 0.f;
     uint32_t last_launches = 0;
@@ -439,12 +444,22 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
         u.D = D;
         const uint64_t tiles = (n_out + kChanUOut - 1) / kChanUOut;
         if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
+        const int n_streams = (int)std::min<size_t>(c->taps_u.size(), 1 + sdr_chan::kSide);
+        if (n_streams > 1) {
+            SDR_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+            for (int s = 1; s < n_streams; s++) SDR_CUDA_TRY(cudaStreamWaitEvent(c->side[s - 1], c->ev_fork, 0));
+        }
         for (size_t g = 0; g < c->taps_u.size(); g++) {
             u.ch0 = (int)g * kChanUCh;
             u.n_ch = std::min<int>(kChanUCh, (int)c->cfg.n_channels - u.ch0);
-            k_chan_fir_u<<<(unsigned)tiles, kChanUThreads, c->smem_u, c->stream>>>(u, c->taps_u[g]);
+            const int s = (int)(g % n_streams);
+            k_chan_fir_u<<<(unsigned)tiles, kChanUThreads, c->smem_u, s ? c->side[s - 1] : c->stream>>>(u, c->taps_u[g]);
             SDR_LAUNCH_CHECK();
             c->last_launches++;
+        }
+        for (int s = 1; s < n_streams; s++) {
+            SDR_CUDA_TRY(cudaEventRecord(c->ev_join[s - 1], c->side[s - 1]));
+            SDR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join[s - 1], 0));
         }
     } else if (n_out) {
         const int MT = c->warps * c->mr;
@@ -561,6 +576,11 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
     cudaError_t e = cudaFuncSetAttribute(pick_kernel(c->warps, c->mr, c->aligned), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < sdr_chan::kSide && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         sdr_chan_free(c);
         return fail(SDR_E_CUDA, "sdr_chan_new: %s", cudaGetErrorString(e));
@@ -626,6 +646,11 @@ void sdr_chan_free(sdr_chan *c) {
     c->d_d.release();
     for (int i = 0; i < 3; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < sdr_chan::kSide; i++) {
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
