@@ -55,7 +55,7 @@ struct FusedArgs {
     unsigned long long n_samples, Ltot, Etot;
     uint32_t S, D, p0, q0, fast, slow;
     int32_t div;
-    uint32_t EB, lp_cap, tile_cap;
+    uint32_t EB, lp_cap, tile_cap, dm_off;   // dm_off: byte offset of the demodulated-sample array in shared memory
     OctTable oct;
 };
 
@@ -239,6 +239,16 @@ __device__ __forceinline__ uint32_t udiv(uint32_t n, UDiv d) {
     return d.shift == 0xffffffffu ? n : (__umulhi(n, d.magic) >> d.shift);
 }
 
+// Exact lowpassed window i of the tile (any D), straight from the raw bytes: the D = 6 path keeps no window
+// array in shared memory, so its rare fix-ups and the carried-state outputs recompute what they need.
+// (re0, im0) = the carried partial window (lp_now) when i is window 0 of the stream, else 0.
+__device__ __noinline__ int2 lp_window_exact(const uint32_t *w32, int32_t off0, uint32_t i, uint32_t D, int32_t re0, int32_t im0) {
+    const int32_t base = off0 + (int32_t)(i * D);
+    int32_t re = re0, im = im0;
+    boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)D, re, im);
+    return make_int2(re, im);
+}
+
 // ================================================================================================
 // Fused kernel: one CTA per tile of EB audio outputs.
 // ================================================================================================
@@ -256,7 +266,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
 
     unsigned char *tile = smem;
     int2 *lp = reinterpret_cast<int2 *>(smem + a.tile_cap);
-    int16_t *dm = reinterpret_cast<int16_t *>(smem + a.tile_cap + (size_t)a.lp_cap * 8);
+    int16_t *dm = reinterpret_cast<int16_t *>(smem + a.dm_off);
     uint8_t *flag = smem + a.tile_cap + (((size_t)a.lp_cap * 10 + 15) & ~size_t(15));   // 16-byte aligned
 
     const int tid = threadIdx.x;
@@ -314,57 +324,154 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     const uint32_t skip = (uint32_t)(jlo - wlo);      // 1 if element 0 is only the predecessor of demod jlo
     const uint32_t D = a.D, fast = a.fast, slow = a.slow;
 
-    // ---- first-of-call flags (while the bulk copy is in flight) --------------------------------
-    {
-        uint32_t *f32 = reinterpret_cast<uint32_t *>(flag);
-        for (uint32_t i = tid; i < (nlp + 3) / 4; i += blockDim.x) f32[i] = 0;
-    }
-    __syncthreads();
-    {
-        const unsigned long long c_hi = sh_chi;
-        for (unsigned long long c = sh_clo + tid; c <= c_hi; c += blockDim.x) {
-            unsigned long long w = udiv64(c * a.S + a.p0, a.d64_D);
-            if (w >= jlo && w < jhi) flag[w - wlo] = 1;
+    int2 lastlp = make_int2(st.demod_pre_re, st.demod_pre_im);   // lp[nlp-1] for the carried state (last tile)
+    if constexpr (DT == 6) {
+        // ---- D = 6 (optimal_settings :189-190): boxcar + discriminator fused, no window array ---------------
+        // Lane L of a warp owns window b + L; lanes 1..31 emit dm (their predecessor arrives by shuffle), lane 0
+        // is the predecessor only.  A window is 3 words (even start) or 4 half-masked words (odd start); the start
+        // parity is tile-uniform and the rotation phase alternates with the window index, whose parity is fixed
+        // per thread (the loop stride 31*8 is even) — so the dp4a coefficient words live in registers.
+        mbar_wait(&bar, parity);
+        const int32_t off0 = sh_off0;
+        const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
+        const int lane = tid & 31, warp = tid >> 5;
+        const int32_t i0 = (int32_t)skip - 1 + 31 * warp + lane;
+        const int32_t pos0 = off0 + 6 * i0;
+        const bool odd = off0 & 1;
+        const bool neg0 = (pos0 >> 1) & 1;
+        uint32_t cr[4], ci[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t m = odd ? (j == 0 ? 0xFFFF0000u : (j == 3 ? 0x0000FFFFu : 0xFFFFFFFFu)) : (j == 3 ? 0u : 0xFFFFFFFFu);
+            const bool sn = neg0 != (bool)(j & 1);
+            cr[j] = (sn ? 0x010000FFu : 0xFF000001u) & m;
+            ci[j] = (sn ? 0x00FFFF00u : 0x00010100u) & m;
         }
-    }
-
-    // ---- phase 1: rotate_90 + centre + boxcar over D samples ------------------------------------
-    mbar_wait(&bar, parity);
-    const int32_t off0 = sh_off0;
-    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
-    for (uint32_t i = tid; i < nlp; i += blockDim.x) {
-        int32_t base = off0 + (int32_t)(i * D);
-        int32_t re = 0, im = 0;
-        if (tile0 && i == 0) {
-            re = st.lp_now_re;
-            im = st.lp_now_im;
+        constexpr unsigned long long PK_RE = ((unsigned long long)(uint16_t)BoxK<6>::re(0)) | ((unsigned long long)(uint16_t)BoxK<6>::re(1) << 16) |
+                                             ((unsigned long long)(uint16_t)BoxK<6>::re(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::re(3) << 48);
+        constexpr unsigned long long PK_IM = ((unsigned long long)(uint16_t)BoxK<6>::im(0)) | ((unsigned long long)(uint16_t)BoxK<6>::im(1) << 16) |
+                                             ((unsigned long long)(uint16_t)BoxK<6>::im(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::im(3) << 48);
+        const int32_t kr = (int32_t)(int16_t)(PK_RE >> ((pos0 & 3) * 16)), ki = (int32_t)(int16_t)(PK_IM >> ((pos0 & 3) * 16));
+        const int32_t last_i = (int32_t)nlp - 1;
+        for (int32_t b = (int32_t)skip - 1 + 31 * warp; b < last_i; b += 31 * 8) {
+            const int32_t i = b + lane;
+            // clamped lanes (window -1 of the first tile, windows past the tile) compute garbage nobody uses
+            int32_t pos = off0 + 6 * (i > last_i ? last_i : i);
+            pos = pos < 0 ? 0 : pos;
+            const uint32_t *w = w32 + (pos >> 1);
+            const uint32_t v0 = w[0], v1 = w[1], v2 = w[2];
+            int32_t re = dp4a_us(v0, cr[0], kr), im = dp4a_us(v0, ci[0], ki);
+            re = dp4a_us(v1, cr[1], re);
+            im = dp4a_us(v1, ci[1], im);
+            re = dp4a_us(v2, cr[2], re);
+            im = dp4a_us(v2, ci[2], im);
+            if (odd) {
+                const uint32_t v3 = w[3];
+                re = dp4a_us(v3, cr[3], re);
+                im = dp4a_us(v3, ci[3], im);
+            }
+            const int32_t pre = __shfl_up_sync(0xffffffffu, re, 1), pim = __shfl_up_sync(0xffffffffu, im, 1);
+            if (lane && i <= last_i) {
+                int32_t cre, cim;
+                d_cmul_conj(make_int2(re, im), make_int2(pre, pim), cre, cim);
+                dm[i] = (int16_t)(uint16_t)(uint32_t)d_fast_atan2(cim, cre);
+            }
         }
-        // base < 0 only for window 0 with p0 > 0: those samples are already in lp_now
-        if (DT > 0 && base >= 0)
-            boxcar_rot_fixed<(DT > 0 ? DT : 2)>(w32, base, re, im);
-        else
-            boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)D, re, im);
-        lp[i] = make_int2(re, im);
-    }
-    if (last && tid == 255) {
-        int32_t re = 0, im = 0;
-        boxcar_rot(w32, (int)sh_tail_from, (int)(sh_tail_from + sh_ntail), re, im);
-        a.st_out->lp_now_re = re;
-        a.st_out->lp_now_im = im;
-    }
-    __syncthreads();
+        if (last && tid == 255) {
+            int32_t re = 0, im = 0;
+            boxcar_rot(w32, (int)sh_tail_from, (int)(sh_tail_from + sh_ntail), re, im);
+            a.st_out->lp_now_re = re;
+            a.st_out->lp_now_im = im;
+        }
+        if (last && tid == 0 && nlp) {
+            const bool w0 = tile0 && nlp == 1;
+            lastlp = lp_window_exact(w32, off0, nlp - 1, D, w0 ? st.lp_now_re : 0, w0 ? st.lp_now_im : 0);
+        }
+        __syncthreads();
+        // ---- fix-ups (rare): dm[i] recomputed exactly for the first sample of each call (fm_demod :353-355 uses the
+        // f64 polar_discriminant there) and for the two samples that see the carried state on the first tile ----
+        const unsigned long long c_lo = sh_clo, c_hi = sh_chi;
+        if (tile0 || c_lo <= c_hi) {
+            const unsigned long long ncall = c_lo <= c_hi ? c_hi - c_lo + 1 : 0ull;
+            for (unsigned long long k = tid; k < ncall + (tile0 ? 2u : 0u); k += blockDim.x) {
+                uint32_t i;
+                if (k < ncall) {
+                    const unsigned long long w = udiv64((c_lo + k) * a.S + a.p0, a.d64_D);
+                    if (w < jlo || w >= jhi) continue;
+                    i = (uint32_t)(w - wlo);
+                } else {
+                    i = (uint32_t)(k - ncall);
+                    if (i >= nlp) continue;
+                }
+                const bool w0 = tile0 && i == 0, w1 = tile0 && i == 1;
+                const int2 cur = lp_window_exact(w32, off0, i, D, w0 ? st.lp_now_re : 0, w0 ? st.lp_now_im : 0);
+                const int2 prev = w0 ? make_int2(st.demod_pre_re, st.demod_pre_im)
+                                     : lp_window_exact(w32, off0, i - 1, D, w1 ? st.lp_now_re : 0, w1 ? st.lp_now_im : 0);
+                int32_t cre, cim;
+                d_cmul_conj(cur, prev, cre, cim);
+                // window w holds the first sample of call c iff w*D <= c*S + p0 < (w+1)*D for some c >= 0
+                const unsigned long long lo = (wlo + i) * D;
+                const unsigned long long c = lo > a.p0 ? udiv64(lo - a.p0 + a.S - 1, a.d64_S) : 0ull;
+                const bool first = c * a.S + a.p0 < lo + D;
+                dm[i] = (int16_t)(uint16_t)(uint32_t)(first ? d_polar_f64(cre, cim, a.oct) : d_fast_atan2(cim, cre));
+            }
+            __syncthreads();
+        }
+    } else {
+        // ---- first-of-call flags (while the bulk copy is in flight) --------------------------------
+        {
+            uint32_t *f32 = reinterpret_cast<uint32_t *>(flag);
+            for (uint32_t i = tid; i < (nlp + 3) / 4; i += blockDim.x) f32[i] = 0;
+        }
+        __syncthreads();
+        {
+            const unsigned long long c_hi = sh_chi;
+            for (unsigned long long c = sh_clo + tid; c <= c_hi; c += blockDim.x) {
+                unsigned long long w = udiv64(c * a.S + a.p0, a.d64_D);
+                if (w >= jlo && w < jhi) flag[w - wlo] = 1;
+            }
+        }
 
-    // ---- phase 2: polar discriminator --------------------------------------------------------------
-    for (uint32_t i = tid; i < nlp; i += blockDim.x) {
-        if (i < skip) continue;   // the predecessor-only element
-        int2 cur = lp[i];
-        int2 prev = (tile0 && i == 0) ? make_int2(st.demod_pre_re, st.demod_pre_im) : lp[i - 1];
-        int32_t cre, cim;
-        d_cmul_conj(cur, prev, cre, cim);
-        int32_t pcm = flag[i] ? d_polar_f64(cre, cim, a.oct) : d_fast_atan2(cim, cre);
-        dm[i] = (int16_t)(uint16_t)(uint32_t)pcm;
+        // ---- phase 1: rotate_90 + centre + boxcar over D samples ------------------------------------
+        mbar_wait(&bar, parity);
+        const int32_t off0 = sh_off0;
+        const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
+        for (uint32_t i = tid; i < nlp; i += blockDim.x) {
+            int32_t base = off0 + (int32_t)(i * D);
+            int32_t re = 0, im = 0;
+            if (tile0 && i == 0) {
+                re = st.lp_now_re;
+                im = st.lp_now_im;
+            }
+            // base < 0 only for window 0 with p0 > 0: those samples are already in lp_now
+            if (DT > 0 && base >= 0)
+                boxcar_rot_fixed<(DT > 0 ? DT : 2)>(w32, base, re, im);
+            else
+                boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)D, re, im);
+            lp[i] = make_int2(re, im);
+        }
+        if (last && tid == 255) {
+            int32_t re = 0, im = 0;
+            boxcar_rot(w32, (int)sh_tail_from, (int)(sh_tail_from + sh_ntail), re, im);
+            a.st_out->lp_now_re = re;
+            a.st_out->lp_now_im = im;
+        }
+        __syncthreads();
+
+        // ---- phase 2: polar discriminator --------------------------------------------------------------
+        for (uint32_t i = tid; i < nlp; i += blockDim.x) {
+            if (i < skip) continue;   // the predecessor-only element
+            int2 cur = lp[i];
+            int2 prev = (tile0 && i == 0) ? make_int2(st.demod_pre_re, st.demod_pre_im) : lp[i - 1];
+            int32_t cre, cim;
+            d_cmul_conj(cur, prev, cre, cim);
+            int32_t pcm = flag[i] ? d_polar_f64(cre, cim, a.oct) : d_fast_atan2(cim, cre);
+            dm[i] = (int16_t)(uint16_t)(uint32_t)pcm;
+        }
+        __syncthreads();
+
+        if (last && tid == 0 && nlp) lastlp = lp[nlp - 1];
     }
-    __syncthreads();
 
     // ---- phase 3: fractional boxcar resampler ------------------------------------------------------
     const uint32_t ne = sh_ne, rb = sh_rb;
@@ -385,7 +492,6 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
         int32_t sum = (a.Etot == 0) ? st.now_lpr : 0;
         for (uint32_t j = dbase + r0; j < nlp; j++) sum = wadd(sum, (int32_t)dm[j]);
         a.st_out->now_lpr = sum;
-        int2 lastlp = nlp ? lp[nlp - 1] : make_int2(st.demod_pre_re, st.demod_pre_im);
         a.st_out->demod_pre_re = lastlp.x;
         a.st_out->demod_pre_im = lastlp.y;
     }
@@ -626,7 +732,7 @@ struct sdr_demod {
     DevBuf d_in[2], d_out[2], d_state, d_a, d_b, d_c;
     PinBuf h_state;
     OctTable oct{};
-    uint32_t EB = 0, lp_cap = 0, tile_cap = 0;
+    uint32_t EB = 0, lp_cap = 0, tile_cap = 0, dm_off = 0;
     size_t smem_bytes = 0;
     bool pending = false;      // async *_dev submission whose state has not been committed yet
     int pending_slot = 0;
@@ -757,6 +863,7 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     a.EB = d->EB;
     a.lp_cap = d->lp_cap;
     a.tile_cap = d->tile_cap;
+    a.dm_off = d->dm_off;
     a.oct = d->oct;
     (void)n_calls;
     uint64_t blocks = pl.Etot ? (pl.Etot + d->EB - 1) / d->EB : 1;
@@ -807,14 +914,22 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     d->cfg = *cfg;
     d->device = cuda_device;
     fill_oct_table(d->oct);
-    // tile geometry: ~16 KB of raw bytes per CTA
+    // tile geometry.  Generic D: ~16 KB of raw bytes per CTA.  D = 6 (the fused boxcar+discriminator path): each of
+    // the 8 warps emits 31 demodulated samples per pass, so a tile is sized to just under 248 * passes of them.
     const uint64_t D = cfg->downsample, fast = cfg->rate_out, slow = cfg->rate_resample;
+    const bool d6 = D == 6;
     uint64_t n_lp_target = 8192 / D;
+    if (d6) {
+        const char *env = getenv("SDR_INT_PASSES");
+        int passes = env ? atoi(env) : 8;
+        if (passes < 1 || passes > 32) passes = 8;
+        n_lp_target = 248ull * passes - 2;
+    }
     if (n_lp_target < 4) n_lp_target = 4;
-    if (n_lp_target > 2048) n_lp_target = 2048;
+    if (n_lp_target > 8192) n_lp_target = 8192;
     uint64_t EB = n_lp_target * slow / fast;
     if (EB < 1) EB = 1;
-    if (EB > 1024) EB = 1024;
+    if (EB > 2048) EB = 2048;
     // the kernel's relative index math and its magic division need (EB+1)*fast + slow < 2^31
     while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 31)) EB /= 2;
     if ((EB + 1) * fast + slow >= (1ull << 31)) {
@@ -824,7 +939,10 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     uint64_t per = (fast + slow - 1) / slow;
     uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
     uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 64;
-    uint64_t smem = tile_cap + ((lp_cap * 10 + 15) & ~15ull) + ((lp_cap + 19) & ~15ull) + 16;
+    // shared memory: raw tile | [generic D: lowpassed windows (int2)] | demodulated samples (i16) | [generic D: flags]
+    uint64_t dm_off = d6 ? tile_cap : tile_cap + lp_cap * 8;
+    uint64_t smem = d6 ? tile_cap + ((lp_cap * 2 + 15) & ~15ull) + 16
+                       : tile_cap + ((lp_cap * 10 + 15) & ~15ull) + ((lp_cap + 19) & ~15ull) + 16;
     if (smem > 200 * 1024) {
         delete d;
         return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
@@ -832,6 +950,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     d->EB = (uint32_t)EB;
     d->lp_cap = (uint32_t)lp_cap;
     d->tile_cap = (uint32_t)tile_cap;
+    d->dm_off = (uint32_t)dm_off;
     d->smem_bytes = (size_t)smem;
     cudaError_t e = cudaFuncSetAttribute(k_demod_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1124,6 +1243,7 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     f.EB = d->EB;
     f.lp_cap = d->lp_cap;
     f.tile_cap = d->tile_cap;
+    f.dm_off = d->dm_off;
     f.oct = d->oct;
     a.ctl = r->d_ctl.as<RingCtl>();
     a.seq_done = r->h_seq_done_dev;
