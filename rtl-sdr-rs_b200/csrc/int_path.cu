@@ -70,19 +70,44 @@ __device__ __forceinline__ int32_t tdiv(int32_t a, int32_t b) {
 }
 
 // Demod::fast_atan2, examples/simple_fm.rs:383-405 — the i64 product is wrapped to i32 BEFORE the divide.
-__device__ __forceinline__ int32_t d_fast_atan2(int32_t y, int32_t x) {
+// Slow form: every corner the reference can reach (den == 0, wrapped |y|, INT32_MIN / -1) with the hardware-emulated
+// ~28-instruction integer division.
+__device__ __noinline__ int32_t d_fast_atan2_slow(int32_t y, int32_t x) {
     const int32_t pi4 = 1 << 12, pi34 = 3 * (1 << 12);
     if (x == 0 && y == 0) return 0;
-    int32_t yabs = y < 0 ? wsub(0, y) : y;
-    int32_t angle;
-    // (pi4 as i64 * v as i64) as i32 with pi4 = 2^12 is exactly the low 32 bits of v << 12.
-    // Both branches of :396-400 share ONE divide here (select operands first): a warp whose lanes see both
-    // signs of x would otherwise execute the ~28-instruction integer division twice.
+    const int32_t yabs = y < 0 ? wsub(0, y) : y;
     const bool xpos = x >= 0;
     const int32_t num = (int32_t)((uint32_t)(xpos ? wsub(x, yabs) : wadd(x, yabs)) << 12);
     const int32_t den = xpos ? wadd(x, yabs) : wsub(yabs, x);
-    angle = wsub(xpos ? pi4 : pi34, tdiv(num, den));
+    const int32_t angle = wsub(xpos ? pi4 : pi34, tdiv(num, den));
     return y < 0 ? wsub(0, angle) : angle;
+}
+
+// Both branches of :396-400 share ONE divide (operands selected first).  (pi4 as i64 * v as i64) as i32 with
+// pi4 = 2^12 is the low 32 bits of v << 12, so |num| = m * 4096 with m <= 2^19: EXACT in f32.  When 0 < den < 2^24
+// (den = |x| + |y| unwrapped, also exact in f32) the true quotient is below 2^21 — either den >= 2^10, or den < 2^10
+// and then |v| <= den means nothing wrapped and |q| <= 4096 — so q' = trunc(f32(|num|) * rcp(f32(den))) carries an
+// absolute error < 2^21 * 1.5 * 2^-23 < 1 and one exact integer remainder test repairs it.  Everything else
+// (den <= 0 covers x = y = 0, the wrapped INT32_MIN cases and |den| >= 2^24) takes the slow form.
+__device__ __forceinline__ int32_t d_fast_atan2(int32_t y, int32_t x) {
+    const int32_t pi4 = 1 << 12, pi34 = 3 * (1 << 12);
+    const int32_t yabs = y < 0 ? wsub(0, y) : y;
+    const bool xpos = x >= 0;
+    const int32_t num = (int32_t)((uint32_t)(xpos ? wsub(x, yabs) : wadd(x, yabs)) << 12);
+    const int32_t den = xpos ? wadd(x, yabs) : wsub(yabs, x);
+    if ((uint32_t)(den - 1) >= (1u << 24) - 1u) return d_fast_atan2_slow(y, x);
+    const uint32_t an = num < 0 ? 0u - (uint32_t)num : (uint32_t)num;
+    // |num| goes to f32 as fabs(f32(num)): converting the integer abs() would let ptxas pick a SIGNED conversion
+    // (I2FP.F32.S32 after IABS), which turns |INT32_MIN| = 2^31 into -2^31
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rn((uint32_t)den)));
+    uint32_t q = __float2uint_rz(fabsf(__int2float_rn(num)) * r);
+    const int32_t rem = (int32_t)(an - q * (uint32_t)den);
+    if (rem < 0) q--;
+    else if (rem >= den) q++;
+    const int32_t quo = num < 0 ? (int32_t)(0u - q) : (int32_t)q;
+    const int32_t angle = (xpos ? pi4 : pi34) - quo;
+    return y < 0 ? -angle : angle;
 }
 
 // a * b.conj() for Complex<i32>, wrapping (examples/simple_fm.rs:371,378)
@@ -481,7 +506,13 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
         uint32_t r0 = t ? udiv(t * fast - rb + slow - 1, a.div_slow) : 0u;
         uint32_t r1 = udiv((t + 1) * fast - rb + slow - 1, a.div_slow);
         int32_t sum = (e0zero && t == 0) ? st.now_lpr : 0;
-        for (uint32_t j = r0; j < r1; j++) sum = wadd(sum, (int32_t)dm[dbase + j]);
+        // r1 - r0 is floor or ceil of fast/slow: eight predicated loads cover the common ratios without a loop
+        const int16_t *dp = dm + dbase + r0;
+        const uint32_t cnt = r1 - r0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++)
+            if (j < cnt) sum = wadd(sum, (int32_t)dp[j]);
+        for (uint32_t j = 8; j < cnt; j++) sum = wadd(sum, (int32_t)dp[j]);
         // truncating sum / (fast/slow): |sum| < 2^31, divide the magnitude with the magic, restore the sign
         const uint32_t mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
         const uint32_t qm = mag >> 31 ? (uint32_t)((int64_t)mag / a.div) : udiv(mag, a.div_audio);
@@ -921,8 +952,8 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     uint64_t n_lp_target = 8192 / D;
     if (d6) {
         const char *env = getenv("SDR_INT_PASSES");
-        int passes = env ? atoi(env) : 8;
-        if (passes < 1 || passes > 32) passes = 8;
+        int passes = env ? atoi(env) : 12;
+        if (passes < 1 || passes > 32) passes = 12;
         n_lp_target = 248ull * passes - 2;
     }
     if (n_lp_target < 4) n_lp_target = 4;

@@ -96,19 +96,57 @@ def test_rotate_90_and_buf_to_complex(S):
     assert e.value.code == -2
 
 
+def np_fast_atan2(y, x):
+    """Vectorised restatement of oracle/sdr_oracle.c orc_fast_atan2 (checked against it below)."""
+    def wrap(v):
+        return ((v + 2**31) % 2**32) - 2**31
+    y64, x64 = y.astype(np.int64), x.astype(np.int64)
+    yabs = np.where(y64 < 0, wrap(-y64), y64)
+    xpos = x64 >= 0
+    num = wrap(np.where(xpos, wrap(x64 - yabs), wrap(x64 + yabs)) * 4096)
+    den = np.where(xpos, wrap(x64 + yabs), wrap(yabs - x64))
+    q = np.zeros_like(num)
+    nz = den != 0
+    q[nz] = (np.abs(num[nz]) // np.abs(den[nz])) * np.sign(num[nz]) * np.sign(den[nz])
+    angle = wrap(np.where(xpos, 4096, 3 * 4096) - wrap(q))
+    res = np.where(y64 < 0, wrap(-angle), angle)
+    res[(x64 == 0) & (y64 == 0)] = 0
+    return res.astype(np.int32)
+
+
 def test_fast_atan2_and_polar_vs_oracle(S):
     rng = np.random.default_rng(2)
     d = S.Demod()
     n = 200_000
     # mix of magnitudes: small, the wrap region (|4096*(x-|y|)| >= 2^31) and full-range i32
-    y = np.concatenate([rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n),
-                        rng.integers(-2**31, 2**31, n), [0, 0, 5, -5, 1, -1, 7]]).astype(np.int32)
-    x = np.concatenate([rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n),
-                        rng.integers(-2**31, 2**31, n), [0, 3, 0, 0, 1, -1, -7]]).astype(np.int32)
+    ys = [rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n), rng.integers(-2**31, 2**31, n), [0, 0, 5, -5, 1, -1, 7]]
+    xs = [rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n), rng.integers(-2**31, 2**31, n), [0, 3, 0, 0, 1, -1, -7]]
+    # the divider's range boundaries: |x| + |y| at 1..3, 2^10, 2^19 (numerator wrap), 2^24 (f32-exact limit), 2^31
+    for den in (1, 2, 3, 5, 1023, 1024, 1025, 2**19 - 1, 2**19, 2**19 + 1, 2**20 + 7, 2**24 - 2, 2**24 - 1, 2**24, 2**24 + 1,
+                2**25 + 3, 2**31 - 1, 2**31):
+        ax = np.unique(np.concatenate([rng.integers(0, den + 1, 4000), [0, 1, den // 2, den - 1, den],
+                                       np.arange(min(den + 1, 600)), den - np.arange(min(den + 1, 600))])).astype(np.int64)
+        ay = den - ax
+        for sx in (1, -1):
+            for sy in (1, -1):
+                xs.append(np.clip(sx * ax, -2**31, 2**31 - 1))
+                ys.append(np.clip(sy * ay, -2**31, 2**31 - 1))
+    # exact multiples / off-by-one remainders around them (the reciprocal estimate's +-1 repair)
+    dd = rng.integers(1, 2**21, 100_000).astype(np.int64)
+    kk = rng.integers(0, 4097, 100_000).astype(np.int64)
+    vv = dd * kk // 4096 + rng.integers(-1, 2, 100_000)          # x - |y| ~ den * k / 4096
+    xx, yy = (dd + vv) // 2, (dd - vv) // 2
+    xs.append(xx)
+    ys.append(yy)
+    xs.append(-yy)
+    ys.append(-xx)
+    y = np.concatenate(ys).astype(np.int32)
+    x = np.concatenate(xs).astype(np.int32)
     got = d.fast_atan2(y, x)
     L = O.lib()
     want = np.array([L.orc_fast_atan2(int(a), int(b)) for a, b in zip(y[::37], x[::37])], np.int32)
-    assert np.array_equal(got[::37], want)
+    assert np.array_equal(np_fast_atan2(y[::37], x[::37]), want)     # pins the numpy restatement to the oracle
+    assert np.array_equal(got, np_fast_atan2(y, x))                  # every point
     a = rng.integers(-768, 769, (50_000, 2)).astype(np.int32)
     b = rng.integers(-768, 769, (50_000, 2)).astype(np.int32)
     a[:64], b[:64] = [[3, 3]] * 64, [[1, 0]] * 64          # exact-octant cases
