@@ -43,7 +43,7 @@ def main(tag):
                 if w in hdr:
                     i = hdr.index(w)
                     lines.append(f"{w:92s} {vals[i]:>18s} {units[i]}")
-            w = name.split("_")[0]
+            w = next((t for t in name.split("_") if t in DOMINANT), None)
             if w in DOMINANT and DOMINANT[w] in vals[hdr.index("Kernel Name")]:
                 def num(m):
                     i = hdr.index(m)
