@@ -85,30 +85,42 @@ __device__ __noinline__ int32_t d_fast_atan2_slow(int32_t y, int32_t x) {
 
 // Both branches of :396-400 share ONE divide (operands selected first).  (pi4 as i64 * v as i64) as i32 with
 // pi4 = 2^12 is the low 32 bits of v << 12, so |num| = m * 4096 with m <= 2^19: EXACT in f32.  When 0 < den < 2^24
-// (den = |x| + |y| unwrapped, also exact in f32) the true quotient is below 2^21 — either den >= 2^10, or den < 2^10
-// and then |v| <= den means nothing wrapped and |q| <= 4096 — so q' = trunc(f32(|num|) * rcp(f32(den))) carries an
-// absolute error < 2^21 * 1.5 * 2^-23 < 1 and one exact integer remainder test repairs it.  Everything else
-// (den <= 0 covers x = y = 0, the wrapped INT32_MIN cases and |den| >= 2^24) takes the slow form.
-__device__ __forceinline__ int32_t d_fast_atan2(int32_t y, int32_t x) {
+// (den = |x| + |y| unwrapped, also exact in f32) the true quotient Q is at most 2^21 — either den >= 2^10, or
+// den < 2^10 and then |v| <= den means nothing wrapped and Q <= 4096.  The estimate
+//     e = fma(f32|num|, rcp.approx(f32 den), -0.5)
+// carries an absolute error below 2^21 * (2^-23 [rcp] + 2^-24 [fma rounding]) = 0.375, so Q - 0.875 < e < Q - 0.125 and
+// trunc(e) (a negative e saturates to 0) is floor(Q) or floor(Q) - 1: ONE exact remainder test (`rem >= den`) repairs it.
+// BOUNDED = the caller guarantees |x| + |y| < 2^24 (true for every product of two D = 6 boxcar sums: <= 1536^2); then
+// den == 0 iff x == y == 0 (result 0, :384-386) and there is no out-of-line path at all.  Otherwise everything the
+// estimate does not cover (den <= 0: x = y = 0 and the wrapped INT32_MIN cases; |den| >= 2^24) takes the slow form.
+template <bool BOUNDED>
+__device__ __forceinline__ int32_t d_fast_atan2_t(int32_t y, int32_t x) {
     const int32_t pi4 = 1 << 12, pi34 = 3 * (1 << 12);
-    const int32_t yabs = y < 0 ? wsub(0, y) : y;
     const bool xpos = x >= 0;
-    const int32_t num = (int32_t)((uint32_t)(xpos ? wsub(x, yabs) : wadd(x, yabs)) << 12);
-    const int32_t den = xpos ? wadd(x, yabs) : wsub(yabs, x);
-    if ((uint32_t)(den - 1) >= (1u << 24) - 1u) return d_fast_atan2_slow(y, x);
+    int32_t num, den;
+    if (BOUNDED) {   // nothing wraps before the shift: x - |y| = |x| - |y| (x >= 0), x + |y| = -(|x| - |y|) (x < 0)
+        const int32_t ax = abs(x), ay = abs(y), m = ax - ay;
+        den = ax + ay;
+        num = (int32_t)((uint32_t)(xpos ? m : -m) << 12);
+    } else {
+        const int32_t yabs = y < 0 ? wsub(0, y) : y;
+        num = (int32_t)((uint32_t)(xpos ? wsub(x, yabs) : wadd(x, yabs)) << 12);
+        den = xpos ? wadd(x, yabs) : wsub(yabs, x);
+        if ((uint32_t)(den - 1) >= (1u << 24) - 1u) return d_fast_atan2_slow(y, x);
+    }
     const uint32_t an = num < 0 ? 0u - (uint32_t)num : (uint32_t)num;
     // |num| goes to f32 as fabs(f32(num)): converting the integer abs() would let ptxas pick a SIGNED conversion
     // (I2FP.F32.S32 after IABS), which turns |INT32_MIN| = 2^31 into -2^31
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rn((uint32_t)den)));
-    uint32_t q = __float2uint_rz(fabsf(__int2float_rn(num)) * r);
-    const int32_t rem = (int32_t)(an - q * (uint32_t)den);
-    if (rem < 0) q--;
-    else if (rem >= den) q++;
+    uint32_t q = __float2uint_rz(fmaf(fabsf(__int2float_rn(num)), r, -0.5f));
+    if ((q + 1u) * (uint32_t)den <= an) q++;   // (q+1)*den <= 2*an < 2^33 only when q+1 is the true quotient's successor: q*den <= an and den < 2^24, no wrap
     const int32_t quo = num < 0 ? (int32_t)(0u - q) : (int32_t)q;
     const int32_t angle = (xpos ? pi4 : pi34) - quo;
-    return y < 0 ? -angle : angle;
+    const int32_t res = y < 0 ? -angle : angle;
+    return (BOUNDED && den == 0) ? 0 : res;   // den == 0: rcp = inf, e = NaN -> q = 0, then repaired to 1; overridden here
 }
+__device__ __forceinline__ int32_t d_fast_atan2(int32_t y, int32_t x) { return d_fast_atan2_t<false>(y, x); }
 
 // a * b.conj() for Complex<i32>, wrapping (examples/simple_fm.rs:371,378)
 __device__ __forceinline__ void d_cmul_conj(int2 a, int2 b, int32_t &cre, int32_t &cim) {
@@ -274,22 +286,286 @@ __device__ __noinline__ int2 lp_window_exact(const uint32_t *w32, int32_t off0, 
     return make_int2(re, im);
 }
 
+// ---- D = 6, even window start (every stream whose calls hold a multiple of 4 samples, i.e. every length rotate_90
+// accepts): rotate_90 + centre + boxcar + discriminator in one register-resident pass -------------------------------
+// A lane owns FOUR consecutive windows = 48 raw bytes, fetched as 3-4 aligned LDS.128 (lane stride 48 B is
+// bank-conflict free per quarter warp).  `a0` = byte offset (16-B aligned, may be -16) of the chunk that holds the first
+// word of window 0; S = word shift of that word inside its chunk (tile-uniform -> template parameter, so every register
+// index, every dp4a coefficient and every window constant below is a compile-time literal).  Window 4g+j starts on a
+// phase-0 word iff ((S ^ j) & 1) == 0 (a window is 3 words and the phase alternates per word).  The predecessor of a
+// lane's first window is the neighbour's last (one shuffle pair per four samples); lane 0 recomputes it from the 3
+// words before its chunk.  The four results leave as one STS.64.  Groups past the tile and the predecessor of window 0
+// produce values nobody reads (dm[0] is either predecessor-only or repaired by the fix-up loop).
+template <int S, int NTH>
+__device__ __forceinline__ void d6_pass_even(const unsigned char *tile, const int32_t a0, const uint32_t ngroups, int16_t *dm) {
+    constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u;   // phase-0 word: re [+1,0,0,-1], im [0,+1,+1,0]
+    constexpr uint32_t CRE2 = 0x010000FFu, CIM2 = 0x00FFFF00u;   // phase-2 word: negated
+    const int lane = threadIdx.x & 31;
+    for (uint32_t gb = threadIdx.x & ~31u; gb < ngroups; gb += NTH) {
+        const uint32_t g = gb + lane;
+        const unsigned char *p = tile + a0 + 48 * (int32_t)(g < ngroups ? g : ngroups - 1);
+        uint32_t v[16];
+        {
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+            const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
+            v[0] = q0.x, v[1] = q0.y, v[2] = q0.z, v[3] = q0.w;
+            v[4] = q1.x, v[5] = q1.y, v[6] = q1.z, v[7] = q1.w;
+            v[8] = q2.x, v[9] = q2.y, v[10] = q2.z, v[11] = q2.w;
+            if (S > 0) {
+                const uint4 q3 = p4[3];
+                v[12] = q3.x, v[13] = q3.y, v[14] = q3.z, v[15] = q3.w;
+            }
+        }
+        int32_t re[4], im[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool neg = (S ^ j) & 1;
+            int32_t r = neg ? BoxK<6>::re(2) : BoxK<6>::re(0), i = neg ? BoxK<6>::im(2) : BoxK<6>::im(0);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const bool wn = neg != (bool)(k & 1);
+                r = dp4a_us(v[S + 3 * j + k], wn ? CRE2 : CRE0, r);
+                i = dp4a_us(v[S + 3 * j + k], wn ? CIM2 : CIM0, i);
+            }
+            re[j] = r;
+            im[j] = i;
+        }
+        int32_t pre = __shfl_up_sync(0xffffffffu, re[3], 1), pim = __shfl_up_sync(0xffffffffu, im[3], 1);
+        if (lane == 0 && g > 0) {   // window 4g-1: the three words before word S of this chunk
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(p) + (S - 3);
+            const bool neg = (S ^ 1) & 1;
+            pre = neg ? BoxK<6>::re(2) : BoxK<6>::re(0);
+            pim = neg ? BoxK<6>::im(2) : BoxK<6>::im(0);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const bool wn = neg != (bool)(k & 1);
+                pre = dp4a_us(w[k], wn ? CRE2 : CRE0, pre);
+                pim = dp4a_us(w[k], wn ? CIM2 : CIM0, pim);
+            }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int32_t cre, cim;
+            d_cmul_conj(make_int2(re[j], im[j]), j ? make_int2(re[j - 1], im[j - 1]) : make_int2(pre, pim), cre, cim);
+            o[j] = (uint32_t)d_fast_atan2_t<true>(cim, cre);
+        }
+        if (g < ngroups)
+            *reinterpret_cast<uint2 *>(dm + 4 * g) = make_uint2(__byte_perm(o[0], o[1], 0x5410), __byte_perm(o[2], o[3], 0x5410));
+    }
+}
+
 // ================================================================================================
-// Fused kernel: one CTA per tile of EB audio outputs.
+// Tile = EB consecutive audio outputs.  Shared pieces of the one-CTA-per-tile kernel and the persistent ring.
 // ================================================================================================
-// One tile of EB audio outputs.  `first_use`: this CTA has not initialised its mbarrier yet; `parity`: phase
-// of the mbarrier for this use (a persistent CTA flips it per tile).  Ends with a __syncthreads so the
-// shared-memory tile can be reused.
+struct TileInfo {   // geometry of one tile, derived by ONE thread with 64-bit math; everything after it is 32-bit
+    unsigned long long wlo, jlo, jhi, e0;   // first lowpassed window held, demod range [jlo, jhi), first audio output
+    unsigned long long clo, chi;            // calls whose first window can lie in [jlo, jhi)
+    unsigned long long b_lo;                // byte offset of the tile's raw bytes in the input (16-B aligned)
+    uint32_t bytes, ne, rb, nlp, tail_from, ntail;
+    int32_t off0;                           // sample offset of window wlo inside the tile (negative: starts inside lp_now)
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void tile_setup(const FusedArgs &a, const uint32_t tile_idx, const bool last, TileInfo &ti) {
+    const unsigned long long fast = a.fast, slow = a.slow;
+    unsigned long long e0 = (unsigned long long)tile_idx * a.EB;
+    unsigned long long e1 = e0 + a.EB < a.Etot ? e0 + a.EB : a.Etot;
+    if (e0 > a.Etot) e0 = a.Etot;
+    // J(e) = ceil(((e+1)*fast - q0)/slow), J(-1) = 0
+    unsigned long long jlo = e0 ? udiv64(e0 * fast - a.q0 + slow - 1, a.d64_slow) : 0ull;
+    unsigned long long jhi = last ? a.Ltot : (e1 ? udiv64(e1 * fast - a.q0 + slow - 1, a.d64_slow) : 0ull);
+    unsigned long long wlo = jlo ? jlo - 1 : 0ull;
+    // relative form: J(e0-1+u) = jlo + ceil((u*fast - rb)/slow) for u >= 1
+    uint32_t rb = e0 ? (uint32_t)(jlo * slow - (e0 * fast - a.q0)) : a.q0;
+    long long s_lo = (long long)(wlo * a.D) - (long long)a.p0;
+    if (s_lo < 0) s_lo = 0;
+    unsigned long long s_hi = last ? a.n_samples : jhi * a.D - a.p0;
+    unsigned long long b_lo = (2ull * (unsigned long long)s_lo) & ~15ull;
+    unsigned long long b_hi = (2ull * s_hi + 15ull) & ~15ull;
+    ti.wlo = wlo;
+    ti.jlo = jlo;
+    ti.jhi = jhi;
+    ti.e0 = e0;
+    ti.b_lo = b_lo;
+    ti.bytes = (uint32_t)(b_hi - b_lo);
+    ti.ne = (uint32_t)(e1 - e0);
+    ti.rb = rb;
+    ti.nlp = (uint32_t)(jhi - wlo);
+    ti.off0 = (int32_t)((long long)(wlo * a.D) - (long long)a.p0 - (long long)(b_lo >> 1));
+    // tail samples (after the last complete window) feed lp_now' — last tile only
+    ti.tail_from = (uint32_t)((a.Ltot * a.D - a.p0) - (b_lo >> 1));
+    ti.ntail = (uint32_t)(a.n_samples - (a.Ltot * a.D - a.p0));
+}
+// second half (not needed to start the copy): the calls whose first window can lie in [jlo, jhi)
+__device__ __forceinline__ void tile_setup_calls(const FusedArgs &a, TileInfo &ti) {
+    ti.clo = ti.jhi > ti.jlo ? udiv64((ti.jlo + 1) * a.D - a.p0 - 1, a.d64_S) : 1ull;
+    ti.chi = ti.jhi > ti.jlo ? udiv64(ti.jhi * a.D - a.p0 - 1, a.d64_S) : 0ull;
+}
+
+// D = 6 fix-ups (rare): dm[i] recomputed exactly for the first sample of each call (fm_demod :359 uses the f64
+// polar_discriminant there) and for the two samples that see the carried state on the first tile.
+__device__ __forceinline__ void d6_fixups(const FusedArgs &a, const IntState &st, const TileInfo &ti, const uint32_t *w32,
+                                          int16_t *dm, const uint32_t tid, const uint32_t nthreads) {
+    const unsigned long long c_lo = ti.clo, c_hi = ti.chi, wlo = ti.wlo, jlo = ti.jlo, jhi = ti.jhi;
+    const bool tile0 = wlo == 0;
+    const uint32_t D = a.D, nlp = ti.nlp;
+    const unsigned long long ncall = c_lo <= c_hi ? c_hi - c_lo + 1 : 0ull;
+    for (unsigned long long k = tid; k < ncall + (tile0 ? 2u : 0u); k += nthreads) {
+        uint32_t i;
+        if (k < ncall) {
+            const unsigned long long w = udiv64((c_lo + k) * a.S + a.p0, a.d64_D);
+            if (w < jlo || w >= jhi) continue;
+            i = (uint32_t)(w - wlo);
+        } else {
+            i = (uint32_t)(k - ncall);
+            if (i >= nlp) continue;
+        }
+        const bool w0 = tile0 && i == 0, w1 = tile0 && i == 1;
+        const int2 cur = lp_window_exact(w32, ti.off0, i, D, w0 ? st.lp_now_re : 0, w0 ? st.lp_now_im : 0);
+        const int2 prev = w0 ? make_int2(st.demod_pre_re, st.demod_pre_im)
+                             : lp_window_exact(w32, ti.off0, i - 1, D, w1 ? st.lp_now_re : 0, w1 ? st.lp_now_im : 0);
+        int32_t cre, cim;
+        d_cmul_conj(cur, prev, cre, cim);
+        // window w holds the first sample of call c iff w*D <= c*S + p0 < (w+1)*D for some c >= 0
+        const unsigned long long lo = (wlo + i) * D;
+        const unsigned long long c = lo > a.p0 ? udiv64(lo - a.p0 + a.S - 1, a.d64_S) : 0ull;
+        const bool first = c * a.S + a.p0 < lo + D;
+        dm[i] = (int16_t)(uint16_t)(uint32_t)(first ? d_polar_f64(cre, cim, a.oct) : d_fast_atan2(cim, cre));
+    }
+}
+
+// D = 6 main pass over one tile (rotate_90 + centre + boxcar + discriminator -> dm), any window-start parity.
+template <int NTH>
+__device__ __forceinline__ void d6_pass(const unsigned char *tile, const TileInfo &ti, int16_t *dm, const int tid) {
+    const int32_t off0 = ti.off0;
+    const uint32_t nlp = ti.nlp;
+    if (!(off0 & 1)) {
+        const int32_t byte0 = 2 * off0;   // first byte of window 0 (negative on a tile that starts inside it)
+        const int32_t a0 = byte0 & ~15;
+        const uint32_t ngroups = (nlp + 3) >> 2;
+        switch ((byte0 >> 2) & 3) {
+        case 0: d6_pass_even<0, NTH>(tile, a0, ngroups, dm); break;
+        case 1: d6_pass_even<1, NTH>(tile, a0, ngroups, dm); break;
+        case 2: d6_pass_even<2, NTH>(tile, a0, ngroups, dm); break;
+        default: d6_pass_even<3, NTH>(tile, a0, ngroups, dm); break;
+        }
+        return;
+    }
+    // odd window start (only reachable through sdr_demod_set_state with an odd prev_index): one window per lane,
+    // 4 half-masked words; lane L of a warp owns window b + L, lanes 1..31 emit dm (predecessor by shuffle), lane 0
+    // is the predecessor only.  The rotation phase alternates with the window index, whose parity is fixed per thread
+    // (the loop stride 31 * warps is even), so the dp4a coefficient words live in registers.
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
+    const uint32_t skip = (uint32_t)(ti.jlo - ti.wlo);
+    const int lane = tid & 31, warp = tid >> 5;
+    const int32_t i0 = (int32_t)skip - 1 + 31 * warp + lane;
+    const int32_t pos0 = off0 + 6 * i0;
+    const bool neg0 = (pos0 >> 1) & 1;
+    uint32_t cr[4], ci[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t m = j == 0 ? 0xFFFF0000u : (j == 3 ? 0x0000FFFFu : 0xFFFFFFFFu);
+        const bool sn = neg0 != (bool)(j & 1);
+        cr[j] = (sn ? 0x010000FFu : 0xFF000001u) & m;
+        ci[j] = (sn ? 0x00FFFF00u : 0x00010100u) & m;
+    }
+    constexpr unsigned long long PK_RE = ((unsigned long long)(uint16_t)BoxK<6>::re(0)) | ((unsigned long long)(uint16_t)BoxK<6>::re(1) << 16) |
+                                         ((unsigned long long)(uint16_t)BoxK<6>::re(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::re(3) << 48);
+    constexpr unsigned long long PK_IM = ((unsigned long long)(uint16_t)BoxK<6>::im(0)) | ((unsigned long long)(uint16_t)BoxK<6>::im(1) << 16) |
+                                         ((unsigned long long)(uint16_t)BoxK<6>::im(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::im(3) << 48);
+    const int32_t kr = (int32_t)(int16_t)(PK_RE >> ((pos0 & 3) * 16)), ki = (int32_t)(int16_t)(PK_IM >> ((pos0 & 3) * 16));
+    const int32_t last_i = (int32_t)nlp - 1;
+    for (int32_t b = (int32_t)skip - 1 + 31 * warp; b < last_i; b += 31 * (NTH / 32)) {
+        const int32_t i = b + lane;
+        // clamped lanes (window -1 of the first tile, windows past the tile) compute garbage nobody uses
+        int32_t pos = off0 + 6 * (i > last_i ? last_i : i);
+        pos = pos < 0 ? 0 : pos;
+        const uint32_t *w = w32 + (pos >> 1);
+        const uint32_t v0 = w[0], v1 = w[1], v2 = w[2], v3 = w[3];
+        int32_t re = dp4a_us(v0, cr[0], kr), im = dp4a_us(v0, ci[0], ki);
+        re = dp4a_us(v1, cr[1], re);
+        im = dp4a_us(v1, ci[1], im);
+        re = dp4a_us(v2, cr[2], re);
+        im = dp4a_us(v2, ci[2], im);
+        re = dp4a_us(v3, cr[3], re);
+        im = dp4a_us(v3, ci[3], im);
+        const int32_t pre = __shfl_up_sync(0xffffffffu, re, 1), pim = __shfl_up_sync(0xffffffffu, im, 1);
+        if (lane && i <= last_i) {
+            int32_t cre, cim;
+            d_cmul_conj(make_int2(re, im), make_int2(pre, pim), cre, cim);
+            dm[i] = (int16_t)(uint16_t)(uint32_t)d_fast_atan2(cim, cre);
+        }
+    }
+}
+
+// low_pass_real (:408-426) over one tile: audio output t of the tile sums dm[dbase + r(t) .. dbase + r(t+1)), with
+// r(t) = ceil((t*fast - rb)/slow) by magic division, and divides by fast/slow (truncating, :421).
+__device__ __forceinline__ void resample_tile(const FusedArgs &a, const IntState &st, const TileInfo &ti, const int16_t *dm,
+                                              const uint32_t tid, const uint32_t nthreads) {
+    const uint32_t ne = ti.ne, rb = ti.rb, fast = a.fast, slow = a.slow;
+    const uint32_t dbase = (uint32_t)(ti.jlo - ti.wlo);   // dm index of demod sample jlo
+    const bool e0zero = ti.e0 == 0;
+    int16_t *outp = a.out + ti.e0;
+    if (a.div == 5 && a.div_slow.shift != 0xffffffffu && rb < slow) {
+        // The reference's ratio (170k -> 32k, and any other with fast / slow == 5): every window holds 5 or 6 samples
+        // (rb < slow: no unusual carried prev_lpr_index in this tile), n / 5 == umulhi(n, 0xCCCCCCCD) >> 2 for every
+        // 32-bit n — straight-line code, no per-output branches.
+        const uint32_t mg = a.div_slow.magic, sh = a.div_slow.shift;
+        for (uint32_t t = tid; t < ne; t += nthreads) {
+            const uint32_t n0 = t * fast - rb + slow - 1;
+            const uint32_t r0 = t ? __umulhi(n0, mg) >> sh : 0u;
+            const uint32_t r1 = __umulhi(n0 + fast, mg) >> sh;
+            const int16_t *dp = dm + dbase + r0;
+            int32_t sum = (int32_t)dp[0] + (int32_t)dp[1] + (int32_t)dp[2] + (int32_t)dp[3] + (int32_t)dp[4];
+            if (r1 - r0 == 6u) sum += (int32_t)dp[5];
+            if (e0zero && t == 0) sum = wadd(sum, st.now_lpr);
+            const uint32_t mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
+            const uint32_t qm = __umulhi(mag, 0xCCCCCCCDu) >> 2;
+            outp[t] = (int16_t)(uint16_t)(sum < 0 ? (uint32_t)0 - qm : qm);
+        }
+        return;
+    }
+    for (uint32_t t = tid; t < ne; t += nthreads) {
+        const uint32_t r0 = t ? udiv(t * fast - rb + slow - 1, a.div_slow) : 0u;
+        const uint32_t r1 = udiv((t + 1) * fast - rb + slow - 1, a.div_slow);
+        int32_t sum = (e0zero && t == 0) ? st.now_lpr : 0;
+        const int16_t *dp = dm + dbase + r0;
+        const uint32_t cnt = r1 - r0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++)   // cnt is floor or ceil of fast/slow: eight predicated loads cover the common ratios
+            if (j < cnt) sum = wadd(sum, (int32_t)dp[j]);
+        for (uint32_t j = 8; j < cnt; j++) sum = wadd(sum, (int32_t)dp[j]);
+        // truncating sum / (fast/slow): divide the magnitude with the magic, restore the sign
+        const uint32_t mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
+        const uint32_t qm = mag >> 31 ? (uint32_t)((int64_t)mag / a.div) : udiv(mag, a.div_audio);
+        outp[t] = (int16_t)(uint16_t)(sum < 0 ? (uint32_t)0 - qm : qm);
+    }
+}
+
+// carried state after the last tile (one thread): now_lpr' = the demodulated samples after the last audio window,
+// demod_pre' = the last lowpassed sample
+__device__ __forceinline__ void tile_state_out(const FusedArgs &a, const IntState &st, const TileInfo &ti, const int16_t *dm,
+                                               const int2 lastlp) {
+    const uint32_t dbase = (uint32_t)(ti.jlo - ti.wlo);
+    const uint32_t r0 = ti.ne ? udiv(ti.ne * a.fast - ti.rb + a.slow - 1, a.div_slow) : 0u;
+    int32_t sum = (a.Etot == 0) ? st.now_lpr : 0;
+    for (uint32_t j = dbase + r0; j < ti.nlp; j++) sum = wadd(sum, (int32_t)dm[j]);
+    a.st_out->now_lpr = sum;
+    a.st_out->demod_pre_re = lastlp.x;
+    a.st_out->demod_pre_im = lastlp.y;
+}
+
+// One tile per call.  `first_use`: this CTA has not initialised its mbarrier yet; `parity`: phase of the mbarrier
+// for this use (a persistent CTA flips it per tile).  Ends with a __syncthreads so the shared-memory tile can be reused.
 template <int DT>
 __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t tile_idx, const uint32_t n_tiles,
                                            const uint32_t parity, const bool first_use) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned long long sh_wlo, sh_jlo, sh_jhi, sh_e0, sh_clo, sh_chi;
-    __shared__ uint32_t sh_ne, sh_rb, sh_nlp, sh_tail_from, sh_ntail;
-    __shared__ int32_t sh_off0;
+    __shared__ TileInfo sh_ti;
 
-    unsigned char *tile = smem;
+    unsigned char *tile = smem + (DT == 6 ? 16 : 0);   // D = 6: the aligned-chunk pass may read the 16 bytes before the tile
     int2 *lp = reinterpret_cast<int2 *>(smem + a.tile_cap);
     int16_t *dm = reinterpret_cast<int16_t *>(smem + a.dm_off);
     uint8_t *flag = smem + a.tile_cap + (((size_t)a.lp_cap * 10 + 15) & ~size_t(15));   // 16-byte aligned
@@ -303,143 +579,42 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
             mbar_init(&bar, 1);
             fence_barrier_init();
         }
-        const unsigned long long fast = a.fast, slow = a.slow;
-        unsigned long long e0 = (unsigned long long)tile_idx * a.EB;
-        unsigned long long e1 = e0 + a.EB < a.Etot ? e0 + a.EB : a.Etot;
-        if (e0 > a.Etot) e0 = a.Etot;
-        // J(e) = ceil(((e+1)*fast - q0)/slow), J(-1) = 0
-        unsigned long long jlo = e0 ? udiv64(e0 * fast - a.q0 + slow - 1, a.d64_slow) : 0ull;
-        unsigned long long jhi = last ? a.Ltot : (e1 ? udiv64(e1 * fast - a.q0 + slow - 1, a.d64_slow) : 0ull);
-        unsigned long long wlo = jlo ? jlo - 1 : 0ull;
-        // relative form: J(e0-1+u) = jlo + ceil((u*fast - rb)/slow) for u >= 1
-        uint32_t rb = e0 ? (uint32_t)(jlo * slow - (e0 * fast - a.q0)) : a.q0;
-        long long s_lo = (long long)(wlo * a.D) - (long long)a.p0;
-        if (s_lo < 0) s_lo = 0;
-        unsigned long long s_hi = last ? a.n_samples : jhi * a.D - a.p0;
-        unsigned long long b_lo = (2ull * (unsigned long long)s_lo) & ~15ull;
-        unsigned long long b_hi = (2ull * s_hi + 15ull) & ~15ull;
-        uint32_t bytes = (uint32_t)(b_hi - b_lo);
-        sh_wlo = wlo;
-        sh_jlo = jlo;
-        sh_jhi = jhi;
-        sh_e0 = e0;
-        sh_ne = (uint32_t)(e1 - e0);
-        sh_rb = rb;
-        sh_nlp = (uint32_t)(jhi - wlo);
-        sh_off0 = (int32_t)((long long)(wlo * a.D) - (long long)a.p0 - (long long)(b_lo >> 1));
-        // tail samples (after the last complete window) feed lp_now' — last CTA only
-        sh_tail_from = (uint32_t)((a.Ltot * a.D - a.p0) - (b_lo >> 1));
-        sh_ntail = (uint32_t)(a.n_samples - (a.Ltot * a.D - a.p0));
-        if (bytes) {
-            mbar_arrive_expect_tx(&bar, bytes);
-            bulk_g2s_stream(tile, a.in + b_lo, bytes, &bar);
+        tile_setup(a, tile_idx, last, sh_ti);
+        if (sh_ti.bytes) {
+            mbar_arrive_expect_tx(&bar, sh_ti.bytes);
+            bulk_g2s_stream(tile, a.in + sh_ti.b_lo, sh_ti.bytes, &bar);
         } else {
             mbar_arrive(&bar);
         }
-        // calls whose first window can lie in [jlo, jhi): computed while the copy is in flight
-        sh_clo = jhi > jlo ? udiv64((jlo + 1) * a.D - a.p0 - 1, a.d64_S) : 1ull;
-        sh_chi = jhi > jlo ? udiv64(jhi * a.D - a.p0 - 1, a.d64_S) : 0ull;
+        tile_setup_calls(a, sh_ti);   // while the copy is in flight
     }
     __syncthreads();
-    const unsigned long long wlo = sh_wlo, jlo = sh_jlo, jhi = sh_jhi;
-    const uint32_t nlp = sh_nlp;
-
-    // 32-bit forms of the per-element tests (the 64-bit bases are block-uniform)
+    const TileInfo &ti = sh_ti;
+    const unsigned long long wlo = ti.wlo, jlo = ti.jlo, jhi = ti.jhi;
+    const uint32_t nlp = ti.nlp;
     const bool tile0 = wlo == 0;                      // this tile holds lowpassed window 0 / demod 0
     const uint32_t skip = (uint32_t)(jlo - wlo);      // 1 if element 0 is only the predecessor of demod jlo
-    const uint32_t D = a.D, fast = a.fast, slow = a.slow;
+    const uint32_t D = a.D;
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
 
     int2 lastlp = make_int2(st.demod_pre_re, st.demod_pre_im);   // lp[nlp-1] for the carried state (last tile)
     if constexpr (DT == 6) {
         // ---- D = 6 (optimal_settings :189-190): boxcar + discriminator fused, no window array ---------------
-        // Lane L of a warp owns window b + L; lanes 1..31 emit dm (their predecessor arrives by shuffle), lane 0
-        // is the predecessor only.  A window is 3 words (even start) or 4 half-masked words (odd start); the start
-        // parity is tile-uniform and the rotation phase alternates with the window index, whose parity is fixed
-        // per thread (the loop stride 31*8 is even) — so the dp4a coefficient words live in registers.
         mbar_wait(&bar, parity);
-        const int32_t off0 = sh_off0;
-        const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
-        const int lane = tid & 31, warp = tid >> 5;
-        const int32_t i0 = (int32_t)skip - 1 + 31 * warp + lane;
-        const int32_t pos0 = off0 + 6 * i0;
-        const bool odd = off0 & 1;
-        const bool neg0 = (pos0 >> 1) & 1;
-        uint32_t cr[4], ci[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t m = odd ? (j == 0 ? 0xFFFF0000u : (j == 3 ? 0x0000FFFFu : 0xFFFFFFFFu)) : (j == 3 ? 0u : 0xFFFFFFFFu);
-            const bool sn = neg0 != (bool)(j & 1);
-            cr[j] = (sn ? 0x010000FFu : 0xFF000001u) & m;
-            ci[j] = (sn ? 0x00FFFF00u : 0x00010100u) & m;
-        }
-        constexpr unsigned long long PK_RE = ((unsigned long long)(uint16_t)BoxK<6>::re(0)) | ((unsigned long long)(uint16_t)BoxK<6>::re(1) << 16) |
-                                             ((unsigned long long)(uint16_t)BoxK<6>::re(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::re(3) << 48);
-        constexpr unsigned long long PK_IM = ((unsigned long long)(uint16_t)BoxK<6>::im(0)) | ((unsigned long long)(uint16_t)BoxK<6>::im(1) << 16) |
-                                             ((unsigned long long)(uint16_t)BoxK<6>::im(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::im(3) << 48);
-        const int32_t kr = (int32_t)(int16_t)(PK_RE >> ((pos0 & 3) * 16)), ki = (int32_t)(int16_t)(PK_IM >> ((pos0 & 3) * 16));
-        const int32_t last_i = (int32_t)nlp - 1;
-        for (int32_t b = (int32_t)skip - 1 + 31 * warp; b < last_i; b += 31 * 8) {
-            const int32_t i = b + lane;
-            // clamped lanes (window -1 of the first tile, windows past the tile) compute garbage nobody uses
-            int32_t pos = off0 + 6 * (i > last_i ? last_i : i);
-            pos = pos < 0 ? 0 : pos;
-            const uint32_t *w = w32 + (pos >> 1);
-            const uint32_t v0 = w[0], v1 = w[1], v2 = w[2];
-            int32_t re = dp4a_us(v0, cr[0], kr), im = dp4a_us(v0, ci[0], ki);
-            re = dp4a_us(v1, cr[1], re);
-            im = dp4a_us(v1, ci[1], im);
-            re = dp4a_us(v2, cr[2], re);
-            im = dp4a_us(v2, ci[2], im);
-            if (odd) {
-                const uint32_t v3 = w[3];
-                re = dp4a_us(v3, cr[3], re);
-                im = dp4a_us(v3, ci[3], im);
-            }
-            const int32_t pre = __shfl_up_sync(0xffffffffu, re, 1), pim = __shfl_up_sync(0xffffffffu, im, 1);
-            if (lane && i <= last_i) {
-                int32_t cre, cim;
-                d_cmul_conj(make_int2(re, im), make_int2(pre, pim), cre, cim);
-                dm[i] = (int16_t)(uint16_t)(uint32_t)d_fast_atan2(cim, cre);
-            }
-        }
+        d6_pass<256>(tile, ti, dm, tid);
         if (last && tid == 255) {
             int32_t re = 0, im = 0;
-            boxcar_rot(w32, (int)sh_tail_from, (int)(sh_tail_from + sh_ntail), re, im);
+            boxcar_rot(w32, (int)ti.tail_from, (int)(ti.tail_from + ti.ntail), re, im);
             a.st_out->lp_now_re = re;
             a.st_out->lp_now_im = im;
         }
         if (last && tid == 0 && nlp) {
             const bool w0 = tile0 && nlp == 1;
-            lastlp = lp_window_exact(w32, off0, nlp - 1, D, w0 ? st.lp_now_re : 0, w0 ? st.lp_now_im : 0);
+            lastlp = lp_window_exact(w32, ti.off0, nlp - 1, D, w0 ? st.lp_now_re : 0, w0 ? st.lp_now_im : 0);
         }
         __syncthreads();
-        // ---- fix-ups (rare): dm[i] recomputed exactly for the first sample of each call (fm_demod :353-355 uses the
-        // f64 polar_discriminant there) and for the two samples that see the carried state on the first tile ----
-        const unsigned long long c_lo = sh_clo, c_hi = sh_chi;
-        if (tile0 || c_lo <= c_hi) {
-            const unsigned long long ncall = c_lo <= c_hi ? c_hi - c_lo + 1 : 0ull;
-            for (unsigned long long k = tid; k < ncall + (tile0 ? 2u : 0u); k += blockDim.x) {
-                uint32_t i;
-                if (k < ncall) {
-                    const unsigned long long w = udiv64((c_lo + k) * a.S + a.p0, a.d64_D);
-                    if (w < jlo || w >= jhi) continue;
-                    i = (uint32_t)(w - wlo);
-                } else {
-                    i = (uint32_t)(k - ncall);
-                    if (i >= nlp) continue;
-                }
-                const bool w0 = tile0 && i == 0, w1 = tile0 && i == 1;
-                const int2 cur = lp_window_exact(w32, off0, i, D, w0 ? st.lp_now_re : 0, w0 ? st.lp_now_im : 0);
-                const int2 prev = w0 ? make_int2(st.demod_pre_re, st.demod_pre_im)
-                                     : lp_window_exact(w32, off0, i - 1, D, w1 ? st.lp_now_re : 0, w1 ? st.lp_now_im : 0);
-                int32_t cre, cim;
-                d_cmul_conj(cur, prev, cre, cim);
-                // window w holds the first sample of call c iff w*D <= c*S + p0 < (w+1)*D for some c >= 0
-                const unsigned long long lo = (wlo + i) * D;
-                const unsigned long long c = lo > a.p0 ? udiv64(lo - a.p0 + a.S - 1, a.d64_S) : 0ull;
-                const bool first = c * a.S + a.p0 < lo + D;
-                dm[i] = (int16_t)(uint16_t)(uint32_t)(first ? d_polar_f64(cre, cim, a.oct) : d_fast_atan2(cim, cre));
-            }
+        if (tile0 || ti.clo <= ti.chi) {
+            d6_fixups(a, st, ti, w32, dm, tid, blockDim.x);
             __syncthreads();
         }
     } else {
@@ -450,8 +625,8 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
         }
         __syncthreads();
         {
-            const unsigned long long c_hi = sh_chi;
-            for (unsigned long long c = sh_clo + tid; c <= c_hi; c += blockDim.x) {
+            const unsigned long long c_hi = ti.chi;
+            for (unsigned long long c = ti.clo + tid; c <= c_hi; c += blockDim.x) {
                 unsigned long long w = udiv64(c * a.S + a.p0, a.d64_D);
                 if (w >= jlo && w < jhi) flag[w - wlo] = 1;
             }
@@ -459,8 +634,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
 
         // ---- phase 1: rotate_90 + centre + boxcar over D samples ------------------------------------
         mbar_wait(&bar, parity);
-        const int32_t off0 = sh_off0;
-        const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
+        const int32_t off0 = ti.off0;
         for (uint32_t i = tid; i < nlp; i += blockDim.x) {
             int32_t base = off0 + (int32_t)(i * D);
             int32_t re = 0, im = 0;
@@ -477,7 +651,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
         }
         if (last && tid == 255) {
             int32_t re = 0, im = 0;
-            boxcar_rot(w32, (int)sh_tail_from, (int)(sh_tail_from + sh_ntail), re, im);
+            boxcar_rot(w32, (int)ti.tail_from, (int)(ti.tail_from + ti.ntail), re, im);
             a.st_out->lp_now_re = re;
             a.st_out->lp_now_im = im;
         }
@@ -499,33 +673,8 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     }
 
     // ---- phase 3: fractional boxcar resampler ------------------------------------------------------
-    const uint32_t ne = sh_ne, rb = sh_rb;
-    const uint32_t dbase = (uint32_t)(jlo - wlo);   // dm index of demod sample jlo
-    const bool e0zero = sh_e0 == 0;
-    for (uint32_t t = tid; t < ne; t += blockDim.x) {
-        uint32_t r0 = t ? udiv(t * fast - rb + slow - 1, a.div_slow) : 0u;
-        uint32_t r1 = udiv((t + 1) * fast - rb + slow - 1, a.div_slow);
-        int32_t sum = (e0zero && t == 0) ? st.now_lpr : 0;
-        // r1 - r0 is floor or ceil of fast/slow: eight predicated loads cover the common ratios without a loop
-        const int16_t *dp = dm + dbase + r0;
-        const uint32_t cnt = r1 - r0;
-#pragma unroll
-        for (uint32_t j = 0; j < 8; j++)
-            if (j < cnt) sum = wadd(sum, (int32_t)dp[j]);
-        for (uint32_t j = 8; j < cnt; j++) sum = wadd(sum, (int32_t)dp[j]);
-        // truncating sum / (fast/slow): |sum| < 2^31, divide the magnitude with the magic, restore the sign
-        const uint32_t mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
-        const uint32_t qm = mag >> 31 ? (uint32_t)((int64_t)mag / a.div) : udiv(mag, a.div_audio);
-        a.out[sh_e0 + t] = (int16_t)(uint16_t)(sum < 0 ? (uint32_t)0 - qm : qm);
-    }
-    if (last && tid == 0) {
-        uint32_t r0 = ne ? udiv(ne * a.fast - rb + a.slow - 1, a.div_slow) : 0u;
-        int32_t sum = (a.Etot == 0) ? st.now_lpr : 0;
-        for (uint32_t j = dbase + r0; j < nlp; j++) sum = wadd(sum, (int32_t)dm[j]);
-        a.st_out->now_lpr = sum;
-        a.st_out->demod_pre_re = lastlp.x;
-        a.st_out->demod_pre_im = lastlp.y;
-    }
+    resample_tile(a, st, ti, dm, tid, blockDim.x);
+    if (last && tid == 0) tile_state_out(a, st, ti, dm, lastlp);
     if (last) __threadfence();   // the state words are consumed by another CTA in ring mode
     __syncthreads();   // the shared-memory tile (and the mbarrier phase) may now be reused
 }
@@ -735,7 +884,11 @@ __global__ void k_low_pass_real(const int16_t *in, unsigned long long n, uint32_
 __global__ void k_fast_atan2_v(const int32_t *y, const int32_t *x, size_t n, int32_t *out) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = d_fast_atan2(y[i], x[i]);
+    {
+        // the BOUNDED form (used by the D = 6 pass) is exercised on its whole domain, the general one elsewhere
+        const int64_t mag = llabs((long long)y[i]) + llabs((long long)x[i]);
+        out[i] = mag < (1ll << 24) ? d_fast_atan2_t<true>(y[i], x[i]) : d_fast_atan2(y[i], x[i]);
+    }
 }
 
 __global__ void k_polar_v(const int2 *a, const int2 *b, size_t n, int fast, OctTable oct, int32_t *out) {
@@ -952,15 +1105,16 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     uint64_t n_lp_target = 8192 / D;
     if (d6) {
         const char *env = getenv("SDR_INT_PASSES");
-        int passes = env ? atoi(env) : 12;
-        if (passes < 1 || passes > 32) passes = 12;
-        n_lp_target = 248ull * passes - 2;
+        int passes = env ? atoi(env) : 3;
+        if (passes < 1 || passes > 8) passes = 3;
+        n_lp_target = 1024ull * passes - 2;   // 256 lanes x 4 windows per pass
     }
     if (n_lp_target < 4) n_lp_target = 4;
     if (n_lp_target > 8192) n_lp_target = 8192;
     uint64_t EB = n_lp_target * slow / fast;
     if (EB < 1) EB = 1;
     if (EB > 2048) EB = 2048;
+    if (EB >= 8) EB &= ~3ull;   // tiles start on 8-byte boundaries of the i16 output (vector stores)
     // the kernel's relative index math and its magic division need (EB+1)*fast + slow < 2^31
     while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 31)) EB /= 2;
     if ((EB + 1) * fast + slow >= (1ull << 31)) {
@@ -969,11 +1123,12 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     }
     uint64_t per = (fast + slow - 1) / slow;
     uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
-    uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 64;
+    uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 96;   // slack: 16-B pad in front (D = 6), bulk-copy rounding, chunk over-read
     // shared memory: raw tile | [generic D: lowpassed windows (int2)] | demodulated samples (i16) | [generic D: flags]
     uint64_t dm_off = d6 ? tile_cap : tile_cap + lp_cap * 8;
-    uint64_t smem = d6 ? tile_cap + ((lp_cap * 2 + 15) & ~15ull) + 16
-                       : tile_cap + ((lp_cap * 10 + 15) & ~15ull) + ((lp_cap + 19) & ~15ull) + 16;
+    // + 80: the resampler's four-outputs-per-thread form may read (and drop) up to 3 windows past the last demodulated sample
+    uint64_t smem = d6 ? tile_cap + ((lp_cap * 2 + 15) & ~15ull) + 80
+                       : tile_cap + ((lp_cap * 10 + 15) & ~15ull) + ((lp_cap + 19) & ~15ull) + 80;
     if (smem > 200 * 1024) {
         delete d;
         return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
