@@ -242,6 +242,50 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def per_buffer_bench(S, device: int, buf_len: int, n_bufs: int = 400) -> dict:
+    """Latency/throughput of the drop-in call pattern: one `buf_len`-byte host buffer per call."""
+    src = S.Source.open_synth(SEED + 77)
+    bufs = np.empty((8, buf_len), np.uint8)
+    for b in bufs:
+        assert src.read_sync(b) == buf_len
+    src.close()
+    d = S.Demod(device=device)
+    for i in range(20):
+        d.demodulate(bufs[i % 8])
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(n_bufs):
+        t1 = time.perf_counter()
+        d.demodulate(bufs[i % 8])
+        lat.append(time.perf_counter() - t1)
+    sync_s = time.perf_counter() - t0
+    lat.sort()
+    out = {"buf_len": buf_len, "calls": n_bufs,
+           "sync_call": {"api": "sdr_demod_demodulate", "us_per_call_median": round(lat[len(lat) // 2] * 1e6, 1),
+                         "us_per_call_p99": round(lat[int(len(lat) * 0.99)] * 1e6, 1),
+                         "msamples_per_s": round(n_bufs * (buf_len // 2) / sync_s / 1e6, 1)}}
+    d.close()
+    # ring: producer keeps up to n_slots - 1 buffers in flight, consumer collects in order
+    d = S.Demod(device=device)
+    slots = 8
+    ring = S.Ring(d, buf_len, slots)
+    for i in range(slots - 1):
+        ring.submit(bufs[i % 8])
+    t0 = time.perf_counter()
+    for i in range(n_bufs):
+        ring.collect()
+        ring.submit(bufs[i % 8])
+    ring_s = time.perf_counter() - t0
+    for i in range(slots - 1):
+        ring.collect()
+    ring.close()
+    d.close()
+    out["ring"] = {"api": "sdr_ring_acquire/commit/collect", "slots": slots,
+                   "us_per_buffer": round(ring_s / n_bufs * 1e6, 1),
+                   "msamples_per_s": round(n_bufs * (buf_len // 2) / ring_s / 1e6, 1)}
+    return out
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -471,6 +515,12 @@ def main():
                "api": "sdr_demod_demodulate_batch" if w["name"] == "cfg1" else "sdr_fmrx_process",
                "note": "pinned host input -> chunked H2D overlapped with the kernels -> D2H of the audio, per step"}
 
+    # ---- the reference's own call pattern (examples/simple_fm.rs:80,153): ONE 262144-byte buffer per demodulate() call,
+    # host buffers in and out, (a) one synchronous call per buffer, (b) the persistent ring (no launch per buffer)
+    per_buffer = None
+    if w["name"] == "cfg1" and not args.no_e2e and rank == 0:
+        per_buffer = per_buffer_bench(S, device, w["buf_len"])
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -503,6 +553,8 @@ def main():
         "e2e": e2e,
         "gpu_launches": int(launches),
     }
+    if per_buffer is not None:
+        line["per_buffer"] = per_buffer
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w)
     print(json.dumps(line))

@@ -296,7 +296,7 @@ __device__ __noinline__ int2 lp_window_exact(const uint32_t *w32, int32_t off0, 
 // lane's first window is the neighbour's last (one shuffle pair per four samples); lane 0 recomputes it from the 3
 // words before its chunk.  The four results leave as one STS.64.  Groups past the tile and the predecessor of window 0
 // produce values nobody reads (dm[0] is either predecessor-only or repaired by the fix-up loop).
-template <int S, int NTH>
+template <int S, int NTH, bool GLOBAL>
 __device__ __forceinline__ void d6_pass_even(const unsigned char *tile, const int32_t a0, const uint32_t ngroups, int16_t *dm) {
     constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u;   // phase-0 word: re [+1,0,0,-1], im [0,+1,+1,0]
     constexpr uint32_t CRE2 = 0x010000FFu, CIM2 = 0x00FFFF00u;   // phase-2 word: negated
@@ -306,13 +306,15 @@ __device__ __forceinline__ void d6_pass_even(const unsigned char *tile, const in
         const unsigned char *p = tile + a0 + 48 * (int32_t)(g < ngroups ? g : ngroups - 1);
         uint32_t v[16];
         {
+            // GLOBAL: the chunks come straight from the input buffer (read-only path; the two lanes that share a
+            // 32-byte sector meet in L1), otherwise from the shared-memory tile
             const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
-            const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
+            const uint4 q0 = GLOBAL ? __ldg(p4) : p4[0], q1 = GLOBAL ? __ldg(p4 + 1) : p4[1], q2 = GLOBAL ? __ldg(p4 + 2) : p4[2];
             v[0] = q0.x, v[1] = q0.y, v[2] = q0.z, v[3] = q0.w;
             v[4] = q1.x, v[5] = q1.y, v[6] = q1.z, v[7] = q1.w;
             v[8] = q2.x, v[9] = q2.y, v[10] = q2.z, v[11] = q2.w;
             if (S > 0) {
-                const uint4 q3 = p4[3];
+                const uint4 q3 = GLOBAL ? __ldg(p4 + 3) : p4[3];
                 v[12] = q3.x, v[13] = q3.y, v[14] = q3.z, v[15] = q3.w;
             }
         }
@@ -436,7 +438,7 @@ __device__ __forceinline__ void d6_fixups(const FusedArgs &a, const IntState &st
 }
 
 // D = 6 main pass over one tile (rotate_90 + centre + boxcar + discriminator -> dm), any window-start parity.
-template <int NTH>
+template <int NTH, bool GLOBAL>
 __device__ __forceinline__ void d6_pass(const unsigned char *tile, const TileInfo &ti, int16_t *dm, const int tid) {
     const int32_t off0 = ti.off0;
     const uint32_t nlp = ti.nlp;
@@ -445,10 +447,10 @@ __device__ __forceinline__ void d6_pass(const unsigned char *tile, const TileInf
         const int32_t a0 = byte0 & ~15;
         const uint32_t ngroups = (nlp + 3) >> 2;
         switch ((byte0 >> 2) & 3) {
-        case 0: d6_pass_even<0, NTH>(tile, a0, ngroups, dm); break;
-        case 1: d6_pass_even<1, NTH>(tile, a0, ngroups, dm); break;
-        case 2: d6_pass_even<2, NTH>(tile, a0, ngroups, dm); break;
-        default: d6_pass_even<3, NTH>(tile, a0, ngroups, dm); break;
+        case 0: d6_pass_even<0, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
+        case 1: d6_pass_even<1, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
+        case 2: d6_pass_even<2, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
+        default: d6_pass_even<3, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
         }
         return;
     }
@@ -558,16 +560,21 @@ __device__ __forceinline__ void tile_state_out(const FusedArgs &a, const IntStat
 
 // One tile per call.  `first_use`: this CTA has not initialised its mbarrier yet; `parity`: phase of the mbarrier
 // for this use (a persistent CTA flips it per tile).  Ends with a __syncthreads so the shared-memory tile can be reused.
-template <int DT>
+// DIRECT (D = 6 batch kernel): no shared-memory tile at all — the pass reads its 16-byte chunks straight from the input
+// buffer, so a CTA costs only the 6 KB dm array, the SM holds as many CTAs as the register file allows and the HBM
+// latency is hidden by warps, not by a per-CTA copy-then-compute phase.  The ring keeps the staged form (its input slots
+// are written by the copy engine while the kernel is resident; the mbarrier orders those bytes).
+template <int DT, bool DIRECT = false>
 __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t tile_idx, const uint32_t n_tiles,
                                            const uint32_t parity, const bool first_use) {
+    static_assert(!DIRECT || DT == 6, "the direct form exists for D = 6 only");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ TileInfo sh_ti;
 
-    unsigned char *tile = smem + (DT == 6 ? 16 : 0);   // D = 6: the aligned-chunk pass may read the 16 bytes before the tile
+    unsigned char *tile_s = smem + (DT == 6 ? 16 : 0);   // D = 6: the aligned-chunk pass may read the 16 bytes before the tile
     int2 *lp = reinterpret_cast<int2 *>(smem + a.tile_cap);
-    int16_t *dm = reinterpret_cast<int16_t *>(smem + a.dm_off);
+    int16_t *dm = reinterpret_cast<int16_t *>(smem + (DIRECT ? 0 : a.dm_off));
     uint8_t *flag = smem + a.tile_cap + (((size_t)a.lp_cap * 10 + 15) & ~size_t(15));   // 16-byte aligned
 
     const int tid = threadIdx.x;
@@ -575,21 +582,24 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     const IntState st = *a.st_in;
 
     if (tid == 0) {
-        if (first_use) {
+        if (!DIRECT && first_use) {
             mbar_init(&bar, 1);
             fence_barrier_init();
         }
         tile_setup(a, tile_idx, last, sh_ti);
-        if (sh_ti.bytes) {
-            mbar_arrive_expect_tx(&bar, sh_ti.bytes);
-            bulk_g2s_stream(tile, a.in + sh_ti.b_lo, sh_ti.bytes, &bar);
-        } else {
-            mbar_arrive(&bar);
+        if (!DIRECT) {
+            if (sh_ti.bytes) {
+                mbar_arrive_expect_tx(&bar, sh_ti.bytes);
+                bulk_g2s_stream(tile_s, a.in + sh_ti.b_lo, sh_ti.bytes, &bar);
+            } else {
+                mbar_arrive(&bar);
+            }
         }
         tile_setup_calls(a, sh_ti);   // while the copy is in flight
     }
     __syncthreads();
     const TileInfo &ti = sh_ti;
+    const unsigned char *tile = DIRECT ? a.in + ti.b_lo : tile_s;
     const unsigned long long wlo = ti.wlo, jlo = ti.jlo, jhi = ti.jhi;
     const uint32_t nlp = ti.nlp;
     const bool tile0 = wlo == 0;                      // this tile holds lowpassed window 0 / demod 0
@@ -600,8 +610,8 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     int2 lastlp = make_int2(st.demod_pre_re, st.demod_pre_im);   // lp[nlp-1] for the carried state (last tile)
     if constexpr (DT == 6) {
         // ---- D = 6 (optimal_settings :189-190): boxcar + discriminator fused, no window array ---------------
-        mbar_wait(&bar, parity);
-        d6_pass<256>(tile, ti, dm, tid);
+        if (!DIRECT) mbar_wait(&bar, parity);
+        d6_pass<256, DIRECT>(tile, ti, dm, tid);
         if (last && tid == 255) {
             int32_t re = 0, im = 0;
             boxcar_rot(w32, (int)ti.tail_from, (int)(ti.tail_from + ti.ntail), re, im);
@@ -681,9 +691,18 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
 
 // One launch per batch of calls: one CTA per tile.
 // DT = compile-time downsample (0 = any): the reference's own setting, 6 (optimal_settings :189-190), is specialised.
+#ifndef SDR_INT_MINB
+#define SDR_INT_MINB 5
+#endif
 template <int DT>
-__global__ void __launch_bounds__(256) k_demod_fused(const FusedArgs a) {
+__global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedArgs a) {
     demod_tile<DT>(a, blockIdx.x, gridDim.x, 0, true);
+}
+#ifndef SDR_INT_MINB_DIRECT
+#define SDR_INT_MINB_DIRECT 8
+#endif
+__global__ void __launch_bounds__(256, SDR_INT_MINB_DIRECT) k_demod_d6_direct(const FusedArgs a) {
+    demod_tile<6, true>(a, blockIdx.x, gridDim.x, 0, true);
 }
 
 // ================================================================================================
@@ -907,6 +926,40 @@ using namespace sdr;
 // ================================================================================================
 // Host side
 // ================================================================================================
+// Tile geometry: EB audio outputs per tile and the shared-memory layout that follows from it.
+struct Geom {
+    uint32_t EB = 0, lp_cap = 0, tile_cap = 0, dm_off = 0;
+    size_t smem_staged = 0;   // raw tile | [generic D: lowpassed windows (int2)] | demodulated samples (i16) | [generic D: flags]
+    size_t smem_direct = 0;   // demodulated samples only (D = 6 direct kernel)
+};
+
+// n_lp_target = lowpassed windows per tile to aim for.  False: rate_out too large for the kernel's 32-bit relative math.
+static bool make_geom(uint64_t D, uint64_t fast, uint64_t slow, uint64_t n_lp_target, Geom &g) {
+    if (n_lp_target < 4) n_lp_target = 4;
+    if (n_lp_target > 8192) n_lp_target = 8192;
+    uint64_t EB = n_lp_target * slow / fast;
+    if (EB < 1) EB = 1;
+    if (EB > 4096) EB = 4096;
+    if (EB >= 8) EB &= ~3ull;   // tiles start on 8-byte boundaries of the i16 output
+    // the kernel's relative index math and its magic division need (EB+1)*fast + slow < 2^31
+    while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 31)) EB /= 2;
+    if ((EB + 1) * fast + slow >= (1ull << 31)) return false;
+    const bool d6 = D == 6;
+    const uint64_t per = (fast + slow - 1) / slow;
+    const uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
+    // slack: 16-B pad in front (D = 6), bulk-copy rounding, chunk over-read
+    const uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 96;
+    g.EB = (uint32_t)EB;
+    g.lp_cap = (uint32_t)lp_cap;
+    g.tile_cap = (uint32_t)tile_cap;
+    g.dm_off = (uint32_t)(d6 ? tile_cap : tile_cap + lp_cap * 8);
+    // + 80: slack after the demodulated samples (whole-group stores of the D = 6 pass)
+    g.smem_staged = (size_t)(d6 ? tile_cap + ((lp_cap * 2 + 15) & ~15ull) + 80
+                                : tile_cap + ((lp_cap * 10 + 15) & ~15ull) + ((lp_cap + 19) & ~15ull) + 80);
+    g.smem_direct = (size_t)(((lp_cap * 2 + 15) & ~15ull) + 80);
+    return true;
+}
+
 struct sdr_demod {
     sdr_demod_config cfg{};
     int device = 0;
@@ -916,7 +969,9 @@ struct sdr_demod {
     DevBuf d_in[2], d_out[2], d_state, d_a, d_b, d_c;
     PinBuf h_state;
     OctTable oct{};
-    uint32_t EB = 0, lp_cap = 0, tile_cap = 0, dm_off = 0;
+    Geom geo;                // staged-tile geometry (generic D, the ring, odd window starts)
+    Geom geo_direct[4];      // D = 6 direct kernel: tiles of 1, 2, 4, 8 passes (1024 windows each); the launch picks by batch size
+    int n_direct = 0;        // 0: direct kernel disabled (SDR_INT_DIRECT=0 or D != 6)
     size_t smem_bytes = 0;
     bool pending = false;      // async *_dev submission whose state has not been committed yet
     int pending_slot = 0;
@@ -1044,15 +1099,34 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     a.d64_slow = magic64(d->cfg.rate_resample);
     a.d64_S = magic64(S);
     a.d64_D = magic64(d->cfg.downsample);
-    a.EB = d->EB;
-    a.lp_cap = d->lp_cap;
-    a.tile_cap = d->tile_cap;
-    a.dm_off = d->dm_off;
     a.oct = d->oct;
     (void)n_calls;
-    uint64_t blocks = pl.Etot ? (pl.Etot + d->EB - 1) / d->EB : 1;
+    // D = 6 with an even window start (every stream that was not given an odd prev_index by hand): direct kernel, with
+    // the largest tile that still leaves `kDirectWaves` full waves of 8 CTAs per SM (SDR_INT_DIRECT_PASSES pins it)
+    const Geom *g = &d->geo;
+    const bool direct = d->n_direct > 0 && !(p0 & 1);
+    if (direct) {
+        constexpr uint64_t kDirectWaves = 4;
+        int k = d->n_direct - 1;
+        const char *ep = getenv("SDR_INT_DIRECT_PASSES");
+        if (ep) {
+            const int want = atoi(ep);
+            k = want >= 8 ? 3 : want >= 4 ? 2 : want >= 2 ? 1 : 0;
+            if (k > d->n_direct - 1) k = d->n_direct - 1;
+        } else {
+            while (k > 0 && pl.Etot / d->geo_direct[k].EB < kDirectWaves * 8 * (uint64_t)sm_count(d->device)) k--;
+        }
+        g = &d->geo_direct[k];
+    }
+    a.EB = g->EB;
+    a.lp_cap = g->lp_cap;
+    a.tile_cap = g->tile_cap;
+    a.dm_off = g->dm_off;
+    uint64_t blocks = pl.Etot ? (pl.Etot + g->EB - 1) / g->EB : 1;
     if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "batch too large for one launch");
-    if (d->cfg.downsample == 6)
+    if (direct)
+        k_demod_d6_direct<<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a);
+    else if (d->cfg.downsample == 6)
         k_demod_fused<6><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
     else
         k_demod_fused<0><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
@@ -1098,8 +1172,10 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     d->cfg = *cfg;
     d->device = cuda_device;
     fill_oct_table(d->oct);
-    // tile geometry.  Generic D: ~16 KB of raw bytes per CTA.  D = 6 (the fused boxcar+discriminator path): each of
-    // the 8 warps emits 31 demodulated samples per pass, so a tile is sized to just under 248 * passes of them.
+    // tile geometry.  Generic D: ~16 KB of raw bytes per CTA.  D = 6: 256 lanes x 4 windows per pass; the staged form
+    // (ring, odd window starts) uses SDR_INT_PASSES passes per tile (3: five CTAs per SM), the direct batch kernel picks
+    // 1, 2, 4 or 8 passes per tile at launch time from the batch size (large tiles amortise the per-tile code, small
+    // ones keep a single 262144-byte call spread over many SMs).
     const uint64_t D = cfg->downsample, fast = cfg->rate_out, slow = cfg->rate_resample;
     const bool d6 = D == 6;
     uint64_t n_lp_target = 8192 / D;
@@ -1107,37 +1183,26 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
         const char *env = getenv("SDR_INT_PASSES");
         int passes = env ? atoi(env) : 3;
         if (passes < 1 || passes > 8) passes = 3;
-        n_lp_target = 1024ull * passes - 2;   // 256 lanes x 4 windows per pass
+        n_lp_target = 1024ull * passes - 2;
     }
-    if (n_lp_target < 4) n_lp_target = 4;
-    if (n_lp_target > 8192) n_lp_target = 8192;
-    uint64_t EB = n_lp_target * slow / fast;
-    if (EB < 1) EB = 1;
-    if (EB > 2048) EB = 2048;
-    if (EB >= 8) EB &= ~3ull;   // tiles start on 8-byte boundaries of the i16 output (vector stores)
-    // the kernel's relative index math and its magic division need (EB+1)*fast + slow < 2^31
-    while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 31)) EB /= 2;
-    if ((EB + 1) * fast + slow >= (1ull << 31)) {
+    if (!make_geom(D, fast, slow, n_lp_target, d->geo)) {
         delete d;
         return fail(SDR_E_ARG, "rate_out too large");
     }
-    uint64_t per = (fast + slow - 1) / slow;
-    uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
-    uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 96;   // slack: 16-B pad in front (D = 6), bulk-copy rounding, chunk over-read
-    // shared memory: raw tile | [generic D: lowpassed windows (int2)] | demodulated samples (i16) | [generic D: flags]
-    uint64_t dm_off = d6 ? tile_cap : tile_cap + lp_cap * 8;
-    // + 80: the resampler's four-outputs-per-thread form may read (and drop) up to 3 windows past the last demodulated sample
-    uint64_t smem = d6 ? tile_cap + ((lp_cap * 2 + 15) & ~15ull) + 80
-                       : tile_cap + ((lp_cap * 10 + 15) & ~15ull) + ((lp_cap + 19) & ~15ull) + 80;
+    const size_t smem = d->geo.smem_staged;
     if (smem > 200 * 1024) {
         delete d;
         return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
     }
-    d->EB = (uint32_t)EB;
-    d->lp_cap = (uint32_t)lp_cap;
-    d->tile_cap = (uint32_t)tile_cap;
-    d->dm_off = (uint32_t)dm_off;
-    d->smem_bytes = (size_t)smem;
+    d->smem_bytes = smem;
+    {
+        const char *ed = getenv("SDR_INT_DIRECT");
+        if (d6 && !(ed && atoi(ed) == 0)) {
+            for (int k = 0; k < 4; k++)
+                if (make_geom(D, fast, slow, (1024ull << k) - 2, d->geo_direct[k])) d->n_direct = k + 1;
+                else break;
+        }
+    }
     cudaError_t e = cudaFuncSetAttribute(k_demod_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
@@ -1426,10 +1491,10 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     f.d64_slow = magic64(d->cfg.rate_resample);
     f.d64_S = magic64(S);
     f.d64_D = magic64(d->cfg.downsample);
-    f.EB = d->EB;
-    f.lp_cap = d->lp_cap;
-    f.tile_cap = d->tile_cap;
-    f.dm_off = d->dm_off;
+    f.EB = d->geo.EB;
+    f.lp_cap = d->geo.lp_cap;
+    f.tile_cap = d->geo.tile_cap;
+    f.dm_off = d->geo.dm_off;
     f.oct = d->oct;
     a.ctl = r->d_ctl.as<RingCtl>();
     a.seq_done = r->h_seq_done_dev;
@@ -1442,7 +1507,7 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     a.p0 = r->p0;
     a.q0 = r->q0;
     a.d64_fast = magic64(d->cfg.rate_out);
-    unsigned tiles = (unsigned)((pl.Etot + 1 + d->EB - 1) / d->EB + 1);
+    unsigned tiles = (unsigned)((pl.Etot + 1 + d->geo.EB - 1) / d->geo.EB + 1);
     unsigned grid = std::max(1u, std::min(tiles, (unsigned)sm_count(d->device) / 2));
     const bool d6 = d->cfg.downsample == 6;
     e = d6 ? cudaFuncSetAttribute(k_demod_ring<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes)

@@ -196,6 +196,12 @@ class Demod:
             return out[:n].copy(), lp[: nlp.value].copy(), dm[: nlp.value].copy()
         return out[:n].copy()
 
+    def set_state(self, prev_index=0, now_lpr=0, prev_lpr_index=0, lp_now=(0, 0), demod_pre=(0, 0)):
+        s = self.st
+        s.prev_index, s.now_lpr, s.prev_lpr_index = prev_index, now_lpr, prev_lpr_index
+        s.lp_now_re, s.lp_now_im = lp_now
+        s.demod_pre_re, s.demod_pre_im = demod_pre
+
     def state(self) -> dict:
         s = self.st
         return dict(prev_index=int(s.prev_index), now_lpr=s.now_lpr, prev_lpr_index=s.prev_lpr_index,

@@ -195,6 +195,37 @@ def test_fused_demodulate_ragged_calls(S, D, fast, slow):
         assert g.state() == o.state()
 
 
+@pytest.mark.parametrize("D,fast,slow", [(6, 170_000, 32_000), (6, 48_000, 48_000), (15, 160_000, 32_000)])
+def test_fused_demodulate_from_arbitrary_carried_state(S, D, fast, slow):
+    """struct Demod's fields (:234-238) set to values no zero-initialised stream reaches: an odd prev_index (the
+    D = 6 kernel's odd-window-start pass), prev_lpr_index >= rate_resample (a first audio window with fewer samples
+    than fast/slow), large lp_now / demod_pre / now_lpr (wrapping products, the slow divider)."""
+    rng = np.random.default_rng(7 * D + fast % 97)
+    states = [dict(prev_index=1, now_lpr=123, prev_lpr_index=slow - 1, lp_now=(5, -9), demod_pre=(300, -20)),
+              dict(prev_index=D - 1, now_lpr=-70_000, prev_lpr_index=fast - 1, lp_now=(-700, 650), demod_pre=(-768, 768)),
+              dict(prev_index=3 % D, now_lpr=2**31 - 5, prev_lpr_index=min(fast - 1, slow + 17), lp_now=(2**20, -2**21),
+                   demod_pre=(2**15, -2**15)),
+              dict(prev_index=2 % D, now_lpr=-2**31, prev_lpr_index=0, lp_now=(-2**31, 2**31 - 1), demod_pre=(0, 0))]
+    for st in states:
+        g, o = S.Demod(cfg_of(S, D, fast, slow)), O.Demod(ocfg_of(D, fast, slow))
+        for ln in (8 * 40, 262144, 8 * 3001, 262144 * 5):
+            buf = rng.integers(0, 256, ln, dtype=np.uint8)
+            if ln == 8 * 40:   # (re)install the state before the first call of each sequence
+                g.set_state(**st)
+                o.set_state(**st)
+            want = o.demodulate(buf)
+            got = g.demodulate(buf)
+            assert np.array_equal(got, want), (st, ln, got[:8], want[:8])
+            assert g.state() == o.state()
+        # a batch of calls that starts from the same odd state
+        g.set_state(**st)
+        o.set_state(**st)
+        data = rng.integers(0, 256, 4096 * 37, dtype=np.uint8)
+        want = np.concatenate([o.demodulate(data[i * 4096:(i + 1) * 4096]) for i in range(37)])
+        assert np.array_equal(g.demodulate_batch(data, 4096), want)
+        assert g.state() == o.state()
+
+
 def test_fused_rejects_what_the_reference_panics_on(S):
     d = S.Demod()
     for bad in (12, 16, 0):
