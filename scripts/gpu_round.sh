@@ -25,7 +25,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fi
     python bench.py --workload cfg2 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full_cfg2_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fir_fast -s 3 -c 1 -f -o $OUT/prof_fir_cfg3_$TAG \
     python bench.py --workload cfg3 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full_cfg3_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_demod_fused -s 3 -c 1 -f -o $OUT/prof_int_cfg1_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_demod_d -s 3 -c 1 -f -o $OUT/prof_int_cfg1_$TAG \
     python bench.py --workload cfg1 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full_cfg1_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_chan_fir -s 3 -c 1 -f -o $OUT/prof_chan_$TAG \
     python bench.py --workload chan --steps 1 --warmup 3 > $OUT/ncu_full_chan_$TAG.log 2>&1
