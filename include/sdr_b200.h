@@ -198,6 +198,17 @@ int sdr_fmrx_last_timing(const sdr_fmrx *r, float ms[3], uint32_t *n_launches, i
 /* Sums of the per-kernel device times ([0] fused FIR, [1] resampler, [2] rest) over all timed
  * process*() calls since the last reset, harvested from a ring of CUDA events (no per-call sync). */
 int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, int reset);
+/* Which convert+FIR(+demod) kernel the handle runs: 0 = generic (one warp per output), 1 = pre-compiled
+ * k_fir_fast (the BASELINE.json shapes), 2 = k_fir_fast compiled at sdr_fmrx_new() time for this (n_taps, decim)
+ * by NVRTC (same source as the pre-compiled instances, bit-identical arithmetic).  When 0 and a specialised kernel
+ * was wanted, *note (optional, valid until the handle is freed) says why it could not be had.
+ * SDR_FIR_RTC=0 in the environment disables run-time compilation. */
+int sdr_fmrx_kernel_kind(const sdr_fmrx *r, const char **note);
+/* Diagnostic, needs no GPU: compile the kernel for (n_taps, decim) with NVRTC exactly as sdr_fmrx_new() would and
+ * return the cubin bytes (shape[4] = {blocks per thread, threads per CTA, bytes per load, instantiations compiled
+ * now rather than taken from the on-disk cache});
+ * < 0: SDR_E_ARG (shape outside the kernel's range), SDR_E_STATE (no libnvrtc / compile error, see sdr_last_error()). */
+long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]);
 int sdr_fmrx_span_begin(sdr_fmrx *r);
 int sdr_fmrx_span_end(sdr_fmrx *r, float *ms);
 /* Reposition a fresh stream at global sample index n (history = mid-scale): lets a rank that owns

@@ -62,62 +62,11 @@ struct PinBuf {
 
 constexpr size_t kDevRoom = 4096;   // head/tail room of sdr_dev_alloc()
 
-// ---- device-side PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ---------
-#ifdef __CUDACC__
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    // make the init visible to the async (TMA) proxy
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-// global -> shared bulk copy; src/dst 16-B aligned, bytes % 16 == 0; completes on `bar`.
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-// same, with an L2 evict-first policy: the IQ stream is read exactly once
-__device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, uint32_t bytes,
-                                                uint64_t *bar) {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
-#endif  // __CUDACC__
+// ---- device-side PTX helpers (mbarrier, bulk async copy): ptx_helpers.cuh -------------------------
+
 
 }  // namespace sdr
+
+#ifdef __CUDACC__
+#include "ptx_helpers.cuh"
+#endif

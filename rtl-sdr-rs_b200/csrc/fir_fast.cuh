@@ -1,0 +1,242 @@
+// fir_fast.cuh — the fused u8->f32 convert + decimating FIR + discriminator kernel k_fir_fast<T,D,B,NT,WB,PH>.
+//
+// This file is compiled twice: by nvcc into libsdr_b200.so for the shapes in fx_path.cu's table, and at run time by
+// NVRTC (csrc/rtc.cpp) for any other (taps, decimation) a caller asks for — same source, same arithmetic, so a
+// run-time-compiled shape is bit-identical to a pre-compiled one.  Keep it free of host-only headers.
+#pragma once
+#include "ptx_helpers.cuh"
+
+namespace sdr {
+
+struct FirArgs {
+    const uint8_t *x;          // call input, 16-B aligned
+    const uint8_t *carry_end;  // one past the last carried byte (16-B aligned); carry holds the samples before x
+    long long n_samples;       // samples in x
+    long long n_out;           // outputs this call produces
+    uint32_t r;                // samples of the current decimation block already consumed before x
+    float gain;
+    float2 *y_out;             // optional [n_out]
+    float *d_out;              // optional [n_out]
+    float2 *last_y;            // y of the last output of the call (stage-level fm_demod state)
+};
+
+template <int T>
+struct Taps {
+    float h[T];
+};
+
+// Accurate 2x2 determinant / dot (Kahan): a*b - c*d with one rounding error of the result.
+__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
+    float cd = c * d;
+    float err = fmaf(-c, d, cd);
+    float dop = fmaf(a, b, -cd);
+    return dop + err;
+}
+__device__ __forceinline__ float discriminate(float2 y, float2 p, float gain) {
+    float cre = diff_of_products(y.x, p.x, -y.y, p.y);   // y.re*p.re + y.im*p.im
+    float cim = diff_of_products(y.y, p.x, y.x, p.y);    // y.im*p.re - y.re*p.im
+    if (cre == 0.f && cim == 0.f) return 0.f;            // zero predecessor (stream start): 0 by definition, not +-pi
+    return gain * atan2f(cim, cre);
+}
+
+// Stage one CTA tile [s0, s1) (call-local sample indices, s0 may be negative = carry) into smem.
+// Returns the byte offset of sample s0 inside `tile`.  Executed by one thread.
+__device__ __forceinline__ uint32_t load_tile(unsigned char *tile, const FirArgs &a, long long s0, long long s1,
+                                              uint64_t *bar) {
+    const uint32_t soff = (uint32_t)((2 * s0) & 15);   // two's complement & 15 == positive mod 16
+    uint32_t total = 0;
+    long long x_lo = s0 > 0 ? s0 : 0;
+    uint32_t carry_bytes = 0, x_bytes = 0;
+    if (s0 < 0) {
+        long long c_hi = s1 < 0 ? s1 : 0;                       // carry part is [s0, c_hi)
+        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
+    }
+    if (s1 > 0) {
+        long long b_lo = (2 * x_lo) & ~15ll;
+        long long b_hi = (2 * s1 + 15) & ~15ll;
+        x_bytes = (uint32_t)(b_hi - b_lo);
+    }
+    total = carry_bytes + x_bytes;
+    mbar_arrive_expect_tx(bar, total);
+    if (carry_bytes) bulk_g2s(tile, a.carry_end + 2 * s0 - soff, carry_bytes, bar);
+    if (x_bytes) {
+        long long b_lo = (2 * x_lo) & ~15ll;
+        // smem position of x byte b_lo: soff + (b_lo - 2*s0)
+        bulk_g2s_stream(tile + soff + (b_lo - 2 * s0), a.x + b_lo, x_bytes, bar);
+    }
+    return soff;
+}
+
+// =================================================================================================
+// Specialised kernel
+// =================================================================================================
+// halo blocks: >= Q so that y[m-1] of the first owned output is complete, and such that the tile stride (OUT*D
+// samples) is a whole number of load units, which keeps the load phase CTA-uniform
+__host__ __device__ constexpr int fast_pick_hb(int Q, int NBLK, int D, int SPL) {
+    int hb = Q;
+    while (((NBLK - hb) * D) % SPL != 0) hb++;
+    return hb;
+}
+template <int T, int D, int B, int NT, int WB>
+struct FastGeom {
+    static constexpr int Q = (T + D - 1) / D;           // lags: outputs a sample contributes to
+    static constexpr int NBLK = NT * B;                 // decimation blocks per CTA tile
+    static constexpr int SPL = WB / 2;                  // samples per shared-memory load (LDS.32 / LDS.64)
+    static constexpr int HB = fast_pick_hb(Q, NBLK, D, SPL);
+    static constexpr int OUT = NBLK - HB;               // outputs owned per CTA
+    static constexpr int TILE_BYTES = NBLK * D * 2;
+    static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32;
+    static constexpr int SM_PART = NBLK * Q * 8;        // float2 partial per (block, lag)
+    static constexpr int SM_Y = NBLK * 8;
+    static constexpr int SMEM = SM_TILE + SM_PART + SM_Y;
+    static_assert(WB == 4 || WB == 8, "LDS.32 or LDS.64");
+    static_assert((B * D) % SPL == 0, "thread span must be a whole number of load units");
+    static_assert(OUT > HB, "tile too small");
+};
+
+// One PRMT builds the half2 (1024+I, 1024+Q) (fp16 0x64bb == 1024+bb exactly); the Blackwell
+// mixed-precision add (PTX add.rn.f32.f16, SASS FHADD) then yields the centred f32 sample in one
+// instruction per component: 3 instructions per complex sample, all exact.
+struct CvtConst {
+    float bias;        // -(1024 + 127)
+    uint32_t h1024;    // 0x64646464: fp16 exponent byte of 1024 for PRMT
+};
+__device__ __forceinline__ CvtConst cvt_consts() {
+    // Both constants are made opaque AND per-thread (tid >> 31 == 0) so that they live in ordinary vector
+    // registers: as literals / uniform values the compiler re-materialises them with one MOV per use
+    // (FHADD takes no immediate or uniform operand), which costs more than the conversion itself.
+    CvtConst c;
+    asm volatile(
+        "{\n"
+        ".reg .u32 t;\n"
+        "mov.u32 t, %%tid.x;\n"
+        "shr.u32 t, t, 31;\n"
+        "or.b32 %0, t, 0xC48FE000;\n"
+        "or.b32 %1, t, 0x64646464;\n"
+        "}\n"
+        : "=f"(c.bias), "=r"(c.h1024));
+    return c;
+}
+// Packed FP32: Blackwell's FFMA2 (PTX fma.rn.f32x2) does the re and im lanes of one tap in ONE issue slot;
+// ptxas turns the duplicated tap {h, h} into a scalar-broadcast uniform operand (FFMA2 R, R.F32x2, UR.F32, R)
+// fed by one LDCU.128 per four taps.  Each half is an ordinary IEEE fma, so results are bit-identical to fmaf.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void fma_f32x2(unsigned long long &acc, float h, unsigned long long x) {
+    const unsigned long long hh = pack_f32x2(h, h);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(hh), "l"(x));
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
+__device__ __forceinline__ void cvt_iq(uint32_t w, int half, const CvtConst &c, float &xr, float &xi) {
+    const uint32_t pair = __byte_perm(w, c.h1024, half ? 0x4342u : 0x4140u);
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(c.bias));
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(c.bias));
+}
+
+template <int T, int D, int B, int NT, int WB, int PH>
+__global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_constant__ Taps<T> taps) {
+    using G = FastGeom<T, D, B, NT, WB>;
+    constexpr int Q = G::Q, SPL = G::SPL;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t sh_soff;
+    unsigned char *tile = smem;
+    float2 *part = reinterpret_cast<float2 *>(smem + G::SM_TILE);
+    float2 *ysm = reinterpret_cast<float2 *>(smem + G::SM_TILE + G::SM_PART);
+
+    const int tid = threadIdx.x;
+    const long long out0 = (long long)blockIdx.x * G::OUT;          // first owned output (call-local)
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        // tile = blocks [out0 - HB, out0 - HB + NBLK); block b covers samples [b*D - r, (b+1)*D - r)
+        long long s0 = (out0 - G::HB) * D - (long long)a.r;
+        long long last_out = out0 + G::OUT < a.n_out ? out0 + G::OUT : a.n_out;   // exclusive
+        long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
+        sh_soff = load_tile(tile, a, s0, s1, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    // ---- convert once, accumulate per (block, lag) ----------------------------------------------
+    // The thread's first sample sits PH samples into load unit (soff / WB) + tid * (B*D/SPL).
+    const unsigned char *ubase = tile + (size_t)((sh_soff / WB) + tid * (B * D / SPL)) * WB;
+    unsigned long long acc[B][Q];   // packed (re, im) accumulators
+#pragma unroll
+    for (int b = 0; b < B; b++)
+#pragma unroll
+        for (int q = 0; q < Q; q++) acc[b][q] = 0ull;
+
+    constexpr int NU = (PH + B * D + SPL - 1) / SPL;
+    const CvtConst bias = cvt_consts();
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+        uint32_t words[WB / 4];
+        if (WB == 8) {
+            const uint2 v = reinterpret_cast<const uint2 *>(ubase)[u];
+            words[0] = v.x;
+            words[WB / 4 - 1] = v.y;
+        } else {
+            words[0] = reinterpret_cast<const uint32_t *>(ubase)[u];
+        }
+#pragma unroll
+        for (int i = 0; i < SPL; i++) {
+            const int j = u * SPL + i - PH;   // sample index inside the thread's span
+            if (j < 0 || j >= B * D) continue;
+            float xr, xi;
+            cvt_iq(words[i >> 1], i & 1, bias, xr, xi);
+            const unsigned long long x2 = pack_f32x2(xr, xi);
+            const int bb = j / D, jj = j % D;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const int k = q * D + (D - 1 - jj);
+                if (k < T) fma_f32x2(acc[bb][q], taps.h[k], x2);
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < B; b++)
+#pragma unroll
+        for (int q = 0; q < Q; q++) part[(tid * B + b) * Q + q] = unpack_f32x2(acc[b][q]);
+    __syncthreads();
+
+    // ---- combine partials oldest block first: y[g] = P[g-Q+1][Q-1] + ... + P[g][0] -----------------
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        const int g = tid + u * NT;
+        float yr = 0.f, yi = 0.f;
+        if (g >= Q - 1) {
+#pragma unroll
+            for (int q = Q - 1; q >= 0; q--) {
+                float2 p = part[(g - q) * Q + q];
+                yr += p.x;
+                yi += p.y;
+            }
+        }
+        ysm[g] = make_float2(yr, yi);
+    }
+    __syncthreads();
+
+    // ---- discriminator + stores ----------------------------------------------------------------------
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        const int g = tid + u * NT;
+        if (g < G::HB) continue;
+        const long long i = out0 + (g - G::HB);
+        if (i >= a.n_out) continue;
+        const float2 y = ysm[g];
+        if (a.y_out) a.y_out[i] = y;
+        if (a.d_out) a.d_out[i] = discriminate(y, ysm[g - 1], a.gain);
+        if (i == a.n_out - 1) *a.last_y = y;
+    }
+}
+
+}  // namespace sdr

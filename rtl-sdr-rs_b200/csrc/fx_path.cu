@@ -19,242 +19,16 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "fir_fast.cuh"
+#include "rtc.h"
 
 namespace sdr {
-
-struct FirArgs {
-    const uint8_t *x;          // call input, 16-B aligned
-    const uint8_t *carry_end;  // one past the last carried byte (16-B aligned); carry holds the samples before x
-    long long n_samples;       // samples in x
-    long long n_out;           // outputs this call produces
-    uint32_t r;                // samples of the current decimation block already consumed before x
-    float gain;
-    float2 *y_out;             // optional [n_out]
-    float *d_out;              // optional [n_out]
-    float2 *last_y;            // y of the last output of the call (stage-level fm_demod state)
-};
-
-template <int T>
-struct Taps {
-    float h[T];
-};
-
-// Accurate 2x2 determinant / dot (Kahan): a*b - c*d with one rounding error of the result.
-__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
-    float cd = c * d;
-    float err = fmaf(-c, d, cd);
-    float dop = fmaf(a, b, -cd);
-    return dop + err;
-}
-__device__ __forceinline__ float discriminate(float2 y, float2 p, float gain) {
-    float cre = diff_of_products(y.x, p.x, -y.y, p.y);   // y.re*p.re + y.im*p.im
-    float cim = diff_of_products(y.y, p.x, y.x, p.y);    // y.im*p.re - y.re*p.im
-    if (cre == 0.f && cim == 0.f) return 0.f;            // zero predecessor (stream start): 0 by definition, not +-pi
-    return gain * atan2f(cim, cre);
-}
-
-// Stage one CTA tile [s0, s1) (call-local sample indices, s0 may be negative = carry) into smem.
-// Returns the byte offset of sample s0 inside `tile`.  Executed by one thread.
-__device__ __forceinline__ uint32_t load_tile(unsigned char *tile, const FirArgs &a, long long s0, long long s1,
-                                              uint64_t *bar) {
-    const uint32_t soff = (uint32_t)((2 * s0) & 15);   // two's complement & 15 == positive mod 16
-    uint32_t total = 0;
-    long long x_lo = s0 > 0 ? s0 : 0;
-    uint32_t carry_bytes = 0, x_bytes = 0;
-    if (s0 < 0) {
-        long long c_hi = s1 < 0 ? s1 : 0;                       // carry part is [s0, c_hi)
-        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
-    }
-    if (s1 > 0) {
-        long long b_lo = (2 * x_lo) & ~15ll;
-        long long b_hi = (2 * s1 + 15) & ~15ll;
-        x_bytes = (uint32_t)(b_hi - b_lo);
-    }
-    total = carry_bytes + x_bytes;
-    mbar_arrive_expect_tx(bar, total);
-    if (carry_bytes) bulk_g2s(tile, a.carry_end + 2 * s0 - soff, carry_bytes, bar);
-    if (x_bytes) {
-        long long b_lo = (2 * x_lo) & ~15ll;
-        // smem position of x byte b_lo: soff + (b_lo - 2*s0)
-        bulk_g2s_stream(tile + soff + (b_lo - 2 * s0), a.x + b_lo, x_bytes, bar);
-    }
-    return soff;
-}
-
-// =================================================================================================
-// Specialised kernel
-// =================================================================================================
-template <int T, int D, int B, int NT, int WB>
-struct FastGeom {
-    static constexpr int Q = (T + D - 1) / D;           // lags: outputs a sample contributes to
-    static constexpr int NBLK = NT * B;                 // decimation blocks per CTA tile
-    static constexpr int SPL = WB / 2;                  // samples per shared-memory load (LDS.32 / LDS.64)
-    // halo blocks: >= Q so that y[m-1] of the first owned output is complete, and such that the tile
-    // stride (OUT*D samples) is a whole number of load units, which keeps the load phase CTA-uniform
-    static constexpr int pick_hb() {
-        int hb = Q;
-        while (((NBLK - hb) * D) % SPL != 0) hb++;
-        return hb;
-    }
-    static constexpr int HB = pick_hb();
-    static constexpr int OUT = NBLK - HB;               // outputs owned per CTA
-    static constexpr int TILE_BYTES = NBLK * D * 2;
-    static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32;
-    static constexpr int SM_PART = NBLK * Q * 8;        // float2 partial per (block, lag)
-    static constexpr int SM_Y = NBLK * 8;
-    static constexpr int SMEM = SM_TILE + SM_PART + SM_Y;
-    static_assert(WB == 4 || WB == 8, "LDS.32 or LDS.64");
-    static_assert((B * D) % SPL == 0, "thread span must be a whole number of load units");
-    static_assert(OUT > HB, "tile too small");
-};
-
-// One PRMT builds the half2 (1024+I, 1024+Q) (fp16 0x64bb == 1024+bb exactly); the Blackwell
-// mixed-precision add (PTX add.rn.f32.f16, SASS FHADD) then yields the centred f32 sample in one
-// instruction per component: 3 instructions per complex sample, all exact.
-struct CvtConst {
-    float bias;        // -(1024 + 127)
-    uint32_t h1024;    // 0x64646464: fp16 exponent byte of 1024 for PRMT
-};
-__device__ __forceinline__ CvtConst cvt_consts() {
-    // Both constants are made opaque AND per-thread (tid >> 31 == 0) so that they live in ordinary vector
-    // registers: as literals / uniform values the compiler re-materialises them with one MOV per use
-    // (FHADD takes no immediate or uniform operand), which costs more than the conversion itself.
-    CvtConst c;
-    asm volatile(
-        "{\n"
-        ".reg .u32 t;\n"
-        "mov.u32 t, %%tid.x;\n"
-        "shr.u32 t, t, 31;\n"
-        "or.b32 %0, t, 0xC48FE000;\n"
-        "or.b32 %1, t, 0x64646464;\n"
-        "}\n"
-        : "=f"(c.bias), "=r"(c.h1024));
-    return c;
-}
-// Packed FP32: Blackwell's FFMA2 (PTX fma.rn.f32x2) does the re and im lanes of one tap in ONE issue slot;
-// ptxas turns the duplicated tap {h, h} into a scalar-broadcast uniform operand (FFMA2 R, R.F32x2, UR.F32, R)
-// fed by one LDCU.128 per four taps.  Each half is an ordinary IEEE fma, so results are bit-identical to fmaf.
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void fma_f32x2(unsigned long long &acc, float h, unsigned long long x) {
-    const unsigned long long hh = pack_f32x2(h, h);
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(hh), "l"(x));
-}
-__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-
-__device__ __forceinline__ void cvt_iq(uint32_t w, int half, const CvtConst &c, float &xr, float &xi) {
-    const uint32_t pair = __byte_perm(w, c.h1024, half ? 0x4342u : 0x4140u);
-    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(c.bias));
-    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(c.bias));
-}
-
-template <int T, int D, int B, int NT, int WB, int PH>
-__global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_constant__ Taps<T> taps) {
-    using G = FastGeom<T, D, B, NT, WB>;
-    constexpr int Q = G::Q, SPL = G::SPL;
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t sh_soff;
-    unsigned char *tile = smem;
-    float2 *part = reinterpret_cast<float2 *>(smem + G::SM_TILE);
-    float2 *ysm = reinterpret_cast<float2 *>(smem + G::SM_TILE + G::SM_PART);
-
-    const int tid = threadIdx.x;
-    const long long out0 = (long long)blockIdx.x * G::OUT;          // first owned output (call-local)
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_barrier_init();
-        // tile = blocks [out0 - HB, out0 - HB + NBLK); block b covers samples [b*D - r, (b+1)*D - r)
-        long long s0 = (out0 - G::HB) * D - (long long)a.r;
-        long long last_out = out0 + G::OUT < a.n_out ? out0 + G::OUT : a.n_out;   // exclusive
-        long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
-        sh_soff = load_tile(tile, a, s0, s1, &bar);
-    }
-    __syncthreads();
-    mbar_wait(&bar, 0);
-
-    // ---- convert once, accumulate per (block, lag) ----------------------------------------------
-    // The thread's first sample sits PH samples into load unit (soff / WB) + tid * (B*D/SPL).
-    const unsigned char *ubase = tile + (size_t)((sh_soff / WB) + tid * (B * D / SPL)) * WB;
-    unsigned long long acc[B][Q];   // packed (re, im) accumulators
-#pragma unroll
-    for (int b = 0; b < B; b++)
-#pragma unroll
-        for (int q = 0; q < Q; q++) acc[b][q] = 0ull;
-
-    constexpr int NU = (PH + B * D + SPL - 1) / SPL;
-    const CvtConst bias = cvt_consts();
-#pragma unroll
-    for (int u = 0; u < NU; u++) {
-        uint32_t words[WB / 4];
-        if (WB == 8) {
-            const uint2 v = reinterpret_cast<const uint2 *>(ubase)[u];
-            words[0] = v.x;
-            words[WB / 4 - 1] = v.y;
-        } else {
-            words[0] = reinterpret_cast<const uint32_t *>(ubase)[u];
-        }
-#pragma unroll
-        for (int i = 0; i < SPL; i++) {
-            const int j = u * SPL + i - PH;   // sample index inside the thread's span
-            if (j < 0 || j >= B * D) continue;
-            float xr, xi;
-            cvt_iq(words[i >> 1], i & 1, bias, xr, xi);
-            const unsigned long long x2 = pack_f32x2(xr, xi);
-            const int bb = j / D, jj = j % D;
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-                const int k = q * D + (D - 1 - jj);
-                if (k < T) fma_f32x2(acc[bb][q], taps.h[k], x2);
-            }
-        }
-    }
-#pragma unroll
-    for (int b = 0; b < B; b++)
-#pragma unroll
-        for (int q = 0; q < Q; q++) part[(tid * B + b) * Q + q] = unpack_f32x2(acc[b][q]);
-    __syncthreads();
-
-    // ---- combine partials oldest block first: y[g] = P[g-Q+1][Q-1] + ... + P[g][0] -----------------
-#pragma unroll
-    for (int u = 0; u < B; u++) {
-        const int g = tid + u * NT;
-        float yr = 0.f, yi = 0.f;
-        if (g >= Q - 1) {
-#pragma unroll
-            for (int q = Q - 1; q >= 0; q--) {
-                float2 p = part[(g - q) * Q + q];
-                yr += p.x;
-                yi += p.y;
-            }
-        }
-        ysm[g] = make_float2(yr, yi);
-    }
-    __syncthreads();
-
-    // ---- discriminator + stores ----------------------------------------------------------------------
-#pragma unroll
-    for (int u = 0; u < B; u++) {
-        const int g = tid + u * NT;
-        if (g < G::HB) continue;
-        const long long i = out0 + (g - G::HB);
-        if (i >= a.n_out) continue;
-        const float2 y = ysm[g];
-        if (a.y_out) a.y_out[i] = y;
-        if (a.d_out) a.d_out[i] = discriminate(y, ysm[g - 1], a.gain);
-        if (i == a.n_out - 1) *a.last_y = y;
-    }
-}
 
 // =================================================================================================
 // Generic kernel: one warp per output, lanes stride the taps, butterfly reduction.
@@ -491,6 +265,7 @@ struct FastVariant {
     int out_per_cta, hb, smem, nt, wb, b;
     void (*launch)(const FirArgs &, const float *taps, int phase, int grid, int smem, cudaStream_t);
     cudaError_t (*prepare)(int smem);
+    const RtcModule *rtc = nullptr;   // run-time-compiled instance (launch/prepare unused): fns[PH], PH < wb / 2
 };
 
 template <int T, int D, int B, int NT, int WB, int PH>
@@ -554,6 +329,83 @@ const FastVariant *find_variant(uint32_t T, uint32_t D) {
     return first;
 }
 
+// ---- run-time specialisation: k_fir_fast for a (taps, decimation) shape that has no pre-compiled instance --------
+// (B, NT, WB) are chosen the way the table above was tuned by hand:
+//   * a thread owns ~128 samples (B blocks), with at most 16 packed accumulators (B * Q);
+//   * the thread stride in load units decides the shared-memory bank conflicts of the per-thread loads: a warp's
+//     LDS.32 hits gcd(B*D/2, 32) ways, an LDS.64 gcd(B*D/4, 16) ways — minimise wavefronts per sample;
+//   * the CTA is the smallest multiple of 32 threads whose halo (>= Q blocks of NT*B) costs <= 3 % and whose tile is
+//     >= 6 KB, within 56 KB of shared memory (several CTAs per SM overlap copy and compute).
+bool pick_fast_params(int T, int D, int *Bo, int *NTo, int *WBo) {
+    // D <= 256 and <= 16 packed accumulators keep the fully unrolled body (B*D samples x Q lags) small enough for
+    // ptxas to finish in seconds
+    if (T < 1 || D < 1 || T > 4096 || D > 256) return false;
+    const int Q = (T + D - 1) / D;
+    if (Q > 16) return false;   // too many lags per sample for register accumulators: generic kernel
+    if ((long)((D & 1) ? 2 : 1) * D * Q > 800) return false;   // smallest possible body already takes ptxas minutes
+    const int bmax = std::max(1, std::min(16 / Q, std::max(160 / D, (D & 1) ? 2 : 1)));   // odd D: B must be even
+    int best_b = 0, best_wb = 0;
+    double best_cost = 1e30;
+    for (int B = 1; B <= bmax; B++) {
+        const int span = B * D;
+        if ((long)span * Q > 800 && B > ((D & 1) ? 2 : 1)) break;
+
+        for (int WB : {8, 4}) {
+            const int spl = WB / 2;
+            if (span % spl) continue;
+            const int ways = WB == 8 ? std::__gcd(span / 4, 16) : std::__gcd(span / 2, 32);
+            // wavefronts per sample, then distance of the span from ~160 samples as the tie-break
+            const double cost = (double)ways / spl + 1e-3 * std::abs(span - 128) / 128.0 + (span < 48 ? 0.5 : 0.0);
+            if (cost < best_cost) best_cost = cost, best_b = B, best_wb = WB;
+        }
+    }
+    if (!best_b) return false;
+    const int B = best_b, WB = best_wb, spl = WB / 2;
+    int pick = 0;
+    for (int NT = 32; NT <= 512; NT += 32) {
+        const int nblk = NT * B, hb = fast_pick_hb(Q, nblk, D, spl);
+        const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)nblk * Q * 8 + (long)nblk * 8;
+        if (nblk - hb <= hb) continue;
+        if (smem > 56 * 1024) break;
+        pick = NT;
+        if (nblk >= 32 * hb && (long)nblk * D * 2 >= 6 * 1024) break;
+    }
+    if (!pick) return false;
+    *Bo = B, *NTo = pick, *WBo = WB;
+    return true;
+}
+
+std::string fast_name_expr(int T, int D, int B, int NT, int WB, int PH) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "sdr::k_fir_fast<%d,%d,%d,%d,%d,%d>", T, D, B, NT, WB, PH);
+    return buf;
+}
+
+// Build (or fetch) the run-time-compiled variant of a shape.  nullptr + *why when it cannot be had.
+const FastVariant *rtc_variant(int device, uint32_t T, uint32_t D, int B, int NT, int WB, std::string *why) {
+    static std::mutex mu;
+    static std::map<std::string, FastVariant *> cache;
+    char key[96];
+    snprintf(key, sizeof key, "fir_fast<%u,%u,%d,%d,%d>", T, D, B, NT, WB);
+    std::lock_guard<std::mutex> lk(mu);
+    const std::string full = std::to_string(device) + "|" + key;
+    auto it = cache.find(full);
+    if (it != cache.end()) return it->second;
+    const int Q = ((int)T + (int)D - 1) / (int)D, spl = WB / 2, nblk = NT * B;
+    const int hb = fast_pick_hb(Q, nblk, (int)D, spl);
+    const int smem = ((nblk * (int)D * 2 + 15) / 16) * 16 + 32 + nblk * Q * 8 + nblk * 8;
+    std::vector<std::string> names;
+    for (int ph = 0; ph < spl; ph++) names.push_back(fast_name_expr((int)T, (int)D, B, NT, WB, ph));
+    const RtcModule *mod = nullptr;
+    if (rtc_get_module(device, key, names, smem, &mod)) {
+        if (why) *why = err_buf();
+        return nullptr;
+    }
+    FastVariant *v = new FastVariant{(int)T, (int)D, nblk - hb, hb, smem, NT, WB, B, nullptr, nullptr, mod};
+    cache[full] = v;
+    return v;
+}
+
 constexpr size_t kFxChunkSamples = size_t(16) << 20;   // 32 MiB of IQ per pipelined chunk (host API)
 
 }  // namespace
@@ -564,6 +416,8 @@ struct sdr_fmrx {
     std::vector<float> taps, taps2;
     float gain = 0.f;
     const FastVariant *fast = nullptr;
+    int kernel_kind = 0;     // 0 generic (k_fir_generic), 1 pre-compiled k_fir_fast, 2 run-time-compiled k_fir_fast
+    std::string rtc_note;    // why run-time compilation was not used, when it was wanted
     // generic geometry
     int gen_opc = 0;
     uint32_t gen_sm_tile = 0, gen_smem = 0;
@@ -662,6 +516,13 @@ int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint6
         const long long s0 = -((long long)v->hb * r->cfg.decim + rphase);
         const uint32_t soff = (uint32_t)((2 * s0) & 15);
         const int phase = (int)((soff % (uint32_t)v->wb) / 2);
+        if (v->rtc) {
+            void *params[2] = {&a, (void *)r->taps.data()};   // (FirArgs, Taps<T>) by value
+            int rc = rtc_launch(v->rtc->fns[phase % (v->wb / 2)], (unsigned)grid, (unsigned)v->nt, (unsigned)v->smem, r->stream, params);
+            if (rc) return rc;
+            r->last_launches++;
+            return SDR_OK;
+        }
         v->launch(a, r->taps.data(), phase, (int)grid, v->smem, r->stream);
     } else {
         GenArgs g{};
@@ -805,6 +666,22 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
     if (cfg->n_taps2) r->taps2.assign(taps2, taps2 + cfg->n_taps2);
     r->gain = cfg->gain != 0.f ? cfg->gain : (float)(16384.0 / 3.14159265358979323846);
     r->fast = find_variant(cfg->n_taps, cfg->decim);
+    r->kernel_kind = r->fast ? 1 : 0;
+    {
+        // SDR_FIR_RTC=0: never compile at run time; SDR_FIR_RTC=force: also re-compile the pre-compiled shapes (tests)
+        const char *er = getenv("SDR_FIR_RTC");
+        const bool off = (er && !strcmp(er, "0")) || getenv("SDR_FORCE_GENERIC"), force = er && !strcmp(er, "force");
+        int B = 0, NT = 0, WB = 0;
+        bool have = false;
+        if (r->fast && force) B = r->fast->b, NT = r->fast->nt, WB = r->fast->wb, have = true;
+        else if (!r->fast && !off) have = pick_fast_params((int)cfg->n_taps, (int)cfg->decim, &B, &NT, &WB);
+        if (have) {
+            const FastVariant *v = rtc_variant(cuda_device, cfg->n_taps, cfg->decim, B, NT, WB, &r->rtc_note);
+            if (v) r->fast = v, r->kernel_kind = 2;
+        } else if (!r->fast && !off) {
+            r->rtc_note = "shape outside the block-owner kernel's range (decim > 256, more than 16 lags per sample, or an unrolled body of more than 800 tap-samples)";
+        }
+    }
     const uint64_t T = cfg->n_taps, D = cfg->decim;
     // generic geometry: ~32 KB of raw bytes per CTA
     uint64_t opc = (16384 > T ? (16384 - T) : 0) / D;
@@ -830,7 +707,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         r->h2 = r->Jp + 16;
     }
     cudaError_t e = cudaFuncSetAttribute(k_fir_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem);
-    if (e == cudaSuccess && r->fast) e = r->fast->prepare(r->fast->smem);
+    if (e == cudaSuccess && r->fast && !r->fast->rtc) e = r->fast->prepare(r->fast->smem);
     if (e == cudaSuccess && r->h2 * sizeof(float) > 48 * 1024)
         e = cudaFuncSetAttribute(k_shift_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(r->h2 * sizeof(float)));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
@@ -1089,6 +966,30 @@ int sdr_fmrx_last_timing(const sdr_fmrx *r, float ms[3], uint32_t *n_launches, i
     if (n_launches) *n_launches = r->last_launches;
     if (specialised) *specialised = r->fast ? 1 : 0;
     return SDR_OK;
+}
+
+int sdr_fmrx_kernel_kind(const sdr_fmrx *r, const char **note) {
+    if (!r) return fail(SDR_E_ARG, "null handle");
+    if (note) *note = r->rtc_note.c_str();
+    return r->kernel_kind;
+}
+
+long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]) {
+    int B = 0, NT = 0, WB = 0;
+    if (n_taps > 4096 || decim > 256 || !pick_fast_params((int)n_taps, (int)decim, &B, &NT, &WB))
+        return fail(SDR_E_ARG, "(%u taps, /%u) is outside the block-owner kernel's range", n_taps, decim);
+    if (shape) shape[0] = B, shape[1] = NT, shape[2] = WB;
+    std::vector<std::string> names;
+    for (int ph = 0; ph < WB / 2; ph++) names.push_back(fast_name_expr((int)n_taps, (int)decim, B, NT, WB, ph));
+    std::vector<std::vector<char>> cubins;
+    std::vector<std::string> lowered;
+    int n_compiled = 0;
+    int rc = rtc_compile_cubins(names, &cubins, &lowered, &n_compiled);
+    if (rc) return rc;
+    if (shape) shape[3] = n_compiled;
+    size_t total = 0;
+    for (const auto &c : cubins) total += c.size();
+    return (long)total;
 }
 
 int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, int reset) {

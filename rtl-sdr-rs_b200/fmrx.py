@@ -100,6 +100,12 @@ class FmRx:
     def seek(self, global_sample_index: int):
         F.check(F.lib().sdr_fmrx_seek(self._h, global_sample_index))
 
+    def kernel_kind(self):
+        """(kind, note): 0 generic, 1 pre-compiled k_fir_fast, 2 run-time-compiled k_fir_fast (sdr_fmrx_kernel_kind)."""
+        note = C.c_char_p()
+        kind = F.check(F.lib().sdr_fmrx_kernel_kind(self._h, C.byref(note)))
+        return kind, (note.value or b"").decode()
+
     def timing_totals(self, reset: bool = False):
         sums = (C.c_double * 3)()
         n = C.c_uint64(0)

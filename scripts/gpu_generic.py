@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""Throughput of the non-specialised shapes: integer Demod for several `downsample`, f32 receiver for (T, D) that have no
+compiled k_fir_fast instance.  Device-resident 2^28 samples, CUDA-event kernel time.  python scripts/gpu_generic.py"""
+import sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import sdrpkg
+from sigutil import channel_taps
+S = sdrpkg.load()
+n = 1 << 28
+d_in = S.DevBuffer(2 * n)
+S.synth_fill_dev(d_in, 2 * n, 0xB2000001)
+BUF = 262144
+for D, fast, slow in ((6, 170_000, 32_000), (5, 200_000, 32_000), (4, 250_000, 48_000), (8, 125_000, 32_000), (11, 100_000, 32_000),
+                      (16, 150_000, 48_000), (21, 50_000, 32_000), (32, 32_000, 32_000)):
+    cfg = S.DemodConfig(fast * D, fast, slow, D, 42)
+    h = S.Demod(cfg)
+    n_bufs = 2 * n // BUF
+    cap = (h.out_len(BUF) + 2) * n_bufs + 64
+    d_out = S.DevBuffer(2 * cap)
+    best = 1e9
+    for _ in range(5):
+        h.demodulate_batch_dev(d_in, BUF, n_bufs, d_out, cap); h.sync()
+        ms, _ = h.last_timing(); best = min(best, ms)
+    print(f"int D={D:3d} {fast}->{slow}: {best:.3f} ms  {2.0 * n / best / 1e6:.0f} GB/s")
+    d_out.free(); h.close()
+for T, D in ((127, 75), (255, 100), (127, 50), (63, 25), (201, 64), (511, 100), (31, 10)):
+    taps = channel_taps(T, D)
+    h = S.FmRx(taps, D, None, 1, 1)
+    _, na = h.out_lens(n)
+    d_out = S.DevBuffer(4 * (na + n // D + 64))
+    best = 1e9
+    for _ in range(5):
+        h.timing_totals(reset=True)
+        h.process_dev(d_in, n, d_out, na + n // D + 64); h.sync()
+        sums, calls = h.timing_totals(); best = min(best, sums[0] / max(calls, 1))
+    print(f"f32 T={T:3d} D={D:3d}: {best:.3f} ms  {2.0 * n / best / 1e6:.0f} GB/s")
+    d_out.free(); h.close()

@@ -2,6 +2,7 @@
 include/sdr_b200.h declares, the ctypes table covers exactly that set, and compute entry points fail
 LOUDLY (SDR_E_CUDA) instead of falling back to anything when no device is present."""
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -156,3 +157,28 @@ def test_source_rtl_tcp_wire_format(S):
     srv.close()
     with pytest.raises(S.SdrError):
         S.Source.open_rtl_tcp("127.0.0.1", 1)                     # nothing listens there
+
+
+def test_rtc_compiles_a_new_shape_without_a_gpu(tmp_path, monkeypatch):
+    """NVRTC specialisation of k_fir_fast (csrc/rtc.cpp): compile-only self-test, no device needed.  A fresh cache
+    directory forces a real compile; the second call must be served from the on-disk cache."""
+    import ctypes as C
+    import subprocess
+    import sys
+    code = (
+        "import ctypes as C, sys; sys.path.insert(0, %r)\n"
+        "import sdrpkg; sdrpkg.load()\n"
+        "from rtl_sdr_rs_b200 import _ffi as F\n"
+        "L = F.lib(); sh = (C.c_int * 4)()\n"
+        "n1 = L.sdr_rtc_selftest(31, 10, C.byref(sh)); c1 = sh[3]\n"
+        "n2 = L.sdr_rtc_selftest(31, 10, C.byref(sh)); c2 = sh[3]\n"
+        "bad = L.sdr_rtc_selftest(200, 3, C.byref(sh))\n"
+        "print(n1, c1, n2, c2, bad, sh[0] if n1 > 0 else L.sdr_last_error().decode())\n" % str(ROOT))
+    env = dict(os.environ, SDR_RTC_CACHE=str(tmp_path / "cubins"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n1, c1, n2, c2, bad = (int(v) for v in r.stdout.split()[:5])
+    assert n1 > 10_000 and n2 == n1, r.stdout          # a real cubin, identical bytes the second time
+    assert c1 >= 1 and c2 == 0, r.stdout               # compiled once, then cached
+    assert bad == -1                                   # SDR_E_ARG: 67 lags per sample is outside the kernel's range
+    assert len(list((tmp_path / "cubins").glob("*.cubin"))) == c1

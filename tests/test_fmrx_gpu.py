@@ -29,20 +29,27 @@ def ragged_cuts(n, rng, pieces):
     return [0, *cuts.tolist(), n]
 
 
-SHAPES = [  # (T, D, specialised?)
-    (127, 75, True), (255, 100, True), (6, 6, True),
-    (63, 20, False), (31, 7, False), (1, 1, False), (200, 3, False), (5, 64, False), (1001, 250, False),
+SHAPES = [  # (T, D, kernel kind: 1 = pre-compiled k_fir_fast, 2 = k_fir_fast compiled by NVRTC for the shape, 0 = generic)
+    (127, 75, 1), (255, 100, 1), (6, 6, 1),
+    (63, 20, 2), (31, 7, 2), (1, 1, 2), (5, 64, 2), (127, 50, 2), (201, 64, 2), (33, 125, 2),
+    (200, 3, 0), (300, 301, 0), (1001, 250, 0),   # > 16 lags per sample / decim > 256 / unrolled body too large: generic kernel
 ]
 
 
-@pytest.mark.parametrize("T,D,spec", SHAPES)
-def test_low_pass_streaming_vs_oracle(S, T, D, spec):
+@pytest.fixture()
+def no_rtc(monkeypatch):
+    monkeypatch.setenv("SDR_FIR_RTC", "0")
+
+
+@pytest.mark.parametrize("T,D,kind", SHAPES)
+def test_low_pass_streaming_vs_oracle(S, T, D, kind):
     rng = np.random.default_rng(T * 1000 + D)
     taps = channel_taps(T, D) if T > 1 else np.ones(1, np.float32)
     n = max(40 * D, 3 * T) + 12345
     iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
     g = S.FmRx(taps, D)
-    assert g.last_timing()[2] == int(spec)
+    assert g.kernel_kind()[0] == kind, g.kernel_kind()
+    assert g.last_timing()[2] == int(kind != 0)
     o = O.FxChain(taps, D)
     # ragged calls: odd lengths exercise both 4-byte phases, tiny calls exercise the carry
     cuts = [0, 1, 2, 3 + D // 2, 3 + D // 2 + 1] + [c for c in ragged_cuts(n, rng, 7)[1:-1] if c > 3 + D // 2 + 1] + [n]
@@ -51,6 +58,41 @@ def test_low_pass_streaming_vs_oracle(S, T, D, spec):
         got = g.low_pass(iq[2 * lo:2 * hi])
         assert got.shape == want.shape, (lo, hi)
         assert_close(got, want, what=f"low_pass T={T} D={D} [{lo},{hi})")
+
+
+@pytest.mark.parametrize("T,D", [(63, 20), (31, 7), (5, 64), (127, 50)])
+def test_generic_kernel_matches_oracle_when_rtc_is_off(S, no_rtc, T, D):
+    """SDR_FIR_RTC=0: shapes without a pre-compiled instance run k_fir_generic (the path a box without libnvrtc takes)."""
+    rng = np.random.default_rng(T + D)
+    taps = channel_taps(T, D)
+    n = 50 * D + 4321
+    iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+    g = S.FmRx(taps, D)
+    assert g.kernel_kind()[0] == 0
+    o = O.FxChain(taps, D)
+    for lo, hi in ((0, n // 3), (n // 3, n // 3 + 1), (n // 3 + 1, n)):
+        want, _, _ = o.process(iq[2 * lo:2 * hi])
+        assert_close(g.low_pass(iq[2 * lo:2 * hi]), want, what=f"generic T={T} D={D}")
+
+
+@pytest.mark.parametrize("T,D", [(127, 75), (255, 100)])
+def test_rtc_instance_is_bit_identical_to_the_precompiled_one(S, monkeypatch, T, D):
+    """SDR_FIR_RTC=force re-compiles a pre-compiled shape with NVRTC (same CTA shape, same source): every output bit
+    of y and of the discriminator must agree, for ragged calls that exercise every load phase."""
+    rng = np.random.default_rng(T * 7 + D)
+    taps = channel_taps(T, D)
+    n = 300 * D + 777
+    iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+    a = S.FmRx(taps, D)
+    monkeypatch.setenv("SDR_FIR_RTC", "force")
+    b = S.FmRx(taps, D)
+    assert a.kernel_kind()[0] == 1 and b.kernel_kind()[0] == 2, (a.kernel_kind(), b.kernel_kind())
+    cuts = [0, 1, 3, 10, 10 + D, 11 + 3 * D, n // 2 + 1, n]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        ya, da, _ = a.process(iq[2 * lo:2 * hi])
+        yb, db, _ = b.process(iq[2 * lo:2 * hi])
+        assert np.array_equal(ya.view(np.uint32), yb.view(np.uint32)), (lo, hi)
+        assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), (lo, hi)
 
 
 @pytest.mark.parametrize("T,D", [(127, 75), (255, 100), (63, 20)])
