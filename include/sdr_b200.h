@@ -205,7 +205,7 @@ int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, in
  * SDR_FIR_RTC=0 in the environment disables run-time compilation. */
 int sdr_fmrx_kernel_kind(const sdr_fmrx *r, const char **note);
 /* Diagnostic, needs no GPU: compile the kernel for (n_taps, decim) with NVRTC exactly as sdr_fmrx_new() would and
- * return the cubin bytes (shape[4] = {blocks per thread, threads per CTA, bytes per load, instantiations compiled
+ * return the cubin bytes (shape[4] = {blocks per thread, threads per CTA, bytes per load + 256 * row padding, instantiations compiled
  * now rather than taken from the on-disk cache});
  * < 0: SDR_E_ARG (shape outside the kernel's range), SDR_E_STATE (no libnvrtc / compile error, see sdr_last_error()). */
 long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]);

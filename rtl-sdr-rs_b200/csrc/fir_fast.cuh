@@ -67,6 +67,42 @@ __device__ __forceinline__ uint32_t load_tile(unsigned char *tile, const FirArgs
     return soff;
 }
 
+// Same tile, staged ROW bytes at a time with PAD bytes of shared memory skipped after every row (a row = the bytes one
+// thread owns): when ROW is a multiple of 128 every thread's loads would otherwise hit the same bank.  Executed by
+// warp 0: lane 0 posts the byte count, then the 32 lanes issue the row copies (one or two per row: a row may straddle
+// the carry / call-input boundary).  ROW and every piece are multiples of 16 bytes.
+template <int ROW, int PAD>
+__device__ __forceinline__ uint32_t load_tile_rows(unsigned char *tile, const FirArgs &a, long long s0, long long s1,
+                                                   uint64_t *bar, const int lane) {
+    static_assert(ROW % 16 == 0 && PAD % 16 == 0, "bulk copies move 16-byte multiples");
+    const uint32_t soff = (uint32_t)((2 * s0) & 15);
+    long long x_lo = s0 > 0 ? s0 : 0;
+    uint32_t carry_bytes = 0, x_bytes = 0;
+    if (s0 < 0) {
+        long long c_hi = s1 < 0 ? s1 : 0;
+        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
+    }
+    long long b_lo = 0;
+    if (s1 > 0) {
+        b_lo = (2 * x_lo) & ~15ll;
+        x_bytes = (uint32_t)(((2 * s1 + 15) & ~15ll) - b_lo);
+    }
+    const uint32_t total = carry_bytes + x_bytes;
+    if (lane == 0) mbar_arrive_expect_tx(bar, total);
+    __syncwarp();
+    // flat tile byte f lives in the carry for f < carry_bytes, in x after that (the two parts abut, see load_tile)
+    const unsigned char *csrc = a.carry_end + 2 * s0 - soff;
+    const unsigned char *xsrc = a.x + b_lo;
+    for (uint32_t f = (uint32_t)lane * ROW; f < total; f += 32u * ROW) {
+        const uint32_t end = f + ROW < total ? f + ROW : total;
+        unsigned char *dst = tile + (size_t)(f / ROW) * (ROW + PAD);
+        const uint32_t cut = carry_bytes < f ? f : (carry_bytes < end ? carry_bytes : end);   // [f, cut) carry, [cut, end) x
+        if (cut > f) bulk_g2s(dst, csrc + f, cut - f, bar);
+        if (end > cut) bulk_g2s_stream(dst + (cut - f), xsrc + (cut - carry_bytes), end - cut, bar);
+    }
+    return soff;
+}
+
 // =================================================================================================
 // Specialised kernel
 // =================================================================================================
@@ -77,7 +113,7 @@ __host__ __device__ constexpr int fast_pick_hb(int Q, int NBLK, int D, int SPL) 
     while (((NBLK - hb) * D) % SPL != 0) hb++;
     return hb;
 }
-template <int T, int D, int B, int NT, int WB>
+template <int T, int D, int B, int NT, int WB, int PAD = 0>
 struct FastGeom {
     static constexpr int Q = (T + D - 1) / D;           // lags: outputs a sample contributes to
     static constexpr int NBLK = NT * B;                 // decimation blocks per CTA tile
@@ -85,13 +121,15 @@ struct FastGeom {
     static constexpr int HB = fast_pick_hb(Q, NBLK, D, SPL);
     static constexpr int OUT = NBLK - HB;               // outputs owned per CTA
     static constexpr int TILE_BYTES = NBLK * D * 2;
-    static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32;
+    static constexpr int ROW = B * D * 2;                // bytes one thread owns
+    static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32 + (NT + 1) * PAD;
     static constexpr int SM_PART = NBLK * Q * 8;        // float2 partial per (block, lag)
     static constexpr int SM_Y = NBLK * 8;
     static constexpr int SMEM = SM_TILE + SM_PART + SM_Y;
     static_assert(WB == 4 || WB == 8, "LDS.32 or LDS.64");
     static_assert((B * D) % SPL == 0, "thread span must be a whole number of load units");
     static_assert(OUT > HB, "tile too small");
+    static_assert(PAD == 0 || (ROW % 16 == 0 && PAD % 16 == 0), "padded rows are staged by 16-byte bulk copies");
 };
 
 // One PRMT builds the half2 (1024+I, 1024+Q) (fp16 0x64bb == 1024+bb exactly); the Blackwell
@@ -141,9 +179,9 @@ __device__ __forceinline__ void cvt_iq(uint32_t w, int half, const CvtConst &c, 
     asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(c.bias));
 }
 
-template <int T, int D, int B, int NT, int WB, int PH>
+template <int T, int D, int B, int NT, int WB, int PH, int PAD = 0>
 __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_constant__ Taps<T> taps) {
-    using G = FastGeom<T, D, B, NT, WB>;
+    using G = FastGeom<T, D, B, NT, WB, PAD>;
     constexpr int Q = G::Q, SPL = G::SPL;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -154,21 +192,32 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
 
     const int tid = threadIdx.x;
     const long long out0 = (long long)blockIdx.x * G::OUT;          // first owned output (call-local)
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_barrier_init();
+    if (tid < (PAD ? 32 : 1)) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_barrier_init();
+        }
         // tile = blocks [out0 - HB, out0 - HB + NBLK); block b covers samples [b*D - r, (b+1)*D - r)
         long long s0 = (out0 - G::HB) * D - (long long)a.r;
         long long last_out = out0 + G::OUT < a.n_out ? out0 + G::OUT : a.n_out;   // exclusive
         long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
-        sh_soff = load_tile(tile, a, s0, s1, &bar);
+        if constexpr (PAD != 0) {
+            __syncwarp();
+            const uint32_t so = load_tile_rows<G::ROW, PAD>(tile, a, s0, s1, &bar, tid);
+            if (tid == 0) sh_soff = so;
+        } else {
+            sh_soff = load_tile(tile, a, s0, s1, &bar);
+        }
     }
     __syncthreads();
     mbar_wait(&bar, 0);
 
     // ---- convert once, accumulate per (block, lag) ----------------------------------------------
-    // The thread's first sample sits PH samples into load unit (soff / WB) + tid * (B*D/SPL).
-    const unsigned char *ubase = tile + (size_t)((sh_soff / WB) + tid * (B * D / SPL)) * WB;
+    // The thread's first sample sits PH samples into load unit (soff / WB) + tid * (B*D/SPL); with PAD every thread's
+    // row of U load units is followed by PAD unused bytes.
+    constexpr int U = B * D / SPL;
+    const uint32_t ubias = sh_soff / WB;   // < 16 / WB
+    const unsigned char *ubase = tile + (size_t)tid * (G::ROW + PAD) + (size_t)ubias * WB;
     unsigned long long acc[B][Q];   // packed (re, im) accumulators
 #pragma unroll
     for (int b = 0; b < B; b++)
@@ -180,12 +229,15 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
 #pragma unroll
     for (int u = 0; u < NU; u++) {
         uint32_t words[WB / 4];
+        // unit u of this thread is unit ubias + u of its row; only the last few can spill into the next row
+        const unsigned char *up = ubase + u * WB;
+        if (PAD && u + 16 / WB > U) up += (ubias + u >= (uint32_t)U) ? PAD : 0;
         if (WB == 8) {
-            const uint2 v = reinterpret_cast<const uint2 *>(ubase)[u];
+            const uint2 v = *reinterpret_cast<const uint2 *>(up);
             words[0] = v.x;
             words[WB / 4 - 1] = v.y;
         } else {
-            words[0] = reinterpret_cast<const uint32_t *>(ubase)[u];
+            words[0] = *reinterpret_cast<const uint32_t *>(up);
         }
 #pragma unroll
         for (int i = 0; i < SPL; i++) {

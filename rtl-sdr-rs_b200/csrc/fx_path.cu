@@ -266,6 +266,7 @@ struct FastVariant {
     void (*launch)(const FirArgs &, const float *taps, int phase, int grid, int smem, cudaStream_t);
     cudaError_t (*prepare)(int smem);
     const RtcModule *rtc = nullptr;   // run-time-compiled instance (launch/prepare unused): fns[PH], PH < wb / 2
+    int pad = 0;                      // bytes of shared memory skipped after every thread's row (run-time instances)
 };
 
 template <int T, int D, int B, int NT, int WB, int PH>
@@ -333,10 +334,12 @@ const FastVariant *find_variant(uint32_t T, uint32_t D) {
 // (B, NT, WB) are chosen the way the table above was tuned by hand:
 //   * a thread owns ~128 samples (B blocks), with at most 16 packed accumulators (B * Q);
 //   * the thread stride in load units decides the shared-memory bank conflicts of the per-thread loads: a warp's
-//     LDS.32 hits gcd(B*D/2, 32) ways, an LDS.64 gcd(B*D/4, 16) ways — minimise wavefronts per sample;
+//     LDS.32 hits gcd(stride, 32) ways, an LDS.64 gcd(stride, 16) ways; 16 bytes of padding per thread row (staged by
+//     one bulk copy per row instead of one per tile) shifts the stride off the powers of two — minimise wavefronts
+//     per sample;
 //   * the CTA is the smallest multiple of 32 threads whose halo (>= Q blocks of NT*B) costs <= 3 % and whose tile is
 //     >= 6 KB, within 56 KB of shared memory (several CTAs per SM overlap copy and compute).
-bool pick_fast_params(int T, int D, int *Bo, int *NTo, int *WBo) {
+bool pick_fast_params(int T, int D, int *Bo, int *NTo, int *WBo, int *PADo) {
     // D <= 256 and <= 16 packed accumulators keep the fully unrolled body (B*D samples x Q lags) small enough for
     // ptxas to finish in seconds
     if (T < 1 || D < 1 || T > 4096 || D > 256) return false;
@@ -344,64 +347,70 @@ bool pick_fast_params(int T, int D, int *Bo, int *NTo, int *WBo) {
     if (Q > 16) return false;   // too many lags per sample for register accumulators: generic kernel
     if ((long)((D & 1) ? 2 : 1) * D * Q > 800) return false;   // smallest possible body already takes ptxas minutes
     const int bmax = std::max(1, std::min(16 / Q, std::max(160 / D, (D & 1) ? 2 : 1)));   // odd D: B must be even
-    int best_b = 0, best_wb = 0;
+    int best_b = 0, best_wb = 0, best_pad = 0;
     double best_cost = 1e30;
     for (int B = 1; B <= bmax; B++) {
         const int span = B * D;
         if ((long)span * Q > 800 && B > ((D & 1) ? 2 : 1)) break;
-
         for (int WB : {8, 4}) {
             const int spl = WB / 2;
             if (span % spl) continue;
-            const int ways = WB == 8 ? std::__gcd(span / 4, 16) : std::__gcd(span / 2, 32);
-            // wavefronts per sample, then distance of the span from ~160 samples as the tie-break
-            const double cost = (double)ways / spl + 1e-3 * std::abs(span - 128) / 128.0 + (span < 48 ? 0.5 : 0.0);
-            if (cost < best_cost) best_cost = cost, best_b = B, best_wb = WB;
+            // 16 bytes of padding per row (rows must then be 16-byte multiples) changes the stride by 16 / WB units
+            for (int pad : {0, 16}) {
+                if (pad && (span * 2) % 16) continue;
+                const int stride = span * 2 / WB + pad / WB;
+                const int ways = WB == 8 ? std::__gcd(stride, 16) : std::__gcd(stride, 32);
+                // wavefronts per sample; then a small charge for the row-wise staging, and the distance of the span
+                // from ~128 samples as the tie-break
+                const double cost = (double)ways / spl + (pad ? 0.05 : 0.0) + 1e-3 * std::abs(span - 128) / 128.0 +
+                                    (span < 48 ? 0.5 : 0.0);
+                if (cost < best_cost) best_cost = cost, best_b = B, best_wb = WB, best_pad = pad;
+            }
         }
     }
     if (!best_b) return false;
-    const int B = best_b, WB = best_wb, spl = WB / 2;
+    const int B = best_b, WB = best_wb, PAD = best_pad, spl = WB / 2;
     int pick = 0;
     for (int NT = 32; NT <= 512; NT += 32) {
         const int nblk = NT * B, hb = fast_pick_hb(Q, nblk, D, spl);
-        const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)nblk * Q * 8 + (long)nblk * 8;
+        const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)(NT + 1) * PAD + (long)nblk * Q * 8 + (long)nblk * 8;
         if (nblk - hb <= hb) continue;
         if (smem > 56 * 1024) break;
         pick = NT;
         if (nblk >= 32 * hb && (long)nblk * D * 2 >= 6 * 1024) break;
     }
     if (!pick) return false;
-    *Bo = B, *NTo = pick, *WBo = WB;
+    *Bo = B, *NTo = pick, *WBo = WB, *PADo = PAD;
     return true;
 }
 
-std::string fast_name_expr(int T, int D, int B, int NT, int WB, int PH) {
+std::string fast_name_expr(int T, int D, int B, int NT, int WB, int PH, int PAD) {
     char buf[128];
-    snprintf(buf, sizeof buf, "sdr::k_fir_fast<%d,%d,%d,%d,%d,%d>", T, D, B, NT, WB, PH);
+    snprintf(buf, sizeof buf, "sdr::k_fir_fast<%d,%d,%d,%d,%d,%d,%d>", T, D, B, NT, WB, PH, PAD);
     return buf;
 }
 
 // Build (or fetch) the run-time-compiled variant of a shape.  nullptr + *why when it cannot be had.
-const FastVariant *rtc_variant(int device, uint32_t T, uint32_t D, int B, int NT, int WB, std::string *why) {
+const FastVariant *rtc_variant(int device, uint32_t T, uint32_t D, int B, int NT, int WB, int PAD, std::string *why) {
     static std::mutex mu;
     static std::map<std::string, FastVariant *> cache;
     char key[96];
-    snprintf(key, sizeof key, "fir_fast<%u,%u,%d,%d,%d>", T, D, B, NT, WB);
+    snprintf(key, sizeof key, "fir_fast<%u,%u,%d,%d,%d,%d>", T, D, B, NT, WB, PAD);
     std::lock_guard<std::mutex> lk(mu);
     const std::string full = std::to_string(device) + "|" + key;
     auto it = cache.find(full);
     if (it != cache.end()) return it->second;
     const int Q = ((int)T + (int)D - 1) / (int)D, spl = WB / 2, nblk = NT * B;
     const int hb = fast_pick_hb(Q, nblk, (int)D, spl);
-    const int smem = ((nblk * (int)D * 2 + 15) / 16) * 16 + 32 + nblk * Q * 8 + nblk * 8;
+    const int smem = ((nblk * (int)D * 2 + 15) / 16) * 16 + 32 + (NT + 1) * PAD + nblk * Q * 8 + nblk * 8;
     std::vector<std::string> names;
-    for (int ph = 0; ph < spl; ph++) names.push_back(fast_name_expr((int)T, (int)D, B, NT, WB, ph));
+    for (int ph = 0; ph < spl; ph++) names.push_back(fast_name_expr((int)T, (int)D, B, NT, WB, ph, PAD));
     const RtcModule *mod = nullptr;
     if (rtc_get_module(device, key, names, smem, &mod)) {
         if (why) *why = err_buf();
         return nullptr;
     }
-    FastVariant *v = new FastVariant{(int)T, (int)D, nblk - hb, hb, smem, NT, WB, B, nullptr, nullptr, mod};
+    FastVariant *v = new FastVariant{(int)T, (int)D, nblk - hb, hb, smem, NT, WB, B, nullptr, nullptr, mod, PAD};
     cache[full] = v;
     return v;
 }
@@ -671,12 +680,12 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         // SDR_FIR_RTC=0: never compile at run time; SDR_FIR_RTC=force: also re-compile the pre-compiled shapes (tests)
         const char *er = getenv("SDR_FIR_RTC");
         const bool off = (er && !strcmp(er, "0")) || getenv("SDR_FORCE_GENERIC"), force = er && !strcmp(er, "force");
-        int B = 0, NT = 0, WB = 0;
+        int B = 0, NT = 0, WB = 0, PAD = 0;
         bool have = false;
         if (r->fast && force) B = r->fast->b, NT = r->fast->nt, WB = r->fast->wb, have = true;
-        else if (!r->fast && !off) have = pick_fast_params((int)cfg->n_taps, (int)cfg->decim, &B, &NT, &WB);
+        else if (!r->fast && !off) have = pick_fast_params((int)cfg->n_taps, (int)cfg->decim, &B, &NT, &WB, &PAD);
         if (have) {
-            const FastVariant *v = rtc_variant(cuda_device, cfg->n_taps, cfg->decim, B, NT, WB, &r->rtc_note);
+            const FastVariant *v = rtc_variant(cuda_device, cfg->n_taps, cfg->decim, B, NT, WB, PAD, &r->rtc_note);
             if (v) r->fast = v, r->kernel_kind = 2;
         } else if (!r->fast && !off) {
             r->rtc_note = "shape outside the block-owner kernel's range (decim > 256, more than 16 lags per sample, or an unrolled body of more than 800 tap-samples)";
@@ -975,12 +984,12 @@ int sdr_fmrx_kernel_kind(const sdr_fmrx *r, const char **note) {
 }
 
 long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]) {
-    int B = 0, NT = 0, WB = 0;
-    if (n_taps > 4096 || decim > 256 || !pick_fast_params((int)n_taps, (int)decim, &B, &NT, &WB))
+    int B = 0, NT = 0, WB = 0, PAD = 0;
+    if (n_taps > 4096 || decim > 256 || !pick_fast_params((int)n_taps, (int)decim, &B, &NT, &WB, &PAD))
         return fail(SDR_E_ARG, "(%u taps, /%u) is outside the block-owner kernel's range", n_taps, decim);
-    if (shape) shape[0] = B, shape[1] = NT, shape[2] = WB;
+    if (shape) shape[0] = B, shape[1] = NT, shape[2] = WB + 256 * PAD;
     std::vector<std::string> names;
-    for (int ph = 0; ph < WB / 2; ph++) names.push_back(fast_name_expr((int)n_taps, (int)decim, B, NT, WB, ph));
+    for (int ph = 0; ph < WB / 2; ph++) names.push_back(fast_name_expr((int)n_taps, (int)decim, B, NT, WB, ph, PAD));
     std::vector<std::vector<char>> cubins;
     std::vector<std::string> lowered;
     int n_compiled = 0;

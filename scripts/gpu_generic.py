@@ -26,7 +26,8 @@ for D, fast, slow in ((6, 170_000, 32_000), (5, 200_000, 32_000), (4, 250_000, 4
         ms, _ = h.last_timing(); best = min(best, ms)
     print(f"int D={D:3d} {fast}->{slow}: {best:.3f} ms  {2.0 * n / best / 1e6:.0f} GB/s")
     d_out.free(); h.close()
-for T, D in ((127, 75), (255, 100), (127, 50), (63, 25), (201, 64), (511, 100), (31, 10)):
+for T, D in ((127, 75), (255, 100), (127, 50), (63, 25), (201, 64), (511, 100), (31, 10), (129, 16), (65, 32), (127, 48), (255, 96),
+             (33, 8), (127, 40), (200, 3)):
     taps = channel_taps(T, D)
     h = S.FmRx(taps, D, None, 1, 1)
     _, na = h.out_lens(n)
@@ -36,5 +37,5 @@ for T, D in ((127, 75), (255, 100), (127, 50), (63, 25), (201, 64), (511, 100), 
         h.timing_totals(reset=True)
         h.process_dev(d_in, n, d_out, na + n // D + 64); h.sync()
         sums, calls = h.timing_totals(); best = min(best, sums[0] / max(calls, 1))
-    print(f"f32 T={T:3d} D={D:3d}: {best:.3f} ms  {2.0 * n / best / 1e6:.0f} GB/s")
+    print(f"f32 T={T:3d} D={D:3d} kind={h.kernel_kind()[0]}: {best:.3f} ms  {2.0 * n / best / 1e6:.0f} GB/s")
     d_out.free(); h.close()

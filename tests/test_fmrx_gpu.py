@@ -31,7 +31,7 @@ def ragged_cuts(n, rng, pieces):
 
 SHAPES = [  # (T, D, kernel kind: 1 = pre-compiled k_fir_fast, 2 = k_fir_fast compiled by NVRTC for the shape, 0 = generic)
     (127, 75, 1), (255, 100, 1), (6, 6, 1),
-    (63, 20, 2), (31, 7, 2), (1, 1, 2), (5, 64, 2), (127, 50, 2), (201, 64, 2), (33, 125, 2),
+    (63, 20, 2), (31, 7, 2), (1, 1, 2), (5, 64, 2), (127, 50, 2), (201, 64, 2), (33, 125, 2), (129, 16, 2), (65, 32, 2),
     (200, 3, 0), (300, 301, 0), (1001, 250, 0),   # > 16 lags per sample / decim > 256 / unrolled body too large: generic kernel
 ]
 
