@@ -546,7 +546,7 @@ def main():
                    "device": info["name"], "sm_count": info["sm_count"]},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "k_demod_d6_direct" if w["name"] == "cfg1" else "k_fir_fast (fused convert+FIR+demod)",
+                     "kernel": "k_demod_direct<6>" if w["name"] == "cfg1" else "k_fir_fast (fused convert+FIR+demod)",
                      "kernel_ms": round(kern_ms, 4), "alg_bytes_per_sample": round(bps, 4),
                      "kernel_share_of_step": round(kern_ms / ms_per_step, 4)},
         "clocks": clocks,

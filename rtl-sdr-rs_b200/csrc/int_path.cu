@@ -286,74 +286,91 @@ __device__ __noinline__ int2 lp_window_exact(const uint32_t *w32, int32_t off0, 
     return make_int2(re, im);
 }
 
-// ---- D = 6, even window start (every stream whose calls hold a multiple of 4 samples, i.e. every length rotate_90
-// accepts): rotate_90 + centre + boxcar + discriminator in one register-resident pass -------------------------------
-// A lane owns FOUR consecutive windows = 48 raw bytes, fetched as 3-4 aligned LDS.128 (lane stride 48 B is
-// bank-conflict free per quarter warp).  `a0` = byte offset (16-B aligned, may be -16) of the chunk that holds the first
-// word of window 0; S = word shift of that word inside its chunk (tile-uniform -> template parameter, so every register
-// index, every dp4a coefficient and every window constant below is a compile-time literal).  Window 4g+j starts on a
-// phase-0 word iff ((S ^ j) & 1) == 0 (a window is 3 words and the phase alternates per word).  The predecessor of a
-// lane's first window is the neighbour's last (one shuffle pair per four samples); lane 0 recomputes it from the 3
-// words before its chunk.  The four results leave as one STS.64.  Groups past the tile and the predecessor of window 0
-// produce values nobody reads (dm[0] is either predecessor-only or repaired by the fix-up loop).
-template <int S, int NTH, bool GLOBAL>
-__device__ __forceinline__ void d6_pass_even(const unsigned char *tile, const int32_t a0, const uint32_t ngroups, int16_t *dm) {
+// ---- even downsample, even window start (every stream whose calls hold a multiple of 4 samples, i.e. every length
+// rotate_90 accepts): rotate_90 + centre + boxcar + discriminator in one register-resident pass ---------------------
+// A lane owns KW consecutive windows = KW * DT * 2 raw bytes (a multiple of 16: 48 bytes for the reference's DT = 6),
+// fetched as aligned 128-bit loads (for DT = 6 the 48-byte lane stride is bank-conflict free per quarter warp).  `a0` =
+// byte offset (16-B aligned, may be -16) of the chunk that holds the first word of window 0; S = word shift of that word
+// inside its chunk (tile-uniform -> template parameter, so every register index, every dp4a coefficient and every
+// window constant below is a compile-time literal).  A window is DT/2 words and the rotate_90 phase alternates per
+// word, so word S + j*DT/2 + k of the lane's row is a phase-2 word iff that index is odd.  The predecessor of a lane's
+// first window is the neighbour's last (one shuffle pair per KW samples); lane 0 recomputes it from the DT/2 words
+// before its row.  The KW results leave as one store.  Groups past the tile and the predecessor of window 0 produce
+// values nobody reads (dm[0] is either predecessor-only or repaired by the fix-up loop).
+template <int DT>
+struct PassGeom {   // windows per lane: the row must be a multiple of 16 bytes and fit in registers
+    static constexpr int KW = DT == 2 ? 8 : DT == 12 ? 2 : 4;
+    static constexpr int ROW_WORDS = KW * DT / 2;
+    static_assert(DT % 2 == 0 && DT >= 2 && DT <= 12, "register-resident pass: even downsample up to 12");
+    static_assert((ROW_WORDS * 4) % 16 == 0, "a lane's row is a whole number of 16-byte chunks");
+    // the bounded atan2 needs |x| + |y| <= (2 * 128 * DT)^2 < 2^24
+    static_assert(4ll * 128 * 128 * DT * DT < (1ll << 24), "products of two boxcar sums must stay below 2^24");
+};
+constexpr bool has_fused_pass(int DT) { return DT == 2 || DT == 4 || DT == 6 || DT == 8 || DT == 10 || DT == 12; }
+
+template <int DT, int S, int NTH, bool GLOBAL>
+__device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const int32_t a0, const uint32_t ngroups, int16_t *dm) {
+    using PG = PassGeom<DT>;
+    constexpr int KW = PG::KW, HW = DT / 2, NCH = (PG::ROW_WORDS + S + 3) / 4;   // windows per lane, words per window, chunks
     constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u;   // phase-0 word: re [+1,0,0,-1], im [0,+1,+1,0]
     constexpr uint32_t CRE2 = 0x010000FFu, CIM2 = 0x00FFFF00u;   // phase-2 word: negated
     const int lane = threadIdx.x & 31;
     for (uint32_t gb = threadIdx.x & ~31u; gb < ngroups; gb += NTH) {
         const uint32_t g = gb + lane;
-        const unsigned char *p = tile + a0 + 48 * (int32_t)(g < ngroups ? g : ngroups - 1);
-        uint32_t v[16];
+        const unsigned char *p = tile + a0 + (PG::ROW_WORDS * 4) * (int32_t)(g < ngroups ? g : ngroups - 1);
+        uint32_t v[NCH * 4];
         {
-            // GLOBAL: the chunks come straight from the input buffer (read-only path; the two lanes that share a
-            // 32-byte sector meet in L1), otherwise from the shared-memory tile
+            // GLOBAL: the chunks come straight from the input buffer (read-only path; lanes that share a 32-byte
+            // sector meet in L1), otherwise from the shared-memory tile
             const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
-            const uint4 q0 = GLOBAL ? __ldg(p4) : p4[0], q1 = GLOBAL ? __ldg(p4 + 1) : p4[1], q2 = GLOBAL ? __ldg(p4 + 2) : p4[2];
-            v[0] = q0.x, v[1] = q0.y, v[2] = q0.z, v[3] = q0.w;
-            v[4] = q1.x, v[5] = q1.y, v[6] = q1.z, v[7] = q1.w;
-            v[8] = q2.x, v[9] = q2.y, v[10] = q2.z, v[11] = q2.w;
-            if (S > 0) {
-                const uint4 q3 = GLOBAL ? __ldg(p4 + 3) : p4[3];
-                v[12] = q3.x, v[13] = q3.y, v[14] = q3.z, v[15] = q3.w;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const uint4 q = GLOBAL ? __ldg(p4 + c) : p4[c];
+                v[4 * c] = q.x, v[4 * c + 1] = q.y, v[4 * c + 2] = q.z, v[4 * c + 3] = q.w;
             }
         }
-        int32_t re[4], im[4];
+        int32_t re[KW], im[KW];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const bool neg = (S ^ j) & 1;
-            int32_t r = neg ? BoxK<6>::re(2) : BoxK<6>::re(0), i = neg ? BoxK<6>::im(2) : BoxK<6>::im(0);
+        for (int j = 0; j < KW; j++) {
+            const bool neg = (S + j * HW) & 1;
+            int32_t r = neg ? BoxK<DT>::re(2) : BoxK<DT>::re(0), i = neg ? BoxK<DT>::im(2) : BoxK<DT>::im(0);
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
+            for (int k = 0; k < HW; k++) {
                 const bool wn = neg != (bool)(k & 1);
-                r = dp4a_us(v[S + 3 * j + k], wn ? CRE2 : CRE0, r);
-                i = dp4a_us(v[S + 3 * j + k], wn ? CIM2 : CIM0, i);
+                r = dp4a_us(v[S + HW * j + k], wn ? CRE2 : CRE0, r);
+                i = dp4a_us(v[S + HW * j + k], wn ? CIM2 : CIM0, i);
             }
             re[j] = r;
             im[j] = i;
         }
-        int32_t pre = __shfl_up_sync(0xffffffffu, re[3], 1), pim = __shfl_up_sync(0xffffffffu, im[3], 1);
-        if (lane == 0 && g > 0) {   // window 4g-1: the three words before word S of this chunk
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(p) + (S - 3);
-            const bool neg = (S ^ 1) & 1;
-            pre = neg ? BoxK<6>::re(2) : BoxK<6>::re(0);
-            pim = neg ? BoxK<6>::im(2) : BoxK<6>::im(0);
+        int32_t pre = __shfl_up_sync(0xffffffffu, re[KW - 1], 1), pim = __shfl_up_sync(0xffffffffu, im[KW - 1], 1);
+        if (lane == 0 && g > 0) {   // window KW*g - 1: the HW words before word S of this row
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(p) + (S - HW);
+            const bool neg = (S + HW) & 1;   // same parity as S - HW
+            pre = neg ? BoxK<DT>::re(2) : BoxK<DT>::re(0);
+            pim = neg ? BoxK<DT>::im(2) : BoxK<DT>::im(0);
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
+            for (int k = 0; k < HW; k++) {
                 const bool wn = neg != (bool)(k & 1);
                 pre = dp4a_us(w[k], wn ? CRE2 : CRE0, pre);
                 pim = dp4a_us(w[k], wn ? CIM2 : CIM0, pim);
             }
         }
-        uint32_t o[4];
+        uint32_t o[KW];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < KW; j++) {
             int32_t cre, cim;
             d_cmul_conj(make_int2(re[j], im[j]), j ? make_int2(re[j - 1], im[j - 1]) : make_int2(pre, pim), cre, cim);
             o[j] = (uint32_t)d_fast_atan2_t<true>(cim, cre);
         }
-        if (g < ngroups)
-            *reinterpret_cast<uint2 *>(dm + 4 * g) = make_uint2(__byte_perm(o[0], o[1], 0x5410), __byte_perm(o[2], o[3], 0x5410));
+        if (g < ngroups) {
+            uint32_t pk[KW / 2];
+#pragma unroll
+            for (int j = 0; j < KW / 2; j++) pk[j] = __byte_perm(o[2 * j], o[2 * j + 1], 0x5410);
+            if (KW == 2) *reinterpret_cast<uint32_t *>(dm + 2 * g) = pk[0];
+            if (KW == 4) *reinterpret_cast<uint2 *>(dm + 4 * g) = make_uint2(pk[0], pk[KW / 2 - 1]);
+            if (KW == 8) *reinterpret_cast<uint4 *>(dm + 8 * g) = make_uint4(pk[0], pk[KW / 8], pk[KW / 4], pk[KW / 2 - 1]);
+        }
     }
 }
 
@@ -437,20 +454,22 @@ __device__ __forceinline__ void d6_fixups(const FusedArgs &a, const IntState &st
     }
 }
 
-// D = 6 main pass over one tile (rotate_90 + centre + boxcar + discriminator -> dm), any window-start parity.
-template <int NTH, bool GLOBAL>
-__device__ __forceinline__ void d6_pass(const unsigned char *tile, const TileInfo &ti, int16_t *dm, const int tid) {
+// Main pass over one tile (rotate_90 + centre + boxcar + discriminator -> dm) for the downsamples that have the
+// register-resident form; D = 6 also handles an odd window start (below).
+template <int DT, int NTH, bool GLOBAL>
+__device__ __forceinline__ void dn_pass(const unsigned char *tile, const TileInfo &ti, int16_t *dm, const int tid) {
     const int32_t off0 = ti.off0;
     const uint32_t nlp = ti.nlp;
-    if (!(off0 & 1)) {
+    if (DT != 6 || !(off0 & 1)) {   // DT != 6: the host only launches this form for even window starts
+        constexpr int KW = PassGeom<DT>::KW;
         const int32_t byte0 = 2 * off0;   // first byte of window 0 (negative on a tile that starts inside it)
         const int32_t a0 = byte0 & ~15;
-        const uint32_t ngroups = (nlp + 3) >> 2;
+        const uint32_t ngroups = (nlp + KW - 1) / KW;
         switch ((byte0 >> 2) & 3) {
-        case 0: d6_pass_even<0, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
-        case 1: d6_pass_even<1, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
-        case 2: d6_pass_even<2, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
-        default: d6_pass_even<3, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
+        case 0: dn_pass_even<DT, 0, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
+        case 1: dn_pass_even<DT, 1, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
+        case 2: dn_pass_even<DT, 2, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
+        default: dn_pass_even<DT, 3, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
         }
         return;
     }
@@ -560,14 +579,14 @@ __device__ __forceinline__ void tile_state_out(const FusedArgs &a, const IntStat
 
 // One tile per call.  `first_use`: this CTA has not initialised its mbarrier yet; `parity`: phase of the mbarrier
 // for this use (a persistent CTA flips it per tile).  Ends with a __syncthreads so the shared-memory tile can be reused.
-// DIRECT (D = 6 batch kernel): no shared-memory tile at all — the pass reads its 16-byte chunks straight from the input
+// DIRECT (batch kernel for the even downsamples up to 12): no shared-memory tile at all — the pass reads its 16-byte chunks straight from the input
 // buffer, so a CTA costs only the 6 KB dm array, the SM holds as many CTAs as the register file allows and the HBM
 // latency is hidden by warps, not by a per-CTA copy-then-compute phase.  The ring keeps the staged form (its input slots
 // are written by the copy engine while the kernel is resident; the mbarrier orders those bytes).
 template <int DT, bool DIRECT = false>
 __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t tile_idx, const uint32_t n_tiles,
                                            const uint32_t parity, const bool first_use) {
-    static_assert(!DIRECT || DT == 6, "the direct form exists for D = 6 only");
+    static_assert(!DIRECT || has_fused_pass(DT), "the direct form exists for the downsamples with a register-resident pass");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ TileInfo sh_ti;
@@ -608,10 +627,10 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
 
     int2 lastlp = make_int2(st.demod_pre_re, st.demod_pre_im);   // lp[nlp-1] for the carried state (last tile)
-    if constexpr (DT == 6) {
+    if constexpr (DT == 6 || DIRECT) {
         // ---- D = 6 (optimal_settings :189-190): boxcar + discriminator fused, no window array ---------------
         if (!DIRECT) mbar_wait(&bar, parity);
-        d6_pass<256, DIRECT>(tile, ti, dm, tid);
+        dn_pass<DT, 256, DIRECT>(tile, ti, dm, tid);
         if (last && tid == 255) {
             int32_t re = 0, im = 0;
             boxcar_rot(w32, (int)ti.tail_from, (int)(ti.tail_from + ti.ntail), re, im);
@@ -698,11 +717,12 @@ template <int DT>
 __global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedArgs a) {
     demod_tile<DT>(a, blockIdx.x, gridDim.x, 0, true);
 }
-#ifndef SDR_INT_MINB_DIRECT
-#define SDR_INT_MINB_DIRECT 8
-#endif
-__global__ void __launch_bounds__(256, SDR_INT_MINB_DIRECT) k_demod_d6_direct(const FusedArgs a) {
-    demod_tile<6, true>(a, blockIdx.x, gridDim.x, 0, true);
+// CTAs per SM the register allocation aims for: 8 (32 registers) while a lane's row is at most 16 words, fewer for
+// the wider rows of DT = 8 / 10 (a spilled row costs more than the lost occupancy)
+constexpr int direct_min_blocks(int DT) { return DT == 10 ? 5 : DT == 8 ? 6 : 8; }
+template <int DT>
+__global__ void __launch_bounds__(256, direct_min_blocks(DT)) k_demod_direct(const FusedArgs a) {
+    demod_tile<DT, true>(a, blockIdx.x, gridDim.x, 0, true);
 }
 
 // ================================================================================================
@@ -970,8 +990,8 @@ struct sdr_demod {
     PinBuf h_state;
     OctTable oct{};
     Geom geo;                // staged-tile geometry (generic D, the ring, odd window starts)
-    Geom geo_direct[4];      // D = 6 direct kernel: tiles of 1, 2, 4, 8 passes (1024 windows each); the launch picks by batch size
-    int n_direct = 0;        // 0: direct kernel disabled (SDR_INT_DIRECT=0 or D != 6)
+    Geom geo_direct[4];      // direct kernel: tiles of 1, 2, 4, 8 passes (256 lanes x KW windows each); the launch picks by batch size
+    int n_direct = 0;        // 0: direct kernel disabled (SDR_INT_DIRECT=0 or a downsample without the register-resident pass)
     size_t smem_bytes = 0;
     bool pending = false;      // async *_dev submission whose state has not been committed yet
     int pending_slot = 0;
@@ -1124,9 +1144,16 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     a.dm_off = g->dm_off;
     uint64_t blocks = pl.Etot ? (pl.Etot + g->EB - 1) / g->EB : 1;
     if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "batch too large for one launch");
-    if (direct)
-        k_demod_d6_direct<<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a);
-    else if (d->cfg.downsample == 6)
+    if (direct) {
+        switch (d->cfg.downsample) {
+        case 2: k_demod_direct<2><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+        case 4: k_demod_direct<4><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+        case 6: k_demod_direct<6><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+        case 8: k_demod_direct<8><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+        case 10: k_demod_direct<10><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+        default: k_demod_direct<12><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+        }
+    } else if (d->cfg.downsample == 6)
         k_demod_fused<6><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
     else
         k_demod_fused<0><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
@@ -1197,10 +1224,13 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     d->smem_bytes = smem;
     {
         const char *ed = getenv("SDR_INT_DIRECT");
-        if (d6 && !(ed && atoi(ed) == 0)) {
+        if (has_fused_pass((int)D) && !(ed && atoi(ed) == 0)) {
+            const uint64_t kw = D == 2 ? 8 : D == 12 ? 2 : 4;   // PassGeom<D>::KW: windows per lane
             for (int k = 0; k < 4; k++)
-                if (make_geom(D, fast, slow, (1024ull << k) - 2, d->geo_direct[k])) d->n_direct = k + 1;
-                else break;
+                if (make_geom(D, fast, slow, ((256 * kw) << k) - 2, d->geo_direct[k]) && d->geo_direct[k].smem_direct <= 48 * 1024)
+                    d->n_direct = k + 1;
+                else
+                    break;
         }
     }
     cudaError_t e = cudaFuncSetAttribute(k_demod_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -178,7 +178,10 @@ def test_stage_streams_with_state_carry(S, D, fast, slow):
 # ---- fused demodulate vs oracle -----------------------------------------------------------------------
 
 @pytest.mark.parametrize("D,fast,slow", [(6, 170_000, 32_000), (15, 160_000, 32_000), (3, 48_000, 48_000),
-                                         (7, 100_003, 31_999), (64, 250_000, 48_000)])
+                                         (7, 100_003, 31_999), (64, 250_000, 48_000),
+                                         # the other even downsamples with the register-resident direct kernel
+                                         (2, 96_000, 48_000), (4, 250_000, 48_000), (8, 125_000, 32_000),
+                                         (10, 100_000, 32_000), (12, 170_000, 32_000)])
 def test_fused_demodulate_ragged_calls(S, D, fast, slow):
     rng = np.random.default_rng(100 + D)
     g, o = S.Demod(cfg_of(S, D, fast, slow)), O.Demod(ocfg_of(D, fast, slow))
@@ -195,7 +198,8 @@ def test_fused_demodulate_ragged_calls(S, D, fast, slow):
         assert g.state() == o.state()
 
 
-@pytest.mark.parametrize("D,fast,slow", [(6, 170_000, 32_000), (6, 48_000, 48_000), (15, 160_000, 32_000)])
+@pytest.mark.parametrize("D,fast,slow", [(6, 170_000, 32_000), (6, 48_000, 48_000), (15, 160_000, 32_000),
+                                         (8, 125_000, 32_000), (12, 170_000, 32_000)])
 def test_fused_demodulate_from_arbitrary_carried_state(S, D, fast, slow):
     """struct Demod's fields (:234-238) set to values no zero-initialised stream reaches: an odd prev_index (the
     D = 6 kernel's odd-window-start pass), prev_lpr_index >= rate_resample (a first audio window with fewer samples
@@ -224,6 +228,28 @@ def test_fused_demodulate_from_arbitrary_carried_state(S, D, fast, slow):
         want = np.concatenate([o.demodulate(data[i * 4096:(i + 1) * 4096]) for i in range(37)])
         assert np.array_equal(g.demodulate_batch(data, 4096), want)
         assert g.state() == o.state()
+
+
+@pytest.mark.parametrize("D,fast,slow", [(6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48_000),
+                                         (8, 125_000, 32_000), (10, 100_000, 32_000), (12, 170_000, 32_000)])
+@pytest.mark.parametrize("passes", [1, 2, 4, 8])
+def test_direct_kernel_every_tile_size(S, monkeypatch, D, fast, slow, passes):
+    """The direct kernel picks its tile size from the batch size; pin each size (SDR_INT_DIRECT_PASSES) on a batch
+    that spans many tiles and call boundaries: same bits as the oracle, same carried state."""
+    monkeypatch.setenv("SDR_INT_DIRECT_PASSES", str(passes))
+    rng = np.random.default_rng(D * 10 + passes)
+    buf_len, n_bufs = 8 * 1531, 61
+    data = rng.integers(0, 256, buf_len * n_bufs, dtype=np.uint8)
+    data[rng.random(data.size) < 0.03] = 255
+    o = O.Demod(ocfg_of(D, fast, slow))
+    want = np.concatenate([o.demodulate(data[i * buf_len:(i + 1) * buf_len]) for i in range(n_bufs)])
+    g = S.Demod(cfg_of(S, D, fast, slow))
+    got = g.demodulate_batch(data, buf_len)
+    assert np.array_equal(got, want)
+    assert g.state() == o.state()
+    # and one whole-buffer call on the same handle continues the stream
+    more = rng.integers(0, 256, 262144, dtype=np.uint8)
+    assert np.array_equal(g.demodulate(more), o.demodulate(more))
 
 
 def test_fused_rejects_what_the_reference_panics_on(S):
