@@ -298,15 +298,16 @@ __device__ __noinline__ int2 lp_window_exact(const uint32_t *w32, int32_t off0, 
 // before its row.  The KW results leave as one store.  Groups past the tile and the predecessor of window 0 produce
 // values nobody reads (dm[0] is either predecessor-only or repaired by the fix-up loop).
 template <int DT>
-struct PassGeom {   // windows per lane: the row must be a multiple of 16 bytes and fit in registers
-    static constexpr int KW = DT == 2 ? 8 : DT == 12 ? 2 : 4;
+struct PassGeom {   // windows per lane: the row must be whole 16-byte (even DT) / 8-byte (odd DT) chunks and fit in registers
+    static constexpr bool ODD = (DT & 1) != 0;
+    static constexpr int KW = ODD ? 4 : (DT == 2 ? 8 : DT == 12 ? 2 : 4);
     static constexpr int ROW_WORDS = KW * DT / 2;
-    static_assert(DT % 2 == 0 && DT >= 2 && DT <= 12, "register-resident pass: even downsample up to 12");
-    static_assert((ROW_WORDS * 4) % 16 == 0, "a lane's row is a whole number of 16-byte chunks");
+    static_assert(DT >= 2 && DT <= 13, "register-resident pass: downsample 2..13");
+    static_assert((ROW_WORDS * 4) % (ODD ? 8 : 16) == 0, "a lane's row is a whole number of load chunks");
     // the bounded atan2 needs |x| + |y| <= (2 * 128 * DT)^2 < 2^24
     static_assert(4ll * 128 * 128 * DT * DT < (1ll << 24), "products of two boxcar sums must stay below 2^24");
 };
-constexpr bool has_fused_pass(int DT) { return DT == 2 || DT == 4 || DT == 6 || DT == 8 || DT == 10 || DT == 12; }
+constexpr bool has_fused_pass(int DT) { return DT >= 2 && DT <= 13; }
 
 template <int DT, int S, int NTH, bool GLOBAL>
 __device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const int32_t a0, const uint32_t ngroups, int16_t *dm) {
@@ -370,6 +371,92 @@ __device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const in
             if (KW == 2) *reinterpret_cast<uint32_t *>(dm + 2 * g) = pk[0];
             if (KW == 4) *reinterpret_cast<uint2 *>(dm + 4 * g) = make_uint2(pk[0], pk[KW / 2 - 1]);
             if (KW == 8) *reinterpret_cast<uint4 *>(dm + 8 * g) = make_uint4(pk[0], pk[KW / 8], pk[KW / 4], pk[KW / 2 - 1]);
+        }
+    }
+}
+
+// ---- odd downsample: windows alternate between even and odd start samples, so the unit is a PAIR of windows =
+// 2*DT samples = DT words starting on an even sample: window A = (DT-1)/2 whole words + the low half of the middle
+// word, window B = the high half of the middle word + (DT-1)/2 whole words (half-masked dp4a coefficients).  A lane
+// owns two pairs (four windows, 8*DT bytes, 64-bit loads); E = 1 when window 0 of the tile starts on an odd sample —
+// it is then the B window of a pair whose A window lies before the tile (computed from whatever bytes are there and
+// never stored).  S = word shift of the first pair inside its 8-byte chunk.  The rotate_90 phase of row word x is its
+// parity, as in the even form (a lane's row starts on an even word).  Direct (global-memory) form only.
+template <int DT, int S, int E, int NTH>
+__device__ __forceinline__ void dn_pass_odd(const unsigned char *tile, const int32_t a0, const uint32_t ngroups,
+                                            const int32_t last_w, int16_t *dm) {
+    constexpr int HW = (DT - 1) / 2, RW = 2 * DT, NCH = (RW + S + 1) / 2;   // whole words per window, row words, 8-byte chunks
+    constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u, CRE2 = 0x010000FFu, CIM2 = 0x00FFFF00u;
+    constexpr uint32_t LO = 0x0000FFFFu, HI = 0xFFFF0000u;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t gb = threadIdx.x & ~31u; gb < ngroups; gb += NTH) {
+        const uint32_t g = gb + lane;
+        const unsigned char *p = tile + a0 + (RW * 4) * (int32_t)(g < ngroups ? g : ngroups - 1);
+        uint32_t v[NCH * 2];
+        {
+            const uint2 *p2 = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const uint2 q = __ldg(p2 + c);
+                v[2 * c] = q.x, v[2 * c + 1] = q.y;
+            }
+        }
+        int32_t re[4], im[4];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int f = S + q * DT;   // row index of the pair's first word
+            // window A: starts on the first sample of word f
+            {
+                const int ph = 2 * (f & 1);
+                int32_t r = BoxK<DT>::re(ph), i = BoxK<DT>::im(ph);
+#pragma unroll
+                for (int k = 0; k <= HW; k++) {
+                    const bool wn = (f + k) & 1;
+                    const uint32_t m = k == HW ? LO : 0xFFFFFFFFu;
+                    r = dp4a_us(v[f + k], (wn ? CRE2 : CRE0) & m, r);
+                    i = dp4a_us(v[f + k], (wn ? CIM2 : CIM0) & m, i);
+                }
+                re[2 * q] = r;
+                im[2 * q] = i;
+            }
+            // window B: starts on the second sample of word f + HW
+            {
+                const int ph = (2 * ((f + HW) & 1) + 1) & 3;
+                int32_t r = BoxK<DT>::re(ph), i = BoxK<DT>::im(ph);
+#pragma unroll
+                for (int k = HW; k < DT; k++) {
+                    const bool wn = (f + k) & 1;
+                    const uint32_t m = k == HW ? HI : 0xFFFFFFFFu;
+                    r = dp4a_us(v[f + k], (wn ? CRE2 : CRE0) & m, r);
+                    i = dp4a_us(v[f + k], (wn ? CIM2 : CIM0) & m, i);
+                }
+                re[2 * q + 1] = r;
+                im[2 * q + 1] = i;
+            }
+        }
+        int32_t pre = __shfl_up_sync(0xffffffffu, re[3], 1), pim = __shfl_up_sync(0xffffffffu, im[3], 1);
+        if (lane == 0 && g > 0) {   // the B window of the pair before this row: row indices S - DT + HW .. S - 1
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
+            const int f = S - DT;
+            const int ph = (2 * ((f + HW) & 1) + 1) & 3;
+            pre = BoxK<DT>::re(ph);
+            pim = BoxK<DT>::im(ph);
+#pragma unroll
+            for (int k = HW; k < DT; k++) {
+                const bool wn = (f + k) & 1;
+                const uint32_t m = k == HW ? HI : 0xFFFFFFFFu;
+                pre = dp4a_us(__ldg(w + (f + k)), (wn ? CRE2 : CRE0) & m, pre);
+                pim = dp4a_us(__ldg(w + (f + k)), (wn ? CIM2 : CIM0) & m, pim);
+            }
+        }
+        const int32_t w0 = 4 * (int32_t)g - E;   // tile-relative index of the row's first window
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int32_t cre, cim;
+            d_cmul_conj(make_int2(re[j], im[j]), j ? make_int2(re[j - 1], im[j - 1]) : make_int2(pre, pim), cre, cim);
+            const int32_t o = d_fast_atan2_t<true>(cim, cre);
+            const int32_t w = w0 + j;
+            if (g < ngroups && (E == 0 || j > 0 || w >= 0) && w <= last_w) dm[w] = (int16_t)(uint16_t)(uint32_t)o;
         }
     }
 }
@@ -460,7 +547,21 @@ template <int DT, int NTH, bool GLOBAL>
 __device__ __forceinline__ void dn_pass(const unsigned char *tile, const TileInfo &ti, int16_t *dm, const int tid) {
     const int32_t off0 = ti.off0;
     const uint32_t nlp = ti.nlp;
-    if (DT != 6 || !(off0 & 1)) {   // DT != 6: the host only launches this form for even window starts
+    if constexpr (PassGeom<DT>::ODD) {
+        static_assert(GLOBAL, "the odd-downsample pass exists in the direct form only");
+        const int e = off0 & 1;                                   // window 0 starts on an odd sample
+        const int32_t byte0 = 2 * (off0 - e * DT);                // first byte of the pair that holds window 0
+        const int32_t a0 = byte0 & ~7;
+        const uint32_t ngroups = (nlp + (uint32_t)e + 3) / 4;
+        const int32_t last_w = (int32_t)nlp - 1;
+        switch (((byte0 >> 2) & 1) * 2 + e) {
+        case 0: dn_pass_odd<DT, 0, 0, NTH>(tile, a0, ngroups, last_w, dm); break;
+        case 1: dn_pass_odd<DT, 0, 1, NTH>(tile, a0, ngroups, last_w, dm); break;
+        case 2: dn_pass_odd<DT, 1, 0, NTH>(tile, a0, ngroups, last_w, dm); break;
+        default: dn_pass_odd<DT, 1, 1, NTH>(tile, a0, ngroups, last_w, dm); break;
+        }
+        return;
+    } else if (DT != 6 || !(off0 & 1)) {   // even DT != 6: the host only launches this form for even window starts
         constexpr int KW = PassGeom<DT>::KW;
         const int32_t byte0 = 2 * off0;   // first byte of window 0 (negative on a tile that starts inside it)
         const int32_t a0 = byte0 & ~15;
@@ -719,7 +820,7 @@ __global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedAr
 }
 // CTAs per SM the register allocation aims for: 8 (32 registers) while a lane's row is at most 16 words, fewer for
 // the wider rows of DT = 8 / 10 (a spilled row costs more than the lost occupancy)
-constexpr int direct_min_blocks(int DT) { return DT == 10 ? 5 : DT == 8 ? 6 : 8; }
+constexpr int direct_min_blocks(int DT) { return DT == 13 ? 4 : (DT == 10 || DT == 11) ? 5 : (DT == 8 || DT == 9) ? 6 : 8; }
 template <int DT>
 __global__ void __launch_bounds__(256, direct_min_blocks(DT)) k_demod_direct(const FusedArgs a) {
     demod_tile<DT, true>(a, blockIdx.x, gridDim.x, 0, true);
@@ -1124,7 +1225,7 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     // D = 6 with an even window start (every stream that was not given an odd prev_index by hand): direct kernel, with
     // the largest tile that still leaves `kDirectWaves` full waves of 8 CTAs per SM (SDR_INT_DIRECT_PASSES pins it)
     const Geom *g = &d->geo;
-    const bool direct = d->n_direct > 0 && !(p0 & 1);
+    const bool direct = d->n_direct > 0 && ((d->cfg.downsample & 1) || !(p0 & 1));   // odd downsamples take any window start
     if (direct) {
         constexpr uint64_t kDirectWaves = 4;
         int k = d->n_direct - 1;
@@ -1145,14 +1246,14 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     uint64_t blocks = pl.Etot ? (pl.Etot + g->EB - 1) / g->EB : 1;
     if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "batch too large for one launch");
     if (direct) {
+#define SDR_DIRECT_CASE(DT_) \
+    case DT_: k_demod_direct<DT_><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
         switch (d->cfg.downsample) {
-        case 2: k_demod_direct<2><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
-        case 4: k_demod_direct<4><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
-        case 6: k_demod_direct<6><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
-        case 8: k_demod_direct<8><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
-        case 10: k_demod_direct<10><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
-        default: k_demod_direct<12><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+            SDR_DIRECT_CASE(2) SDR_DIRECT_CASE(3) SDR_DIRECT_CASE(4) SDR_DIRECT_CASE(5) SDR_DIRECT_CASE(6) SDR_DIRECT_CASE(7)
+            SDR_DIRECT_CASE(8) SDR_DIRECT_CASE(9) SDR_DIRECT_CASE(10) SDR_DIRECT_CASE(11) SDR_DIRECT_CASE(12)
+            default: k_demod_direct<13><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
         }
+#undef SDR_DIRECT_CASE
     } else if (d->cfg.downsample == 6)
         k_demod_fused<6><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
     else
@@ -1225,7 +1326,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     {
         const char *ed = getenv("SDR_INT_DIRECT");
         if (has_fused_pass((int)D) && !(ed && atoi(ed) == 0)) {
-            const uint64_t kw = D == 2 ? 8 : D == 12 ? 2 : 4;   // PassGeom<D>::KW: windows per lane
+            const uint64_t kw = (D & 1) ? 4 : D == 2 ? 8 : D == 12 ? 2 : 4;   // PassGeom<D>::KW: windows per lane
             for (int k = 0; k < 4; k++)
                 if (make_geom(D, fast, slow, ((256 * kw) << k) - 2, d->geo_direct[k]) && d->geo_direct[k].smem_direct <= 48 * 1024)
                     d->n_direct = k + 1;

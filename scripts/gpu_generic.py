@@ -14,7 +14,8 @@ d_in = S.DevBuffer(2 * n)
 S.synth_fill_dev(d_in, 2 * n, 0xB2000001)
 BUF = 262144
 for D, fast, slow in ((6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48_000), (8, 125_000, 32_000), (10, 100_000, 32_000),
-                      (12, 170_000, 32_000), (5, 200_000, 32_000), (11, 100_000, 32_000), (16, 150_000, 48_000), (21, 50_000, 32_000),
+                      (12, 170_000, 32_000), (3, 334_000, 48_000), (5, 200_000, 32_000), (7, 143_000, 32_000), (9, 112_000, 32_000),
+                      (11, 100_000, 32_000), (13, 80_000, 32_000), (16, 150_000, 48_000), (21, 50_000, 32_000),
                       (32, 32_000, 32_000)):
     cfg = S.DemodConfig(fast * D, fast, slow, D, 42)
     h = S.Demod(cfg)

@@ -181,7 +181,9 @@ def test_stage_streams_with_state_carry(S, D, fast, slow):
                                          (7, 100_003, 31_999), (64, 250_000, 48_000),
                                          # the other even downsamples with the register-resident direct kernel
                                          (2, 96_000, 48_000), (4, 250_000, 48_000), (8, 125_000, 32_000),
-                                         (10, 100_000, 32_000), (12, 170_000, 32_000)])
+                                         (10, 100_000, 32_000), (12, 170_000, 32_000),
+                                         # odd downsamples: pair-of-windows pass
+                                         (5, 200_000, 32_000), (9, 112_000, 32_000), (11, 100_000, 48_000), (13, 80_000, 32_000)])
 def test_fused_demodulate_ragged_calls(S, D, fast, slow):
     rng = np.random.default_rng(100 + D)
     g, o = S.Demod(cfg_of(S, D, fast, slow)), O.Demod(ocfg_of(D, fast, slow))
@@ -199,7 +201,7 @@ def test_fused_demodulate_ragged_calls(S, D, fast, slow):
 
 
 @pytest.mark.parametrize("D,fast,slow", [(6, 170_000, 32_000), (6, 48_000, 48_000), (15, 160_000, 32_000),
-                                         (8, 125_000, 32_000), (12, 170_000, 32_000)])
+                                         (8, 125_000, 32_000), (12, 170_000, 32_000), (5, 200_000, 32_000), (7, 143_000, 32_000)])
 def test_fused_demodulate_from_arbitrary_carried_state(S, D, fast, slow):
     """struct Demod's fields (:234-238) set to values no zero-initialised stream reaches: an odd prev_index (the
     D = 6 kernel's odd-window-start pass), prev_lpr_index >= rate_resample (a first audio window with fewer samples
@@ -231,7 +233,9 @@ def test_fused_demodulate_from_arbitrary_carried_state(S, D, fast, slow):
 
 
 @pytest.mark.parametrize("D,fast,slow", [(6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48_000),
-                                         (8, 125_000, 32_000), (10, 100_000, 32_000), (12, 170_000, 32_000)])
+                                         (8, 125_000, 32_000), (10, 100_000, 32_000), (12, 170_000, 32_000),
+                                         (3, 334_000, 48_000), (5, 200_000, 32_000), (7, 143_000, 32_000),
+                                         (9, 112_000, 32_000), (11, 100_000, 48_000), (13, 80_000, 32_000)])
 @pytest.mark.parametrize("passes", [1, 2, 4, 8])
 def test_direct_kernel_every_tile_size(S, monkeypatch, D, fast, slow, passes):
     """The direct kernel picks its tile size from the batch size; pin each size (SDR_INT_DIRECT_PASSES) on a batch
