@@ -684,7 +684,7 @@ __device__ __forceinline__ void tile_state_out(const FusedArgs &a, const IntStat
 // buffer, so a CTA costs only the 6 KB dm array, the SM holds as many CTAs as the register file allows and the HBM
 // latency is hidden by warps, not by a per-CTA copy-then-compute phase.  The ring keeps the staged form (its input slots
 // are written by the copy engine while the kernel is resident; the mbarrier orders those bytes).
-template <int DT, bool DIRECT = false>
+template <int DT, bool DIRECT = false, int NTH = 256>
 __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t tile_idx, const uint32_t n_tiles,
                                            const uint32_t parity, const bool first_use) {
     static_assert(!DIRECT || has_fused_pass(DT), "the direct form exists for the downsamples with a register-resident pass");
@@ -731,8 +731,8 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     if constexpr (DT == 6 || DIRECT) {
         // ---- D = 6 (optimal_settings :189-190): boxcar + discriminator fused, no window array ---------------
         if (!DIRECT) mbar_wait(&bar, parity);
-        dn_pass<DT, 256, DIRECT>(tile, ti, dm, tid);
-        if (last && tid == 255) {
+        dn_pass<DT, NTH, DIRECT>(tile, ti, dm, tid);
+        if (last && tid == NTH - 1) {
             int32_t re = 0, im = 0;
             boxcar_rot(w32, (int)ti.tail_from, (int)(ti.tail_from + ti.ntail), re, im);
             a.st_out->lp_now_re = re;
@@ -779,7 +779,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
                 boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)D, re, im);
             lp[i] = make_int2(re, im);
         }
-        if (last && tid == 255) {
+        if (last && tid == NTH - 1) {
             int32_t re = 0, im = 0;
             boxcar_rot(w32, (int)ti.tail_from, (int)(ti.tail_from + ti.ntail), re, im);
             a.st_out->lp_now_re = re;
@@ -821,9 +821,13 @@ __global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedAr
 // CTAs per SM the register allocation aims for: 8 (32 registers) while a lane's row is at most 16 words, fewer for
 // the wider rows of DT = 8 / 10 (a spilled row costs more than the lost occupancy)
 constexpr int direct_min_blocks(int DT) { return DT == 13 ? 4 : (DT == 10 || DT == 11) ? 5 : (DT == 8 || DT == 9) ? 6 : 8; }
+#ifndef SDR_INT_DIRECT_NTH
+#define SDR_INT_DIRECT_NTH 256   // threads per CTA of the direct kernel (128: 0.420 vs 0.426 ms on cfg1, 64 and 512 slower)
+#endif
+constexpr int kDirectNth = SDR_INT_DIRECT_NTH;
 template <int DT>
-__global__ void __launch_bounds__(256, direct_min_blocks(DT)) k_demod_direct(const FusedArgs a) {
-    demod_tile<DT, true>(a, blockIdx.x, gridDim.x, 0, true);
+__global__ void __launch_bounds__(kDirectNth, direct_min_blocks(DT) * 256 / kDirectNth) k_demod_direct(const FusedArgs a) {
+    demod_tile<DT, true, kDirectNth>(a, blockIdx.x, gridDim.x, 0, true);
 }
 
 // ================================================================================================
@@ -1247,11 +1251,11 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "batch too large for one launch");
     if (direct) {
 #define SDR_DIRECT_CASE(DT_) \
-    case DT_: k_demod_direct<DT_><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+    case DT_: k_demod_direct<DT_><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
         switch (d->cfg.downsample) {
             SDR_DIRECT_CASE(2) SDR_DIRECT_CASE(3) SDR_DIRECT_CASE(4) SDR_DIRECT_CASE(5) SDR_DIRECT_CASE(6) SDR_DIRECT_CASE(7)
             SDR_DIRECT_CASE(8) SDR_DIRECT_CASE(9) SDR_DIRECT_CASE(10) SDR_DIRECT_CASE(11) SDR_DIRECT_CASE(12)
-            default: k_demod_direct<13><<<(unsigned)blocks, 256, g->smem_direct, d->stream>>>(a); break;
+            default: k_demod_direct<13><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
         }
 #undef SDR_DIRECT_CASE
     } else if (d->cfg.downsample == 6)
@@ -1328,7 +1332,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
         if (has_fused_pass((int)D) && !(ed && atoi(ed) == 0)) {
             const uint64_t kw = (D & 1) ? 4 : D == 2 ? 8 : D == 12 ? 2 : 4;   // PassGeom<D>::KW: windows per lane
             for (int k = 0; k < 4; k++)
-                if (make_geom(D, fast, slow, ((256 * kw) << k) - 2, d->geo_direct[k]) && d->geo_direct[k].smem_direct <= 48 * 1024)
+                if (make_geom(D, fast, slow, ((kDirectNth * kw) << k) - 2, d->geo_direct[k]) && d->geo_direct[k].smem_direct <= 48 * 1024)
                     d->n_direct = k + 1;
                 else
                     break;

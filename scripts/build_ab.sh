@@ -10,7 +10,7 @@ for f in csrc/*.cu; do
   nvcc $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr $FLAGS -c $f -o build/ab_$NAME/$(basename $f .cu).o &
 done
 for f in csrc/*.cpp; do
-  nvcc -O2 -std=c++17 -Xcompiler -fPIC $FLAGS -c $f -o build/ab_$NAME/$(basename $f .cpp).o &
+  nvcc -O2 -std=c++17 -Ibuild -Xcompiler -fPIC $FLAGS -c $f -o build/ab_$NAME/$(basename $f .cpp).o &
 done
 wait
 nvcc $ARCH -shared -o lib/ab/libsdr_$NAME.so build/ab_$NAME/*.o -lpthread -ldl
