@@ -197,11 +197,8 @@ __device__ __forceinline__ void boxcar_rot(const uint32_t *w32, int pos, int end
     }
 }
 
-// Compile-time-D version for whole windows (DT even): straight-line code.  With the phase-0 coefficient
-// vectors C (phase-2 words use -C), half-word masks m_j for an odd start, and the per-sample constants
-// folded into K[pos & 3]:
-//     re = sgn * ( sum_{j even} dp4a(w_j, Cre & m_j) - sum_{j odd} dp4a(w_j, Cre & m_j) ) + Kre[pos & 3]
-// where w_j are the words the window touches and sgn = -1 iff the first word is a phase-2 word.
+// Sum of the per-sample constants of a DT-sample window that starts at sample phase ph (the `255 - x` then `- 127`
+// asymmetry of rotate_90 + centring lives here; the dp4a coefficients carry the +-1 factors).
 template <int DT>
 struct BoxK {   // constants of a DT-sample window that starts at sample phase ph: sum of the per-sample constants
     static constexpr int re(int ph) {
@@ -221,53 +218,6 @@ struct BoxK {   // constants of a DT-sample window that starts at sample phase p
         return k;
     }
 };
-
-template <int DT>
-__device__ __forceinline__ void boxcar_rot_fixed(const uint32_t *w32, int pos, int32_t &re, int32_t &im) {
-    static_assert(DT >= 2 && DT % 2 == 0, "even window length");
-    constexpr uint32_t CRE = 0xFF000001u, CIM = 0x00010100u;   // phase-0 word: re [+1,0,0,-1], im [0,+1,+1,0]
-    constexpr int NWE = DT / 2;
-    const uint32_t *w = w32 + (pos >> 1);
-    int32_t er = 0, orr = 0, ei = 0, oi = 0;
-    if (!(pos & 1)) {
-#pragma unroll
-        for (int j = 0; j < NWE; j++) {
-            const uint32_t v = w[j];
-            if (j & 1) {
-                orr = dp4a_us(v, CRE, orr);
-                oi = dp4a_us(v, CIM, oi);
-            } else {
-                er = dp4a_us(v, CRE, er);
-                ei = dp4a_us(v, CIM, ei);
-            }
-        }
-    } else {   // head = upper half of w[0], tail = lower half of w[NWE]
-#pragma unroll
-        for (int j = 0; j <= NWE; j++) {
-            const uint32_t v = w[j];
-            const uint32_t m = j == 0 ? 0xFFFF0000u : (j == NWE ? 0x0000FFFFu : 0xFFFFFFFFu);
-            if (j & 1) {
-                orr = dp4a_us(v, CRE & m, orr);
-                oi = dp4a_us(v, CIM & m, oi);
-            } else {
-                er = dp4a_us(v, CRE & m, er);
-                ei = dp4a_us(v, CIM & m, ei);
-            }
-        }
-    }
-    const bool neg = (pos >> 1) & 1;   // first word is a phase-2 word
-    const int32_t sr = er - orr, si = ei - oi;
-    // K[pos & 3] from two packed 64-bit literals (4 x int16): one shift + sign-extend instead of a select tree
-    constexpr unsigned long long PK_RE = ((unsigned long long)(uint16_t)BoxK<DT>::re(0)) | ((unsigned long long)(uint16_t)BoxK<DT>::re(1) << 16) |
-                                         ((unsigned long long)(uint16_t)BoxK<DT>::re(2) << 32) | ((unsigned long long)(uint16_t)BoxK<DT>::re(3) << 48);
-    constexpr unsigned long long PK_IM = ((unsigned long long)(uint16_t)BoxK<DT>::im(0)) | ((unsigned long long)(uint16_t)BoxK<DT>::im(1) << 16) |
-                                         ((unsigned long long)(uint16_t)BoxK<DT>::im(2) << 32) | ((unsigned long long)(uint16_t)BoxK<DT>::im(3) << 48);
-    static_assert(DT * 128 < 32768, "window constants must fit int16");
-    const int sh = (pos & 3) * 16;
-    const int32_t kr = (int32_t)(int16_t)(PK_RE >> sh), ki = (int32_t)(int16_t)(PK_IM >> sh);
-    re = wadd(re, wadd(neg ? -sr : sr, kr));
-    im = wadd(im, wadd(neg ? -si : si, ki));
-}
 
 __device__ __forceinline__ unsigned long long udiv64(unsigned long long n, UDiv64 d) {
     return d.shift == 0xffffffffu ? n : (__umul64hi(n, d.magic) >> d.shift);
@@ -542,7 +492,7 @@ __device__ __forceinline__ void d6_fixups(const FusedArgs &a, const IntState &st
 }
 
 // Main pass over one tile (rotate_90 + centre + boxcar + discriminator -> dm) for the downsamples that have the
-// register-resident form; D = 6 also handles an odd window start (below).
+// register-resident form.
 template <int DT, int NTH, bool GLOBAL>
 __device__ __forceinline__ void dn_pass(const unsigned char *tile, const TileInfo &ti, int16_t *dm, const int tid) {
     const int32_t off0 = ti.off0;
@@ -561,7 +511,9 @@ __device__ __forceinline__ void dn_pass(const unsigned char *tile, const TileInf
         default: dn_pass_odd<DT, 1, 1, NTH>(tile, a0, ngroups, last_w, dm); break;
         }
         return;
-    } else if (DT != 6 || !(off0 & 1)) {   // even DT != 6: the host only launches this form for even window starts
+    } else {
+        // even downsample: the host launches this form for even window starts only (an odd one needs an odd prev_index
+        // set by hand, sdr_demod_set_state, and takes the generic three-phase kernel)
         constexpr int KW = PassGeom<DT>::KW;
         const int32_t byte0 = 2 * off0;   // first byte of window 0 (negative on a tile that starts inside it)
         const int32_t a0 = byte0 & ~15;
@@ -571,52 +523,6 @@ __device__ __forceinline__ void dn_pass(const unsigned char *tile, const TileInf
         case 1: dn_pass_even<DT, 1, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
         case 2: dn_pass_even<DT, 2, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
         default: dn_pass_even<DT, 3, NTH, GLOBAL>(tile, a0, ngroups, dm); break;
-        }
-        return;
-    }
-    // odd window start (only reachable through sdr_demod_set_state with an odd prev_index): one window per lane,
-    // 4 half-masked words; lane L of a warp owns window b + L, lanes 1..31 emit dm (predecessor by shuffle), lane 0
-    // is the predecessor only.  The rotation phase alternates with the window index, whose parity is fixed per thread
-    // (the loop stride 31 * warps is even), so the dp4a coefficient words live in registers.
-    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
-    const uint32_t skip = (uint32_t)(ti.jlo - ti.wlo);
-    const int lane = tid & 31, warp = tid >> 5;
-    const int32_t i0 = (int32_t)skip - 1 + 31 * warp + lane;
-    const int32_t pos0 = off0 + 6 * i0;
-    const bool neg0 = (pos0 >> 1) & 1;
-    uint32_t cr[4], ci[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t m = j == 0 ? 0xFFFF0000u : (j == 3 ? 0x0000FFFFu : 0xFFFFFFFFu);
-        const bool sn = neg0 != (bool)(j & 1);
-        cr[j] = (sn ? 0x010000FFu : 0xFF000001u) & m;
-        ci[j] = (sn ? 0x00FFFF00u : 0x00010100u) & m;
-    }
-    constexpr unsigned long long PK_RE = ((unsigned long long)(uint16_t)BoxK<6>::re(0)) | ((unsigned long long)(uint16_t)BoxK<6>::re(1) << 16) |
-                                         ((unsigned long long)(uint16_t)BoxK<6>::re(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::re(3) << 48);
-    constexpr unsigned long long PK_IM = ((unsigned long long)(uint16_t)BoxK<6>::im(0)) | ((unsigned long long)(uint16_t)BoxK<6>::im(1) << 16) |
-                                         ((unsigned long long)(uint16_t)BoxK<6>::im(2) << 32) | ((unsigned long long)(uint16_t)BoxK<6>::im(3) << 48);
-    const int32_t kr = (int32_t)(int16_t)(PK_RE >> ((pos0 & 3) * 16)), ki = (int32_t)(int16_t)(PK_IM >> ((pos0 & 3) * 16));
-    const int32_t last_i = (int32_t)nlp - 1;
-    for (int32_t b = (int32_t)skip - 1 + 31 * warp; b < last_i; b += 31 * (NTH / 32)) {
-        const int32_t i = b + lane;
-        // clamped lanes (window -1 of the first tile, windows past the tile) compute garbage nobody uses
-        int32_t pos = off0 + 6 * (i > last_i ? last_i : i);
-        pos = pos < 0 ? 0 : pos;
-        const uint32_t *w = w32 + (pos >> 1);
-        const uint32_t v0 = w[0], v1 = w[1], v2 = w[2], v3 = w[3];
-        int32_t re = dp4a_us(v0, cr[0], kr), im = dp4a_us(v0, ci[0], ki);
-        re = dp4a_us(v1, cr[1], re);
-        im = dp4a_us(v1, ci[1], im);
-        re = dp4a_us(v2, cr[2], re);
-        im = dp4a_us(v2, ci[2], im);
-        re = dp4a_us(v3, cr[3], re);
-        im = dp4a_us(v3, ci[3], im);
-        const int32_t pre = __shfl_up_sync(0xffffffffu, re, 1), pim = __shfl_up_sync(0xffffffffu, im, 1);
-        if (lane && i <= last_i) {
-            int32_t cre, cim;
-            d_cmul_conj(make_int2(re, im), make_int2(pre, pim), cre, cim);
-            dm[i] = (int16_t)(uint16_t)(uint32_t)d_fast_atan2(cim, cre);
         }
     }
 }
@@ -773,10 +679,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
                 im = st.lp_now_im;
             }
             // base < 0 only for window 0 with p0 > 0: those samples are already in lp_now
-            if (DT > 0 && base >= 0)
-                boxcar_rot_fixed<(DT > 0 ? DT : 2)>(w32, base, re, im);
-            else
-                boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)D, re, im);
+            boxcar_rot(w32, base < 0 ? 0 : base, base + (int32_t)D, re, im);
             lp[i] = make_int2(re, im);
         }
         if (last && tid == NTH - 1) {
@@ -1059,7 +962,8 @@ struct Geom {
 };
 
 // n_lp_target = lowpassed windows per tile to aim for.  False: rate_out too large for the kernel's 32-bit relative math.
-static bool make_geom(uint64_t D, uint64_t fast, uint64_t slow, uint64_t n_lp_target, Geom &g) {
+// fused_layout: the staged D = 6 kernel keeps no window array and no flags in shared memory.
+static bool make_geom(uint64_t D, uint64_t fast, uint64_t slow, uint64_t n_lp_target, Geom &g, bool fused_layout) {
     if (n_lp_target < 4) n_lp_target = 4;
     if (n_lp_target > 8192) n_lp_target = 8192;
     uint64_t EB = n_lp_target * slow / fast;
@@ -1069,7 +973,7 @@ static bool make_geom(uint64_t D, uint64_t fast, uint64_t slow, uint64_t n_lp_ta
     // the kernel's relative index math and its magic division need (EB+1)*fast + slow < 2^31
     while (EB > 1 && (EB + 1) * fast + slow >= (1ull << 31)) EB /= 2;
     if ((EB + 1) * fast + slow >= (1ull << 31)) return false;
-    const bool d6 = D == 6;
+    const bool d6 = fused_layout;
     const uint64_t per = (fast + slow - 1) / slow;
     const uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
     // slack: 16-B pad in front (D = 6), bulk-copy rounding, chunk over-read
@@ -1094,7 +998,8 @@ struct sdr_demod {
     DevBuf d_in[2], d_out[2], d_state, d_a, d_b, d_c;
     PinBuf h_state;
     OctTable oct{};
-    Geom geo;                // staged-tile geometry (generic D, the ring, odd window starts)
+    Geom geo;                // staged-tile geometry of the handle's usual kernel (k_demod_fused<6> for D = 6, else <0>)
+    Geom geo_gen;            // D = 6 only: geometry of the generic kernel, which takes the odd window starts
     Geom geo_direct[4];      // direct kernel: tiles of 1, 2, 4, 8 passes (256 lanes x KW windows each); the launch picks by batch size
     int n_direct = 0;        // 0: direct kernel disabled (SDR_INT_DIRECT=0 or a downsample without the register-resident pass)
     size_t smem_bytes = 0;
@@ -1228,7 +1133,8 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     (void)n_calls;
     // D = 6 with an even window start (every stream that was not given an odd prev_index by hand): direct kernel, with
     // the largest tile that still leaves `kDirectWaves` full waves of 8 CTAs per SM (SDR_INT_DIRECT_PASSES pins it)
-    const Geom *g = &d->geo;
+    const bool odd_start_d6 = d->cfg.downsample == 6 && (p0 & 1);   // prev_index set by hand: generic kernel
+    const Geom *g = odd_start_d6 ? &d->geo_gen : &d->geo;
     const bool direct = d->n_direct > 0 && ((d->cfg.downsample & 1) || !(p0 & 1));   // odd downsamples take any window start
     if (direct) {
         constexpr uint64_t kDirectWaves = 4;
@@ -1258,7 +1164,7 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
             default: k_demod_direct<13><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
         }
 #undef SDR_DIRECT_CASE
-    } else if (d->cfg.downsample == 6)
+    } else if (d->cfg.downsample == 6 && !(p0 & 1))
         k_demod_fused<6><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
     else
         k_demod_fused<0><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
@@ -1317,11 +1223,11 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
         if (passes < 1 || passes > 8) passes = 3;
         n_lp_target = 1024ull * passes - 2;
     }
-    if (!make_geom(D, fast, slow, n_lp_target, d->geo)) {
+    if (!make_geom(D, fast, slow, n_lp_target, d->geo, d6) || !make_geom(D, fast, slow, 8192 / D, d->geo_gen, false)) {
         delete d;
         return fail(SDR_E_ARG, "rate_out too large");
     }
-    const size_t smem = d->geo.smem_staged;
+    const size_t smem = std::max(d->geo.smem_staged, d->geo_gen.smem_staged);
     if (smem > 200 * 1024) {
         delete d;
         return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
@@ -1332,7 +1238,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
         if (has_fused_pass((int)D) && !(ed && atoi(ed) == 0)) {
             const uint64_t kw = (D & 1) ? 4 : D == 2 ? 8 : D == 12 ? 2 : 4;   // PassGeom<D>::KW: windows per lane
             for (int k = 0; k < 4; k++)
-                if (make_geom(D, fast, slow, ((kDirectNth * kw) << k) - 2, d->geo_direct[k]) && d->geo_direct[k].smem_direct <= 48 * 1024)
+                if (make_geom(D, fast, slow, ((kDirectNth * kw) << k) - 2, d->geo_direct[k], true) && d->geo_direct[k].smem_direct <= 48 * 1024)
                     d->n_direct = k + 1;
                 else
                     break;
@@ -1626,10 +1532,12 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     f.d64_slow = magic64(d->cfg.rate_resample);
     f.d64_S = magic64(S);
     f.d64_D = magic64(d->cfg.downsample);
-    f.EB = d->geo.EB;
-    f.lp_cap = d->geo.lp_cap;
-    f.tile_cap = d->geo.tile_cap;
-    f.dm_off = d->geo.dm_off;
+    const bool d6 = d->cfg.downsample == 6 && !(r->p0 & 1);   // an odd window start takes the generic kernel
+    const Geom &rg = (d->cfg.downsample == 6 && !d6) ? d->geo_gen : d->geo;
+    f.EB = rg.EB;
+    f.lp_cap = rg.lp_cap;
+    f.tile_cap = rg.tile_cap;
+    f.dm_off = rg.dm_off;
     f.oct = d->oct;
     a.ctl = r->d_ctl.as<RingCtl>();
     a.seq_done = r->h_seq_done_dev;
@@ -1642,9 +1550,8 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     a.p0 = r->p0;
     a.q0 = r->q0;
     a.d64_fast = magic64(d->cfg.rate_out);
-    unsigned tiles = (unsigned)((pl.Etot + 1 + d->geo.EB - 1) / d->geo.EB + 1);
+    unsigned tiles = (unsigned)((pl.Etot + 1 + rg.EB - 1) / rg.EB + 1);
     unsigned grid = std::max(1u, std::min(tiles, (unsigned)sm_count(d->device) / 2));
-    const bool d6 = d->cfg.downsample == 6;
     e = d6 ? cudaFuncSetAttribute(k_demod_ring<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes)
            : cudaFuncSetAttribute(k_demod_ring<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes);
     if (e == cudaSuccess) {
