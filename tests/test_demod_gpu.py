@@ -256,6 +256,38 @@ def test_direct_kernel_every_tile_size(S, monkeypatch, D, fast, slow, passes):
     assert np.array_equal(g.demodulate(more), o.demodulate(more))
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_configs_states_and_chunkings_vs_oracle(S, seed):
+    """Randomised sweep: downsample 1..20 (every kernel family: direct even/odd, generic), arbitrary rate ratios
+    (fast/slow == 5 among them: the straight-line resampler), random carried state, random call lengths, single calls
+    and batches — bit-exact audio and state against the oracle."""
+    rng = np.random.default_rng(0xB200 + seed)
+    for _ in range(5):
+        D = int(rng.integers(1, 21))
+        fast = int(rng.choice([8_000, 48_000, 100_003, 160_000, 170_000, 250_000, 400_000]))
+        slow = int(rng.choice([max(1, fast // 5 - 1), fast // 5, max(1, fast // 5 + 7), fast, max(1, fast // 3), 32_000 if fast >= 32_000 else fast]))
+        slow = min(slow, fast)
+        g, o = S.Demod(cfg_of(S, D, fast, slow)), O.Demod(ocfg_of(D, fast, slow))
+        st = dict(prev_index=int(rng.integers(0, D)), now_lpr=int(rng.integers(-50_000, 50_000)),
+                  prev_lpr_index=int(rng.integers(0, fast)), lp_now=(int(rng.integers(-700, 700)), int(rng.integers(-700, 700))),
+                  demod_pre=(int(rng.integers(-768, 769)), int(rng.integers(-768, 769))))
+        g.set_state(**st)
+        o.set_state(**st)
+        min_len = ((2 * D * 2 + 7) // 8 + 1) * 8
+        for _ in range(4):
+            ln = min_len + 8 * int(rng.integers(0, 40_000))
+            buf = rng.integers(0, 256, ln, dtype=np.uint8)
+            want = o.demodulate(buf)
+            got = g.demodulate(buf)
+            assert np.array_equal(got, want), (D, fast, slow, st, ln)
+            assert g.state() == o.state(), (D, fast, slow, st, ln)
+        buf_len, n_bufs = min_len + 8 * int(rng.integers(0, 3000)), int(rng.integers(2, 40))
+        data = rng.integers(0, 256, buf_len * n_bufs, dtype=np.uint8)
+        want = np.concatenate([o.demodulate(data[i * buf_len:(i + 1) * buf_len]) for i in range(n_bufs)])
+        assert np.array_equal(g.demodulate_batch(data, buf_len), want), (D, fast, slow, buf_len, n_bufs)
+        assert g.state() == o.state()
+
+
 def test_fused_rejects_what_the_reference_panics_on(S):
     d = S.Demod()
     for bad in (12, 16, 0):
