@@ -1000,6 +1000,8 @@ struct sdr_demod {
     OctTable oct{};
     Geom geo;                // staged-tile geometry of the handle's usual kernel (k_demod_fused<6> for D = 6, else <0>)
     Geom geo_gen;            // D = 6 only: geometry of the generic kernel, which takes the odd window starts
+    Geom geo_ring;           // the persistent ring's tiles (D = 6: SDR_RING_PASSES passes, default 1 — one USB buffer is
+                             // only ~21845 windows, small tiles spread it over more CTAs)
     Geom geo_direct[4];      // direct kernel: tiles of 1, 2, 4, 8 passes (256 lanes x KW windows each); the launch picks by batch size
     int n_direct = 0;        // 0: direct kernel disabled (SDR_INT_DIRECT=0 or a downsample without the register-resident pass)
     size_t smem_bytes = 0;
@@ -1227,7 +1229,14 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
         delete d;
         return fail(SDR_E_ARG, "rate_out too large");
     }
-    const size_t smem = std::max(d->geo.smem_staged, d->geo_gen.smem_staged);
+    d->geo_ring = d->geo;
+    if (d6) {
+        const char *er = getenv("SDR_RING_PASSES");
+        int rp = er ? atoi(er) : 1;
+        if (rp < 1 || rp > 8) rp = 1;
+        if (!make_geom(D, fast, slow, 1024ull * rp - 2, d->geo_ring, true)) d->geo_ring = d->geo;
+    }
+    const size_t smem = std::max(std::max(d->geo.smem_staged, d->geo_gen.smem_staged), d->geo_ring.smem_staged);
     if (smem > 200 * 1024) {
         delete d;
         return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
@@ -1533,7 +1542,7 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     f.d64_S = magic64(S);
     f.d64_D = magic64(d->cfg.downsample);
     const bool d6 = d->cfg.downsample == 6 && !(r->p0 & 1);   // an odd window start takes the generic kernel
-    const Geom &rg = (d->cfg.downsample == 6 && !d6) ? d->geo_gen : d->geo;
+    const Geom &rg = (d->cfg.downsample == 6 && !d6) ? d->geo_gen : d->geo_ring;
     f.EB = rg.EB;
     f.lp_cap = rg.lp_cap;
     f.tile_cap = rg.tile_cap;
@@ -1556,9 +1565,9 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
            : cudaFuncSetAttribute(k_demod_ring<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes);
     if (e == cudaSuccess) {
         if (d6)
-            k_demod_ring<6><<<grid, 256, d->smem_bytes, r->ring_stream>>>(a);
+            k_demod_ring<6><<<grid, 256, rg.smem_staged, r->ring_stream>>>(a);
         else
-            k_demod_ring<0><<<grid, 256, d->smem_bytes, r->ring_stream>>>(a);
+            k_demod_ring<0><<<grid, 256, rg.smem_staged, r->ring_stream>>>(a);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {
