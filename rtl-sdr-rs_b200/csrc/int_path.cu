@@ -997,6 +997,12 @@ struct sdr_demod {
     cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_t0 = nullptr, ev_t1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
     DevBuf d_in[2], d_out[2], d_state, d_a, d_b, d_c;
     PinBuf h_state;
+    // small synchronous calls (one USB buffer per demodulate(), the reference's call pattern): pinned staging both
+    // ways, ONE H2D (input [+ state]), one launch, ONE D2H (audio + state), one stream.  The carried state stays on
+    // the device between such calls (slot of d_small_out that holds it, -1 = the host copy is the newer one).
+    PinBuf h_small_in, h_small_out;
+    DevBuf d_small_in, d_small_out[2];
+    int dev_state_slot = -1;
     OctTable oct{};
     Geom geo;                // staged-tile geometry of the handle's usual kernel (k_demod_fused<6> for D = 6, else <0>)
     Geom geo_gen;            // D = 6 only: geometry of the generic kernel, which takes the odd window starts
@@ -1175,6 +1181,65 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     return SDR_OK;
 }
 
+constexpr size_t kSmallCallBytes = size_t(1) << 20;
+
+// One synchronous call of n_bufs buffers whose bytes fit in kSmallCallBytes.  `total` = the plan of the whole call.
+int demodulate_small(sdr_demod *d, const uint8_t *buf, size_t buf_len, size_t n_bufs, const Plan &total, int16_t *out) {
+    const size_t in_bytes = buf_len * n_bufs;
+    const size_t in_pad = (in_bytes + 255) & ~size_t(255);          // state rides behind the input, clear of over-reads
+    const size_t out_cap_b = (kSmallCallBytes / 2 / std::max<uint32_t>(1, d->cfg.downsample) + 64) * sizeof(int16_t);
+    const size_t st_off = (out_cap_b + 15) & ~size_t(15);            // fixed place of the state behind the audio
+    int rc;
+    if ((rc = d->h_small_in.reserve(kSmallCallBytes + 512)) || (rc = d->h_small_out.reserve(st_off + sizeof(IntState))) ||
+        (rc = d->d_small_in.reserve(kSmallCallBytes + 512)))
+        return rc;
+    for (int i = 0; i < 2; i++)
+        if ((rc = d->d_small_out[i].reserve(st_off + sizeof(IntState)))) return rc;
+    if (total.Etot * sizeof(int16_t) > out_cap_b) return SDR_E_STATE;   // caller falls back to the general path
+    uint8_t *hin = d->h_small_in.as<uint8_t>();
+    memcpy(hin, buf, in_bytes);
+    size_t h2d = in_bytes;
+    const IntState *st_in;
+    if (d->dev_state_slot < 0) {
+        to_dev_state(d->st, *reinterpret_cast<IntState *>(hin + in_pad));
+        h2d = in_pad + sizeof(IntState);
+        st_in = reinterpret_cast<const IntState *>(d->d_small_in.as<uint8_t>() + in_pad);
+    } else {
+        st_in = reinterpret_cast<const IntState *>(d->d_small_out[d->dev_state_slot].as<uint8_t>() + st_off);
+    }
+    const int nslot = d->dev_state_slot < 0 ? 0 : d->dev_state_slot ^ 1;
+    uint8_t *dout = d->d_small_out[nslot].as<uint8_t>();
+    d->dev_state_slot = -1;   // until the call has completed
+    SDR_CUDA_TRY(cudaMemcpyAsync(d->d_small_in.p, hin, h2d, cudaMemcpyHostToDevice, d->stream));
+    d->last_launches = 0;
+    d->timing_valid = false;
+    if ((rc = launch_fused(d, d->d_small_in.as<uint8_t>(), buf_len / 2, n_bufs, (uint32_t)d->st.prev_index,
+                           (uint32_t)d->st.prev_lpr_index, total, st_in, reinterpret_cast<IntState *>(dout + st_off),
+                           reinterpret_cast<int16_t *>(dout))))
+        return rc;
+    // audio and state in one copy: [0, Etot*2) and [st_off, st_off + 32); the gap between them is a few KB at most
+    const size_t audio_b = (total.Etot * sizeof(int16_t) + 15) & ~size_t(15);
+    uint8_t *hout = d->h_small_out.as<uint8_t>();
+    if (st_off - audio_b <= 16384) {
+        SDR_CUDA_TRY(cudaMemcpyAsync(hout, dout, st_off + sizeof(IntState), cudaMemcpyDeviceToHost, d->stream));
+    } else {
+        if (audio_b) SDR_CUDA_TRY(cudaMemcpyAsync(hout, dout, audio_b, cudaMemcpyDeviceToHost, d->stream));
+        SDR_CUDA_TRY(cudaMemcpyAsync(hout + st_off, dout + st_off, sizeof(IntState), cudaMemcpyDeviceToHost, d->stream));
+    }
+    SDR_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    memcpy(out, hout, total.Etot * sizeof(int16_t));
+    const IntState *h = reinterpret_cast<const IntState *>(hout + st_off);
+    d->st.lp_now_re = h->lp_now_re;
+    d->st.lp_now_im = h->lp_now_im;
+    d->st.demod_pre_re = h->demod_pre_re;
+    d->st.demod_pre_im = h->demod_pre_im;
+    d->st.now_lpr = h->now_lpr;
+    d->st.prev_index = total.p1;
+    d->st.prev_lpr_index = (int32_t)total.q1;
+    d->dev_state_slot = nslot;
+    return SDR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1285,6 +1350,7 @@ void sdr_demod_free(sdr_demod *d) {
     for (int i = 0; i < 2; i++) {
         d->d_in[i].release();
         d->d_out[i].release();
+        d->d_small_out[i].release();
         if (d->ev_h2d[i]) cudaEventDestroy(d->ev_h2d[i]);
         if (d->ev_done[i]) cudaEventDestroy(d->ev_done[i]);
     }
@@ -1293,6 +1359,9 @@ void sdr_demod_free(sdr_demod *d) {
     d->d_b.release();
     d->d_c.release();
     d->h_state.release();
+    d->d_small_in.release();
+    d->h_small_in.release();
+    d->h_small_out.release();
     if (d->ev_t0) cudaEventDestroy(d->ev_t0);
     if (d->ev_t1) cudaEventDestroy(d->ev_t1);
     if (d->ev_s0) cudaEventDestroy(d->ev_s0);
@@ -1318,6 +1387,7 @@ int sdr_demod_set_state(sdr_demod *d, const sdr_demod_state *st) {
     if (st->prev_lpr_index < 0 || (uint32_t)st->prev_lpr_index >= d->cfg.rate_out)
         return fail(SDR_E_ARG, "prev_lpr_index must be in [0, rate_out)");
     d->st = *st;
+    d->dev_state_slot = -1;
     return SDR_OK;
 }
 
@@ -1350,6 +1420,12 @@ long sdr_demod_demodulate_batch(sdr_demod *d, const uint8_t *buf, size_t buf_len
             q = one.q1;
         }
     }
+    if (buf_len * n_bufs <= kSmallCallBytes && !getenv("SDR_INT_NO_SMALL_PATH")) {
+        rc = demodulate_small(d, buf, buf_len, n_bufs, total, out);
+        if (rc == SDR_OK) return (long)total.Etot;
+        if (rc != SDR_E_STATE) return rc;   // SDR_E_STATE: does not fit the small buffers, take the general path
+    }
+    d->dev_state_slot = -1;   // the general path leaves the newest state on the host
     size_t per_chunk = kChunkBytes / buf_len;
     if (per_chunk < 1) per_chunk = 1;
     if (per_chunk > n_bufs) per_chunk = n_bufs;
@@ -1419,6 +1495,7 @@ long sdr_demod_demodulate_batch_dev(sdr_demod *d, const uint8_t *d_buf, size_t b
     Plan pl = make_plan(d->cfg, p0, q0, S, n_bufs);
     if (pl.Etot > out_cap)
         return fail(SDR_E_CAP, "output capacity %zu < %llu audio samples", out_cap, (unsigned long long)pl.Etot);
+    d->dev_state_slot = -1;
     IntState *dst = d->d_state.as<IntState>();
     IntState hs;
     to_dev_state(d->st, hs);
@@ -1652,6 +1729,7 @@ int sdr_ring_close(sdr_ring *r) {
     if (e == cudaSuccess) {
         const uint64_t S = r->buf_len / 2;
         Plan pl = make_plan(d->cfg, r->p0, r->q0, S, n);
+        d->dev_state_slot = -1;
         d->st.prev_index = pl.p1;
         d->st.prev_lpr_index = (int32_t)pl.q1;
         d->st.lp_now_re = hs.lp_now_re;
@@ -1751,6 +1829,7 @@ long sdr_low_pass_complex(sdr_demod *d, const int32_t *iq, size_t n, int32_t *ou
     if (L) SDR_CUDA_TRY(cudaMemcpyAsync(out_pairs, d->d_b.p, L * 8, cudaMemcpyDeviceToHost, d->stream));
     IntState hs;
     if ((rc = download_state(d, &hs))) return rc;
+    d->dev_state_slot = -1;
     d->st.lp_now_re = hs.lp_now_re;
     d->st.lp_now_im = hs.lp_now_im;
     d->st.prev_index = (p0 + (uint64_t)n) % D;
@@ -1773,6 +1852,7 @@ long sdr_fm_demod(sdr_demod *d, const int32_t *iq, size_t n, int16_t *out, size_
     SDR_CUDA_TRY(cudaMemcpyAsync(out, d->d_b.p, n * 2, cudaMemcpyDeviceToHost, d->stream));
     IntState hs;
     if ((rc = download_state(d, &hs))) return rc;
+    d->dev_state_slot = -1;
     d->st.demod_pre_re = hs.demod_pre_re;
     d->st.demod_pre_im = hs.demod_pre_im;
     return (long)n;
@@ -1799,6 +1879,7 @@ long sdr_low_pass_real(sdr_demod *d, const int16_t *in, size_t n, int16_t *out, 
     if (E) SDR_CUDA_TRY(cudaMemcpyAsync(out, d->d_b.p, E * 2, cudaMemcpyDeviceToHost, d->stream));
     IntState hs;
     if ((rc = download_state(d, &hs))) return rc;
+    d->dev_state_slot = -1;
     d->st.now_lpr = hs.now_lpr;
     d->st.prev_lpr_index = (int32_t)(uint32_t)(t % fast);
     return (long)E;
