@@ -244,8 +244,8 @@ __device__ __noinline__ int2 lp_window_exact(const uint32_t *w32, int32_t off0, 
 // inside its chunk (tile-uniform -> template parameter, so every register index, every dp4a coefficient and every
 // window constant below is a compile-time literal).  A window is DT/2 words and the rotate_90 phase alternates per
 // word, so word S + j*DT/2 + k of the lane's row is a phase-2 word iff that index is odd.  The predecessor of a lane's
-// first window is the neighbour's last (one shuffle pair per KW samples); lane 0 recomputes it from the DT/2 words
-// before its row.  The KW results leave as one store.  Groups past the tile and the predecessor of window 0 produce
+// first window comes from the DT/2 words before its row: recomputed by every lane in the direct form, taken from the
+// neighbour lane by shuffle in the staged form (lane 0 recomputes it).  The KW results leave as one store.  Groups past the tile and the predecessor of window 0 produce
 // values nobody reads (dm[0] is either predecessor-only or repaired by the fix-up loop).
 template <int DT>
 struct PassGeom {   // windows per lane: the row must be whole 16-byte (even DT) / 8-byte (odd DT) chunks and fit in registers
@@ -265,6 +265,50 @@ __device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const in
     constexpr int KW = PG::KW, HW = DT / 2, NCH = (PG::ROW_WORDS + S + 3) / 4;   // windows per lane, words per window, chunks
     constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u;   // phase-0 word: re [+1,0,0,-1], im [0,+1,+1,0]
     constexpr uint32_t CRE2 = 0x010000FFu, CIM2 = 0x00FFFF00u;   // phase-2 word: negated
+    if constexpr (GLOBAL && DT != 8) {   // DT = 8: the extra chunk costs registers the 40-register budget does not have (4.4 vs 4.1 TB/s)
+        // direct form: every lane computes the predecessor of its first window itself from the chunk(s) before its row
+        // (one more 128-bit load, DT more dp4a): no shuffle, no divergent lane-0 branch, no warp-uniform loop —
+        // 0.428 -> 0.416 ms on cfg1
+        constexpr int PC = HW > S ? (HW - S + 3) / 4 : 0, O = PC * 4;
+        for (uint32_t g = threadIdx.x; g < ngroups; g += NTH) {
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(tile + a0 + (PG::ROW_WORDS * 4) * (int32_t)g);
+            uint32_t v[(PC + NCH) * 4];
+#pragma unroll
+            for (int c = -PC; c < NCH; c++) {
+                const uint4 q = __ldg(p4 + c);
+                v[O + 4 * c] = q.x, v[O + 4 * c + 1] = q.y, v[O + 4 * c + 2] = q.z, v[O + 4 * c + 3] = q.w;
+            }
+            int32_t re[KW + 1], im[KW + 1];   // [0] = the window before the row
+#pragma unroll
+            for (int j = -1; j < KW; j++) {
+                const bool neg = (S + (j + 2) * HW) & 1;   // parity of S + j*HW (HW*2 is even)
+                int32_t r = neg ? BoxK<DT>::re(2) : BoxK<DT>::re(0), i = neg ? BoxK<DT>::im(2) : BoxK<DT>::im(0);
+#pragma unroll
+                for (int k = 0; k < HW; k++) {
+                    const bool wn = neg != (bool)(k & 1);
+                    r = dp4a_us(v[O + S + HW * j + k], wn ? CRE2 : CRE0, r);
+                    i = dp4a_us(v[O + S + HW * j + k], wn ? CIM2 : CIM0, i);
+                }
+                re[j + 1] = r;
+                im[j + 1] = i;
+            }
+            uint32_t o[KW];
+#pragma unroll
+            for (int j = 0; j < KW; j++) {
+                int32_t cre, cim;
+                d_cmul_conj(make_int2(re[j + 1], im[j + 1]), make_int2(re[j], im[j]), cre, cim);
+                o[j] = (uint32_t)d_fast_atan2_t<true>(cim, cre);
+            }
+            uint32_t pk[KW / 2];
+#pragma unroll
+            for (int j = 0; j < KW / 2; j++) pk[j] = __byte_perm(o[2 * j], o[2 * j + 1], 0x5410);
+            if (KW == 2) *reinterpret_cast<uint32_t *>(dm + 2 * g) = pk[0];
+            if (KW == 4) *reinterpret_cast<uint2 *>(dm + 4 * g) = make_uint2(pk[0], pk[KW / 2 - 1]);
+            if (KW == 8) *reinterpret_cast<uint4 *>(dm + 8 * g) = make_uint4(pk[0], pk[KW / 8], pk[KW / 4], pk[KW / 2 - 1]);
+        }
+        return;
+    }
+    // staged form (shared-memory tile) and DT = 8: predecessor by shuffle, lane 0 recomputes it
     const int lane = threadIdx.x & 31;
     for (uint32_t gb = threadIdx.x & ~31u; gb < ngroups; gb += NTH) {
         const uint32_t g = gb + lane;
