@@ -275,7 +275,7 @@ __device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const in
             uint32_t v[(PC + NCH) * 4];
 #pragma unroll
             for (int c = -PC; c < NCH; c++) {
-                const uint4 q = __ldg(p4 + c);
+                const uint4 q = __ldg(p4 + c);   // (an L2 evict-first policy on these loads measured no difference)
                 v[O + 4 * c] = q.x, v[O + 4 * c + 1] = q.y, v[O + 4 * c + 2] = q.z, v[O + 4 * c + 3] = q.w;
             }
             int32_t re[KW + 1], im[KW + 1];   // [0] = the window before the row
@@ -649,7 +649,9 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
 
     const int tid = threadIdx.x;
     const bool last = tile_idx == n_tiles - 1;
-    const IntState st = *a.st_in;
+    // a reference, not a copy: the five words are needed by a handful of threads of the first and last tile only, and
+    // eight registers held across the pass would be spilled at the 32-register budget of the direct kernel
+    const IntState &st = *a.st_in;
 
     if (tid == 0) {
         if (!DIRECT && first_use) {
