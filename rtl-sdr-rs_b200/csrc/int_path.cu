@@ -769,7 +769,10 @@ __global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedAr
 }
 // CTAs per SM the register allocation aims for: 8 (32 registers) while a lane's row is at most 16 words, fewer for
 // the wider rows of DT = 8 / 10 (a spilled row costs more than the lost occupancy)
-constexpr int direct_min_blocks(int DT) { return DT == 13 ? 4 : (DT == 10 || DT == 11) ? 5 : (DT == 8 || DT == 9) ? 6 : 8; }
+#ifndef SDR_INT_DIRECT_MINB
+#define SDR_INT_DIRECT_MINB 8
+#endif
+constexpr int direct_min_blocks(int DT) { return DT == 13 ? 4 : (DT == 10 || DT == 11) ? 5 : (DT == 8 || DT == 9) ? 6 : SDR_INT_DIRECT_MINB; }
 #ifndef SDR_INT_DIRECT_NTH
 #define SDR_INT_DIRECT_NTH 256   // threads per CTA of the direct kernel (128: 0.420 vs 0.426 ms on cfg1, 64 and 512 slower)
 #endif
