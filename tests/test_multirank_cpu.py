@@ -56,3 +56,29 @@ def test_planner_matches_sequential_bookkeeping():
         assert (st.prev_index, st.prev_lpr_index) == (o.state()["prev_index"], o.state()["prev_lpr_index"])
     lo, hi = zip(*(S.shard_range(1003, 4, r, 8) for r in range(4)))
     assert lo[0] == 0 and hi[-1] == 1003 and list(hi[:-1]) == list(lo[1:]) and all(x % 8 == 0 for x in lo)
+
+
+def test_demod_plan_matches_the_oracle_for_random_configs_and_states():
+    """sdr_demod_plan (closed-form counts and index state, pure host arithmetic) against the oracle's sequential loops:
+    random downsample / rate ratio / starting state / call geometry."""
+    import oracle_ffi as O
+    S = sdrpkg.load()
+    rng = np.random.default_rng(20261017)
+    for _ in range(60):
+        D = int(rng.integers(1, 40))
+        fast = int(rng.integers(1000, 400_000))
+        slow = int(rng.integers(1, fast + 1))
+        ocfg = O.DemodConfig(fast * D, fast, slow, D, 42)
+        cfg = S.DemodConfig(fast * D, fast, slow, D, 42)
+        o = O.Demod(ocfg)
+        p0, q0 = int(rng.integers(0, D)), int(rng.integers(0, fast))
+        o.set_state(prev_index=p0, prev_lpr_index=q0)
+        st = S.DemodState(p0, 0, q0, 0, 0, 0, 0)
+        min_len = ((2 * D * 2 + 7) // 8 + 1) * 8
+        bl, nb = min_len + 8 * int(rng.integers(0, 600)), int(rng.integers(1, 6))
+        buf = rng.integers(0, 256, nb * bl, dtype=np.uint8)
+        n_audio = sum(o.demodulate(buf[i * bl:(i + 1) * bl]).size for i in range(nb))
+        nl, na, after = S.demod_plan(cfg, bl, nb, st)
+        assert na == n_audio, (D, fast, slow, p0, q0, bl, nb)
+        assert nl == (p0 + nb * (bl // 2)) // D
+        assert (after.prev_index, after.prev_lpr_index) == (o.state()["prev_index"], o.state()["prev_lpr_index"])
