@@ -209,6 +209,11 @@ int sdr_fmrx_kernel_kind(const sdr_fmrx *r, const char **note);
  * now rather than taken from the on-disk cache});
  * < 0: SDR_E_ARG (shape outside the kernel's range), SDR_E_STATE (no libnvrtc / compile error, see sdr_last_error()). */
 long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]);
+/* The CTA shape sdr_fmrx_new() would compile for (n_taps, decim), without compiling: shape[4] = {blocks per thread,
+ * threads per CTA, bytes per load, row padding}.  1 = a shape was picked and satisfies the kernel's compile-time
+ * requirements, 0 = outside the specialised kernel's range (the generic kernel runs), < 0 = the picker chose a shape the
+ * kernel would reject (a bug; sdr_last_error() says which requirement). */
+int sdr_rtc_pick_shape(uint32_t n_taps, uint32_t decim, int shape[4]);
 int sdr_fmrx_span_begin(sdr_fmrx *r);
 int sdr_fmrx_span_end(sdr_fmrx *r, float *ms);
 /* Reposition a fresh stream at global sample index n (history = mid-scale): lets a rank that owns

@@ -112,6 +112,7 @@ SIGNATURES = {
     "sdr_fmrx_timing_totals": (_i, [_vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_uint64), _i]),
     "sdr_fmrx_kernel_kind": (_i, [_vp, C.POINTER(C.c_char_p)]),
     "sdr_rtc_selftest": (_l, [C.c_uint32, C.c_uint32, C.POINTER(_i * 4)]),
+    "sdr_rtc_pick_shape": (_i, [C.c_uint32, C.c_uint32, C.POINTER(_i * 4)]),
     "sdr_fmrx_span_begin": (_i, [_vp]),
     "sdr_fmrx_span_end": (_i, [_vp, C.POINTER(C.c_float)]),
     "sdr_fmrx_seek": (_i, [_vp, C.c_uint64]),

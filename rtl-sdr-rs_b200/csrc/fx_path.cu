@@ -983,6 +983,24 @@ int sdr_fmrx_kernel_kind(const sdr_fmrx *r, const char **note) {
     return r->kernel_kind;
 }
 
+int sdr_rtc_pick_shape(uint32_t n_taps, uint32_t decim, int shape[4]) {
+    int B = 0, NT = 0, WB = 0, PAD = 0;
+    if (n_taps > 4096 || decim > 256 || !pick_fast_params((int)n_taps, (int)decim, &B, &NT, &WB, &PAD)) return 0;
+    if (shape) shape[0] = B, shape[1] = NT, shape[2] = WB, shape[3] = PAD;
+    // the kernel's own compile-time requirements (FastGeom's static_asserts), re-stated on the host
+    const int T = (int)n_taps, D = (int)decim, Q = (T + D - 1) / D, spl = WB / 2, nblk = NT * B;
+    const int hb = fast_pick_hb(Q, nblk, D, spl), row = B * D * 2;
+    const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)(NT + 1) * PAD + (long)nblk * Q * 8 + (long)nblk * 8;
+    if (WB != 4 && WB != 8) return fail(SDR_E_STATE, "picked load width %d", WB);
+    if ((B * D) % spl) return fail(SDR_E_STATE, "thread span %d is not a whole number of %d-sample loads", B * D, spl);
+    if (nblk - hb <= hb) return fail(SDR_E_STATE, "tile of %d blocks is all halo (%d)", nblk, hb);
+    if (PAD && (row % 16 || PAD % 16)) return fail(SDR_E_STATE, "padded rows of %d bytes cannot be bulk-copied", row);
+    if (NT % 32 || NT < 32 || NT > 1024) return fail(SDR_E_STATE, "CTA of %d threads", NT);
+    if (smem > 227 * 1024) return fail(SDR_E_STATE, "%ld bytes of shared memory", smem);
+    if (B * Q > 16) return fail(SDR_E_STATE, "%d packed accumulators", B * Q);
+    return 1;
+}
+
 long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]) {
     int B = 0, NT = 0, WB = 0, PAD = 0;
     if (n_taps > 4096 || decim > 256 || !pick_fast_params((int)n_taps, (int)decim, &B, &NT, &WB, &PAD))

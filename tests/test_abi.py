@@ -182,3 +182,26 @@ def test_rtc_compiles_a_new_shape_without_a_gpu(tmp_path, monkeypatch):
     assert c1 >= 1 and c2 == 0, r.stdout               # compiled once, then cached
     assert bad == -1                                   # SDR_E_ARG: 67 lags per sample is outside the kernel's range
     assert len(list((tmp_path / "cubins").glob("*.cubin"))) == c1
+
+
+def test_rtc_shape_picker_only_picks_shapes_the_kernel_accepts(S):
+    """Every (taps, decimation) the picker accepts must satisfy k_fir_fast's compile-time requirements (FastGeom's
+    static_asserts, re-stated on the host by sdr_rtc_pick_shape): a violation would only show up as an NVRTC error when
+    somebody asks for that shape."""
+    from rtl_sdr_rs_b200 import _ffi as F
+    L = F.lib()
+    sh = (C.c_int * 4)()
+    picked = outside = 0
+    for D in range(1, 300):
+        for T in sorted({1, 2, D - 1, D, D + 1, 2 * D - 1, 2 * D + 1, 3 * D, 5 * D + 3, 16 * D, 16 * D + 1, 127, 255, 1023, 4096, 4097}):
+            if T < 1:
+                continue
+            rc = L.sdr_rtc_pick_shape(T, D, C.byref(sh))
+            assert rc >= 0, (T, D, list(sh), L.sdr_last_error().decode())
+            if rc:
+                picked += 1
+                B, NT, WB, PAD = list(sh)
+                assert (B * D) % (WB // 2) == 0 and B * ((T + D - 1) // D) <= 16 and D <= 256
+            else:
+                outside += 1
+    assert picked > 1500 and outside > 300, (picked, outside)
