@@ -345,13 +345,13 @@ bool pick_fast_params(int T, int D, int *Bo, int *NTo, int *WBo, int *PADo) {
     if (T < 1 || D < 1 || T > 4096 || D > 256) return false;
     const int Q = (T + D - 1) / D;
     if (Q > 16) return false;   // too many lags per sample for register accumulators: generic kernel
-    if ((long)((D & 1) ? 2 : 1) * D * Q > 800) return false;   // smallest possible body already takes ptxas minutes
+    if ((long)((D & 1) ? 2 : 1) * D * Q > 640) return false;   // smallest possible body already takes ptxas the better part of a minute
     const int bmax = std::max(1, std::min(16 / Q, std::max(160 / D, (D & 1) ? 2 : 1)));   // odd D: B must be even
     int best_b = 0, best_wb = 0, best_pad = 0;
     double best_cost = 1e30;
     for (int B = 1; B <= bmax; B++) {
         const int span = B * D;
-        if ((long)span * Q > 800 && B > ((D & 1) ? 2 : 1)) break;
+        if ((long)span * Q > 640 && B > ((D & 1) ? 2 : 1)) break;
         for (int WB : {8, 4}) {
             const int spl = WB / 2;
             if (span % spl) continue;
@@ -688,7 +688,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
             const FastVariant *v = rtc_variant(cuda_device, cfg->n_taps, cfg->decim, B, NT, WB, PAD, &r->rtc_note);
             if (v) r->fast = v, r->kernel_kind = 2;
         } else if (!r->fast && !off) {
-            r->rtc_note = "shape outside the block-owner kernel's range (decim > 256, more than 16 lags per sample, or an unrolled body of more than 800 tap-samples)";
+            r->rtc_note = "shape outside the block-owner kernel's range (decim > 256, more than 16 lags per sample, or an unrolled body of more than 640 tap-samples)";
         }
     }
     const uint64_t T = cfg->n_taps, D = cfg->decim;
