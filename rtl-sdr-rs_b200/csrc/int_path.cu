@@ -503,9 +503,9 @@ __device__ __forceinline__ void tile_setup_calls(const FusedArgs &a, TileInfo &t
     ti.chi = ti.jhi > ti.jlo ? udiv64(ti.jhi * a.D - a.p0 - 1, a.d64_S) : 0ull;
 }
 
-// D = 6 fix-ups (rare): dm[i] recomputed exactly for the first sample of each call (fm_demod :359 uses the f64
+// Fix-ups after the register-resident pass (rare): dm[i] recomputed exactly for the first sample of each call (fm_demod :359 uses the f64
 // polar_discriminant there) and for the two samples that see the carried state on the first tile.
-__device__ __forceinline__ void d6_fixups(const FusedArgs &a, const IntState &st, const TileInfo &ti, const uint32_t *w32,
+__device__ __forceinline__ void pass_fixups(const FusedArgs &a, const IntState &st, const TileInfo &ti, const uint32_t *w32,
                                           int16_t *dm, const uint32_t tid, const uint32_t nthreads) {
     const unsigned long long c_lo = ti.clo, c_hi = ti.chi, wlo = ti.wlo, jlo = ti.jlo, jhi = ti.jhi;
     const bool tile0 = wlo == 0;
@@ -696,7 +696,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
         }
         __syncthreads();
         if (tile0 || ti.clo <= ti.chi) {
-            d6_fixups(a, st, ti, w32, dm, tid, blockDim.x);
+            pass_fixups(a, st, ti, w32, dm, tid, blockDim.x);
             __syncthreads();
         }
     } else {
