@@ -127,8 +127,10 @@ int sdr_demod_span_end(sdr_demod *d, float *ms);
  * producer thread acquires the next pinned slot (blocks while all n_slots are in flight), fills it (read_sync
  * straight into it) and commits it; the consumer thread collects the audio of the oldest buffer.  Output is
  * bit-identical to one sdr_demod_demodulate(buf_len) call per buffer.  While a ring is open the Demod handle
- * is owned by it, and nothing else may allocate or device-synchronise on that GPU (the ring kernel never
- * retires until sdr_ring_close, which also hands the carried state back to the handle). */
+ * is owned by it (its other entry points return SDR_E_STATE); sdr_ring_close retires the kernel and hands the
+ * carried state back to the handle, and sdr_demod_free closes a ring that is still open.  Other handles on the
+ * same GPU keep working while a ring is resident: the library never waits for the whole device then — memory it
+ * frees is parked until the last ring on that device closes, and sdr_device_sync() returns SDR_E_STATE. */
 typedef struct sdr_ring sdr_ring;
 int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots /* 2..64 */, sdr_ring **out);
 int sdr_ring_acquire(sdr_ring *r, uint8_t **buf);                 /* producer */
@@ -294,8 +296,10 @@ int sdr_source_rtl_tcp_command(sdr_source *s, uint8_t cmd, uint32_t param);
  * read, examples/simple_fm.rs:121-125) or SDR_E_IO. */
 long sdr_source_read_sync(sdr_source *s, uint8_t *buf, size_t len);
 /* Extension the reference only has as a TODO (src/lib.rs:147): librtlsdr-style async reads.
- * Spawns the reader thread of examples/simple_fm.rs:89-132; cb runs on it for each full buffer
- * (buf_num buffers of buf_len bytes are cycled); returns when the source ends or is cancelled. */
+ * Spawns the reader thread of examples/simple_fm.rs:89-132, which cycles buf_num buffers of buf_len bytes; cb
+ * runs on the CALLING thread (the `process` role, :135-160) for each full buffer; returns when the source ends
+ * or is cancelled.  sdr_source_cancel_async may be called from cb or from any other thread; it also wakes a
+ * reader blocked on an rtl_tcp socket. */
 typedef void (*sdr_read_async_cb)(const uint8_t *buf, size_t len, void *ctx);
 int sdr_source_read_async(sdr_source *s, sdr_read_async_cb cb, void *ctx, uint32_t buf_num, uint32_t buf_len);
 int sdr_source_cancel_async(sdr_source *s);

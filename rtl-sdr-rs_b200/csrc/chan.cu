@@ -37,6 +37,7 @@ struct ChanArgs {
     long long cap;
     int T4, D, pad;               // taps padded to a multiple of 4; pad: xs origin shift (alignment)
     int n_tiles;
+    int n_ch;                     // channels that exist: rows >= n_ch of the last group are never stored
     uint32_t sm_taps, sm_xs, sm_xb;   // byte sizes of the smem regions
 };
 
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_chan_fir(const ChanArgs a) {
             const int n_here = (int)(a.n_out - i0 < MT ? a.n_out - i0 : MT);
             for (int e = tid; e < kChanGroup * MT; e += blockDim.x) {
                 const int c = e / MT, o = e % MT;
-                if (o < n_here) a.y_out[(size_t)(group * kChanGroup + c) * a.cap + i0 + o] = ys[e];
+                if (o < n_here && group * kChanGroup + c < a.n_ch) a.y_out[(size_t)(group * kChanGroup + c) * a.cap + i0 + o] = ys[e];
             }
         }
         __syncthreads();   // xs free for the next tile's conversion
@@ -480,6 +481,7 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
         uint64_t tiles = (n_out + MT - 1) / MT;
         if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
         a.n_tiles = (int)tiles;
+        a.n_ch = (int)c->cfg.n_channels;
         a.sm_taps = c->sm_taps;
         a.sm_xs = c->sm_xs;
         a.sm_xb = c->sm_xb;
@@ -573,7 +575,7 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
         return fail(SDR_E_ARG, "n_taps=%u / decim=%u do not fit the channeliser's shared-memory tile", cfg->n_taps, cfg->decim);
     }
     c->cs = (int)(((size_t)T4 + D + 16 + 7) & ~size_t(7));
-    cudaError_t e = cudaFuncSetAttribute(pick_kernel(c->warps, c->mr, c->aligned), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+    cudaError_t e = raise_dyn_smem(pick_kernel(c->warps, c->mr, c->aligned), c->smem);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -593,8 +595,9 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
     }
     std::vector<uint32_t> fw(c->C_pad, 0u);
     std::copy(freq_words, freq_words + cfg->n_channels, fw.begin());
-    e = cudaMemcpy(c->d_taps.p, taps, cfg->n_taps * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(c->d_fw.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice);
+    e = cudaMemcpyAsync(c->d_taps.p, taps, cfg->n_taps * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_fw.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
         sdr_chan_free(c);
         return fail(SDR_E_CUDA, "sdr_chan_new: %s", cudaGetErrorString(e));
@@ -614,7 +617,7 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
             }
         c->smem_u = (((size_t)kChanUOut * D + cfg->n_taps + 16) * 2 + 15 + 32) & ~size_t(15);
         if (c->smem_u > 200 * 1024) c->use_uniform = false;
-        else e = cudaFuncSetAttribute(k_chan_fir_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_u);
+        else e = raise_dyn_smem(k_chan_fir_u, c->smem_u);
         if (e != cudaSuccess) {
             sdr_chan_free(c);
             return fail(SDR_E_CUDA, "sdr_chan_new: %s", cudaGetErrorString(e));

@@ -40,6 +40,26 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 int use_device(int device);
 int sm_count(int device);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one value per (kernel, device) for the whole process, while every
+// handle wants its own size: only ever RAISE it (running maximum under a mutex), so that a later handle with a smaller
+// tile cannot make an earlier handle's launches fail.  Applies to the current device.
+cudaError_t raise_dyn_smem_raw(const void *func, size_t bytes);
+template <typename F>
+inline cudaError_t raise_dyn_smem(F *func, size_t bytes) {
+    return raise_dyn_smem_raw(reinterpret_cast<const void *>(func), bytes);
+}
+
+// Persistent rings keep one kernel resident on a device.  While one is open there, nothing in the library may call
+// anything that waits for the whole device (cudaDeviceSynchronize, cudaFree, cudaFreeHost): allocations clear their
+// memory on a private stream, frees are parked and carried out when the last ring on the device closes.
+void ring_opened(int device);
+void ring_closed(int device);          // frees everything parked for the device when its last ring closes
+bool ring_is_open(int device);         // device < 0: on any device
+void dev_free_or_park(void *raw);      // cudaFree now, or later if a ring is resident on the current device
+void host_free_or_park(void *p);       // cudaFreeHost now, or later if a ring is resident on any device
+// fill freshly allocated device memory without touching the legacy stream or the other handles' streams
+int dev_fill(void *p, int value, size_t bytes);
+
 // Growable device scratch buffer owned by a handle.
 struct DevBuf {
     void *p = nullptr;

@@ -286,13 +286,11 @@ void launch_fast(const FirArgs &a, const float *taps, int phase, int grid, int s
 }
 template <int T, int D, int B, int NT, int WB>
 cudaError_t prepare_fast(int smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = raise_dyn_smem(k_fir_fast<T, D, B, NT, WB, 0>, smem);
+    if (e == cudaSuccess) e = raise_dyn_smem(k_fir_fast<T, D, B, NT, WB, 1>, smem);
     if (WB == 8) {
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 2 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 3 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = raise_dyn_smem(k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 2 : 0)>, smem);
+        if (e == cudaSuccess) e = raise_dyn_smem(k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 3 : 1)>, smem);
     }
     return e;
 }
@@ -715,10 +713,10 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         r->Jp = (r->J + 15) & ~15;
         r->h2 = r->Jp + 16;
     }
-    cudaError_t e = cudaFuncSetAttribute(k_fir_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem);
+    cudaError_t e = raise_dyn_smem(k_fir_generic, gen_smem);
     if (e == cudaSuccess && r->fast && !r->fast->rtc) e = r->fast->prepare(r->fast->smem);
     if (e == cudaSuccess && r->h2 * sizeof(float) > 48 * 1024)
-        e = cudaFuncSetAttribute(k_shift_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(r->h2 * sizeof(float)));
+        e = raise_dyn_smem(k_shift_hist, r->h2 * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
@@ -738,7 +736,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         sdr_fmrx_free(r);
         return rc;
     }
-    e = cudaMemcpy(r->d_taps.p, taps, T * 4, cudaMemcpyHostToDevice);
+    e = cudaMemcpyAsync(r->d_taps.p, taps, T * 4, cudaMemcpyHostToDevice, r->stream);
     if (e == cudaSuccess && cfg->n_taps2) {
         // polyphase layout gp[phase][j] = g[phase + j*L] (zero padded); for L = 1 this is g padded to Jp
         std::vector<float> gp((size_t)cfg->up * r->J + r->Jp + 16, 0.f);
@@ -747,10 +745,11 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
                 size_t k = ph + (size_t)j * cfg->up;
                 if (k < cfg->n_taps2) gp[(size_t)ph * r->J + j] = taps2[k];
             }
-        e = cudaMemcpy(r->d_taps2.p, gp.data(), gp.size() * 4, cudaMemcpyHostToDevice);
+        e = cudaMemcpyAsync(r->d_taps2.p, gp.data(), gp.size() * 4, cudaMemcpyHostToDevice, r->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);   // gp is a local
         size_t sm = fir_real_smem(r->Jp);
         if (e == cudaSuccess && sm > 48 * 1024)
-            e = cudaFuncSetAttribute(k_fir_real_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            e = raise_dyn_smem(k_fir_real_r8, sm);
     }
     if (e != cudaSuccess) {
         sdr_fmrx_free(r);

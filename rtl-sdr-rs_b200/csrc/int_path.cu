@@ -841,7 +841,10 @@ __global__ void __launch_bounds__(256) k_demod_ring(const RingArgs r) {
             unsigned int go = 2;
             while (go == 2) {
                 if (ld_acquire_u32(&r.ctl->seq_ready[slot]) == (unsigned int)(k + 1)) go = 1;
-                else if (ld_acquire_u32(&r.ctl->stop)) go = 0;
+                else if (ld_acquire_u32(&r.ctl->stop))
+                    // the doorbell of a buffer committed just before close was written BEFORE stop (same copy stream):
+                    // it may have landed between the two loads above, so look once more before retiring
+                    go = ld_acquire_u32(&r.ctl->seq_ready[slot]) == (unsigned int)(k + 1) ? 1 : 0;
                 else __nanosleep(100);
             }
             sh_go = go;
@@ -1066,6 +1069,7 @@ struct sdr_demod {
     uint32_t last_launches = 0;
     bool timing_valid = false;
     bool ring_open = false;    // a persistent ring owns the handle until sdr_ring_close()
+    struct sdr_ring *ring = nullptr;   // that ring (sdr_demod_free closes it first)
 };
 
 namespace {
@@ -1367,8 +1371,8 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
                     break;
         }
     }
-    cudaError_t e = cudaFuncSetAttribute(k_demod_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(k_demod_fused<0>, smem);
+    if (e == cudaSuccess) e = raise_dyn_smem(k_demod_fused<6>, smem);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
@@ -1394,6 +1398,9 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
 void sdr_demod_free(sdr_demod *d) {
     if (!d) return;
     cudaSetDevice(d->device);
+    // a ring that is still open (Python GC order, a forgotten close) would keep its kernel resident for ever and leave
+    // a dangling back-pointer: retire it first
+    if (d->ring_open && d->ring) sdr_ring_close(d->ring);
     if (d->stream) cudaStreamSynchronize(d->stream);
     if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     for (int i = 0; i < 2; i++) {
@@ -1598,15 +1605,19 @@ struct sdr_ring {
 
 static void ring_release(sdr_ring *r) {
     if (!r) return;
+    if (r->d && r->d->ring_open && r->d->ring == r) {   // this ring's kernel has retired (or never started)
+        r->d->ring_open = false;
+        r->d->ring = nullptr;
+        ring_closed(r->d->device);
+    }
     if (r->ring_stream) cudaStreamDestroy(r->ring_stream);
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
-    if (r->h_in) cudaFreeHost(r->h_in);
-    if (r->h_out) cudaFreeHost(r->h_out);
-    if (r->h_seq_done) cudaFreeHost((void *)r->h_seq_done);
-    if (r->h_doorbell) cudaFreeHost(r->h_doorbell);
+    host_free_or_park(r->h_in);
+    host_free_or_park(r->h_out);
+    host_free_or_park((void *)r->h_seq_done);
+    host_free_or_park(r->h_doorbell);
     r->d_in.release();
     r->d_ctl.release();
-    if (r->d) r->d->ring_open = false;
     delete r;
 }
 
@@ -1646,9 +1657,10 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     RingCtl *h_ctl = new RingCtl();
     memset(h_ctl, 0, sizeof(RingCtl));
     to_dev_state(d->st, h_ctl->states[0]);
-    e = cudaMemcpy(r->d_ctl.p, h_ctl, sizeof(RingCtl), cudaMemcpyHostToDevice);
+    // stream-ordered and waited for on this ring's own stream: no device-wide wait (another ring may be resident)
+    e = cudaMemcpyAsync(r->d_ctl.p, h_ctl, sizeof(RingCtl), cudaMemcpyHostToDevice, r->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->copy_stream);
     delete h_ctl;
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         ring_release(r);
         return fail(SDR_E_CUDA, "sdr_demod_ring_open: %s", cudaGetErrorString(e));
@@ -1687,8 +1699,7 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     a.d64_fast = magic64(d->cfg.rate_out);
     unsigned tiles = (unsigned)((pl.Etot + 1 + rg.EB - 1) / rg.EB + 1);
     unsigned grid = std::max(1u, std::min(tiles, (unsigned)sm_count(d->device) / 2));
-    e = d6 ? cudaFuncSetAttribute(k_demod_ring<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes)
-           : cudaFuncSetAttribute(k_demod_ring<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes);
+    e = d6 ? raise_dyn_smem(k_demod_ring<6>, d->smem_bytes) : raise_dyn_smem(k_demod_ring<0>, d->smem_bytes);
     if (e == cudaSuccess) {
         if (d6)
             k_demod_ring<6><<<grid, 256, rg.smem_staged, r->ring_stream>>>(a);
@@ -1702,6 +1713,8 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     }
     count_launch();
     d->ring_open = true;
+    d->ring = r;
+    ring_opened(d->device);
     *out = r;
     return SDR_OK;
 }
@@ -1774,7 +1787,9 @@ int sdr_ring_close(sdr_ring *r) {
     const uint64_t n = r->head.load();
     IntState hs{};
     if (e == cudaSuccess)
-        e = cudaMemcpy(&hs, &r->d_ctl.as<RingCtl>()->states[n % (r->n_slots + 1)], sizeof(IntState), cudaMemcpyDeviceToHost);
+        e = cudaMemcpyAsync(&hs, &r->d_ctl.as<RingCtl>()->states[n % (r->n_slots + 1)], sizeof(IntState), cudaMemcpyDeviceToHost,
+                            r->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->copy_stream);
     if (e == cudaSuccess) {
         const uint64_t S = r->buf_len / 2;
         Plan pl = make_plan(d->cfg, r->p0, r->q0, S, n);

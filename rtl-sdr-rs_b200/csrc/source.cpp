@@ -254,6 +254,9 @@ int sdr_source_read_async(sdr_source *s, sdr_read_async_cb cb, void *ctx, uint32
 int sdr_source_cancel_async(sdr_source *s) {
     if (!s) return fail(SDR_E_ARG, "null source");
     s->cancel.store(true);
+    // a reader blocked in recv() on an rtl_tcp socket would never look at the flag: shut the read side down, which
+    // makes recv() return 0 (end of stream) at once
+    if (s->kind == sdr_source::RTL_TCP && s->sock >= 0) shutdown(s->sock, SHUT_RD);
     return SDR_OK;
 }
 

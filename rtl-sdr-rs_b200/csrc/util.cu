@@ -1,6 +1,7 @@
 // util.cu — error plumbing, device/pinned memory, synthetic IQ generator.
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -40,22 +41,117 @@ int sm_count(int device) {
     return v > 0 ? v : 148;
 }
 
+namespace {
+constexpr int kMaxDev = 64;
+std::mutex g_mu;
+std::unordered_map<uint64_t, size_t> g_dyn_smem;          // (device, kernel) -> largest size set so far
+int g_rings[kMaxDev] = {0};                               // open rings per device
+std::vector<void *> g_parked_dev[kMaxDev], g_parked_host;
+cudaStream_t g_fill_stream[kMaxDev] = {nullptr};
+
+int cur_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 0;
+    return dev;
+}
+}  // namespace
+
+cudaError_t raise_dyn_smem_raw(const void *func, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uint64_t key = ((uint64_t)cur_device() << 56) ^ (uint64_t)reinterpret_cast<uintptr_t>(func);
+    auto it = g_dyn_smem.find(key);
+    // sizes up to the 48 KB default need no attribute at all
+    const size_t have = it == g_dyn_smem.end() ? 48 * 1024 : it->second;
+    if (bytes <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) g_dyn_smem[key] = bytes;
+    return e;
+}
+
+void ring_opened(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (device >= 0 && device < kMaxDev) g_rings[device]++;
+}
+bool ring_is_open(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (device >= 0) return device < kMaxDev && g_rings[device] > 0;
+    for (int i = 0; i < kMaxDev; i++)
+        if (g_rings[i] > 0) return true;
+    return false;
+}
+void ring_closed(int device) {
+    std::vector<void *> dev_list, host_list;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (device < 0 || device >= kMaxDev || g_rings[device] <= 0) return;
+        if (--g_rings[device] > 0) return;
+        dev_list.swap(g_parked_dev[device]);
+        bool any = false;
+        for (int i = 0; i < kMaxDev; i++) any = any || g_rings[i] > 0;
+        if (!any) host_list.swap(g_parked_host);
+    }
+    int prev = cur_device();
+    cudaSetDevice(device);
+    for (void *q : dev_list) cudaFree(q);
+    for (void *q : host_list) cudaFreeHost(q);
+    cudaSetDevice(prev);
+}
+void dev_free_or_park(void *raw) {
+    if (!raw) return;
+    const int dev = cur_device();
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_rings[dev] > 0) {
+            g_parked_dev[dev].push_back(raw);
+            return;
+        }
+    }
+    cudaFree(raw);
+}
+void host_free_or_park(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (int i = 0; i < kMaxDev; i++)
+            if (g_rings[i] > 0) {
+                g_parked_host.push_back(p);
+                return;
+            }
+    }
+    cudaFreeHost(p);
+}
+int dev_fill(void *p, int value, size_t bytes) {
+    const int dev = cur_device();
+    cudaStream_t st;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_fill_stream[dev]) SDR_CUDA_TRY(cudaStreamCreateWithFlags(&g_fill_stream[dev], cudaStreamNonBlocking));
+        st = g_fill_stream[dev];
+    }
+    // NOT the legacy stream (whose memset the handles' non-blocking streams would not order against) and no
+    // device-wide wait (which a resident ring kernel would never let return)
+    SDR_CUDA_TRY(cudaMemsetAsync(p, value, bytes, st));
+    SDR_CUDA_TRY(cudaStreamSynchronize(st));
+    return SDR_OK;
+}
+
 int DevBuf::reserve(size_t bytes) {
     if (bytes <= cap && p) return SDR_OK;
     release();
     size_t want = bytes + 2 * kDevRoom;
     void *q = nullptr;
     SDR_CUDA_TRY(cudaMalloc(&q, want));
-    // cudaMemset runs on the legacy stream, which the handles' non-blocking streams do NOT order against:
-    // wait for it, or it could land on top of data a handle stream copies into the new buffer.
-    SDR_CUDA_TRY(cudaMemset(q, 127, want));
-    SDR_CUDA_TRY(cudaDeviceSynchronize());
+    int rc = dev_fill(q, 127, want);
+    if (rc) {
+        dev_free_or_park(q);
+        return rc;
+    }
     p = static_cast<char *>(q) + kDevRoom;
     cap = bytes;
     return SDR_OK;
 }
 void DevBuf::release() {
-    if (p) cudaFree(static_cast<char *>(p) - kDevRoom);
+    if (p) dev_free_or_park(static_cast<char *>(p) - kDevRoom);
     p = nullptr;
     cap = 0;
 }
@@ -67,7 +163,7 @@ int PinBuf::reserve(size_t bytes) {
     return SDR_OK;
 }
 void PinBuf::release() {
-    if (p) cudaFreeHost(p);
+    if (p) host_free_or_park(p);
     p = nullptr;
     cap = 0;
 }
@@ -141,13 +237,15 @@ void *sdr_dev_alloc(int device, size_t bytes) {
         fail(SDR_E_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
-    cudaMemset(q, 127, want);   // head/tail room reads as mid-scale (centred zero)
-    cudaDeviceSynchronize();    // the legacy-stream memset must not race with non-blocking handle streams
+    if (dev_fill(q, 127, want)) {   // head/tail room reads as mid-scale (centred zero)
+        dev_free_or_park(q);
+        return nullptr;
+    }
     return static_cast<char *>(q) + kDevRoom;
 }
 void sdr_dev_free(int device, void *p) {
     if (!p || use_device(device)) return;
-    cudaFree(static_cast<char *>(p) - kDevRoom);
+    dev_free_or_park(static_cast<char *>(p) - kDevRoom);
 }
 void *sdr_host_alloc(size_t bytes) {
     void *p = nullptr;
@@ -157,9 +255,7 @@ void *sdr_host_alloc(size_t bytes) {
     }
     return p;
 }
-void sdr_host_free(void *p) {
-    if (p) cudaFreeHost(p);
-}
+void sdr_host_free(void *p) { host_free_or_park(p); }
 int sdr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes) {
     int rc = use_device(device);
     if (rc) return rc;
@@ -184,14 +280,21 @@ int sdr_synth_fill_dev(int device, uint8_t *d_buf, size_t bytes, uint64_t seed, 
     if (!d_buf) return fail(SDR_E_ARG, "sdr_synth_fill_dev: null buffer");
     if (bytes == 0) return SDR_OK;
     int blocks = sm_count(device) * 8;
-    k_synth_fill<<<blocks, 256>>>(d_buf, bytes, seed, byte_offset);
-    SDR_LAUNCH_CHECK();
-    SDR_CUDA_TRY(cudaDeviceSynchronize());
+    cudaStream_t st;
+    SDR_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    k_synth_fill<<<blocks, 256, 0, st>>>(d_buf, bytes, seed, byte_offset);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (e != cudaSuccess) return fail(SDR_E_CUDA, "sdr_synth_fill_dev: %s", cudaGetErrorString(e));
+    count_launch();
     return SDR_OK;
 }
 int sdr_device_sync(int device) {
     int rc = use_device(device);
     if (rc) return rc;
+    if (ring_is_open(device))
+        return fail(SDR_E_STATE, "a persistent ring is resident on device %d: a device-wide wait would never return (close the ring, or sync the handles)", device);
     SDR_CUDA_TRY(cudaDeviceSynchronize());
     return SDR_OK;
 }

@@ -114,6 +114,41 @@ private:
     sdr_demod *h_ = nullptr;
 };
 
+// Persistent ring around a Demod (sdr_demod_ring_*): the reader -> channel -> processor pair of
+// examples/simple_fm.rs:55-60 with the channel living in pinned memory and ONE resident kernel behind it.
+// acquire/commit belong to the producer thread, collect to the consumer thread.
+class Ring {
+public:
+    Ring(Demod &d, size_t buf_len, uint32_t n_slots = 8) : buf_len_(buf_len) {
+        check(sdr_demod_ring_open(d.raw(), buf_len, n_slots, &h_));
+        out_cap_ = buf_len / 2 / d.config.downsample + 16;
+    }
+    ~Ring() { close(); }
+    Ring(const Ring &) = delete;
+    Ring &operator=(const Ring &) = delete;
+    uint8_t *acquire() {   // blocks while every slot is in flight
+        uint8_t *p = nullptr;
+        check(sdr_ring_acquire(h_, &p));
+        return p;
+    }
+    void commit() { check(sdr_ring_commit(h_)); }
+    size_t collect(std::vector<int16_t> &out) {   // audio of the oldest committed buffer
+        out.resize(out_cap_);
+        long n = check(sdr_ring_collect(h_, out.data(), out.size()));
+        out.resize((size_t)n);
+        return (size_t)n;
+    }
+    void close() {
+        if (h_) sdr_ring_close(h_);
+        h_ = nullptr;
+    }
+    size_t buf_len() const { return buf_len_; }
+
+private:
+    sdr_ring *h_ = nullptr;
+    size_t buf_len_ = 0, out_cap_ = 0;
+};
+
 // Buffer source with the read_sync contract of RtlSdr (src/lib.rs:153-155)
 class Source {
 public:
