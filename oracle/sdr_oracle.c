@@ -264,6 +264,50 @@ long orc_demodulate_ref_like(orc_demod *d, const uint8_t *buf, size_t len, int16
     return r;
 }
 
+/* BASELINE.md §3 leg 2, "oracle_fused": the same call (:256-269) as ONE pass over the buffer with no intermediate
+ * vectors — rotate_90 (:285-295) and the centring (:258) are folded into the per-phase sample formulas, every
+ * completed boxcar window (:337-352) goes straight through the discriminator (:355-367; f64 path for the first window
+ * of the call) into the fractional boxcar (:408-426).  Bit-identical to orc_demodulate (tests/test_oracle.py). */
+long orc_demodulate_fused(orc_demod *d, const uint8_t *buf, size_t len, int16_t *out) {
+    if (len % 8 != 0) return -1;
+    const size_t ns = len / 2;
+    const uint64_t D = d->config.downsample;
+    if (D == 0 || (d->prev_index + ns) / D < 2) return -1;   /* fm_demod's assert, :356 */
+    const uint32_t slow = d->config.rate_resample, fast = d->config.rate_out;
+    const int32_t div = (int32_t)(slow ? fast / slow : 0u);
+    int32_t re = d->lp_now_re, im = d->lp_now_im, pre = d->demod_pre_re, pim = d->demod_pre_im;
+    int32_t now_lpr = d->now_lpr, lpr_idx = d->prev_lpr_index;
+    uint64_t pi = d->prev_index;
+    int first = 1;
+    size_t w = 0;
+    for (size_t g = 0; g < len; g += 8) {
+        const uint8_t *b = buf + g;
+        /* rotated, centred samples of this 8-byte group */
+        const int32_t sr[4] = {(int32_t)b[0] - 127, 128 - (int32_t)b[3], 128 - (int32_t)b[4], (int32_t)b[7] - 127};
+        const int32_t si[4] = {(int32_t)b[1] - 127, (int32_t)b[2] - 127, 128 - (int32_t)b[5], 128 - (int32_t)b[6]};
+        for (int k = 0; k < 4; k++) {
+            re = wadd(re, sr[k]);
+            im = wadd(im, si[k]);
+            if (++pi < D) continue;
+            pi = 0;
+            int32_t pcm = first ? orc_polar_discriminant(re, im, pre, pim) : orc_polar_discriminant_fast(re, im, pre, pim);
+            first = 0;
+            pre = re;
+            pim = im;
+            re = im = 0;
+            now_lpr = wadd(now_lpr, (int32_t)(int16_t)(uint16_t)(uint32_t)pcm);
+            lpr_idx = wadd(lpr_idx, (int32_t)slow);
+            if (lpr_idx < (int32_t)fast) continue;
+            out[w++] = (int16_t)(uint16_t)(uint32_t)tdiv(now_lpr, div);
+            lpr_idx = wsub(lpr_idx, (int32_t)fast);
+            now_lpr = 0;
+        }
+    }
+    d->lp_now_re = re, d->lp_now_im = im, d->demod_pre_re = pre, d->demod_pre_im = pim;
+    d->now_lpr = now_lpr, d->prev_lpr_index = lpr_idx, d->prev_index = pi;
+    return (long)w;
+}
+
 typedef struct {
     const orc_demod_config *cfg;
     const uint8_t *buf;
@@ -272,6 +316,7 @@ typedef struct {
     int threads;
     long *totals;
     int *failed;
+    int fused;
 } orc_many_ctx;
 
 static void orc_many_range(long lo, long hi, int tid, void *p) {
@@ -281,7 +326,8 @@ static void orc_many_range(long lo, long hi, int tid, void *p) {
     int16_t *tmp = (int16_t *)malloc((c->buf_len / 2 + 1) * sizeof(int16_t));
     long total = 0;
     for (long b = lo; b < hi; b++) {
-        long r = orc_demodulate_ref_like(&d, c->buf + (size_t)b * c->buf_len, c->buf_len, tmp);
+        long r = c->fused ? orc_demodulate_fused(&d, c->buf + (size_t)b * c->buf_len, c->buf_len, tmp)
+                          : orc_demodulate_ref_like(&d, c->buf + (size_t)b * c->buf_len, c->buf_len, tmp);
         if (r < 0) {
             c->failed[tid] = 1;
             break;
@@ -296,11 +342,16 @@ static void orc_many_range(long lo, long hi, int tid, void *p) {
 
 long orc_demodulate_many_mt(const orc_demod_config *cfg, const uint8_t *buf, size_t buf_len,
                             size_t n_bufs, int16_t *out, size_t out_cap, int threads) {
+    return orc_demodulate_many_mt2(cfg, buf, buf_len, n_bufs, out, out_cap, threads, 0);
+}
+
+long orc_demodulate_many_mt2(const orc_demod_config *cfg, const uint8_t *buf, size_t buf_len,
+                             size_t n_bufs, int16_t *out, size_t out_cap, int threads, int fused) {
     if (threads < 1) threads = 1;
     if ((size_t)threads > n_bufs) threads = (int)(n_bufs ? n_bufs : 1);
     long *totals = (long *)calloc((size_t)threads, sizeof(long));
     int *failed = (int *)calloc((size_t)threads, sizeof(int));
-    orc_many_ctx c = {cfg, buf, buf_len, n_bufs, out_cap, out, threads, totals, failed};
+    orc_many_ctx c = {cfg, buf, buf_len, n_bufs, out_cap, out, threads, totals, failed, fused};
     orc_par_for(threads, (long)n_bufs, orc_many_range, &c);
     long total = 0;
     int bad = 0;

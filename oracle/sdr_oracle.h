@@ -79,11 +79,18 @@ long orc_demodulate(orc_demod *d, const uint8_t *buf, size_t len, int16_t *out,
 /* Same arithmetic, but structured like the reference (one fresh heap vector per stage,
  * :256-269) — this is the "reference CPU path" leg that bench.py times. */
 long orc_demodulate_ref_like(orc_demod *d, const uint8_t *buf, size_t len, int16_t *out);
+/* Same call as ONE fused pass with no intermediate vectors (BASELINE.md §3 "oracle_fused" timing leg);
+ * bit-identical to orc_demodulate. */
+long orc_demodulate_fused(orc_demod *d, const uint8_t *buf, size_t len, int16_t *out);
 /* n_bufs consecutive demodulate() calls of buf_len bytes each, `threads` pthreads
  * each running an INDEPENDENT Demod over its own slice of buffers (timing leg only: the
  * output differs from a single sequential Demod at the slice seams). Returns total audio. */
 long orc_demodulate_many_mt(const orc_demod_config *cfg, const uint8_t *buf, size_t buf_len,
                             size_t n_bufs, int16_t *out, size_t out_cap, int threads);
+
+/* fused != 0: every thread runs orc_demodulate_fused instead of orc_demodulate_ref_like. */
+long orc_demodulate_many_mt2(const orc_demod_config *cfg, const uint8_t *buf, size_t buf_len,
+                             size_t n_bufs, int16_t *out, size_t out_cap, int threads, int fused);
 
 /* ---- f64 extension path ("parity unpinned" by the reference) ------------ */
 

@@ -364,6 +364,16 @@ __global__ void k_chan_update_carry(const uint16_t *old_carry, const uint16_t *x
     }
 }
 
+#define SDR_K(x) ((const void *)(x))
+static const KernelList kChanKernels{
+    SDR_K((k_chan_fir<16, 4, true>)), SDR_K((k_chan_fir<16, 4, false>)), SDR_K((k_chan_fir<16, 2, true>)),
+    SDR_K((k_chan_fir<16, 2, false>)), SDR_K((k_chan_fir<16, 1, true>)), SDR_K((k_chan_fir<16, 1, false>)),
+    SDR_K((k_chan_fir<8, 8, true>)), SDR_K((k_chan_fir<8, 8, false>)), SDR_K((k_chan_fir<8, 4, true>)),
+    SDR_K((k_chan_fir<8, 4, false>)), SDR_K((k_chan_fir<8, 2, true>)), SDR_K((k_chan_fir<8, 2, false>)),
+    SDR_K((k_chan_fir<8, 1, true>)), SDR_K((k_chan_fir<8, 1, false>)), SDR_K(k_chan_fir_u), SDR_K(k_chan_fold_taps),
+    SDR_K(k_chan_demod), SDR_K(k_chan_store_prev), SDR_K(k_chan_update_carry)};
+#undef SDR_K
+
 }  // namespace sdr
 
 using namespace sdr;

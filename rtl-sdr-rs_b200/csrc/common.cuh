@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 
 #include "../../include/sdr_b200.h"
 
@@ -59,6 +60,14 @@ void dev_free_or_park(void *raw);      // cudaFree now, or later if a ring is re
 void host_free_or_park(void *p);       // cudaFreeHost now, or later if a ring is resident on any device
 // fill freshly allocated device memory without touching the legacy stream or the other handles' streams
 int dev_fill(void *p, int value, size_t bytes);
+// CUDA loads kernels lazily, on their first launch, and that load can wait for the whole context — for ever, behind a
+// resident ring kernel.  Every translation unit therefore lists its __global__ functions (a static KernelList), and
+// the first ring to open on a device loads them all beforehand (cudaFuncGetAttributes forces the load).
+struct KernelList {
+    KernelList(std::initializer_list<const void *> fns);
+};
+int preload_kernels();   // current device; cheap after the first call per device
+void fx_touch_variants();   // fx_path.cu: instantiates its shape table (whose kernels join the list)
 
 // Growable device scratch buffer owned by a handle.
 struct DevBuf {

@@ -251,6 +251,10 @@ __global__ void __launch_bounds__(256) k_resample_poly(const float *dbuf, int h2
     }
 }
 
+static const KernelList kFxKernels{(const void *)k_fir_generic, (const void *)k_update_carry, (const void *)k_shift_hist,
+                                   (const void *)k_fm_demod_f32, (const void *)k_store_prev, (const void *)k_fir_real_r8,
+                                   (const void *)k_resample_poly};
+
 }  // namespace sdr
 
 using namespace sdr;
@@ -297,6 +301,10 @@ cudaError_t prepare_fast(int smem) {
 template <int T, int D, int B, int NT, int WB>
 FastVariant make_variant() {
     using G = FastGeom<T, D, B, NT, WB>;
+    // the load-phase instantiations of this shape join the preload list (see KernelList in common.cuh)
+    static const KernelList kl{(const void *)k_fir_fast<T, D, B, NT, WB, 0>, (const void *)k_fir_fast<T, D, B, NT, WB, 1>,
+                               (const void *)k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 2 : 0)>,
+                               (const void *)k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 3 : 1)>};
     return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, WB, B, &launch_fast<T, D, B, NT, WB>, &prepare_fast<T, D, B, NT, WB>};
 }
 
@@ -412,6 +420,13 @@ const FastVariant *rtc_variant(int device, uint32_t T, uint32_t D, int B, int NT
     cache[full] = v;
     return v;
 }
+
+}  // namespace
+namespace sdr {
+// the shape table is a function-local static: make sure it exists (and has listed its kernels) before a preload
+void fx_touch_variants() { (void)find_variant(0, 0); }
+}  // namespace sdr
+namespace {
 
 constexpr size_t kFxChunkSamples = size_t(16) << 20;   // 32 MiB of IQ per pipelined chunk (host API)
 

@@ -999,6 +999,16 @@ __global__ void k_polar_v(const int2 *a, const int2 *b, size_t n, int fast, OctT
     }
 }
 
+#define SDR_K(x) ((const void *)(x))
+static const KernelList kIntKernels{
+    SDR_K(k_demod_fused<0>), SDR_K(k_demod_fused<6>), SDR_K(k_demod_ring<0>), SDR_K(k_demod_ring<6>),
+    SDR_K(k_demod_direct<2>), SDR_K(k_demod_direct<3>), SDR_K(k_demod_direct<4>), SDR_K(k_demod_direct<5>),
+    SDR_K(k_demod_direct<6>), SDR_K(k_demod_direct<7>), SDR_K(k_demod_direct<8>), SDR_K(k_demod_direct<9>),
+    SDR_K(k_demod_direct<10>), SDR_K(k_demod_direct<11>), SDR_K(k_demod_direct<12>), SDR_K(k_demod_direct<13>),
+    SDR_K(k_rotate_90), SDR_K(k_buf_to_complex), SDR_K(k_low_pass_complex), SDR_K(k_fm_demod), SDR_K(k_low_pass_real),
+    SDR_K(k_fast_atan2_v), SDR_K(k_polar_v)};
+#undef SDR_K
+
 }  // namespace sdr
 
 using namespace sdr;
@@ -1664,6 +1674,11 @@ int sdr_demod_ring_open(sdr_demod *d, size_t buf_len, uint32_t n_slots, sdr_ring
     if (e != cudaSuccess) {
         ring_release(r);
         return fail(SDR_E_CUDA, "sdr_demod_ring_open: %s", cudaGetErrorString(e));
+    }
+    // nothing may be loaded lazily once a ring kernel is resident (see KernelList in common.cuh)
+    if ((rc = preload_kernels())) {
+        ring_release(r);
+        return rc;
     }
     RingArgs a{};
     Plan pl = make_plan(d->cfg, 0, 0, S, 1);

@@ -120,6 +120,41 @@ void host_free_or_park(void *p) {
     }
     cudaFreeHost(p);
 }
+namespace {
+std::vector<const void *> &kernel_registry() {
+    static std::vector<const void *> v;   // function-local: safe to use from other units' static initialisers
+    return v;
+}
+bool g_preloaded[kMaxDev] = {false};
+}  // namespace
+
+KernelList::KernelList(std::initializer_list<const void *> fns) {
+    auto &v = kernel_registry();
+    v.insert(v.end(), fns.begin(), fns.end());
+}
+
+int preload_kernels() {
+    const int dev = cur_device();
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_preloaded[dev]) return SDR_OK;
+    }
+    fx_touch_variants();
+    for (const void *fn : kernel_registry()) {
+        cudaFuncAttributes attr;
+        SDR_CUDA_TRY(cudaFuncGetAttributes(&attr, fn));
+    }
+    // the memset kernel of dev_fill() as well
+    void *q = nullptr;
+    SDR_CUDA_TRY(cudaMalloc(&q, 256));
+    int rc = dev_fill(q, 0, 256);
+    cudaFree(q);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_preloaded[dev] = true;
+    return SDR_OK;
+}
+
 int dev_fill(void *p, int value, size_t bytes) {
     const int dev = cur_device();
     cudaStream_t st;
@@ -194,6 +229,8 @@ __global__ void k_synth_fill(uint8_t *buf, size_t bytes, uint64_t seed, uint64_t
         }
     }
 }
+
+static const KernelList kUtilKernels{(const void *)k_synth_fill};
 
 }  // namespace sdr
 

@@ -34,6 +34,30 @@ def fm_test_signal(n: int, fs: float, seed: int = 0xB2000001, f_dev: float = 75e
     return out
 
 
+def saturated_stream(rng, n_bytes):
+    """Bytes whose rotate_90 + (-127) image sits on the rails for long runs, so that boxcar sums reach +-128*D and the
+    products of two of them leave i32 (D >= 256), mixed with noise runs and sign flips."""
+    assert n_bytes % 8 == 0
+    out = np.empty(n_bytes, np.uint8)
+    pos = 0
+    while pos < n_bytes:
+        ln = min(n_bytes - pos, 8 * int(rng.integers(20, 900)))
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            out[pos:pos + ln] = rng.integers(0, 256, ln, dtype=np.uint8)
+        else:
+            # rotated group = [b0, b1, 255-b3, b2, 255-b4, 255-b5, b7, 255-b6]; pick rails (re_hi, im_hi) for the run
+            re_hi, im_hi = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+            R, I = (255 if re_hi else 0), (255 if im_hi else 0)
+            grp = np.array([R, I, R, 255 - I, 255 - R, 255 - I, 255 - R, I], np.uint8)   # rotates to (R, I) x 4
+            out[pos:pos + ln] = np.tile(grp, ln // 8)
+            if kind == 3:   # sprinkle noise on the rails
+                idx = rng.integers(0, ln, ln // 16)
+                out[pos + idx] = rng.integers(0, 256, idx.size, dtype=np.uint8)
+        pos += ln
+    return out
+
+
 def rel_err(got: np.ndarray, ref: np.ndarray) -> float:
     """Norm-wise relative error max|got-ref| / max|ref|."""
     ref = np.asarray(ref, np.float64)

@@ -55,15 +55,20 @@ def test_other_handles_work_while_a_ring_is_resident():
         rng = np.random.default_rng(7)
         data = rng.integers(0, 256, 6 * BUF, dtype=np.uint8)
         d1, o1 = S.Demod(), O.Demod()
+        def step(msg):
+            print(msg, file=sys.stderr, flush=True)      # a timeout report shows how far the child got
         ring = S.Ring(d1, BUF, n_slots=4)
         ring.submit(data[:BUF])
+        step("ring open, one buffer committed")
         # a second integer Demod: new (allocates), several calls (the first grows its buffers), free
         d2, o2 = S.Demod(S.DemodConfig(160000, 160000, 32000, 5, 1)), O.Demod(O.DemodConfig(160000, 160000, 32000, 5, 1))
         for c in range(3):
             assert np.array_equal(d2.demodulate(data[c * BUF:(c + 1) * BUF]), o2.demodulate(data[c * BUF:(c + 1) * BUF]))
+        step("second Demod: small calls done")
         big = np.tile(data, 8)                       # 12 MiB: the chunked path, fresh device buffers
         assert np.array_equal(d2.demodulate(big), o2.demodulate(big))
         d2.close()
+        step("second Demod: chunked call and free done")
         # an f32 receiver and a device buffer come and go as well
         taps = channel_taps(127, 75)
         rx = S.FmRx(taps, 75)
@@ -71,8 +76,10 @@ def test_other_handles_work_while_a_ring_is_resident():
         yo, do, _ = O.FxChain(taps, 75).process(data[:75 * 2 * 2000])
         assert np.allclose(y, yo, rtol=1e-4, atol=1e-2)
         rx.close()
+        step("FmRx done")
         b = S.DevBuffer(1 << 20); b.free()
         h = S.HostBuffer(1 << 20); h.free()
+        step("buffers done")
         # a device-wide wait is refused, not entered
         try:
             S.lib().sdr_device_sync(0)
@@ -88,6 +95,7 @@ def test_other_handles_work_while_a_ring_is_resident():
         # commit immediately followed by close: the committed buffer must still be processed and its state handed back
         ring.submit(data[4 * BUF:5 * BUF])
         ring.close()
+        step("ring closed")
         want = [o1.demodulate(data[c * BUF:(c + 1) * BUF]) for c in range(5)]
         for g, w in zip(got, want):
             assert np.array_equal(g, w)
