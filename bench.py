@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — headline benchmark of the IQ-sample DSP hot path (driver contract in the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1|chan] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic IQ that is ALREADY RESIDENT in HBM.
 
@@ -11,10 +11,17 @@ One "step" = one pass of the hot path over one batch of synthetic IQ that is ALR
   cfg3 (configs[2]): 20 Msps-equivalent, 255-tap FIR /100, FM demod, 200k->32k (4/25) resampler.
   cfg1 (configs[0] semantics at scale): the reference-exact integer Demod (boxcar-6, fast_atan2,
         170k->32k) over 8192 x 262144-byte buffers per step.
+  chan (configs[3]/[4]): the 64-channel-per-GPU wideband channeliser.
 
-N > 1 (launched by torchrun, one rank per GPU): every rank owns one time slice of the same synthetic
-stream (weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
-`--impl reference` times the CPU restatement of the same workload (oracle port; the reference itself is
+The ONE JSON line rank 0 prints carries the headline workload in `value` / `roofline` / `e2e` / `cpu_baseline`, and
+— so that every BASELINE.json config is measured by the same driver-run command —
+  `extra`     : cfg1 {ms, GB/s, frac, e2e pinned + pageable, per_buffer, CPU legs incl. the single-thread ref_like}, the
+                other f32 config {ms, frac}, the channeliser {ms per slab, roofline}  (N = 1; measured after the timed region);
+  `multi_gpu` : (N > 1, under torchrun) north_star's partition — 64 channels per rank, the raw u8 slabs broadcast from
+                rank 0 with one ncclBroadcast each: {channels_total, input_msamples_per_s, channel_msamples_per_s,
+                bcast_gbs, exposed_bcast_ms, ...} and the box's bare N-rank H2D ceiling next to the e2e figure.
+The headline workload at N > 1: every rank owns one time slice of the same synthetic stream (weak scaling, no data-path
+collective).  `--impl reference` times the CPU restatement of the same workload (oracle port; the reference itself is
 Rust and cannot be built in this image) on the box's host cores.
 """
 from __future__ import annotations
@@ -60,112 +67,14 @@ def workload_spec(name: str) -> dict:
     raise SystemExit(f"unknown workload {name}")
 
 
-def run_chan(args, w):
-    """Channeliser bench (FP32-FMA-bound, not HBM-bound): rank r owns channels [64r, 64r+64) of 64*N; every
-    rank needs the whole raw stream, which rank 0 broadcasts slab by slab on its own stream while the
-    previous slab is being channelised."""
-    rank, local_rank, world = dist_env()
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
-    device = local_rank
-    import sdrpkg
-    from sigutil import channel_taps
-    S = sdrpkg.load()
-    info = S.device_info(device)
-    C, T, D, n, slab = w["C"], w["T"], w["D"], w["n"], w["slab"]
-    c_tot = C * world
-    taps = channel_taps(T, D)
-    offs = (np.arange(c_tot) - (c_tot - 1) / 2.0) * (w["fs"] / c_tot)
-    fw_all = (np.round(offs / w["fs"] * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
-    ch = S.Channeliser(taps, D, fw_all[rank * C:(rank + 1) * C], device=device)
-    d_in = S.DevBuffer(2 * n, device)
-    if rank == 0:
-        S.synth_fill_dev(d_in, 2 * n, SEED)
-    cap = slab // D + 1
-    d_dem = S.DevBuffer(4 * C * cap, device)
-    comm = None
-    if world > 1:
-        import torch
-        uid = [S.Comm.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        comm = S.Comm(device, rank, world, uid[0])
-    n_slabs = n // slab
-
-    def step():
-        if comm is not None:
-            comm.wait_chan(ch)                          # the slab memory is reused every step: wait for the previous
-        for s in range(n_slabs):                        # step's channelising once, then broadcast(s+1) overlaps process(s)
-            if comm is not None:
-                comm.bcast_u8(d_in, 2 * slab, 0, offset=2 * slab * s)
-                comm.chan_wait(ch)
-            from rtl_sdr_rs_b200 import _ffi as F
-            F.check(F.lib().sdr_chan_process_dev(ch._h, d_in.at(2 * slab * s), slab, None, d_dem.ptr, cap))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier(device_ids=[local_rank])
-        ch.sync()
-        if comm is not None:
-            comm.sync()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches0 = S.kernel_launch_count()
-    sampler = ClockSampler(device)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    kern_ms = 0.0
-    for _ in range(args.steps):
-        step()
-    ch.sync()
-    if comm is not None:
-        comm.sync()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    kern_ms = ch.last_timing()[0]                       # device time of the last slab's k_chan_fir launch
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = S.kernel_launch_count() - launches0
-    if dist is not None:
-        import torch
-        t = torch.tensor([wall_ms, kern_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall_ms, kern_ms = float(t[0]), float(t[1])
-        lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt[0])
-    if rank == 0:
-        ms_per_step = wall_ms / args.steps
-        fma_per_sample = 4.0 * C * T / D                # complex tap x complex sample = 4 FMAs
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        fma_peak = info["sm_count"] * 128 * sm_mhz * 1e6 / 1e12          # TFMA/s at the observed clock
-        ach = fma_per_sample * slab / (kern_ms * 1e-3) / 1e12
-        line = {
-            "metric": "channel-Msamples/s (input Msamples/s x channels) through the channeliser", "workload": "chan",
-            "value": round(c_tot * n / (ms_per_step * 1e-3) / 1e6, 1), "unit": "channel-Msamples/s",
-            "input_msamples_per_s": round(n / (ms_per_step * 1e-3) / 1e6, 1), "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "channels_total": c_tot, "samples_per_step": n, "slab_samples": slab,
-                       "timing": "host wall clock around K steps bracketed by stream syncs (multi-stream pipeline), max over ranks",
-                       "device": info["name"]},
-            "roofline": {"bound": "fp32-fma (CUDA cores; no tensor cores by north_star)", "achieved": round(ach, 2),
-                         "peak": round(fma_peak, 2), "unit": "TFMA/s", "frac": round(ach / fma_peak, 4),
-                         "kernel": "k_chan_fir", "kernel_ms_per_slab": round(kern_ms, 4),
-                         "hbm_gbs": round((2.0 + C * 12.0 / D) * slab / (kern_ms * 1e-3) / 1e9, 1),
-                         "note": "peak = SMs x 128 FMA/clk x observed SM clock"},
-            "clocks": clocks, "gpu_launches": int(launches),
-        }
-        print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+def config_of(w: dict, info: dict | None = None) -> dict:
+    """The `config` object of a JSON line: identical keys for the GPU arm and the reference arm."""
+    c = {"workload": w["desc"], "samples_per_gpu_per_step": w["n"], "input_bytes_per_gpu": 2 * w["n"],
+         "l2_policy": "input (2 GiB) is larger than L2 (126 MB); no flush needed",
+         "sharding": "each rank owns one time slice of the same seeded stream; no data-path collective"}
+    if info is not None:
+        c["device"], c["sm_count"] = info["name"], info["sm_count"]
+    return c
 
 
 def taps_for(w: dict):
@@ -242,6 +151,218 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class Ctx:
+    """Rank / device / torch.distributed plumbing shared by every leg."""
+
+    def __init__(self):
+        self.rank, self.local_rank, self.world = dist_env()
+        self.dist = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl")
+            self.dist, self.torch = dist, torch
+        self.device = self.local_rank
+        import sdrpkg
+        self.S = sdrpkg.load()
+        if self.S.device_count() < 1:
+            raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+        self.info = self.S.device_info(self.device)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier(device_ids=[self.local_rank])
+
+    def max_over_ranks(self, *vals):
+        if self.dist is None:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=f"cuda:{self.local_rank}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def sum_over_ranks(self, val: int) -> int:
+        if self.dist is None:
+            return int(val)
+        t = self.torch.tensor([val], dtype=self.torch.int64, device=f"cuda:{self.local_rank}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t[0])
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------
+def measure_stream(cx: Ctx, w: dict, d_in, steps: int, warmup: int, sample_clocks: bool = False) -> dict:
+    """cfg1 / cfg2 / cfg3 with the input resident in HBM: W warm-up steps, then exactly K steps between a barrier +
+    stream sync on both sides, device time from CUDA events on the handle's stream, max over ranks."""
+    S, n = cx.S, w["n"]
+    if w["name"] == "cfg1":
+        h = S.Demod(device=cx.device)
+        out_cap = (h.out_len(w["buf_len"]) + 1) * w["n_bufs"] + 64
+        d_out = S.DevBuffer(2 * out_cap, cx.device)
+
+        def step():
+            return h.demodulate_batch_dev(d_in, w["buf_len"], w["n_bufs"], d_out, out_cap)
+    else:
+        taps, taps2 = taps_for(w)
+        h = S.FmRx(taps, w["D"], taps2, w["up"], w["down"], device=cx.device)
+        h.seek(n * cx.rank)
+        _, na = h.out_lens(n)
+        out_cap = na + 64
+        d_out = S.DevBuffer(4 * out_cap, cx.device)
+
+        def step():
+            return h.process_dev(d_in, n, d_out, out_cap)
+
+    def barrier():
+        cx.barrier()
+        h.sync()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    if w["name"] != "cfg1":
+        h.timing_totals(reset=True)
+    launches0 = S.kernel_launch_count()
+    sampler = ClockSampler(cx.device) if (sample_clocks and cx.rank == 0) else None
+    if sampler:
+        sampler.start()
+    barrier()
+    h.span_begin()
+    for _ in range(steps):
+        step()
+    total_ms = h.span_end()          # records the closing event and waits for it
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = S.kernel_launch_count() - launches0
+    if w["name"] == "cfg1":
+        kern_ms = total_ms / steps
+    else:
+        sums, calls = h.timing_totals()
+        kern_ms = sums[0] / max(calls, 1)
+    total_ms, kern_ms = cx.max_over_ranks(total_ms, kern_ms)
+    launches = cx.sum_over_ranks(launches)
+    h.close()
+    d_out.free()
+    return {"total_ms": total_ms, "ms_per_step": total_ms / steps, "kern_ms": kern_ms, "launches": launches,
+            "clocks": clocks, "steps": steps}
+
+
+def roofline_of(w: dict, m: dict) -> dict:
+    peak, peak_src = measured_peak()
+    bps = alg_bytes_per_sample(w)
+    achieved = bps * w["n"] / (m["kern_ms"] * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / f"traffic_{w['name']}.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": traffic,
+            "traffic_source": f"profiles/traffic_{w['name']}.json (one `ncu --set full` capture of this kernel at this size; "
+                              "not re-measured in this run)" if traffic else None,
+            "peak_source": peak_src,
+            "kernel": "k_demod_direct<6>" if w["name"] == "cfg1" else "k_fir_fast (fused convert+FIR+demod)",
+            "kernel_ms": round(m["kern_ms"], 4), "alg_bytes_per_sample": round(bps, 4),
+            "kernel_share_of_step": round(m["kern_ms"] / m["ms_per_step"], 4),
+            "whole_step_gbs": round((bps * w["n"]) / (m["ms_per_step"] * 1e-3) / 1e9, 1),
+            "whole_step_frac": round((bps * w["n"]) / (m["ms_per_step"] * 1e-3) / 1e9 / peak, 4),
+            "note": "peak is the pool's COPY benchmark (half of its bytes are writes); this kernel's bytes are "
+                    ">= 97 % reads, so frac can exceed 1 — against the 7.7 TB/s HBM3e nominal it is "
+                    f"{achieved / 7700.0:.3f}"}
+
+
+def measure_e2e(cx: Ctx, w: dict, steps: int, pageable: bool = False) -> dict:
+    """The same metric through the public C-ABI call with HOST buffers: H2D of the input and D2H of the audio inside the
+    timed region, every step.  pageable=False: pinned host memory (sdr_host_alloc); True: an ordinary heap array, which is
+    what a drop-in caller's Vec<u8> is (examples/simple_fm.rs:80,153)."""
+    S = cx.S
+    from rtl_sdr_rs_b200 import _ffi as F
+    n_e = 1 << 27
+    hb = S.HostBuffer(2 * n_e)
+    src = S.Source.open_synth(SEED + 1 + cx.rank)
+    assert src.read_sync(hb.array) == 2 * n_e
+    src.close()
+    in_arr = hb.array
+    if pageable:
+        in_arr = np.empty(2 * n_e, np.uint8)
+        in_arr[:] = hb.array
+        hb.free()
+    in_ptr = F.ptr(in_arr)
+    e_steps = max(3, min(steps, 10))
+    if w["name"] == "cfg1":
+        he = S.Demod(device=cx.device)
+        n_out_cap = n_e // 6 + 64
+        out_h = S.HostBuffer(2 * n_out_cap, np.int16) if not pageable else None
+        out_arr = out_h.array if out_h else np.empty(n_out_cap, np.int16)
+
+        def e_step():
+            return F.check(F.lib().sdr_demod_demodulate_batch(he._h, in_ptr, w["buf_len"], 2 * n_e // w["buf_len"],
+                                                              F.ptr(out_arr), out_arr.size, None))
+    else:
+        taps, taps2 = taps_for(w)
+        he = S.FmRx(taps, w["D"], taps2, w["up"], w["down"], device=cx.device)
+        n_out_cap = n_e // w["D"] * w["up"] // w["down"] + 64
+        out_h = S.HostBuffer(4 * n_out_cap, np.float32) if not pageable else None
+        out_arr = out_h.array if out_h else np.empty(n_out_cap, np.float32)
+
+        def e_step():
+            return F.check(F.lib().sdr_fmrx_process(he._h, in_ptr, n_e, None, 0, None, 0, F.ptr(out_arr), out_arr.size))
+    n_out_e = 0
+    for _ in range(2):
+        n_out_e = e_step()
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        n_out_e = e_step()          # synchronous: returns when the host output buffer is filled
+    e_s = time.perf_counter() - t0
+    (e_s,) = cx.max_over_ranks(e_s)
+    he.close()
+    if not pageable:
+        hb.free()
+    if out_h:
+        out_h.free()
+    return {"value": round(cx.world * n_e * e_steps / e_s / 1e6, 2), "unit": "Msamples/s",
+            "h2d_bytes_per_step": 2 * n_e, "d2h_bytes_per_step": int(n_out_e) * (2 if w["name"] == "cfg1" else 4),
+            "steps": e_steps, "samples_per_step": n_e,
+            "api": "sdr_demod_demodulate_batch" if w["name"] == "cfg1" else "sdr_fmrx_process",
+            "host_memory": "pageable (ordinary heap array, like the caller's Vec<u8>)" if pageable else "pinned (sdr_host_alloc)",
+            "note": "host input -> chunked H2D overlapped with the kernels -> D2H of the audio, per step"}
+
+
+def measure_h2d_ceiling(cx: Ctx) -> dict:
+    """Bare host->device copy rate of this box with all N ranks copying at once (pinned memory, 256 MiB per copy): the
+    ceiling any end-to-end figure with host input can reach.  No kernels involved."""
+    S = cx.S
+    nbytes = 1 << 28
+    hb = S.HostBuffer(nbytes)
+    hb.array[::4096] = 1                      # touch every page
+    db = S.DevBuffer(nbytes, cx.device)
+    db.upload(hb.array)                       # warm-up
+    cx.barrier()
+    reps = 6
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        db.upload(hb.array)                   # cudaMemcpy from pinned memory: one DMA, returns when done
+    dt = time.perf_counter() - t0
+    (dt,) = cx.max_over_ranks(dt)
+    hb.free()
+    db.free()
+    gbs = cx.world * nbytes * reps / dt / 1e9
+    return {"aggregate_gbs": round(gbs, 1), "msamples_per_s": round(gbs * 1e3 / 2, 1), "ranks": cx.world,
+            "how": f"{reps} x cudaMemcpy(256 MiB, pinned -> device) per rank, all ranks at once, max over ranks"}
+
+
 def per_buffer_bench(S, device: int, buf_len: int, n_bufs: int = 400) -> dict:
     """Latency/throughput of the drop-in call pattern: one `buf_len`-byte host buffer per call."""
     src = S.Source.open_synth(SEED + 77)
@@ -286,14 +407,119 @@ def per_buffer_bench(S, device: int, buf_len: int, n_bufs: int = 400) -> dict:
     return out
 
 
-def dist_env():
-    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+def chan_plan(w: dict, world: int):
+    from sigutil import channel_taps
+    C = w["C"]
+    c_tot = C * world
+    taps = channel_taps(w["T"], w["D"])
+    offs = (np.arange(c_tot) - (c_tot - 1) / 2.0) * (w["fs"] / c_tot)
+    fw_all = (np.round(offs / w["fs"] * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
+    return taps, fw_all, c_tot
+
+
+def chan_roofline(w: dict, info: dict, kern_ms: float, sm_mhz: float | None) -> dict:
+    C, T, D, slab = w["C"], w["T"], w["D"], w["slab"]
+    fma_per_sample = 4.0 * C * T / D                # direct form: complex tap x complex sample = 4 FMAs
+    mhz = sm_mhz or 1965.0
+    fma_peak = info["sm_count"] * 128 * mhz * 1e6 / 1e12          # TFMA/s at the observed clock
+    ach = fma_per_sample * slab / (kern_ms * 1e-3) / 1e12
+    peak, _ = measured_peak()
+    hbm_bytes = (2.0 + C * 4.0 / D) * slab                        # u8 IQ in, f32 discriminator out per channel
+    return {"kernel_ms_per_slab": round(kern_ms, 4), "slab_samples": slab,
+            "direct_form_tfma_per_s": round(ach, 2), "fp32_fma_peak_tfma_per_s": round(fma_peak, 2),
+            "direct_form_fma_frac": round(ach / fma_peak, 4),
+            "hbm_gbs": round(hbm_bytes / (kern_ms * 1e-3) / 1e9, 1), "hbm_frac": round(hbm_bytes / (kern_ms * 1e-3) / 1e9 / peak, 4),
+            "note": "direct_form_* counts the 4*C*T/D FMAs per input sample of the direct definition (a value above 1 means "
+                    "the kernel does less arithmetic than the direct form); hbm_* counts 2 B in + 4*C/D B out per sample"}
+
+
+def measure_chan(cx: Ctx, w: dict, d_in, steps: int, warmup: int, shard: bool) -> dict:
+    """The channeliser over n = 2^28 samples per step in 2^25-sample slabs.  shard=False: this GPU alone, input resident.
+    shard=True (N > 1): rank r owns channels [64r, 64r+64) of 64*N; rank 0 broadcasts every raw slab with one
+    ncclBroadcast(u8) on its own stream; a slab's broadcast waits only for the channelising of the slab that occupied the
+    same memory one step earlier (per-slab marks), so it runs under the previous slab's kernels."""
+    S = cx.S
+    from rtl_sdr_rs_b200 import _ffi as F
+    C, D, n, slab = w["C"], w["D"], w["n"], w["slab"]
+    world = cx.world if shard else 1
+    rank = cx.rank if shard else 0
+    taps, fw_all, c_tot = chan_plan(w, world)
+    ch = S.Channeliser(taps, D, fw_all[rank * C:(rank + 1) * C], device=cx.device)
+    cap = slab // D + 1
+    d_dem = S.DevBuffer(4 * C * cap, cx.device)
+    comm = None
+    if shard and world > 1:
+        uid = [S.Comm.unique_id() if cx.rank == 0 else None]
+        cx.dist.broadcast_object_list(uid, src=0)
+        comm = S.Comm(cx.device, cx.rank, world, uid[0])
+    n_slabs = n // slab
+
+    def step(bcast=True):
+        for s in range(n_slabs):
+            if comm is not None and bcast:
+                comm.wait_mark(s)                       # the slab memory is free once last step's slab s was consumed
+                comm.bcast_u8(d_in, 2 * slab, 0, offset=2 * slab * s)
+                comm.chan_wait(ch)
+            F.check(F.lib().sdr_chan_process_dev(ch._h, d_in.at(2 * slab * s), slab, None, d_dem.ptr, cap))
+            if comm is not None and bcast:
+                comm.mark_chan(ch, s)
+
+    def sync():
+        ch.sync()
+        if comm is not None:
+            comm.sync()
+
+    def timed(k, bcast=True):
+        cx.barrier()
+        sync()
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            step(bcast)
+        sync()
+        (dt,) = cx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        return dt / k
+
+    for _ in range(warmup):
+        step()
+    sync()
+    launches0 = S.kernel_launch_count()
+    ms_step = timed(steps)
+    launches = cx.sum_over_ranks(S.kernel_launch_count() - launches0)
+    (kern_ms,) = cx.max_over_ranks(ch.last_timing()[0])   # device time of the last slab's channeliser kernels
+    out = {"channels_total": c_tot, "channels_per_gpu": C, "n_gpus": world, "samples_per_step": n, "slab_samples": slab,
+           "ms_per_step": round(ms_step, 3), "input_msamples_per_s": round(n / (ms_step * 1e-3) / 1e6, 1),
+           "channel_msamples_per_s": round(c_tot * n / (ms_step * 1e-3) / 1e6, 1), "gpu_launches": launches,
+           "kernel_ms_per_slab": round(kern_ms, 4),
+           "timing": "host wall clock around K steps bracketed by barrier + stream syncs (multi-stream pipeline), max over ranks"}
+    if comm is not None:
+        # the same steps without the broadcast (every rank channelises what is already in its buffer): the difference
+        # is what the broadcast costs after overlap
+        ms_nobc = timed(steps, bcast=False)
+        # the broadcast alone, back to back
+        cx.barrier()
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            for s in range(n_slabs):
+                comm.bcast_u8(d_in, 2 * slab, 0, offset=2 * slab * s)
+        comm.sync()
+        (bc_ms,) = cx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        bc_ms /= 2 * n_slabs
+        out.update({"ms_per_step_without_bcast": round(ms_nobc, 3), "exposed_bcast_ms": round(ms_step - ms_nobc, 3),
+                    "bcast_ms_per_slab": round(bc_ms, 4), "bcast_gbs": round(2 * slab / (bc_ms * 1e-3) / 1e9, 1),
+                    "collective": "one ncclBroadcast(ncclUint8) per 64 MiB slab from rank 0, own stream; no other collective",
+                    "bcast_fraction_of_step_if_serial": round(bc_ms * n_slabs / ms_step, 3)})
+        comm.close()
+    ch.close()
+    d_dem.free()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
 # CPU arm (cpu_baseline leg and --impl reference): the oracle port timed on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_run(w: dict, sample_samples: int, reps: int, threads: int):
+def cpu_run(w: dict, sample_samples: int, reps: int, threads: int, fused: bool = False):
     """Returns (seconds per rep list, samples per rep).  This is the ONLY place bench.py executes oracle/."""
     import ctypes as C
     import oracle_ffi as O
@@ -307,8 +533,8 @@ def cpu_run(w: dict, sample_samples: int, reps: int, threads: int):
         times = []
         for _ in range(reps):
             t0 = time.perf_counter()
-            r = L.orc_demodulate_many_mt(C.byref(cfg), O._p(data, C.c_uint8), buf_len, n_bufs, O._p(out, C.c_int16),
-                                         out.size, threads)
+            r = L.orc_demodulate_many_mt2(C.byref(cfg), O._p(data, C.c_uint8), buf_len, n_bufs, O._p(out, C.c_int16),
+                                          out.size, threads, int(fused))
             times.append(time.perf_counter() - t0)
             assert r > 0
         return times, n_bufs * buf_len // 2
@@ -326,18 +552,34 @@ def cpu_run(w: dict, sample_samples: int, reps: int, threads: int):
     return times, sample_samples
 
 
+def cpu_leg(w: dict, threads: int, fused: bool, sample: int, budget_s: float) -> dict:
+    t, n = cpu_run(w, sample, 1, threads, fused)          # warm-up / calibration
+    reps = int(max(2, min(200, budget_s / max(t[0], 1e-3))))
+    times, n = cpu_run(w, sample, reps, threads, fused)
+    kind = ("single-pass fused restatement (orc_demodulate_fused)" if fused else
+            "ref-like integer Demod: one fresh vector per stage like examples/simple_fm.rs:256-269 (orc_demodulate_ref_like)") \
+        if w["name"] == "cfg1" else "f32 FIR+atan2f+resampler port"
+    return {"value": round(n / statistics.median(times) / 1e6, 2), "best": round(n / min(times) / 1e6, 2),
+            "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} passes over {n} complex samples (seeded synthetic, same taps/config), oracle port: {kind}, "
+                      f"{threads} thread{'s' if threads != 1 else ''}"
+                      + ("; one independent Demod per thread" if w["name"] == "cfg1" and threads > 1 else "")}
+
+
 def cpu_baseline(w: dict, budget_s: float = 8.0) -> dict:
     import oracle_ffi as O
-    threads = O.max_threads()
-    sample = 1 << 26
-    t, n = cpu_run(w, sample, 1, threads)          # warm-up / calibration
-    reps = int(max(2, min(200, budget_s / max(t[0], 1e-3))))
-    times, n = cpu_run(w, sample, reps, threads)
-    best = n / min(times) / 1e6
-    return {"value": round(n / statistics.median(times) / 1e6, 2), "best": round(best, 2), "unit": "Msamples/s",
-            "cores": threads, "kind": "port",
-            "sample": f"{reps} passes over {n} complex samples (seeded synthetic, same taps/config), "
-                      f"oracle port ({'ref-like integer Demod, one independent Demod per thread' if w['name'] == 'cfg1' else 'f32 FIR+atan2f+resampler'}), {threads} pthreads"}
+    return cpu_leg(w, O.max_threads(), False, 1 << 26, budget_s)
+
+
+def cpu_legs_cfg1(w: dict) -> dict:
+    """BASELINE.md §3: (1) ref_like on ONE thread — the reference's `process` is one thread (examples/simple_fm.rs:60,135);
+    (2) the fused single-pass restatement on one thread and on all threads; plus ref_like on all threads."""
+    import oracle_ffi as O
+    nt = O.max_threads()
+    return {"ref_like_1_thread": cpu_leg(w, 1, False, 1 << 24, 2.5),
+            "fused_1_thread": cpu_leg(w, 1, True, 1 << 24, 2.5),
+            "ref_like_all_threads": cpu_leg(w, nt, False, 1 << 26, 3.0),
+            "fused_all_threads": cpu_leg(w, nt, True, 1 << 26, 3.0)}
 
 
 def run_reference_arm(args, w):
@@ -351,12 +593,22 @@ def run_reference_arm(args, w):
     times = times[args.warmup:]
     total = sum(times)
     value = n * len(times) / total / 1e6
+    info = None
+    try:                                    # same `config` object as the GPU arm (the box's device is part of it)
+        import sdrpkg
+        S = sdrpkg.load()
+        if S.device_count() > 0:
+            info = S.device_info(0)
+    except Exception:
+        info = None
+    cfg = config_of(w, info)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(times), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-        "config": {"workload": w["desc"], "note": "the reference (Rust) cannot be built in this image: this arm is the "
-                   "oracle's CPU restatement of the same workload on all host threads; each step is a bounded sample"},
+        "config": cfg,
+        "note": "the reference (Rust) cannot be built in this image: this arm is the oracle's CPU restatement of the same "
+                f"workload on all host threads; each step is a bounded sample of {n} complex samples of it",
         "cpu_baseline": {"value": round(value, 2), "unit": "Msamples/s", "cores": threads, "kind": "port",
                          "sample": f"each step = {n} complex samples of the workload"},
         "e2e": {"value": round(value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -367,8 +619,35 @@ def run_reference_arm(args, w):
 
 
 # ---------------------------------------------------------------------------------------------------
-# GPU arm
+# main
 # ---------------------------------------------------------------------------------------------------
+def run_chan(args, w):
+    """--workload chan: the channeliser as the headline line (1 GPU: alone; N > 1: the channel shard)."""
+    cx = Ctx()
+    S = cx.S
+    d_in = S.DevBuffer(2 * w["n"], cx.device)
+    if cx.rank == 0 or cx.world == 1:
+        S.synth_fill_dev(d_in, 2 * w["n"], SEED)
+    sampler = ClockSampler(cx.device) if cx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    m = measure_chan(cx, w, d_in, args.steps, max(args.warmup, 3), shard=cx.world > 1)
+    clocks = sampler.stop() if sampler else None
+    if cx.rank == 0:
+        line = {"metric": "channel-Msamples/s (input Msamples/s x channels) through the channeliser", "workload": "chan",
+                "value": m["channel_msamples_per_s"], "unit": "channel-Msamples/s",
+                "input_msamples_per_s": m["input_msamples_per_s"], "n_gpus": cx.world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["desc"], "channels_total": m["channels_total"], "samples_per_step": w["n"],
+                           "slab_samples": w["slab"], "timing": m["timing"], "device": cx.info["name"]},
+                "roofline": chan_roofline(w, cx.info, m["kernel_ms_per_slab"], (clocks or {}).get("sm_mhz")),
+                "multi_gpu": m if cx.world > 1 else None, "clocks": clocks, "gpu_launches": m["gpu_launches"]}
+        print(json.dumps(line))
+    cx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +657,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only (profiling runs)")
     ap.add_argument("--n-log2", type=int, default=0, help="override samples per GPU per step (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -386,183 +666,96 @@ def main():
         w["n"] = 1 << args.n_log2
         if w["name"] == "cfg1":
             w["n_bufs"] = w["n"] // 131072
-    if w["name"] == "chan":
-        if args.impl == "reference":
-            raise SystemExit("--impl reference is defined for cfg1/cfg2/cfg3")
-        return run_chan(args, w)
     if args.impl == "reference":
+        if w["name"] == "chan":
+            raise SystemExit("--impl reference is defined for cfg1/cfg2/cfg3")
         return run_reference_arm(args, w)
+    if w["name"] == "chan":
+        return run_chan(args, w)
 
-    rank, local_rank, world = dist_env()
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
-    device = local_rank
-
-    import sdrpkg
-    S = sdrpkg.load()
-    if S.device_count() < 1:
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    info = S.device_info(device)
+    cx = Ctx()
+    S = cx.S
     n = w["n"]
     # each rank owns the time slice [rank*n, (rank+1)*n) of ONE synthetic stream
-    d_in = S.DevBuffer(2 * n, device)
-    S.synth_fill_dev(d_in, 2 * n, SEED, byte_offset=2 * n * rank)
+    d_in = S.DevBuffer(2 * n, cx.device)
+    S.synth_fill_dev(d_in, 2 * n, SEED, byte_offset=2 * n * cx.rank)
 
-    if w["name"] == "cfg1":
-        h = S.Demod(device=device)
-        out_cap = (h.out_len(w["buf_len"]) + 1) * w["n_bufs"] + 64
-        d_out = S.DevBuffer(2 * out_cap, device)
+    m = measure_stream(cx, w, d_in, args.steps, args.warmup, sample_clocks=True)
+    value = cx.world * n / (m["ms_per_step"] * 1e-3) / 1e6               # whole-job Msamples/s
+    e2e = None if args.no_e2e else measure_e2e(cx, w, args.steps)
 
-        def step():
-            return h.demodulate_batch_dev(d_in, w["buf_len"], w["n_bufs"], d_out, out_cap)
-    else:
-        taps, taps2 = taps_for(w)
-        h = S.FmRx(taps, w["D"], taps2, w["up"], w["down"], device=device)
-        h.seek(n * rank)
-        _, na = h.out_lens(n)
-        out_cap = na + 64
-        d_out = S.DevBuffer(4 * out_cap, device)
+    # ---- everything below runs AFTER the headline's timed region --------------------------------------------------
+    extra, multi = None, None
+    full_size = not args.n_log2
+    if not args.no_extra and full_size:
+        extra = {}
+        x_steps = max(5, min(args.steps, 10))
+        h2d = measure_h2d_ceiling(cx)
+        if e2e is not None:
+            e2e_page = measure_e2e(cx, w, args.steps, pageable=True)
+            e2e["pageable"] = {k: e2e_page[k] for k in ("value", "unit", "host_memory")}
+            e2e["pageable"]["fraction_of_pinned"] = round(e2e_page["value"] / e2e["value"], 3)
+            e2e["h2d_ceiling"] = h2d
+            e2e["fraction_of_h2d_ceiling"] = round(e2e["value"] / h2d["msamples_per_s"], 3)
+        for other in ("cfg1", "cfg3", "cfg2"):
+            if other == w["name"]:
+                continue
+            wo = workload_spec(other)
+            mo = measure_stream(cx, wo, d_in, x_steps, 3)
+            ro = roofline_of(wo, mo)
+            eo = {"workload": wo["desc"], "ms_per_step": round(mo["ms_per_step"], 4),
+                  "msamples_per_s": round(cx.world * wo["n"] / (mo["ms_per_step"] * 1e-3) / 1e6, 1), "steps": x_steps,
+                  "gpu_launches": mo["launches"],
+                  "roofline": {k: ro[k] for k in ("achieved", "peak", "unit", "frac", "kernel", "kernel_ms", "alg_bytes_per_sample",
+                                                  "kernel_share_of_step", "whole_step_frac", "traffic")}}
+            if other == "cfg1" and not args.no_e2e:
+                e1 = measure_e2e(cx, wo, x_steps)
+                e1p = measure_e2e(cx, wo, x_steps, pageable=True)
+                eo["e2e"] = {"value": e1["value"], "unit": "Msamples/s", "api": e1["api"], "host_memory": e1["host_memory"],
+                             "h2d_bytes_per_step": e1["h2d_bytes_per_step"], "d2h_bytes_per_step": e1["d2h_bytes_per_step"],
+                             "pageable_value": e1p["value"], "fraction_of_h2d_ceiling": round(e1["value"] / h2d["msamples_per_s"], 3)}
+                if cx.rank == 0:
+                    eo["per_buffer"] = per_buffer_bench(S, cx.device, wo["buf_len"])
+            if other == "cfg1" and not args.no_cpu_baseline and cx.rank == 0:
+                eo["cpu_baseline"] = cpu_legs_cfg1(wo)
+            extra[other] = eo
+        wc = workload_spec("chan")
+        mc = measure_chan(cx, wc, d_in, max(3, x_steps // 2), 3, shard=False)
+        extra["chan"] = {"workload": wc["desc"], "ms_per_step": mc["ms_per_step"], "input_msamples_per_s": mc["input_msamples_per_s"],
+                         "channel_msamples_per_s": mc["channel_msamples_per_s"], "gpu_launches": mc["gpu_launches"],
+                         "roofline": chan_roofline(wc, cx.info, mc["kernel_ms_per_slab"], (m["clocks"] or {}).get("sm_mhz"))}
+        if cx.world > 1:
+            # north_star's multi-GPU design: the channel shard with the NCCL slab broadcast.  Ranks other than 0 hold
+            # whatever their time slice left in d_in; every slab is overwritten by the broadcast before it is read.
+            multi = measure_chan(cx, wc, d_in, max(3, x_steps // 2), 3, shard=True)
+            multi["single_gpu_ms_per_step"] = mc["ms_per_step"]
+            multi["efficiency_vs_one_gpu_same_run"] = round(mc["ms_per_step"] / multi["ms_per_step"], 4)
 
-        def step():
-            return h.process_dev(d_in, n, d_out, out_cap)
+    if w["name"] == "cfg1" and not args.no_e2e and cx.rank == 0 and (args.no_extra or not full_size):
+        extra = extra or {}
+        extra["per_buffer"] = per_buffer_bench(S, cx.device, w["buf_len"])
 
-    def barrier():
-        if dist is not None:
-            dist.barrier(device_ids=[local_rank])
-        h.sync()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    if w["name"] != "cfg1":
-        h.timing_totals(reset=True)
-    launches0 = S.kernel_launch_count()
-    sampler = ClockSampler(device)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    h.span_begin()
-    for _ in range(args.steps):
-        step()
-    total_ms = h.span_end()          # records the closing event and waits for it
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = S.kernel_launch_count() - launches0
-    if w["name"] == "cfg1":
-        kern_ms = total_ms / args.steps
-    else:
-        sums, calls = h.timing_totals()
-        kern_ms = sums[0] / max(calls, 1)
-
-    if dist is not None:
-        import torch
-        t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms = float(t[0]), float(t[1])
-        lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt[0])
-
-    ms_per_step = total_ms / args.steps
-    value = world * n / (ms_per_step * 1e-3) / 1e6               # whole-job Msamples/s
-
-    # ---- end-to-end through the public C-ABI call with HOST buffers (H2D + D2H inside the timed region)
-    e2e = None
-    if not args.no_e2e:
-        n_e = 1 << 27
-        hb = S.HostBuffer(2 * n_e)
-        src = S.Source.open_synth(SEED + 1 + rank)
-        assert src.read_sync(hb.array) == 2 * n_e
-        src.close()
-        e_steps = max(3, min(args.steps, 10))
-        if w["name"] == "cfg1":
-            he = S.Demod(device=device)
-            out_h = S.HostBuffer(2 * (n_e // 6 + 64), np.int16)
-            import ctypes as C
-            from rtl_sdr_rs_b200 import _ffi as F
-
-            def e_step():
-                return F.check(F.lib().sdr_demod_demodulate_batch(he._h, hb.ptr, w["buf_len"], 2 * n_e // w["buf_len"],
-                                                                  out_h.ptr, out_h.array.size, None))
-        else:
-            he = S.FmRx(taps, w["D"], taps2, w["up"], w["down"], device=device)
-            out_h = S.HostBuffer(4 * (n_e // w["D"] * w["up"] // w["down"] + 64), np.float32)
-            from rtl_sdr_rs_b200 import _ffi as F
-
-            def e_step():
-                return F.check(F.lib().sdr_fmrx_process(he._h, hb.ptr, n_e, None, 0, None, 0, out_h.ptr, out_h.array.size))
-        n_out_e = 0
-        for _ in range(2):
-            n_out_e = e_step()
-        if dist is not None:
-            dist.barrier(device_ids=[local_rank])
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            n_out_e = e_step()          # synchronous: returns when the host output buffer is filled
-        e_s = time.perf_counter() - t0
-        if dist is not None:
-            import torch
-            t = torch.tensor([e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_s = float(t[0])
-        e2e = {"value": round(world * n_e * e_steps / e_s / 1e6, 2), "unit": "Msamples/s",
-               "h2d_bytes_per_step": 2 * n_e, "d2h_bytes_per_step": int(n_out_e) * (2 if w["name"] == "cfg1" else 4),
-               "steps": e_steps, "samples_per_step": n_e,
-               "api": "sdr_demod_demodulate_batch" if w["name"] == "cfg1" else "sdr_fmrx_process",
-               "note": "pinned host input -> chunked H2D overlapped with the kernels -> D2H of the audio, per step"}
-
-    # ---- the reference's own call pattern (examples/simple_fm.rs:80,153): ONE 262144-byte buffer per demodulate() call,
-    # host buffers in and out, (a) one synchronous call per buffer, (b) the persistent ring (no launch per buffer)
-    per_buffer = None
-    if w["name"] == "cfg1" and not args.no_e2e and rank == 0:
-        per_buffer = per_buffer_bench(S, device, w["buf_len"])
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+    if cx.rank != 0:
+        cx.close()
         return 0
 
-    peak, peak_src = measured_peak()
-    bps = alg_bytes_per_sample(w)
-    achieved = bps * n / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tp = ROOT / "profiles" / f"traffic_{w['name']}.json"
-    if tp.exists():
-        try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    cfg = config_of(w, cx.info)
     line = {
-        "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-        "config": {"workload": w["desc"], "samples_per_gpu_per_step": n, "input_bytes_per_gpu": 2 * n,
-                   "l2_policy": "input (2 GiB) is larger than L2 (126 MB); no flush needed",
-                   "sharding": "each rank owns one time slice of the same seeded stream; no data-path collective",
-                   "device": info["name"], "sm_count": info["sm_count"]},
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "k_demod_direct<6>" if w["name"] == "cfg1" else "k_fir_fast (fused convert+FIR+demod)",
-                     "kernel_ms": round(kern_ms, 4), "alg_bytes_per_sample": round(bps, 4),
-                     "kernel_share_of_step": round(kern_ms / ms_per_step, 4),
-                     "note": "peak is the pool's COPY benchmark (half of its bytes are writes); this kernel's bytes are "
-                             ">= 97 % reads, so frac can exceed 1 — against the 7.7 TB/s HBM3e nominal it is "
-                             f"{achieved / 7700.0:.3f}"},
-        "clocks": clocks,
-        "e2e": e2e,
-        "gpu_launches": int(launches),
+        "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": cx.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic", "config": cfg,
+        "roofline": roofline_of(w, m), "clocks": m["clocks"], "e2e": e2e, "gpu_launches": int(m["launches"]),
     }
-    if per_buffer is not None:
-        line["per_buffer"] = per_buffer
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w)
+        if w["name"] == "cfg1":
+            line["cpu_baseline_legs"] = cpu_legs_cfg1(w)
+    if extra:
+        line["extra"] = extra
+    if multi:
+        line["multi_gpu"] = multi
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    cx.close()
     return 0
 
 

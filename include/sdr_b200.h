@@ -274,6 +274,11 @@ int sdr_comm_init(int cuda_device, int rank, int world, const uint8_t id[SDR_NCC
 int sdr_comm_bcast_u8(sdr_comm *c, uint8_t *d_buf, size_t bytes, int root);
 int sdr_comm_chan_wait(sdr_comm *c, sdr_chan *ch);   /* chan stream waits for last bcast */
 int sdr_comm_wait_chan(sdr_comm *c, sdr_chan *ch);   /* bcast stream waits for chan's work */
+/* Slab-granular form of the same ordering, for a ring of slab buffers that is reused step after step: mark(slot)
+ * records "everything enqueued on the channeliser so far" under `slot` (< 32); wait_mark(slot) makes the NEXT
+ * broadcast wait for that mark only — not for the slabs channelised since (a never-marked slot waits for nothing). */
+int sdr_comm_mark_chan(sdr_comm *c, sdr_chan *ch, uint32_t slot);
+int sdr_comm_wait_mark(sdr_comm *c, uint32_t slot);
 int sdr_comm_sync(sdr_comm *c);
 void sdr_comm_free(sdr_comm *c);
 

@@ -133,6 +133,8 @@ SIGNATURES = {
     "sdr_comm_bcast_u8": (_i, [_vp, _vp, _sz, _i]),
     "sdr_comm_chan_wait": (_i, [_vp, _vp]),
     "sdr_comm_wait_chan": (_i, [_vp, _vp]),
+    "sdr_comm_mark_chan": (_i, [_vp, _vp, C.c_uint32]),
+    "sdr_comm_wait_mark": (_i, [_vp, C.c_uint32]),
     "sdr_comm_sync": (_i, [_vp]),
     "sdr_comm_free": (None, [_vp]),
     "sdr_source_open_file": (_i, [C.c_char_p, _i, C.POINTER(_vp)]),

@@ -84,6 +84,12 @@ class Comm:
     def wait_chan(self, ch: Channeliser):
         F.check(F.lib().sdr_comm_wait_chan(self._h, ch._h))
 
+    def mark_chan(self, ch: Channeliser, slot: int):
+        F.check(F.lib().sdr_comm_mark_chan(self._h, ch._h, slot))
+
+    def wait_mark(self, slot: int):
+        F.check(F.lib().sdr_comm_wait_mark(self._h, slot))
+
     def sync(self):
         F.check(F.lib().sdr_comm_sync(self._h))
 

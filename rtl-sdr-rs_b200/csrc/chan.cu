@@ -789,6 +789,8 @@ struct sdr_comm {
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_bcast = nullptr, ev_chan = nullptr;
+    static constexpr int kMarks = 32;
+    cudaEvent_t ev_mark[kMarks]{};   // per-slab "this slab's memory has been consumed" marks (created on first use)
 };
 
 extern "C" {
@@ -854,6 +856,22 @@ int sdr_comm_wait_chan(sdr_comm *c, sdr_chan *ch) {
     return SDR_OK;
 }
 
+int sdr_comm_mark_chan(sdr_comm *c, sdr_chan *ch, uint32_t slot) {
+    if (!c || !ch || slot >= (uint32_t)sdr_comm::kMarks) return fail(SDR_E_ARG, "sdr_comm_mark_chan: bad argument");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    if (!c->ev_mark[slot]) SDR_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_mark[slot], cudaEventDisableTiming));
+    SDR_CUDA_TRY(cudaEventRecord(c->ev_mark[slot], ch->stream));
+    return SDR_OK;
+}
+
+int sdr_comm_wait_mark(sdr_comm *c, uint32_t slot) {
+    if (!c || slot >= (uint32_t)sdr_comm::kMarks) return fail(SDR_E_ARG, "sdr_comm_wait_mark: bad argument");
+    if (!c->ev_mark[slot]) return SDR_OK;   // never marked: nothing to wait for
+    SDR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_mark[slot], 0));
+    return SDR_OK;
+}
+
 int sdr_comm_sync(sdr_comm *c) {
     if (!c) return fail(SDR_E_ARG, "null handle");
     int rc = use_device(c->device);
@@ -869,6 +887,8 @@ void sdr_comm_free(sdr_comm *c) {
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
     if (c->ev_chan) cudaEventDestroy(c->ev_chan);
+    for (cudaEvent_t e : c->ev_mark)
+        if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

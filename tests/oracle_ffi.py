@@ -101,8 +101,12 @@ def lib() -> C.CDLL:
     L.orc_demodulate.restype = C.c_long
     L.orc_demodulate_ref_like.argtypes = [C.POINTER(DemodState), u8p, sz, i16p]
     L.orc_demodulate_ref_like.restype = C.c_long
+    L.orc_demodulate_fused.argtypes = [C.POINTER(DemodState), u8p, sz, i16p]
+    L.orc_demodulate_fused.restype = C.c_long
     L.orc_demodulate_many_mt.argtypes = [C.POINTER(DemodConfig), u8p, sz, sz, i16p, sz, C.c_int]
     L.orc_demodulate_many_mt.restype = C.c_long
+    L.orc_demodulate_many_mt2.argtypes = [C.POINTER(DemodConfig), u8p, sz, sz, i16p, sz, C.c_int, C.c_int]
+    L.orc_demodulate_many_mt2.restype = C.c_long
     L.orc_fx_init.argtypes = [C.POINTER(Fx), f32p, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
     L.orc_fx_init.restype = C.c_int
     L.orc_fx_free.argtypes = [C.POINTER(Fx)]
@@ -177,11 +181,12 @@ class Demod:
         n = lib().orc_low_pass_real(C.byref(self.st), _p(x, C.c_int16), x.size, _p(out, C.c_int16))
         return out[:n].copy()
 
-    def demodulate(self, buf: np.ndarray, stages: bool = False, ref_like: bool = False):
+    def demodulate(self, buf: np.ndarray, stages: bool = False, ref_like: bool = False, fused: bool = False):
         b = np.ascontiguousarray(buf, dtype=np.uint8)
         out = np.empty(b.size // 2 + 1, np.int16)
-        if ref_like:
-            n = lib().orc_demodulate_ref_like(C.byref(self.st), _p(b, C.c_uint8), b.size, _p(out, C.c_int16))
+        if ref_like or fused:
+            fn = lib().orc_demodulate_fused if fused else lib().orc_demodulate_ref_like
+            n = fn(C.byref(self.st), _p(b, C.c_uint8), b.size, _p(out, C.c_int16))
             if n < 0:
                 raise ValueError("demodulate: reference would panic on this input")
             return out[:n].copy()

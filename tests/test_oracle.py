@@ -138,6 +138,26 @@ def test_ref_like_and_fused_agree_on_random():
     assert a.state() == b.state()
 
 
+def test_single_pass_fused_leg_is_bit_identical(golden_dir):
+    """orc_demodulate_fused (the BASELINE.md §3 "oracle_fused" timing leg) against the staged form: capture head, ragged
+    random calls over several configs, and the overflow envelope."""
+    from sigutil import saturated_stream
+    head = np.fromfile(golden_dir / "capture_head.bin", np.uint8)
+    want = np.fromfile(golden_dir / "capture_head_audio.s16le", "<i2")
+    f = O.Demod()
+    got = np.concatenate([f.demodulate(head[c * O.DEFAULT_BUF_LENGTH:(c + 1) * O.DEFAULT_BUF_LENGTH], fused=True) for c in range(4)])
+    assert np.array_equal(got, want)
+    rng = np.random.default_rng(12)
+    for D, fast, slow in ((6, 170_000, 32_000), (1, 48_000, 48_000), (15, 160_000, 32_000), (7, 100_003, 31_999), (300, 96_000, 48_000)):
+        a, b = O.Demod(O.DemodConfig(fast, fast, slow, D, 1)), O.Demod(O.DemodConfig(fast, fast, slow, D, 1))
+        for n in (8 * max(40, D), 8 * 1001, 262144, 8 * (D + 3)):
+            buf = saturated_stream(rng, n) if D >= 256 else rng.integers(0, 256, n, dtype=np.uint8)
+            assert np.array_equal(a.demodulate(buf), b.demodulate(buf, fused=True)), (D, n)
+            assert a.state() == b.state()
+    with pytest.raises(ValueError):
+        O.Demod().demodulate(np.zeros(16, np.uint8), fused=True)
+
+
 def test_demodulate_rejects_what_the_reference_panics_on():
     with pytest.raises(ValueError):
         O.Demod().demodulate(np.zeros(12, np.uint8))      # len % 8 != 0 -> index panic :284-295
