@@ -262,6 +262,15 @@ long sdr_chan_process_dev(sdr_chan *c, const uint8_t *d_iq, size_t n_samples, fl
                           float *d_demod, size_t cap_per_channel);
 int sdr_chan_sync(sdr_chan *c);
 int sdr_chan_last_timing(const sdr_chan *c, float *kernel_ms, uint32_t *n_launches);
+/* Which channeliser kernel the handle runs: 0 = k_chan_fir (taps in shared memory, n_taps > 255), 1 = k_chan_fir_u (direct
+ * form, taps as uniform operands), 2 = k_chan_bank (two-stage polyphase bank: the channels sit on a uniform grid
+ * fw_c = f0 + c * 2^32/K; info = {K, K1, K2, 64-channel groups}).  SDR_CHAN_BANK=0 in the environment keeps the direct form. */
+int sdr_chan_kernel_kind(const sdr_chan *c, uint32_t info[4]);
+/* Diagnostic, needs no GPU: the bank plan sdr_chan_new() would pick for (cfg, freq_words) and, if `tables` is given, the
+ * coefficient blobs the kernel would receive (7680 floats per 64-channel group, layout in csrc/chan_bank.cuh).  Returns the
+ * number of groups, 0 when the channels are not a uniform bank (sdr_last_error() says why), < 0 on bad arguments. */
+long sdr_chan_bank_plan(const sdr_chan_config *cfg, const float *taps, const uint32_t *freq_words, uint32_t info[4],
+                        float *tables, size_t cap_floats);
 
 /* NCCL plumbing for the slab broadcast (libnccl is dlopen()ed lazily; absent => SDR_E_NCCL). */
 #define SDR_NCCL_ID_BYTES 128

@@ -32,7 +32,7 @@ from ._ffi import (  # noqa: F401
 )
 from .demod import Demod, Ring  # noqa: F401
 from .fmrx import FmRx  # noqa: F401
-from .chan import Channeliser, Comm  # noqa: F401
+from .chan import Channeliser, Comm, bank_plan  # noqa: F401
 from .source import Source  # noqa: F401
 
 DEFAULT_BUF_LENGTH = 16 * 16384  # src/lib.rs:25

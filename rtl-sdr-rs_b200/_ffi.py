@@ -128,6 +128,8 @@ SIGNATURES = {
     "sdr_chan_process_dev": (_l, [_vp, _vp, _sz, _vp, _vp, _sz]),
     "sdr_chan_sync": (_i, [_vp]),
     "sdr_chan_last_timing": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "sdr_chan_kernel_kind": (_i, [_vp, C.POINTER(C.c_uint32 * 4)]),
+    "sdr_chan_bank_plan": (_l, [C.POINTER(ChanConfig), _vp, _vp, C.POINTER(C.c_uint32 * 4), _vp, _sz]),
     "sdr_comm_unique_id": (_i, [_vp]),
     "sdr_comm_init": (_i, [_i, _i, _i, _vp, C.POINTER(_vp)]),
     "sdr_comm_bcast_u8": (_i, [_vp, _vp, _sz, _i]),

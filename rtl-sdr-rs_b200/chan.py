@@ -50,6 +50,12 @@ class Channeliser:
         return F.check(F.lib().sdr_chan_process_dev(self._h, d_iq.ptr, n_samples, d_y.ptr if d_y else None,
                                                     d_demod.ptr, cap_per_channel))
 
+    def kernel_kind(self):
+        """(kind, (K, K1, K2, groups)): 0 shared-memory taps, 1 direct form with uniform taps, 2 two-stage polyphase bank."""
+        info = (C.c_uint32 * 4)()
+        kind = F.check(F.lib().sdr_chan_kernel_kind(self._h, C.byref(info)))
+        return kind, tuple(info)
+
     def sync(self):
         F.check(F.lib().sdr_chan_sync(self._h))
 
@@ -57,6 +63,23 @@ class Channeliser:
         ms, n = C.c_float(0), C.c_uint32(0)
         F.check(F.lib().sdr_chan_last_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+def bank_plan(taps, decim: int, freq_words, want_tables: bool = True):
+    """sdr_chan_bank_plan: (K, K1, K2, groups) and the per-group coefficient tables [groups][3840][2] the bank kernel would
+    receive, or None when the channels are not a uniform bank.  Pure host arithmetic."""
+    taps = np.ascontiguousarray(taps, np.float32)
+    fw = np.ascontiguousarray(freq_words, np.uint32)
+    cfg = F.ChanConfig(fw.size, taps.size, decim, 0.0)
+    info = (C.c_uint32 * 4)()
+    g = F.check(F.lib().sdr_chan_bank_plan(C.byref(cfg), F.ptr(taps), F.ptr(fw), C.byref(info), None, 0))
+    if g == 0:
+        return None
+    tabs = None
+    if want_tables:
+        tabs = np.zeros((g, 3840, 2), np.float32)
+        F.check(F.lib().sdr_chan_bank_plan(C.byref(cfg), F.ptr(taps), F.ptr(fw), C.byref(info), F.ptr(tabs), tabs.size))
+    return tuple(info), tabs
 
 
 class Comm:

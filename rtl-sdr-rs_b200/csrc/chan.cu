@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "chan_bank.cuh"
 
 namespace sdr {
 
@@ -370,7 +371,9 @@ static const KernelList kChanKernels{
     SDR_K((k_chan_fir<16, 2, false>)), SDR_K((k_chan_fir<16, 1, true>)), SDR_K((k_chan_fir<16, 1, false>)),
     SDR_K((k_chan_fir<8, 8, true>)), SDR_K((k_chan_fir<8, 8, false>)), SDR_K((k_chan_fir<8, 4, true>)),
     SDR_K((k_chan_fir<8, 4, false>)), SDR_K((k_chan_fir<8, 2, true>)), SDR_K((k_chan_fir<8, 2, false>)),
-    SDR_K((k_chan_fir<8, 1, true>)), SDR_K((k_chan_fir<8, 1, false>)), SDR_K(k_chan_fir_u), SDR_K(k_chan_fold_taps),
+    SDR_K((k_chan_fir<8, 1, true>)), SDR_K((k_chan_fir<8, 1, false>)), SDR_K(k_chan_fir_u), SDR_K(k_chan_bank<1>), SDR_K(k_chan_bank<2>), SDR_K(k_chan_bank<3>),
+    SDR_K(k_chan_bank<4>), SDR_K(k_chan_bank<5>), SDR_K(k_chan_bank<6>), SDR_K(k_chan_bank<7>), SDR_K(k_chan_bank<8>),
+    SDR_K(k_chan_fold_taps),
     SDR_K(k_chan_demod), SDR_K(k_chan_store_prev), SDR_K(k_chan_update_carry)};
 #undef SDR_K
 
@@ -378,12 +381,111 @@ static const KernelList kChanKernels{
 
 using namespace sdr;
 
+// =================================================================================================
+// Uniform-bank planner (host, f64): is fw[] a uniform grid fw_c = f0 + c * 2^32/K ?  which K = K1*K2 split is cheapest ?
+// =================================================================================================
+namespace {
+
+struct BankPlan {
+    uint32_t K = 0, K1 = 0, K2 = 0, groups = 0;
+    double f0 = 0.0;          // ideal NCO word of channel 0 (real-valued: the mean rounding offset is taken out)
+    double max_tap_phase_err = 0.0;
+    const char *why = "";
+};
+
+constexpr double kTwo32 = 4294967296.0;
+inline double wrap_words(double x) { return x - kTwo32 * std::nearbyint(x / kTwo32); }   // into [-2^31, 2^31]
+
+// true: the bank kernel applies and beats the direct form; p is filled in.
+bool plan_bank(const sdr_chan_config &cfg, const uint32_t *fw, BankPlan &p) {
+    const uint32_t C = cfg.n_channels, T = cfg.n_taps;
+    if (C < 8) return p.why = "fewer than 8 channels", false;
+    const uint32_t step = fw[1] - fw[0];
+    uint32_t K = 0;
+    for (uint32_t k = 2; k <= 1024 && !K; k++) {
+        // k * step == 2^32 (mod 2^32) up to the rounding of the two words involved (each +-0.5 -> the product +-k)
+        const uint64_t t = ((uint64_t)k * step) & 0xffffffffull;
+        const uint64_t dist = t < (1ull << 32) - t ? t : (1ull << 32) - t;
+        if (dist > k) continue;
+        // bins must ascend one per channel: s = round(k * step / 2^32) mod k == 1
+        const uint64_t s = (uint64_t)std::llround((double)k * (double)step / kTwo32) % k;
+        if (s == 1 % k) K = k;
+    }
+    if (!K) return p.why = "channel spacing is not 2^32/K for any K <= 1024 (one bin per channel)", false;
+    // every channel against the ideal grid through channel 0; then take the mean offset out
+    double mean = 0.0, worst = 0.0;
+    std::vector<double> diff(C);
+    for (uint32_t c = 0; c < C; c++) {
+        diff[c] = wrap_words((double)(uint32_t)(fw[c] - fw[0]) - (double)c * (kTwo32 / K));
+        if (std::fabs(diff[c]) > 4.0) return p.why = "channels are not on one uniform grid", false;
+        mean += diff[c] / C;
+    }
+    for (uint32_t c = 0; c < C; c++) worst = std::max(worst, std::fabs(diff[c] - mean));
+    p.max_tap_phase_err = worst * (T > 1 ? T - 1 : 1) * (2.0 * 3.14159265358979323846 / kTwo32);
+    if (p.max_tap_phase_err > 2e-6) return p.why = "NCO words deviate from the grid by more than 2e-6 rad over the taps", false;
+    p.f0 = (double)fw[0] + mean;
+    // cheapest split: T*K2 (stage 1, shared) + 64*K1 (stage 2) complex MACs per output time and 64-channel group
+    const uint32_t groups = (C + kBankCH - 1) / kBankCH;
+    uint64_t best = ~0ull;
+    for (uint32_t k2 = 1; k2 <= (uint32_t)kBankMaxK2; k2++) {
+        if (K % k2) continue;
+        const uint32_t k1 = K / k2;
+        if ((uint64_t)T * k2 + (uint64_t)k1 * kBankCH + kBankCH > (uint64_t)kBankTabEntries) continue;
+        const uint64_t cost = (uint64_t)T * k2 + (uint64_t)kBankCH * k1;
+        if (cost < best) best = cost, p.K1 = k1, p.K2 = k2;
+    }
+    if (best == ~0ull) return p.why = "coefficient tables exceed the 30 KB kernel-parameter blob", false;
+    if ((double)best * groups > 0.6 * (double)C * T) return p.why = "no saving over the direct form", false;
+    p.K = K;
+    p.groups = groups;
+    return true;
+}
+
+// Coefficient blob of channel group g (channels 64g ...): layout in chan_bank.cuh.
+void build_bank_tab(const sdr_chan_config &cfg, const float *taps, const uint32_t *fw, const BankPlan &p, uint32_t g, BankTab &tab) {
+    const double PI2 = 2.0 * 3.14159265358979323846;
+    const uint32_t T = cfg.n_taps, K = p.K, K1 = p.K1, K2 = p.K2;
+    memset(&tab, 0, sizeof(tab));
+    const double f0g = p.f0 + (double)g * kBankCH * (kTwo32 / K);   // ideal word of the group's first channel
+    size_t idx = 0;
+    for (uint32_t r1 = 0; r1 < K1; r1++)
+        for (uint32_t k = r1; k < T; k += K1) {
+            const uint32_t r2 = (k % K) / K1;
+            const double base = std::fmod(f0g * (double)k / kTwo32, 1.0);
+            for (uint32_t b2 = 0; b2 < K2; b2++) {
+                const double ph = PI2 * (base + (double)((b2 * r2) % K2) / K2);
+                tab.v[idx++] = make_float2((float)((double)taps[k] * std::cos(ph)), (float)((double)taps[k] * std::sin(ph)));
+            }
+        }
+    for (uint32_t r1 = 0; r1 < K1; r1++)
+        for (uint32_t c = 0; c < (uint32_t)kBankCH; c++) {
+            const double ph = PI2 * (double)(((uint64_t)c * r1) % K) / K;
+            tab.v[idx++] = make_float2((float)std::cos(ph), (float)std::sin(ph));
+        }
+    for (uint32_t c = 0; c < (uint32_t)kBankCH; c++) {
+        const uint32_t ch = g * kBankCH + c;
+        float phi = 0.f;
+        if (ch < cfg.n_channels)   // theta_c(n_m) - theta_c(n_{m-1}) = fw_c * D (mod 2^32), as an angle in (-pi, pi]
+            phi = (float)((double)(int32_t)(fw[ch] * cfg.decim) * (PI2 / kTwo32));
+        tab.v[idx++] = make_float2(phi, 0.f);
+    }
+}
+
+}  // namespace
+
 struct sdr_chan {
     sdr_chan_config cfg{};
     int device = 0;
     int C_pad = 0, groups = 0, T4 = 0, pad = 0, mr = 0, warps = 8;
     bool aligned = false;
     bool use_uniform = false;                  // k_chan_fir_u path (n_taps <= 255)
+    // uniformly spaced channels: the two-stage polyphase bank (chan_bank.cuh); one coefficient blob per 64 channels
+    bool use_bank = false;
+    int bank_K = 0, bank_K1 = 0, bank_K2 = 0;
+    std::vector<BankTab> bank_tabs;
+    size_t smem_bank = 0;
+    DevBuf d_prev2;                            // bank path: the carried S[m-1] ping-pongs between d_prev and d_prev2
+    int prev_cur = 0;
     std::vector<TapsU> taps_u;                 // one 16 KB parameter blob per 8 channels
     size_t smem_u = 0;
     uint32_t sm_taps = 0, sm_xs = 0, sm_xb = 0;
@@ -429,8 +531,10 @@ ChanKernel pick_kernel(int warps, int mr, bool aligned) {
 int chan_reset_state(sdr_chan *c) {
     for (int i = 0; i < 2; i++) SDR_CUDA_TRY(cudaMemsetAsync(c->d_carry[i].p, 127, (size_t)c->cs * 2, c->stream));
     SDR_CUDA_TRY(cudaMemsetAsync(c->d_prev.p, 0, (size_t)c->C_pad * 8, c->stream));
+    if (c->d_prev2.p) SDR_CUDA_TRY(cudaMemsetAsync(c->d_prev2.p, 0, (size_t)c->C_pad * 8, c->stream));
     SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->carry_cur = 0;
+    c->prev_cur = 0;
     c->n_in = 0;
     return SDR_OK;
 }
@@ -440,6 +544,74 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
     const int D = (int)c->cfg.decim;
     c->last_launches = 0;
     SDR_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    if (c->use_bank) {
+        if (n_out) {
+            BankArgs b{};
+            b.x = d_x;
+            b.carry_end = c->d_carry[c->carry_cur].as<uint8_t>() + (size_t)c->cs * 2;
+            b.fw = c->d_fw.as<uint32_t>();
+            b.y_out = d_y;
+            b.d_out = d_d;
+            b.prev_in = (c->prev_cur ? c->d_prev2 : c->d_prev).as<float2>();
+            b.prev_out = (c->prev_cur ? c->d_prev : c->d_prev2).as<float2>();
+            b.n_samples = (long long)n;
+            b.n_out = (long long)n_out;
+            b.cap = (long long)cap;
+            b.r = (uint32_t)(c->n_in % D);
+            b.n0_lo = (uint32_t)c->n_in;
+            b.T = (int)c->cfg.n_taps;
+            b.D = D;
+            b.K1 = c->bank_K1;
+            b.tq = b.T / b.K1;
+            b.trem = b.T % b.K1;
+            b.gain = c->gain;
+            const uint64_t tiles = (n_out + (kBankThreads - 1) - 1) / (kBankThreads - 1);
+            if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
+            const int n_streams = (int)std::min<size_t>(c->bank_tabs.size(), 1 + sdr_chan::kSide);
+            if (n_streams > 1) {
+                SDR_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+                for (int s = 1; s < n_streams; s++) SDR_CUDA_TRY(cudaStreamWaitEvent(c->side[s - 1], c->ev_fork, 0));
+            }
+            for (size_t g = 0; g < c->bank_tabs.size(); g++) {
+                b.ch0 = (int)g * kBankCH;
+                b.n_ch = std::min<int>(kBankCH, (int)c->cfg.n_channels - b.ch0);
+                const int si = (int)(g % n_streams);
+                cudaStream_t st = si ? c->side[si - 1] : c->stream;
+                const unsigned grid = (unsigned)tiles;
+                switch (c->bank_K2) {
+                    case 1: k_chan_bank<1><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                    case 2: k_chan_bank<2><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                    case 3: k_chan_bank<3><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                    case 4: k_chan_bank<4><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                    case 5: k_chan_bank<5><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                    case 6: k_chan_bank<6><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                    case 7: k_chan_bank<7><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                    default: k_chan_bank<8><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
+                }
+                SDR_LAUNCH_CHECK();
+                c->last_launches++;
+            }
+            for (int s = 1; s < n_streams; s++) {
+                SDR_CUDA_TRY(cudaEventRecord(c->ev_join[s - 1], c->side[s - 1]));
+                SDR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join[s - 1], 0));
+            }
+            c->prev_cur ^= 1;
+        }
+        SDR_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        if (n) {
+            int nxt = c->carry_cur ^ 1;
+            k_chan_update_carry<<<(c->cs + 255) / 256, 256, 0, c->stream>>>(c->d_carry[c->carry_cur].as<uint16_t>(),
+                                                                            reinterpret_cast<const uint16_t *>(d_x), (long long)n,
+                                                                            c->cs, c->d_carry[nxt].as<uint16_t>());
+            SDR_LAUNCH_CHECK();
+            c->last_launches++;
+            c->carry_cur = nxt;
+        }
+        SDR_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        c->timing_pending = true;
+        c->n_in += n;
+        return SDR_OK;
+    }
     if (n_out && c->use_uniform) {
         ChanUArgs u{};
         u.x = d_x;
@@ -585,7 +757,34 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
         return fail(SDR_E_ARG, "n_taps=%u / decim=%u do not fit the channeliser's shared-memory tile", cfg->n_taps, cfg->decim);
     }
     c->cs = (int)(((size_t)T4 + D + 16 + 7) & ~size_t(7));
+    {
+        // uniformly spaced channels: the two-stage polyphase bank (SDR_CHAN_BANK=0 keeps the direct kernels, for A/B runs)
+        const char *eb = getenv("SDR_CHAN_BANK");
+        BankPlan bp;
+        if (!(eb && atoi(eb) == 0) && plan_bank(*cfg, freq_words, bp)) {
+            c->use_bank = true;
+            c->bank_K = (int)bp.K, c->bank_K1 = (int)bp.K1, c->bank_K2 = (int)bp.K2;
+            c->bank_tabs.resize(bp.groups);
+            for (uint32_t g = 0; g < bp.groups; g++) build_bank_tab(*cfg, taps, freq_words, bp, g, c->bank_tabs[g]);
+            // the halo lane of the first tile reaches back D + r + T - 1 samples before the call (r < D)
+            c->cs = (int)(((size_t)T4 + 2 * (size_t)D + 16 + 7) & ~size_t(7));
+            c->smem_bank = (((size_t)kBankThreads * D + cfg->n_taps + 16) * 2 + 15 + 32) & ~size_t(15);
+            if (c->smem_bank > 200 * 1024) c->use_bank = false;
+        }
+    }
     cudaError_t e = raise_dyn_smem(pick_kernel(c->warps, c->mr, c->aligned), c->smem);
+    if (e == cudaSuccess && c->use_bank) {
+        switch (c->bank_K2) {
+            case 1: e = raise_dyn_smem(k_chan_bank<1>, c->smem_bank); break;
+            case 2: e = raise_dyn_smem(k_chan_bank<2>, c->smem_bank); break;
+            case 3: e = raise_dyn_smem(k_chan_bank<3>, c->smem_bank); break;
+            case 4: e = raise_dyn_smem(k_chan_bank<4>, c->smem_bank); break;
+            case 5: e = raise_dyn_smem(k_chan_bank<5>, c->smem_bank); break;
+            case 6: e = raise_dyn_smem(k_chan_bank<6>, c->smem_bank); break;
+            case 7: e = raise_dyn_smem(k_chan_bank<7>, c->smem_bank); break;
+            default: e = raise_dyn_smem(k_chan_bank<8>, c->smem_bank); break;
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -599,7 +798,8 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
     }
     if ((rc = c->d_carry[0].reserve((size_t)c->cs * 2)) || (rc = c->d_carry[1].reserve((size_t)c->cs * 2)) ||
         (rc = c->d_taps.reserve(cfg->n_taps * 4)) || (rc = c->d_fw.reserve((size_t)c->C_pad * 4)) ||
-        (rc = c->d_gt.reserve((size_t)c->C_pad * T4 * 8)) || (rc = c->d_prev.reserve((size_t)c->C_pad * 8))) {
+        (rc = c->d_gt.reserve((size_t)c->C_pad * T4 * 8)) || (rc = c->d_prev.reserve((size_t)c->C_pad * 8)) ||
+        (c->use_bank && (rc = c->d_prev2.reserve((size_t)c->C_pad * 8)))) {
         sdr_chan_free(c);
         return rc;
     }
@@ -654,6 +854,7 @@ void sdr_chan_free(sdr_chan *c) {
     c->d_gt.release();
     c->d_fw.release();
     c->d_prev.release();
+    c->d_prev2.release();
     c->d_x.release();
     c->d_y.release();
     c->d_d.release();
@@ -684,12 +885,14 @@ long sdr_chan_process(sdr_chan *c, const uint8_t *iq, size_t n_samples, float *y
     if (n_out > cap) return fail(SDR_E_CAP, "capacity %zu < %llu outputs per channel", cap, (unsigned long long)n_out);
     if (n_samples == 0) return 0;
     const size_t C = c->cfg.n_channels;
-    if ((rc = c->d_x.reserve(n_samples * 2 + 64)) || (rc = c->d_y.reserve((size_t)c->C_pad * (n_out + 1) * 8)) ||
+    const bool need_y = y_pairs || !c->use_bank;   // the bank kernel discriminates on chip: y is optional there
+    if ((rc = c->d_x.reserve(n_samples * 2 + 64)) || (need_y && (rc = c->d_y.reserve((size_t)c->C_pad * (n_out + 1) * 8))) ||
         (rc = c->d_d.reserve(C * (n_out + 1) * 4)))
         return rc;
     SDR_CUDA_TRY(cudaMemcpyAsync(c->d_x.p, iq, n_samples * 2, cudaMemcpyHostToDevice, c->stream));
     const size_t dcap = n_out ? n_out : 1;
-    if ((rc = chan_run(c, c->d_x.as<uint8_t>(), n_samples, c->d_y.as<float2>(), c->d_d.as<float>(), dcap, n_out))) return rc;
+    if ((rc = chan_run(c, c->d_x.as<uint8_t>(), n_samples, need_y ? c->d_y.as<float2>() : nullptr, c->d_d.as<float>(), dcap, n_out)))
+        return rc;
     if (n_out) {
         if (y_pairs)
             SDR_CUDA_TRY(cudaMemcpy2DAsync(y_pairs, cap * 8, c->d_y.p, dcap * 8, n_out * 8, C, cudaMemcpyDeviceToHost, c->stream));
@@ -710,7 +913,7 @@ long sdr_chan_process_dev(sdr_chan *c, const uint8_t *d_iq, size_t n_samples, fl
     if (n_out > cap) return fail(SDR_E_CAP, "capacity %zu < %llu outputs per channel", cap, (unsigned long long)n_out);
     float2 *d_y = reinterpret_cast<float2 *>(d_y_pairs);
     size_t ycap = cap;
-    if (!d_y) {   // caller does not want y: keep it in a library buffer with the caller's row stride
+    if (!d_y && !c->use_bank) {   // caller does not want y: keep it in a library buffer with the caller's row stride
         if (c->d_y.cap < (size_t)c->C_pad * cap * 8) SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));   // before a realloc
         if ((rc = c->d_y.reserve((size_t)c->C_pad * cap * 8))) return rc;
         d_y = c->d_y.as<float2>();
@@ -726,6 +929,37 @@ int sdr_chan_sync(sdr_chan *c) {
     SDR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     chan_collect(c);
     return SDR_OK;
+}
+
+int sdr_chan_kernel_kind(const sdr_chan *c, uint32_t info[4]) {
+    if (!c) return fail(SDR_E_ARG, "null handle");
+    if (info) {
+        info[0] = (uint32_t)c->bank_K, info[1] = (uint32_t)c->bank_K1, info[2] = (uint32_t)c->bank_K2;
+        info[3] = (uint32_t)c->bank_tabs.size();
+    }
+    return c->use_bank ? 2 : (c->use_uniform ? 1 : 0);
+}
+
+long sdr_chan_bank_plan(const sdr_chan_config *cfg, const float *taps, const uint32_t *freq_words, uint32_t info[4],
+                        float *tables, size_t cap_floats) {
+    if (!cfg || !taps || !freq_words) return fail(SDR_E_ARG, "sdr_chan_bank_plan: null argument");
+    if (cfg->n_channels < 1 || cfg->n_taps < 1 || cfg->decim < 1) return fail(SDR_E_ARG, "need n_channels, n_taps, decim >= 1");
+    BankPlan bp;
+    if (!plan_bank(*cfg, freq_words, bp)) {
+        fail(SDR_OK, "not a uniform bank: %s", bp.why);
+        return 0;
+    }
+    if (info) info[0] = bp.K, info[1] = bp.K1, info[2] = bp.K2, info[3] = bp.groups;
+    if (tables) {
+        const size_t per = (size_t)kBankTabEntries * 2;
+        if (cap_floats < per * bp.groups) return fail(SDR_E_CAP, "table capacity %zu < %zu floats", cap_floats, per * bp.groups);
+        BankTab tab;
+        for (uint32_t g = 0; g < bp.groups; g++) {
+            build_bank_tab(*cfg, taps, freq_words, bp, g, tab);
+            memcpy(tables + per * g, tab.v, sizeof(tab.v));
+        }
+    }
+    return (long)bp.groups;
 }
 
 int sdr_chan_last_timing(const sdr_chan *c, float *kernel_ms, uint32_t *n_launches) {

@@ -1,0 +1,228 @@
+// chan_bank.cuh — k_chan_bank<K2>: the channeliser for UNIFORMLY SPACED channels (BASELINE.json configs 4-5), as a
+// two-stage polyphase filter bank on CUDA cores.
+//
+// The direct form (k_chan_fir_u) spends 4*C*T/D FMAs per input sample: every channel runs its own T-tap complex FIR.
+// When the channel centres sit on a uniform grid  fw_c = f0 + c * 2^32/K  (K bins; cfg4: K = 100, the interleaved cfg5
+// plan: K = 64) the C filters share almost all of their work.  With tap index k, r = k mod K = r1 + K1*r2 (K = K1*K2):
+//
+//   S_c[m] = sum_k h[k] e^{+j theta_c(k)} xc[n_m - k]                       (n_m = (m+1)D - 1, xc = x - 127)
+//          = sum_{r1 < K1} E[c][r1] * A[r1][c mod K2],                       E[c][r1] = e^{+j 2 pi c r1 / K}
+//   A[r1][b2] = sum_{k = r1 (mod K1)} G[b2][k] xc[n_m - k],                 G[b2][k] = h[k] e^{+j 2 pi (f0 k / 2^32 + b2 r2(k) / K2)}
+//
+// i.e. stage 1 is K "sub-filters" of T/K1 complex taps each (T*K2 complex MACs per output time, shared by ALL channels),
+// stage 2 a K1-term complex combination per channel (C*K1 MACs) — 2555 complex MACs instead of 16320 for cfg4
+// (K1 = 20, K2 = 5).  Both stages have the shape k_chan_fir_u already runs at 76 % of the FP32 peak: a lane owns one
+// output time, every coefficient is a scalar-broadcast uniform-register operand of a packed FFMA2 fed straight from the
+// kernel-parameter constant bank (no shared-memory coefficient traffic), the only per-lane load is its raw sample.
+// The grid is exact up to the rounding of the 32-bit NCO words the caller passes: the host checks that every tap phase
+// of every channel is within 2e-6 rad of the ideal grid (else the direct kernel runs), and the per-output de-rotation
+// uses the exact words.
+//
+// The discriminator is fused: lane t owns output out0 - 1 + t, so the predecessor S[m-1] is one shuffle away (lane 0 of
+// a CTA is a halo lane that only supplies it).  Because theta_c(n_m) - theta_c(n_{m-1}) = fw_c * D is a per-channel
+// constant, arg(y[m] conj y[m-1]) = arg(S[m] conj S[m-1]) - phi_c: no sincos is needed unless the caller asks for y.
+#pragma once
+#include "ptx_helpers.cuh"
+
+namespace sdr {
+
+constexpr int kBankThreads = 128;      // lanes per CTA (one output time each; lane 0 is the predecessor halo)
+constexpr int kBankCH = 64;            // channels per launch (packed accumulators held in registers)
+constexpr int kBankTabEntries = 3840;  // float2 entries of the coefficient parameter (30 KB of the 32 KB limit)
+constexpr int kBankMaxK2 = 8;
+
+// [0, T*K2): G, sub-filter taps in the order they are consumed: for r1, for j (k = r1 + j*K1 < T), for b2
+// [T*K2, T*K2 + K1*64): E[r1][c];   [.., + 64): (phi_c, 0)
+struct BankTab {
+    float2 v[kBankTabEntries];
+};
+
+struct BankArgs {
+    const uint8_t *x;
+    const uint8_t *carry_end;
+    const uint32_t *fw;        // [C] the caller's exact NCO words (de-rotation when y is wanted)
+    float2 *y_out;             // [C][cap] or nullptr
+    float *d_out;              // [C][cap] or nullptr
+    const float2 *prev_in;     // [C] S of the last output before this call
+    float2 *prev_out;          // [C] S of the last output of this call
+    long long n_samples, n_out, cap;
+    uint32_t r, n0_lo;
+    int ch0, n_ch, T, D, K1;
+    int tq, trem;              // T / K1 and T % K1 (host-computed: keeps the tap bookkeeping on the uniform datapath)
+    float gain;
+};
+
+// atan2 for the fused discriminator: minimax odd polynomial of degree 15 on [0, 1] (max error 1.2e-7 rad in f32) after
+// the usual octant reduction; ~20 instructions instead of atan2f's ~40.  Not both arguments zero.
+__device__ __forceinline__ float bank_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float q = __fdividef(mn, mx);
+    const float s = q * q;
+    float p = -0.004054520279169083f;
+    p = fmaf(p, s, 0.021862786263227463f);
+    p = fmaf(p, s, -0.0559120811522007f);
+    p = fmaf(p, s, 0.09642180055379868f);
+    p = fmaf(p, s, -0.13908623158931732f);
+    p = fmaf(p, s, 0.19946564733982086f);
+    p = fmaf(p, s, -0.33329859375953674f);
+    p = fmaf(p, s, 0.9999993443489075f);
+    p *= q;
+    if (ay > ax) p = 1.57079632679489662f - p;
+    if (x < 0.f) p = 3.14159265358979324f - p;
+    return copysignf(p, y);
+}
+
+__device__ __forceinline__ unsigned long long bk_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void bk_fma2(unsigned long long &acc, float s, unsigned long long x) {
+    const unsigned long long ss = bk_pack(s, s);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ss), "l"(x));
+}
+__device__ __forceinline__ float2 bk_unpack(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
+// One tile's raw bytes: samples [s0, s1) (call-local; negative = carry) -> xb.  One thread.  (Same staging as chan.cu.)
+__device__ __forceinline__ uint32_t bank_load_tile(unsigned char *xb, const BankArgs &a, long long s0, long long s1, uint64_t *bar) {
+    const uint32_t soff = (uint32_t)((2 * s0) & 15);
+    uint32_t carry_bytes = 0, x_bytes = 0;
+    const long long x_lo = s0 > 0 ? s0 : 0;
+    if (s0 < 0) {
+        const long long c_hi = s1 < 0 ? s1 : 0;
+        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
+    }
+    const long long b_lo = (2 * x_lo) & ~15ll;
+    if (s1 > 0) x_bytes = (uint32_t)(((2 * s1 + 15) & ~15ll) - b_lo);
+    mbar_arrive_expect_tx(bar, carry_bytes + x_bytes);
+    if (carry_bytes) bulk_g2s(xb, a.carry_end + 2 * s0 - soff, carry_bytes, bar);
+    if (x_bytes) bulk_g2s(xb + soff + (b_lo - 2 * s0), a.x + b_lo, x_bytes, bar);
+    return soff;
+}
+
+template <int K2>
+__global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a, const __grid_constant__ BankTab tab) {
+    constexpr int CH = kBankCH, NT = kBankThreads, OUT = NT - 1;
+    static_assert(K2 >= 1 && K2 <= kBankMaxK2, "stage-1 accumulators live in registers");
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t sh_soff;
+    __shared__ float2 xch[NT / 32][CH];   // S of each warp's last lane: the predecessor of the next warp's lane 0
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long out0 = (long long)blockIdx.x * OUT;   // first OWNED output; thread t computes output out0 - 1 + t
+    const long long n_here = a.n_out - out0 < OUT ? a.n_out - out0 : OUT;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        const long long s0 = (out0 - 1) * a.D - (long long)a.r - (a.T - 1);
+        const long long s1 = (out0 + n_here) * a.D - (long long)a.r;
+        sh_soff = bank_load_tile(smem, a, s0, s1, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    // newest sample of this thread's output, relative to the tile's first sample
+    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(smem + sh_soff) + (tid + 1) * a.D + a.T - 2;
+
+    unsigned long long Y[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) Y[c] = 0ull;
+    // opaque per-thread conversion constants (fir_fast.cuh: FHADD takes no immediate / uniform operand)
+    float bias;
+    uint32_t h1024;
+    asm volatile(
+        "{\n.reg .u32 t;\nmov.u32 t, %%tid.x;\nshr.u32 t, t, 31;\nor.b32 %0, t, 0xC48FE000;\nor.b32 %1, t, 0x64646464;\n}\n"
+        : "=f"(bias), "=r"(h1024));
+
+    const int T = a.T, K1 = a.K1;
+    const int eoff = T * K2;
+    int goff = 0;
+#pragma unroll 1
+    for (int r1 = 0; r1 < K1; r1++) {
+        const int nj = a.tq + (r1 < a.trem ? 1 : 0);   // taps k = r1 + j*K1 < T
+        // ---- stage 1: the K2 sub-filters of residue r1 (taps k = r1 + j*K1) -----------------------------------------
+        unsigned long long A[K2], B[K2];   // A += Re(G) * x, B += Im(G) * x;  result = (A.re - B.im, A.im + B.re)
+#pragma unroll
+        for (int b = 0; b < K2; b++) A[b] = B[b] = 0ull;
+        const uint16_t *p = t16 - r1;
+#pragma unroll 2
+        for (int j = 0; j < nj; j++) {
+            const uint32_t pair = __byte_perm((uint32_t)p[-j * K1], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
+            float xr, xi;
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(bias));
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(bias));
+            const unsigned long long x2 = bk_pack(xr, xi);
+#pragma unroll
+            for (int b = 0; b < K2; b++) {
+                const float2 g = tab.v[goff + j * K2 + b];
+                bk_fma2(A[b], g.x, x2);
+                bk_fma2(B[b], g.y, x2);
+            }
+        }
+        goff += nj * K2;
+        unsigned long long a2[K2], a2r[K2];   // the sub-filter output a and j*a
+#pragma unroll
+        for (int b = 0; b < K2; b++) {
+            const float2 pa = bk_unpack(A[b]), pb = bk_unpack(B[b]);
+            const float ar = pa.x - pb.y, ai = pa.y + pb.x;
+            a2[b] = bk_pack(ar, ai);
+            a2r[b] = bk_pack(-ai, ar);
+        }
+        // ---- stage 2: every channel adds E[c][r1] * A[r1][c mod K2] ---------------------------------------------------
+        const int eb = eoff + r1 * CH;
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const float2 ev = tab.v[eb + c];
+            bk_fma2(Y[c], ev.x, a2[c % K2]);
+            bk_fma2(Y[c], ev.y, a2r[c % K2]);
+        }
+    }
+
+    // ---- epilogue: discriminator against the predecessor output, optional de-rotated y ------------------------------
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < CH; c++) xch[warp][c] = bk_unpack(Y[c]);
+    }
+    __syncthreads();
+    const long long i = out0 - 1 + tid;                    // call-local output index of this thread
+    const bool owns = tid >= 1 && (long long)(tid - 1) < n_here;
+    const bool first_of_call = i == 0;                     // its predecessor is the carried state
+    const bool last_of_call = owns && i == a.n_out - 1;
+    const int phib = eoff + K1 * CH;
+    const uint32_t nm = a.n0_lo + (uint32_t)((i + 1) * a.D - 1) - a.r;   // global n_m mod 2^32
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        const float2 s = bk_unpack(Y[c]);
+        float2 pv;
+        pv.x = __shfl_up_sync(0xffffffffu, s.x, 1);
+        pv.y = __shfl_up_sync(0xffffffffu, s.y, 1);
+        if (lane == 0 && warp > 0) pv = xch[warp - 1][c];
+        if (c >= a.n_ch || !owns) continue;
+        if (first_of_call) pv = a.prev_in[a.ch0 + c];
+        const size_t o = (size_t)(a.ch0 + c) * a.cap + (size_t)i;
+        if (a.d_out) {
+            const float cre = fmaf(s.x, pv.x, s.y * pv.y);        // Re(S conj P)
+            const float cim = fmaf(s.y, pv.x, -(s.x * pv.y));     // Im(S conj P)
+            float d = 0.f;                                        // zero predecessor (stream start): 0 by definition
+            if (cre != 0.f || cim != 0.f) {
+                float t = bank_atan2(cim, cre) - tab.v[phib + c].x;
+                if (t > 3.14159265358979324f) t -= 6.28318530717958648f;
+                else if (t <= -3.14159265358979324f) t += 6.28318530717958648f;
+                d = a.gain * t;
+            }
+            a.d_out[o] = d;
+        }
+        if (a.y_out) {
+            float si, co;   // e^{+j theta_c(n_m)} from the top 24 phase bits; de-rotate with its conjugate
+            __sincosf((float)(int32_t)(a.fw[a.ch0 + c] * nm) * (3.14159265358979324f / 2147483648.0f), &si, &co);
+            a.y_out[o] = make_float2(s.x * co + s.y * si, s.y * co - s.x * si);
+        }
+        if (last_of_call) a.prev_out[a.ch0 + c] = s;
+    }
+}
+
+}  // namespace sdr
