@@ -407,17 +407,24 @@ def per_buffer_bench(S, device: int, buf_len: int, n_bufs: int = 400) -> dict:
     return out
 
 
-def chan_plan(w: dict, world: int):
+def chan_plan(w: dict, world: int, rank: int):
+    """Channel plan of BASELINE.json configs[3]/[4].  One GPU: 64 channels at f_c = (c - 31.5) * 200 kHz
+    (cfg4).  N GPUs: 64*N channels at f_c = (c - (64N-1)/2) * fs/(64N) (cfg5 is N = 8: (c - 255.5) * fs/512), 64 per
+    rank, INTERLEAVED — rank r owns c = r (mod N), so that its own 64 channels sit on a uniform fs/64 grid and share the
+    polyphase bank's first stage; which 64 a rank owns changes nothing else (outputs stay rank-local)."""
     from sigutil import channel_taps
     C = w["C"]
     c_tot = C * world
     taps = channel_taps(w["T"], w["D"])
-    offs = (np.arange(c_tot) - (c_tot - 1) / 2.0) * (w["fs"] / c_tot)
-    fw_all = (np.round(offs / w["fs"] * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
-    return taps, fw_all, c_tot
+    if world == 1:
+        offs = (np.arange(C) - 31.5) * 200e3
+    else:
+        offs = ((rank + world * np.arange(C)) - (c_tot - 1) / 2.0) * (w["fs"] / c_tot)
+    fw = (np.round(offs / w["fs"] * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
+    return taps, fw, c_tot
 
 
-def chan_roofline(w: dict, info: dict, kern_ms: float, sm_mhz: float | None) -> dict:
+def chan_roofline(w: dict, info: dict, kern_ms: float, sm_mhz: float | None, kernel: str = "") -> dict:
     C, T, D, slab = w["C"], w["T"], w["D"], w["slab"]
     fma_per_sample = 4.0 * C * T / D                # direct form: complex tap x complex sample = 4 FMAs
     mhz = sm_mhz or 1965.0
@@ -425,7 +432,7 @@ def chan_roofline(w: dict, info: dict, kern_ms: float, sm_mhz: float | None) -> 
     ach = fma_per_sample * slab / (kern_ms * 1e-3) / 1e12
     peak, _ = measured_peak()
     hbm_bytes = (2.0 + C * 4.0 / D) * slab                        # u8 IQ in, f32 discriminator out per channel
-    return {"kernel_ms_per_slab": round(kern_ms, 4), "slab_samples": slab,
+    return {"kernel": kernel, "kernel_ms_per_slab": round(kern_ms, 4), "slab_samples": slab,
             "direct_form_tfma_per_s": round(ach, 2), "fp32_fma_peak_tfma_per_s": round(fma_peak, 2),
             "direct_form_fma_frac": round(ach / fma_peak, 4),
             "hbm_gbs": round(hbm_bytes / (kern_ms * 1e-3) / 1e9, 1), "hbm_frac": round(hbm_bytes / (kern_ms * 1e-3) / 1e9 / peak, 4),
@@ -443,8 +450,9 @@ def measure_chan(cx: Ctx, w: dict, d_in, steps: int, warmup: int, shard: bool) -
     C, D, n, slab = w["C"], w["D"], w["n"], w["slab"]
     world = cx.world if shard else 1
     rank = cx.rank if shard else 0
-    taps, fw_all, c_tot = chan_plan(w, world)
-    ch = S.Channeliser(taps, D, fw_all[rank * C:(rank + 1) * C], device=cx.device)
+    taps, fw, c_tot = chan_plan(w, world, rank)
+    ch = S.Channeliser(taps, D, fw, device=cx.device)
+    kind, kinfo = ch.kernel_kind()
     cap = slab // D + 1
     d_dem = S.DevBuffer(4 * C * cap, cx.device)
     comm = None
@@ -491,6 +499,10 @@ def measure_chan(cx: Ctx, w: dict, d_in, steps: int, warmup: int, shard: bool) -
            "ms_per_step": round(ms_step, 3), "input_msamples_per_s": round(n / (ms_step * 1e-3) / 1e6, 1),
            "channel_msamples_per_s": round(c_tot * n / (ms_step * 1e-3) / 1e6, 1), "gpu_launches": launches,
            "kernel_ms_per_slab": round(kern_ms, 4),
+           "kernel": {0: "k_chan_fir (shared-memory taps)", 1: "k_chan_fir_u (direct form)",
+                      2: f"k_chan_bank (two-stage polyphase bank, K = {kinfo[0]} = {kinfo[1]} x {kinfo[2]})"}[kind],
+           "channel_plan": "f_c = (c - 31.5) * 200 kHz" if world == 1 else
+                           f"f_c = (c - {(c_tot - 1) / 2}) * fs/{c_tot}, rank r owns c = r (mod {world})",
            "timing": "host wall clock around K steps bracketed by barrier + stream syncs (multi-stream pipeline), max over ranks"}
     if comm is not None:
         # the same steps without the broadcast (every rank channelises what is already in its buffer): the difference
@@ -641,7 +653,7 @@ def run_chan(args, w):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["desc"], "channels_total": m["channels_total"], "samples_per_step": w["n"],
                            "slab_samples": w["slab"], "timing": m["timing"], "device": cx.info["name"]},
-                "roofline": chan_roofline(w, cx.info, m["kernel_ms_per_slab"], (clocks or {}).get("sm_mhz")),
+                "roofline": chan_roofline(w, cx.info, m["kernel_ms_per_slab"], (clocks or {}).get("sm_mhz"), m["kernel"]),
                 "multi_gpu": m if cx.world > 1 else None, "clocks": clocks, "gpu_launches": m["gpu_launches"]}
         print(json.dumps(line))
     cx.close()
@@ -723,7 +735,8 @@ def main():
         mc = measure_chan(cx, wc, d_in, max(3, x_steps // 2), 3, shard=False)
         extra["chan"] = {"workload": wc["desc"], "ms_per_step": mc["ms_per_step"], "input_msamples_per_s": mc["input_msamples_per_s"],
                          "channel_msamples_per_s": mc["channel_msamples_per_s"], "gpu_launches": mc["gpu_launches"],
-                         "roofline": chan_roofline(wc, cx.info, mc["kernel_ms_per_slab"], (m["clocks"] or {}).get("sm_mhz"))}
+                         "channel_plan": mc["channel_plan"],
+                         "roofline": chan_roofline(wc, cx.info, mc["kernel_ms_per_slab"], (m["clocks"] or {}).get("sm_mhz"), mc["kernel"])}
         if cx.world > 1:
             # north_star's multi-GPU design: the channel shard with the NCCL slab broadcast.  Ranks other than 0 hold
             # whatever their time slice left in d_in; every slab is overwritten by the broadcast before it is read.

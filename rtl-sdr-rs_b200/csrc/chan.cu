@@ -564,6 +564,7 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
             b.K1 = c->bank_K1;
             b.tq = b.T / b.K1;
             b.trem = b.T % b.K1;
+            b.eoff = b.T * c->bank_K2;
             b.gain = c->gain;
             const uint64_t tiles = (n_out + (kBankThreads - 1) - 1) / (kBankThreads - 1);
             if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");

@@ -48,7 +48,7 @@ struct BankArgs {
     long long n_samples, n_out, cap;
     uint32_t r, n0_lo;
     int ch0, n_ch, T, D, K1;
-    int tq, trem;              // T / K1 and T % K1 (host-computed: keeps the tap bookkeeping on the uniform datapath)
+    int tq, trem, eoff;        // T / K1, T % K1, T * K2 (host-computed: keeps the tap bookkeeping on the uniform datapath)
     float gain;
 };
 
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a,
         : "=f"(bias), "=r"(h1024));
 
     const int T = a.T, K1 = a.K1;
-    const int eoff = T * K2;
-    int goff = 0;
+    const int eoff = a.eoff;
+    int gidx = 0, eidx = eoff;
 #pragma unroll 1
     for (int r1 = 0; r1 < K1; r1++) {
         const int nj = a.tq + (r1 < a.trem ? 1 : 0);   // taps k = r1 + j*K1 < T
@@ -148,22 +148,21 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a,
         unsigned long long A[K2], B[K2];   // A += Re(G) * x, B += Im(G) * x;  result = (A.re - B.im, A.im + B.re)
 #pragma unroll
         for (int b = 0; b < K2; b++) A[b] = B[b] = 0ull;
-        const uint16_t *p = t16 - r1;
+        int koff = r1;
 #pragma unroll 2
-        for (int j = 0; j < nj; j++) {
-            const uint32_t pair = __byte_perm((uint32_t)p[-j * K1], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
+        for (int j = 0; j < nj; j++, koff += K1, gidx += K2) {
+            const uint32_t pair = __byte_perm((uint32_t)t16[-koff], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
             float xr, xi;
             asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(bias));
             asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(bias));
             const unsigned long long x2 = bk_pack(xr, xi);
 #pragma unroll
             for (int b = 0; b < K2; b++) {
-                const float2 g = tab.v[goff + j * K2 + b];
+                const float2 g = tab.v[gidx + b];
                 bk_fma2(A[b], g.x, x2);
                 bk_fma2(B[b], g.y, x2);
             }
         }
-        goff += nj * K2;
         unsigned long long a2[K2], a2r[K2];   // the sub-filter output a and j*a
 #pragma unroll
         for (int b = 0; b < K2; b++) {
@@ -173,13 +172,13 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a,
             a2r[b] = bk_pack(-ai, ar);
         }
         // ---- stage 2: every channel adds E[c][r1] * A[r1][c mod K2] ---------------------------------------------------
-        const int eb = eoff + r1 * CH;
 #pragma unroll
         for (int c = 0; c < CH; c++) {
-            const float2 ev = tab.v[eb + c];
+            const float2 ev = tab.v[eidx + c];
             bk_fma2(Y[c], ev.x, a2[c % K2]);
             bk_fma2(Y[c], ev.y, a2r[c % K2]);
         }
+        eidx += CH;
     }
 
     // ---- epilogue: discriminator against the predecessor output, optional de-rotated y ------------------------------

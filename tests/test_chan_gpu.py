@@ -108,3 +108,95 @@ def test_device_resident_and_errors(S):
     with pytest.raises(S.SdrError):
         S.Channeliser(taps, 0, fw)
     d_iq.free(), d_d.free()
+
+
+# ---- two-stage polyphase bank (k_chan_bank): uniformly spaced channels --------------------------------------------------
+BANK_CASES = [  # (name, C, T, D, offsets(C, fs), K)
+    ("cfg4", 64, 255, 100, lambda C, fs: (np.arange(C) - 31.5) * 200e3, 100),
+    ("cfg5-interleaved-rank3of8", 64, 255, 100, lambda C, fs: ((3 + 8 * np.arange(C)) - 255.5) * (fs / 512), 64),
+    ("100-of-128", 100, 63, 20, lambda C, fs: (np.arange(C) - 50) * (fs / 128), 128),
+    ("K16-aliasing-odd-D", 64, 31, 7, lambda C, fs: np.arange(C) * (fs / 16), 16),
+    ("prime-K53", 64, 255, 50, lambda C, fs: (np.arange(C) - 20) * (fs / 53), 53),
+    ("K96-K2=8", 70, 127, 75, lambda C, fs: (np.arange(C) - 10) * (fs / 96), 96),
+]
+
+
+@pytest.mark.parametrize("name,C,T,D,offs,K", BANK_CASES)
+def test_bank_kernel_vs_direct_definition(S, name, C, T, D, offs, K):
+    """Uniform grids take k_chan_bank; outputs against the oracle's direct NCO-mix definition, ragged streaming calls."""
+    fs = 20e6
+    taps = channel_taps(T, D)
+    fw = freq_words(offs(C, fs), fs)
+    n = D * 300 + 37
+    iq = np.random.default_rng(K).integers(0, 256, 2 * n, dtype=np.uint8)
+    ch = S.Channeliser(taps, D, fw)
+    kind, info = ch.kernel_kind()
+    assert kind == 2 and info[0] == K and info[1] * info[2] == K, (kind, info)
+    cuts = [0, 1, D - 1, D + 3, 127 * D + 5, 128 * D, n]        # first tile boundary, sub-decimation calls, carry
+    parts = [ch.process(iq[2 * lo:2 * hi]) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    y = np.concatenate([p[0] for p in parts], axis=1)
+    d = np.concatenate([p[1] for p in parts], axis=1)
+    yo, do = O.channelise(iq, taps, D, fw)
+    assert y.shape == yo.shape and d.shape == do.shape == (C, n // D)
+    for c in range(C):
+        assert_close(y[c], yo[c], what=f"{name} y ch{c}")
+        assert_angle_close(d[c], disc_f64(y[c], GAIN), GAIN * np.pi, what=f"{name} demod stage ch{c}")
+        assert_demod_propagated(d[c], yo[c], do[c], GAIN, what=f"{name} demod ch{c}")
+    from sigutil import rel_err
+    assert rel_err(y, yo) <= 1e-5
+    # one call == ragged calls, bit for bit; and the discriminator does not depend on whether y is asked for
+    ch1 = S.Channeliser(taps, D, fw)
+    y1, d1 = ch1.process(iq)
+    assert np.array_equal(y1, y) and np.array_equal(d1, d)
+    ch2 = S.Channeliser(taps, D, fw)
+    _, d2 = ch2.process(iq, want_y=False)
+    assert np.array_equal(d2, d)
+
+
+def test_bank_and_direct_kernels_agree(S, monkeypatch):
+    fs, C, T, D = 20e6, 64, 255, 100
+    taps = channel_taps(T, D)
+    fw = freq_words((np.arange(C) - 31.5) * 200e3, fs)
+    iq = fm_test_signal(D * 2000, fs=fs, f_c=500e3)
+    a = S.Channeliser(taps, D, fw)
+    monkeypatch.setenv("SDR_CHAN_BANK", "0")
+    b = S.Channeliser(taps, D, fw)
+    assert a.kernel_kind()[0] == 2 and b.kernel_kind()[0] == 1
+    ya, da = a.process(iq)
+    yb, db = b.process(iq)
+    from sigutil import rel_err
+    assert rel_err(ya, yb) < 3e-6, rel_err(ya, yb)
+    strong = np.hypot(yb[..., 0], yb[..., 1]) > 1e-2 * np.abs(yb).max()
+    strong[:, 1:] &= strong[:, :-1]
+    dd = (da - db + GAIN * np.pi) % (2 * GAIN * np.pi) - GAIN * np.pi
+    assert np.abs(dd[strong]).max() < 1e-4 * GAIN * np.pi
+
+
+def test_bank_device_resident_slab(S):
+    """The bench shape: 2^22 samples resident, demod only (y never leaves the chip), two back-to-back slabs."""
+    fs, C, T, D = 20e6, 64, 255, 100
+    taps = channel_taps(T, D)
+    fw = freq_words((np.arange(C) - 31.5) * 200e3, fs)
+    n = 1 << 22
+    d_in = S.DevBuffer(2 * n)
+    S.synth_fill_dev(d_in, 2 * n, 0xB2000001)
+    cap = n // D + 1
+    d_d = S.DevBuffer(4 * C * cap)
+    ch = S.Channeliser(taps, D, fw)
+    m1 = ch.process_dev(d_in, n // 2, d_d, cap)
+    ch.sync()
+    first = d_d.download(np.float32, C * cap).reshape(C, cap)[:, :m1].copy()
+    from rtl_sdr_rs_b200 import _ffi as F
+    m2 = F.check(F.lib().sdr_chan_process_dev(ch._h, d_in.at(n), n // 2, None, d_d.ptr, cap))
+    ch.sync()
+    second = d_d.download(np.float32, C * cap).reshape(C, cap)[:, :m2].copy()
+    assert m1 + m2 == n // D
+    k = 200 * D
+    yo, do = O.channelise(O.synth_fill(2 * k, 0xB2000001), taps, D, fw)
+    for c in (0, 17, 63):
+        assert_demod_propagated(first[c, :200], yo[c], do[c], GAIN, what=f"resident ch{c}")
+    # the same stream in one host call
+    host = S.Channeliser(taps, D, fw).process(O.synth_fill(2 * n, 0xB2000001), want_y=False)[1]
+    assert np.array_equal(np.concatenate([first, second], axis=1), host)
+    ms, launches = ch.last_timing()
+    assert launches == 2 and ms > 0          # one bank launch + the carry update
