@@ -373,7 +373,7 @@ static const KernelList kChanKernels{
     SDR_K((k_chan_fir<8, 4, false>)), SDR_K((k_chan_fir<8, 2, true>)), SDR_K((k_chan_fir<8, 2, false>)),
     SDR_K((k_chan_fir<8, 1, true>)), SDR_K((k_chan_fir<8, 1, false>)), SDR_K(k_chan_fir_u), SDR_K(k_chan_bank<1>), SDR_K(k_chan_bank<2>), SDR_K(k_chan_bank<3>),
     SDR_K(k_chan_bank<4>), SDR_K(k_chan_bank<5>), SDR_K(k_chan_bank<6>), SDR_K(k_chan_bank<7>), SDR_K(k_chan_bank<8>),
-    SDR_K(k_chan_fold_taps),
+    SDR_K((k_chan_bank<5, 20, 13>)), SDR_K((k_chan_bank<4, 16, 16>)), SDR_K(k_chan_fold_taps),
     SDR_K(k_chan_demod), SDR_K(k_chan_store_prev), SDR_K(k_chan_update_carry)};
 #undef SDR_K
 
@@ -429,9 +429,9 @@ bool plan_bank(const sdr_chan_config &cfg, const uint32_t *fw, BankPlan &p) {
     uint64_t best = ~0ull;
     for (uint32_t k2 = 1; k2 <= (uint32_t)kBankMaxK2; k2++) {
         if (K % k2) continue;
-        const uint32_t k1 = K / k2;
-        if ((uint64_t)T * k2 + (uint64_t)k1 * kBankCH + kBankCH > (uint64_t)kBankTabEntries) continue;
-        const uint64_t cost = (uint64_t)T * k2 + (uint64_t)kBankCH * k1;
+        const uint32_t k1 = K / k2, nj = (T + k1 - 1) / k1;   // every residue gets nj taps (zero padded)
+        const uint64_t cost = (uint64_t)k1 * nj * k2 + (uint64_t)kBankCH * k1;
+        if (cost + kBankCH + 1 > (uint64_t)kBankTabEntries) continue;
         if (cost < best) best = cost, p.K1 = k1, p.K2 = k2;
     }
     if (best == ~0ull) return p.why = "coefficient tables exceed the 30 KB kernel-parameter blob", false;
@@ -444,19 +444,22 @@ bool plan_bank(const sdr_chan_config &cfg, const uint32_t *fw, BankPlan &p) {
 // Coefficient blob of channel group g (channels 64g ...): layout in chan_bank.cuh.
 void build_bank_tab(const sdr_chan_config &cfg, const float *taps, const uint32_t *fw, const BankPlan &p, uint32_t g, BankTab &tab) {
     const double PI2 = 2.0 * 3.14159265358979323846;
-    const uint32_t T = cfg.n_taps, K = p.K, K1 = p.K1, K2 = p.K2;
+    const uint32_t T = cfg.n_taps, K = p.K, K1 = p.K1, K2 = p.K2, NJ = (T + K1 - 1) / K1;
     memset(&tab, 0, sizeof(tab));
     const double f0g = p.f0 + (double)g * kBankCH * (kTwo32 / K);   // ideal word of the group's first channel
     size_t idx = 0;
     for (uint32_t r1 = 0; r1 < K1; r1++)
-        for (uint32_t k = r1; k < T; k += K1) {
+        for (uint32_t j = 0; j < NJ; j++) {
+            const uint32_t k = r1 + j * K1;
             const uint32_t r2 = (k % K) / K1;
             const double base = std::fmod(f0g * (double)k / kTwo32, 1.0);
             for (uint32_t b2 = 0; b2 < K2; b2++) {
                 const double ph = PI2 * (base + (double)((b2 * r2) % K2) / K2);
-                tab.v[idx++] = make_float2((float)((double)taps[k] * std::cos(ph)), (float)((double)taps[k] * std::sin(ph)));
+                const double h = k < T ? (double)taps[k] : 0.0;   // zero padding up to Tp = K1*NJ taps
+                tab.v[idx++] = make_float2((float)(h * std::cos(ph)), (float)(h * std::sin(ph)));
             }
         }
+    idx = (idx + 1) & ~size_t(1);   // E starts on an even entry (16-byte aligned pairs)
     for (uint32_t r1 = 0; r1 < K1; r1++)
         for (uint32_t c = 0; c < (uint32_t)kBankCH; c++) {
             const double ph = PI2 * (double)(((uint64_t)c * r1) % K) / K;
@@ -559,12 +562,11 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
             b.cap = (long long)cap;
             b.r = (uint32_t)(c->n_in % D);
             b.n0_lo = (uint32_t)c->n_in;
-            b.T = (int)c->cfg.n_taps;
             b.D = D;
             b.K1 = c->bank_K1;
-            b.tq = b.T / b.K1;
-            b.trem = b.T % b.K1;
-            b.eoff = b.T * c->bank_K2;
+            b.NJ = ((int)c->cfg.n_taps + b.K1 - 1) / b.K1;
+            b.Tp = b.K1 * b.NJ;
+            b.eoff = (b.Tp * c->bank_K2 + 1) & ~1;
             b.gain = c->gain;
             const uint64_t tiles = (n_out + (kBankThreads - 1) - 1) / (kBankThreads - 1);
             if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
@@ -579,6 +581,11 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
                 const int si = (int)(g % n_streams);
                 cudaStream_t st = si ? c->side[si - 1] : c->stream;
                 const unsigned grid = (unsigned)tiles;
+                if (b.K1 == 20 && c->bank_K2 == 5 && b.NJ == 13)        // cfg4: 255 taps on a 100-bin grid
+                    k_chan_bank<5, 20, 13><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]);
+                else if (b.K1 == 16 && c->bank_K2 == 4 && b.NJ == 16)   // interleaved cfg5: 255 taps on a 64-bin grid
+                    k_chan_bank<4, 16, 16><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]);
+                else
                 switch (c->bank_K2) {
                     case 1: k_chan_bank<1><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
                     case 2: k_chan_bank<2><<<grid, kBankThreads, c->smem_bank, st>>>(b, c->bank_tabs[g]); break;
@@ -767,14 +774,18 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
             c->bank_K = (int)bp.K, c->bank_K1 = (int)bp.K1, c->bank_K2 = (int)bp.K2;
             c->bank_tabs.resize(bp.groups);
             for (uint32_t g = 0; g < bp.groups; g++) build_bank_tab(*cfg, taps, freq_words, bp, g, c->bank_tabs[g]);
-            // the halo lane of the first tile reaches back D + r + T - 1 samples before the call (r < D)
-            c->cs = (int)(((size_t)T4 + 2 * (size_t)D + 16 + 7) & ~size_t(7));
-            c->smem_bank = (((size_t)kBankThreads * D + cfg->n_taps + 16) * 2 + 15 + 32) & ~size_t(15);
+            // the halo lane of the first tile reaches back D + r + Tp - 1 samples before the call (r < D, Tp < T + K1)
+            const size_t Tp = (size_t)bp.K1 * ((cfg->n_taps + bp.K1 - 1) / bp.K1);
+            c->cs = (int)((Tp + 2 * (size_t)D + 16 + 7) & ~size_t(7));
+            c->smem_bank = (((size_t)kBankThreads * D + Tp + 16) * 2 + 15 + 32) & ~size_t(15);
             if (c->smem_bank > 200 * 1024) c->use_bank = false;
         }
     }
     cudaError_t e = raise_dyn_smem(pick_kernel(c->warps, c->mr, c->aligned), c->smem);
     if (e == cudaSuccess && c->use_bank) {
+        if (e == cudaSuccess) e = raise_dyn_smem(k_chan_bank<5, 20, 13>, c->smem_bank);
+        if (e == cudaSuccess) e = raise_dyn_smem(k_chan_bank<4, 16, 16>, c->smem_bank);
+        if (e == cudaSuccess)
         switch (c->bank_K2) {
             case 1: e = raise_dyn_smem(k_chan_bank<1>, c->smem_bank); break;
             case 2: e = raise_dyn_smem(k_chan_bank<2>, c->smem_bank); break;

@@ -26,13 +26,24 @@
 
 namespace sdr {
 
-constexpr int kBankThreads = 128;      // lanes per CTA (one output time each; lane 0 is the predecessor halo)
+#ifndef SDR_BANK_NT
+#define SDR_BANK_NT 128
+#endif
+#ifndef SDR_BANK_MINB
+#define SDR_BANK_MINB 3
+#endif
+#ifndef SDR_BANK_UNROLL
+#define SDR_BANK_UNROLL 4
+#endif
+constexpr int kBankUnroll = SDR_BANK_UNROLL;
+constexpr int kBankThreads = SDR_BANK_NT;   // lanes per CTA (one output time each; lane 0 is the predecessor halo)
 constexpr int kBankCH = 64;            // channels per launch (packed accumulators held in registers)
 constexpr int kBankTabEntries = 3840;  // float2 entries of the coefficient parameter (30 KB of the 32 KB limit)
 constexpr int kBankMaxK2 = 8;
 
-// [0, T*K2): G, sub-filter taps in the order they are consumed: for r1, for j (k = r1 + j*K1 < T), for b2
-// [T*K2, T*K2 + K1*64): E[r1][c];   [.., + 64): (phi_c, 0)
+// Every residue r1 gets the same number of taps NJ = ceil(T / K1): the filter is zero-padded to Tp = K1*NJ taps.
+// [0, Tp*K2): G, sub-filter taps in the order they are consumed: for r1, for j (k = r1 + j*K1), for b2
+// [eoff = Tp*K2 rounded up to even, eoff + K1*64): E[r1][c];   [.., + 64): (phi_c, 0)
 struct BankTab {
     float2 v[kBankTabEntries];
 };
@@ -47,8 +58,8 @@ struct BankArgs {
     float2 *prev_out;          // [C] S of the last output of this call
     long long n_samples, n_out, cap;
     uint32_t r, n0_lo;
-    int ch0, n_ch, T, D, K1;
-    int tq, trem, eoff;        // T / K1, T % K1, T * K2 (host-computed: keeps the tap bookkeeping on the uniform datapath)
+    int ch0, n_ch, Tp, D, K1, NJ;   // Tp = K1 * NJ: taps after zero padding
+    int eoff;                       // first E entry (host-computed: keeps the index arithmetic on the uniform datapath)
     float gain;
 };
 
@@ -105,10 +116,13 @@ __device__ __forceinline__ uint32_t bank_load_tile(unsigned char *xb, const Bank
     return soff;
 }
 
-template <int K2>
-__global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a, const __grid_constant__ BankTab tab) {
+// K1T / NJT != 0: the split is a compile-time constant (the BASELINE.json shapes) — the tap loop is fully unrolled, every
+// sample load carries an immediate offset and there is no loop bookkeeping; 0 / 0: any split, run-time loops.
+template <int K2, int K1T = 0, int NJT = 0>
+__global__ void __launch_bounds__(kBankThreads, SDR_BANK_MINB) k_chan_bank(const BankArgs a, const __grid_constant__ BankTab tab) {
     constexpr int CH = kBankCH, NT = kBankThreads, OUT = NT - 1;
     static_assert(K2 >= 1 && K2 <= kBankMaxK2, "stage-1 accumulators live in registers");
+    static_assert((K1T == 0) == (NJT == 0), "either both compile-time or both run-time");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t sh_soff;
@@ -119,14 +133,14 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a,
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
-        const long long s0 = (out0 - 1) * a.D - (long long)a.r - (a.T - 1);
+        const long long s0 = (out0 - 1) * a.D - (long long)a.r - (a.Tp - 1);
         const long long s1 = (out0 + n_here) * a.D - (long long)a.r;
         sh_soff = bank_load_tile(smem, a, s0, s1, &bar);
     }
     __syncthreads();
     mbar_wait(&bar, 0);
     // newest sample of this thread's output, relative to the tile's first sample
-    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(smem + sh_soff) + (tid + 1) * a.D + a.T - 2;
+    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(smem + sh_soff) + (tid + 1) * a.D + a.Tp - 2;
 
     unsigned long long Y[CH];
 #pragma unroll
@@ -138,30 +152,37 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a,
         "{\n.reg .u32 t;\nmov.u32 t, %%tid.x;\nshr.u32 t, t, 31;\nor.b32 %0, t, 0xC48FE000;\nor.b32 %1, t, 0x64646464;\n}\n"
         : "=f"(bias), "=r"(h1024));
 
-    const int T = a.T, K1 = a.K1;
+    const int K1 = K1T ? K1T : a.K1, NJ = NJT ? NJT : a.NJ;
     const int eoff = a.eoff;
     int gidx = 0, eidx = eoff;
 #pragma unroll 1
     for (int r1 = 0; r1 < K1; r1++) {
-        const int nj = a.tq + (r1 < a.trem ? 1 : 0);   // taps k = r1 + j*K1 < T
         // ---- stage 1: the K2 sub-filters of residue r1 (taps k = r1 + j*K1) -----------------------------------------
         unsigned long long A[K2], B[K2];   // A += Re(G) * x, B += Im(G) * x;  result = (A.re - B.im, A.im + B.re)
 #pragma unroll
         for (int b = 0; b < K2; b++) A[b] = B[b] = 0ull;
-        int koff = r1;
-#pragma unroll 2
-        for (int j = 0; j < nj; j++, koff += K1, gidx += K2) {
-            const uint32_t pair = __byte_perm((uint32_t)t16[-koff], h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
+        const uint16_t *p = t16 - r1;
+        auto tap = [&](const uint16_t raw, const int gi) {
+            const uint32_t pair = __byte_perm((uint32_t)raw, h1024, 0x4140u);   // half2 (1024+I, 1024+Q)
             float xr, xi;
             asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xr) : "h"((unsigned short)(pair & 0xffffu)), "f"(bias));
             asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(bias));
             const unsigned long long x2 = bk_pack(xr, xi);
 #pragma unroll
             for (int b = 0; b < K2; b++) {
-                const float2 g = tab.v[gidx + b];
+                const float2 g = tab.v[gi + b];
                 bk_fma2(A[b], g.x, x2);
                 bk_fma2(B[b], g.y, x2);
             }
+        };
+        if constexpr (NJT != 0) {
+#pragma unroll
+            for (int j = 0; j < NJT; j++) tap(p[-j * K1T], gidx + j * K2);
+            gidx += NJT * K2;
+        } else {
+            int koff = 0;
+#pragma unroll kBankUnroll
+            for (int j = 0; j < NJ; j++, koff += K1, gidx += K2) tap(p[-koff], gidx);
         }
         unsigned long long a2[K2], a2r[K2];   // the sub-filter output a and j*a
 #pragma unroll
@@ -172,11 +193,23 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a,
             a2r[b] = bk_pack(-ai, ar);
         }
         // ---- stage 2: every channel adds E[c][r1] * A[r1][c mod K2] ---------------------------------------------------
+        // eight channels at a time: four 16-byte uniform loads (two coefficients each), then the eight real-part FMAs,
+        // then the eight imaginary-part FMAs — the two FMAs into one accumulator are never back to back
 #pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const float2 ev = tab.v[eidx + c];
-            bk_fma2(Y[c], ev.x, a2[c % K2]);
-            bk_fma2(Y[c], ev.y, a2r[c % K2]);
+        for (int c0 = 0; c0 < CH; c0 += 8) {
+            float4 e4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) e4[q] = *reinterpret_cast<const float4 *>(&tab.v[eidx + c0 + 2 * q]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                bk_fma2(Y[c0 + 2 * q], e4[q].x, a2[(c0 + 2 * q) % K2]);
+                bk_fma2(Y[c0 + 2 * q + 1], e4[q].z, a2[(c0 + 2 * q + 1) % K2]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                bk_fma2(Y[c0 + 2 * q], e4[q].y, a2r[(c0 + 2 * q) % K2]);
+                bk_fma2(Y[c0 + 2 * q + 1], e4[q].w, a2r[(c0 + 2 * q + 1) % K2]);
+            }
         }
         eidx += CH;
     }
@@ -190,37 +223,45 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_chan_bank(const BankArgs a,
     const long long i = out0 - 1 + tid;                    // call-local output index of this thread
     const bool owns = tid >= 1 && (long long)(tid - 1) < n_here;
     const bool first_of_call = i == 0;                     // its predecessor is the carried state
-    const bool last_of_call = owns && i == a.n_out - 1;
+    const bool from_xch = lane == 0 && warp > 0;           // its predecessor sits in the previous warp
     const int phib = eoff + K1 * CH;
-    const uint32_t nm = a.n0_lo + (uint32_t)((i + 1) * a.D - 1) - a.r;   // global n_m mod 2^32
+    const size_t row0 = (size_t)a.ch0 * (size_t)a.cap + (size_t)(owns ? i : 0);
+    float *dp = a.d_out ? a.d_out + row0 : nullptr;
+    const bool want_d = owns && dp != nullptr;
+    const float2 *pin = a.prev_in + a.ch0;
 #pragma unroll
     for (int c = 0; c < CH; c++) {
         const float2 s = bk_unpack(Y[c]);
         float2 pv;
         pv.x = __shfl_up_sync(0xffffffffu, s.x, 1);
         pv.y = __shfl_up_sync(0xffffffffu, s.y, 1);
-        if (lane == 0 && warp > 0) pv = xch[warp - 1][c];
-        if (c >= a.n_ch || !owns) continue;
-        if (first_of_call) pv = a.prev_in[a.ch0 + c];
-        const size_t o = (size_t)(a.ch0 + c) * a.cap + (size_t)i;
-        if (a.d_out) {
-            const float cre = fmaf(s.x, pv.x, s.y * pv.y);        // Re(S conj P)
-            const float cim = fmaf(s.y, pv.x, -(s.x * pv.y));     // Im(S conj P)
-            float d = 0.f;                                        // zero predecessor (stream start): 0 by definition
-            if (cre != 0.f || cim != 0.f) {
-                float t = bank_atan2(cim, cre) - tab.v[phib + c].x;
-                if (t > 3.14159265358979324f) t -= 6.28318530717958648f;
-                else if (t <= -3.14159265358979324f) t += 6.28318530717958648f;
-                d = a.gain * t;
-            }
-            a.d_out[o] = d;
-        }
-        if (a.y_out) {
+        if (from_xch) pv = xch[warp - 1][c];
+        if (first_of_call) pv = pin[c];
+        const float cre = fmaf(s.x, pv.x, s.y * pv.y);        // Re(S conj P)
+        const float cim = fmaf(s.y, pv.x, -(s.x * pv.y));     // Im(S conj P)
+        float t = bank_atan2(cim, cre) - tab.v[phib + c].x;
+        t -= t > 3.14159265358979324f ? 6.28318530717958648f : 0.f;
+        t += t <= -3.14159265358979324f ? 6.28318530717958648f : 0.f;
+        // zero predecessor (stream start): 0 by definition (the polynomial's 0/0 is discarded here)
+        const float d = (cre == 0.f && cim == 0.f) ? 0.f : a.gain * t;
+        if (want_d && c < a.n_ch) dp[(size_t)c * (size_t)a.cap] = d;
+    }
+    if (a.y_out && owns) {   // the caller wants the de-rotated channel samples as well
+        const uint32_t nm = a.n0_lo + (uint32_t)((i + 1) * a.D - 1) - a.r;   // global n_m mod 2^32
+        float2 *yp = a.y_out + row0;
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            if (c >= a.n_ch) break;
+            const float2 s = bk_unpack(Y[c]);
             float si, co;   // e^{+j theta_c(n_m)} from the top 24 phase bits; de-rotate with its conjugate
             __sincosf((float)(int32_t)(a.fw[a.ch0 + c] * nm) * (3.14159265358979324f / 2147483648.0f), &si, &co);
-            a.y_out[o] = make_float2(s.x * co + s.y * si, s.y * co - s.x * si);
+            yp[(size_t)c * (size_t)a.cap] = make_float2(s.x * co + s.y * si, s.y * co - s.x * si);
         }
-        if (last_of_call) a.prev_out[a.ch0 + c] = s;
+    }
+    if (owns && i == a.n_out - 1) {   // the last output of the call is the next call's predecessor
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+            if (c < a.n_ch) a.prev_out[a.ch0 + c] = bk_unpack(Y[c]);
     }
 }
 

@@ -25,27 +25,29 @@ def bank_model(iq, taps, D, fw, plan, tabs):
     x = (iq[0::2].astype(np.float64) - 127.0) + 1j * (iq[1::2].astype(np.float64) - 127.0)
     n = x.size
     M = n // D
-    xp = np.concatenate([np.zeros(T, complex), x])            # x[n < 0] = 127 -> centred 0
+    PAD = T + 1100
+    xp = np.concatenate([np.zeros(PAD, complex), x])          # x[n < 0] = 127 -> centred 0
     y = np.zeros((C, M), complex)
     d = np.zeros((C, M))
     for g in range(groups):
         v = tabs[g, :, 0].astype(np.float64) + 1j * tabs[g, :, 1].astype(np.float64)
         S = np.zeros((CH, M), complex)
-        gidx, eidx = 0, T * K2
-        tq, trem = T // K1, T % K1
+        NJ = -(-T // K1)
+        Tp = K1 * NJ                                          # zero-padded taps
+        eoff = (Tp * K2 + 1) & ~1
+        gidx, eidx = 0, eoff
         for r1 in range(K1):
-            nj = tq + (1 if r1 < trem else 0)
             A = np.zeros((K2, M), complex)
-            for j in range(nj):
+            for j in range(NJ):
                 k = r1 + j * K1
-                xs = xp[T + (np.arange(M) + 1) * D - 1 - k]  # x[n_m - k]
+                xs = xp[PAD + (np.arange(M) + 1) * D - 1 - k]  # x[n_m - k]
                 for b in range(K2):
                     A[b] += v[gidx + b] * xs
                 gidx += K2
             for c in range(CH):
                 S[c] += v[eidx + c] * A[c % K2]
             eidx += CH
-        phi = tabs[g, T * K2 + K1 * CH:T * K2 + K1 * CH + CH, 0].astype(np.float64)
+        phi = tabs[g, eoff + K1 * CH:eoff + K1 * CH + CH, 0].astype(np.float64)
         nm = (np.arange(M, dtype=np.uint64) + 1) * D - 1
         for c in range(CH):
             ch = g * CH + c

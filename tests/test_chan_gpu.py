@@ -98,7 +98,7 @@ def test_device_resident_and_errors(S):
     m = ch.process_dev(d_iq, n, d_d, cap)
     ch.sync()
     ms, launches = ch.last_timing()
-    assert m == n // D and ms > 0 and launches == 3 + -(-C // 8)   # one FIR launch per 8 channels + demod, prev, carry
+    assert m == n // D and ms > 0 and launches == 2              # cfg4 plan: one bank launch (discriminator fused) + carry
     d = d_d.download(np.float32, C * cap).reshape(C, cap)[:, :m]
     _, d_host = S.Channeliser(taps, D, fw).process(O.synth_fill(2 * D * 300, 7), want_y=False)
     assert np.array_equal(d[:, :300], d_host)
