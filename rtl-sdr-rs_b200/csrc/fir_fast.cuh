@@ -18,7 +18,24 @@ struct FirArgs {
     float2 *y_out;             // optional [n_out]
     float *d_out;              // optional [n_out]
     float2 *last_y;            // y of the last output of the call (stage-level fm_demod state)
+    // folded bookkeeping (either may be null): the stream carry for the next call = the last `cs` samples of
+    // (old carry ++ x), written by the last CTA; the resampler history of the next call = the last `h2` discriminator
+    // outputs, written next to d_out by the threads that produce them (needs n_out >= h2)
+    uint16_t *carry_out;
+    float *hist_out;
+    int cs, h2;
 };
+
+// new_carry = last cs samples of (old_carry ++ x[0..n)); both carries hold exactly cs samples (u16 each).  Executed by
+// one CTA of the FIR kernel (the carry it writes is the OTHER ping-pong buffer: no CTA of this launch reads it).
+__device__ __forceinline__ void fold_carry_update(const FirArgs &a, const int tid, const int nthreads) {
+    const uint16_t *x16 = reinterpret_cast<const uint16_t *>(a.x);
+    const uint16_t *old = reinterpret_cast<const uint16_t *>(a.carry_end) - a.cs;
+    for (int i = tid; i < a.cs; i += nthreads) {
+        const long long p = a.n_samples - a.cs + i;
+        a.carry_out[i] = p >= 0 ? x16[p] : old[a.cs + p];
+    }
+}
 
 template <int T>
 struct Taps {
@@ -286,9 +303,14 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
         if (i >= a.n_out) continue;
         const float2 y = ysm[g];
         if (a.y_out) a.y_out[i] = y;
-        if (a.d_out) a.d_out[i] = discriminate(y, ysm[g - 1], a.gain);
+        if (a.d_out) {
+            const float dv = discriminate(y, ysm[g - 1], a.gain);
+            a.d_out[i] = dv;
+            if (a.hist_out && i >= a.n_out - a.h2) a.hist_out[i - (a.n_out - a.h2)] = dv;
+        }
         if (i == a.n_out - 1) *a.last_y = y;
     }
+    if (a.carry_out && blockIdx.x == gridDim.x - 1) fold_carry_update(a, tid, NT);
 }
 
 }  // namespace sdr

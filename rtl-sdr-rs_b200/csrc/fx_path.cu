@@ -87,9 +87,14 @@ __global__ void __launch_bounds__(128) k_fir_generic(const GenArgs g) {
         const long long i = out0 + l - 1;
         const float2 y = ysm[l];
         if (a.y_out) a.y_out[i] = y;
-        if (a.d_out) a.d_out[i] = discriminate(y, ysm[l - 1], a.gain);
+        if (a.d_out) {
+            const float dv = discriminate(y, ysm[l - 1], a.gain);
+            a.d_out[i] = dv;
+            if (a.hist_out && i >= a.n_out - a.h2) a.hist_out[i - (a.n_out - a.h2)] = dv;
+        }
         if (i == a.n_out - 1) *a.last_y = y;
     }
+    if (a.carry_out && blockIdx.x == gridDim.x - 1) fold_carry_update(a, tid, blockDim.x);
 }
 
 // =================================================================================================
@@ -104,12 +109,11 @@ __global__ void k_update_carry(const uint16_t *old_carry, const uint16_t *x, lon
     }
 }
 
-// Discriminator history: dbuf = [hist (h2) | new d (n)]; move the last h2 values to the front.
-__global__ void k_shift_hist(float *dbuf, long long n, int h2) {
-    extern __shared__ float tmp[];
-    for (int i = threadIdx.x; i < h2; i += blockDim.x) tmp[i] = dbuf[n + i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < h2; i += blockDim.x) dbuf[i] = tmp[i];
+// Discriminator history: cur = [hist (h2) | new d (n)]; the last h2 values become the head of the NEXT buffer (the
+// buffers rotate, so nothing is moved in place).  Only calls with fewer than h2 new values need this kernel: otherwise
+// the FIR kernel writes the next head itself (FirArgs::hist_out).
+__global__ void k_hist_move(const float *cur, long long n, int h2, float *next) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h2; i += gridDim.x * blockDim.x) next[i] = cur[n + i];
 }
 
 __global__ void k_fm_demod_f32(const float2 *y, long long n, float2 *prev_state, float gain, float *out) {
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(256) k_resample_poly(const float *dbuf, int h2
     }
 }
 
-static const KernelList kFxKernels{(const void *)k_fir_generic, (const void *)k_update_carry, (const void *)k_shift_hist,
+static const KernelList kFxKernels{(const void *)k_fir_generic, (const void *)k_update_carry, (const void *)k_hist_move,
                                    (const void *)k_fm_demod_f32, (const void *)k_store_prev, (const void *)k_fir_real_r8,
                                    (const void *)k_resample_poly};
 
@@ -450,8 +454,15 @@ struct sdr_fmrx {
     int h2 = 0;              // discriminator history length kept for the resampler
     int J = 0, Jp = 0;       // polyphase taps per phase (J = ceil(T2/L)); Jp = J rounded up to 8
     DevBuf d_taps, d_taps2, d_state;
-    DevBuf d_x[2], d_dbuf, d_audio[2], d_y[2], d_tmp;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // discriminator buffers [history h2 | new values]: three of them rotate — call k's FIR kernel fills buffer k%3 and
+    // writes the head (history) of buffer (k+1)%3, while the audio kernel of call k reads buffer k%3 on its own stream
+    // UNDER the FIR kernel of call k+1 (the FIR kernel is HBM-bound and leaves the FMA pipes idle; the audio FIR works
+    // out of L2).  A buffer is written again two calls later, after an event wait on its audio kernel.
+    DevBuf d_x[2], d_dbuf[3], d_audio[2], d_y[2], d_tmp;
+    int dcur = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, audio_stream = nullptr;
+    cudaEvent_t ev_fir[3]{}, ev_aud[3]{}, ev_join = nullptr;
+    bool aud_used[3] = {false, false, false};
     static constexpr int kRing = 64;   // per-call kernel timings are harvested lazily from this ring
     cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_ring[kRing][4]{}, ev_s[2]{};
     cudaEvent_t *ev_t = ev_ring[0];
@@ -471,9 +482,14 @@ namespace {
 int fx_reset_device_state(sdr_fmrx *r) {
     for (int i = 0; i < 2; i++) SDR_CUDA_TRY(cudaMemsetAsync(r->d_carry[i].p, 127, (size_t)r->cs * 2, r->stream));
     SDR_CUDA_TRY(cudaMemsetAsync(r->d_state.p, 0, 64, r->stream));
-    SDR_CUDA_TRY(cudaMemsetAsync(r->d_dbuf.p, 0, r->d_dbuf.cap, r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->audio_stream));
+    for (int i = 0; i < 3; i++) {
+        SDR_CUDA_TRY(cudaMemsetAsync(r->d_dbuf[i].p, 0, r->d_dbuf[i].cap, r->stream));
+        r->aud_used[i] = false;
+    }
     SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     r->carry_cur = 0;
+    r->dcur = 0;
     r->n_in = r->n_y = r->n_a = 0;
     return SDR_OK;
 }
@@ -502,25 +518,39 @@ CallPlan plan_call(const sdr_fmrx *r, uint64_t n_in0, uint64_t n_y0, size_t n) {
 
 int ensure_dbuf(sdr_fmrx *r, size_t n_y) {
     size_t need = ((size_t)r->h2 + n_y + 8) * sizeof(float);
-    if (need <= r->d_dbuf.cap) return SDR_OK;
-    // grow while preserving the history at the front
-    DevBuf nb;
-    int rc = nb.reserve(need * 2);
-    if (rc) return rc;
-    SDR_CUDA_TRY(cudaMemsetAsync(nb.p, 0, nb.cap, r->stream));
-    if (r->d_dbuf.p)
-        SDR_CUDA_TRY(cudaMemcpyAsync(nb.p, r->d_dbuf.p, (size_t)r->h2 * sizeof(float), cudaMemcpyDeviceToDevice, r->stream));
+    if (need <= r->d_dbuf[0].cap) return SDR_OK;
+    // grow all three while preserving the history at the front of the current one; everything in flight first
     SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
-    r->d_dbuf.release();
-    r->d_dbuf = nb;
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->audio_stream));
+    for (int i = 0; i < 3; i++) {
+        DevBuf nb;
+        int rc = nb.reserve(need * 2);
+        if (rc) return rc;
+        SDR_CUDA_TRY(cudaMemsetAsync(nb.p, 0, nb.cap, r->stream));
+        if (i == r->dcur && r->d_dbuf[i].p)
+            SDR_CUDA_TRY(cudaMemcpyAsync(nb.p, r->d_dbuf[i].p, (size_t)r->h2 * sizeof(float), cudaMemcpyDeviceToDevice, r->stream));
+        SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+        r->d_dbuf[i].release();
+        r->d_dbuf[i] = nb;
+        r->aud_used[i] = false;
+    }
     return SDR_OK;
 }
 
+int launch_carry_update(sdr_fmrx *r, const uint8_t *d_x, size_t n);
+
 // Launch FIR(+demod) for one call-chunk whose input is resident at d_x.  d_demod_target: where the
 // discriminator output goes (nullptr = none).
-int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint64_t n_out, float2 *d_y, float *d_d) {
-    if (n_out == 0) return SDR_OK;
+// hist_out: head of the next discriminator buffer (the FIR kernel writes the last h2 values there; needs n_out >= h2), or
+// nullptr.  The stream carry of the next call is always written by the kernel's last CTA (ping-pong buffer).
+int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint64_t n_out, float2 *d_y, float *d_d,
+               float *hist_out = nullptr) {
+    if (n_out == 0) return launch_carry_update(r, d_x, n);   // nothing to filter: only the carry moves on
     FirArgs a{};
+    a.carry_out = r->d_carry[r->carry_cur ^ 1].as<uint16_t>();
+    a.cs = r->cs;
+    a.hist_out = hist_out;
+    a.h2 = r->h2;
     a.x = d_x;
     a.carry_end = r->d_carry[r->carry_cur].as<uint8_t>() + (size_t)r->cs * 2;
     a.n_samples = (long long)n;
@@ -543,6 +573,7 @@ int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint6
             int rc = rtc_launch(v->rtc->fns[phase % (v->wb / 2)], (unsigned)grid, (unsigned)v->nt, (unsigned)v->smem, r->stream, params);
             if (rc) return rc;
             r->last_launches++;
+            r->carry_cur ^= 1;
             return SDR_OK;
         }
         v->launch(a, r->taps.data(), phase, (int)grid, v->smem, r->stream);
@@ -560,6 +591,7 @@ int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint6
     }
     SDR_LAUNCH_CHECK();
     r->last_launches++;
+    r->carry_cur ^= 1;
     return SDR_OK;
 }
 
@@ -576,14 +608,15 @@ int launch_carry_update(sdr_fmrx *r, const uint8_t *d_x, size_t n) {
     return SDR_OK;
 }
 
-int launch_resample(sdr_fmrx *r, uint64_t P0, uint64_t n_new, uint64_t a0, uint64_t n_a, float *d_audio) {
-    // dbuf = [hist h2 | d[P0 .. P0+n_new)]
+// Audio stage over dbuf = [hist h2 | d[P0 .. P0+n_new)] on stream `st`.
+int launch_resample(sdr_fmrx *r, const float *dbuf, uint64_t P0, uint64_t n_new, uint64_t a0, uint64_t n_a, float *d_audio,
+                    cudaStream_t st) {
     if (n_a && r->cfg.up == 1 && r->cfg.down == 1) {
         uint64_t blocks = ceil_div(n_a, (uint64_t)kFirOblk);
         if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
         size_t sm = fir_real_smem(r->Jp);
-        k_fir_real_r8<<<(int)blocks, kFirThreads, sm, r->stream>>>(r->d_dbuf.as<float>(), r->h2, r->d_taps2.as<float>(), r->Jp,
-                                                                  (long long)n_a, (long long)(r->h2 + n_new), d_audio);
+        k_fir_real_r8<<<(int)blocks, kFirThreads, sm, st>>>(dbuf, r->h2, r->d_taps2.as<float>(), r->Jp, (long long)n_a,
+                                                            (long long)(r->h2 + n_new), d_audio);
         SDR_LAUNCH_CHECK();
         r->last_launches++;
     } else if (n_a) {
@@ -594,31 +627,38 @@ int launch_resample(sdr_fmrx *r, uint64_t P0, uint64_t n_new, uint64_t a0, uint6
         size_t span = ((size_t)(r->cfg.up - 1) + 255ull * r->cfg.down) / r->cfg.up + r->J + 1;
         int win_cap = (in_smem && span <= 3072) ? (int)span : 0;
         size_t sm = (in_smem ? tb : 0) + (size_t)win_cap * sizeof(float);
-        k_resample_poly<<<blocks, 256, sm, r->stream>>>(r->d_dbuf.as<float>(), r->h2, P0, r->d_taps2.as<float>(), r->J,
-                                                        r->cfg.up, r->cfg.down, a0, (long long)n_a, in_smem, win_cap,
-                                                        (long long)(r->h2 + n_new), d_audio);
-        SDR_LAUNCH_CHECK();
-        r->last_launches++;
-    }
-    if (n_new) {
-        k_shift_hist<<<1, 256, (size_t)r->h2 * sizeof(float), r->stream>>>(r->d_dbuf.as<float>(), (long long)n_new, r->h2);
+        k_resample_poly<<<blocks, 256, sm, st>>>(dbuf, r->h2, P0, r->d_taps2.as<float>(), r->J, r->cfg.up, r->cfg.down, a0,
+                                                 (long long)n_a, in_smem, win_cap, (long long)(r->h2 + n_new), d_audio);
         SDR_LAUNCH_CHECK();
         r->last_launches++;
     }
     return SDR_OK;
 }
 
+// The history of the next call when the FIR kernel could not write it (fewer than h2 new values): tail of the current
+// buffer -> head of the next one, on the main stream.
+int launch_hist_move(sdr_fmrx *r, int cur, int nxt, uint64_t n_new) {
+    k_hist_move<<<(r->h2 + 255) / 256, 256, 0, r->stream>>>(r->d_dbuf[cur].as<float>(), (long long)n_new, r->h2,
+                                                            r->d_dbuf[nxt].as<float>());
+    SDR_LAUNCH_CHECK();
+    r->last_launches++;
+    return SDR_OK;
+}
+
 void harvest_slot(sdr_fmrx *r, int slot) {
     if (!r->ring_used[slot]) return;
     r->ring_used[slot] = false;
-    if (cudaEventSynchronize(r->ev_ring[slot][3]) != cudaSuccess) return;
-    for (int i = 0; i < 3; i++) {
+    if (cudaEventSynchronize(r->ev_ring[slot][3]) != cudaSuccess || cudaEventSynchronize(r->ev_ring[slot][1]) != cudaSuccess) return;
+    // events 0-1 bracket the FIR kernel on the main stream, 2-3 the audio kernel on the audio stream (it may run under
+    // the next call's FIR kernel); [2] = bookkeeping kernels, folded into the FIR kernel by now
+    for (int i = 0; i < 2; i++) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, r->ev_ring[slot][i], r->ev_ring[slot][i + 1]) == cudaSuccess) {
+        if (cudaEventElapsedTime(&ms, r->ev_ring[slot][2 * i], r->ev_ring[slot][2 * i + 1]) == cudaSuccess) {
             r->last_ms[i] = ms;
             r->sum_ms[i] += ms;
         }
     }
+    r->last_ms[2] = 0.f;
     r->sum_calls++;
 }
 
@@ -638,35 +678,54 @@ void next_timing_slot(sdr_fmrx *r) {
     r->ring_next++;
 }
 
-// One chunk, everything resident.  d_demod / d_y optional; d_audio required when the chain has a tail.
+// One chunk, everything resident.  d_demod / d_y optional; d_audio required when the chain has a tail.  The audio stage
+// (if any) is enqueued on the audio stream; `audio_done` (optional) is recorded behind it there.
 int run_chunk(sdr_fmrx *r, const uint8_t *d_x, size_t n, float2 *d_y, float *d_demod, float *d_audio,
               const CallPlan &pl, bool timed) {
     int rc;
     const bool has_res = r->cfg.n_taps2 != 0;
     if ((rc = ensure_dbuf(r, pl.n_y))) return rc;
-    float *dnew = r->d_dbuf.as<float>() + r->h2;
+    const int cur = r->dcur, nxt = (cur + 1) % 3;
+    float *dnew = r->d_dbuf[cur].as<float>() + r->h2;
     // without a resample stage the discriminator output IS the audio
     float *d_target = has_res ? dnew : (d_audio ? d_audio : dnew);
+    // this call writes the body of `cur` and the head of `nxt`; the last reader of either is the audio kernel of the
+    // call two back (buffer index nxt), which runs on the other stream
+    if (has_res && r->aud_used[nxt]) SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_aud[nxt], 0));
     if (timed) {
         next_timing_slot(r);
         SDR_CUDA_TRY(cudaEventRecord(r->ev_t[0], r->stream));
     }
-    if ((rc = launch_fir(r, d_x, n, pl.r, pl.n_y, d_y, d_target))) return rc;
+    const bool fold_hist = has_res && pl.n_y >= (uint64_t)r->h2;
+    if ((rc = launch_fir(r, d_x, n, pl.r, pl.n_y, d_y, d_target, fold_hist ? r->d_dbuf[nxt].as<float>() : nullptr))) return rc;
     if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[1], r->stream));
     if (has_res) {
-        if ((rc = launch_resample(r, r->n_y, pl.n_y, pl.a0, pl.n_a, d_audio))) return rc;
+        if (!fold_hist && (rc = launch_hist_move(r, cur, nxt, pl.n_y))) return rc;
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_fir[cur], r->stream));
+        SDR_CUDA_TRY(cudaStreamWaitEvent(r->audio_stream, r->ev_fir[cur], 0));
+        if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], r->audio_stream));
+        if ((rc = launch_resample(r, r->d_dbuf[cur].as<float>(), r->n_y, pl.n_y, pl.a0, pl.n_a, d_audio, r->audio_stream))) return rc;
+        if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[3], r->audio_stream));
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_aud[cur], r->audio_stream));
+        r->aud_used[cur] = true;
+        r->dcur = nxt;
+    } else if (timed) {
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], r->stream));
+        SDR_CUDA_TRY(cudaEventRecord(r->ev_t[3], r->stream));
     }
-    if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], r->stream));
     if (d_demod && d_demod != d_target && pl.n_y)
         SDR_CUDA_TRY(cudaMemcpyAsync(d_demod, d_target, pl.n_y * sizeof(float), cudaMemcpyDeviceToDevice, r->stream));
-    if ((rc = launch_carry_update(r, d_x, n))) return rc;
-    if (timed) {
-        SDR_CUDA_TRY(cudaEventRecord(r->ev_t[3], r->stream));
-        r->timing_pending = true;
-    }
+    if (timed) r->timing_pending = true;
     r->n_in += n;
     r->n_y += pl.n_y;
     r->n_a += pl.n_a;
+    return SDR_OK;
+}
+
+// main stream waits for everything enqueued on the audio stream so far
+int join_audio(sdr_fmrx *r) {
+    SDR_CUDA_TRY(cudaEventRecord(r->ev_join, r->audio_stream));
+    SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_join, 0));
     return SDR_OK;
 }
 
@@ -730,9 +789,19 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
     }
     cudaError_t e = raise_dyn_smem(k_fir_generic, gen_smem);
     if (e == cudaSuccess && r->fast && !r->fast->rtc) e = r->fast->prepare(r->fast->smem);
-    if (e == cudaSuccess && r->h2 * sizeof(float) > 48 * 1024)
-        e = raise_dyn_smem(k_shift_hist, r->h2 * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // the audio kernel of one call runs under the FIR kernel of the next: highest priority, so that its CTAs are
+        // placed as soon as FIR CTAs retire
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&r->audio_stream, cudaStreamNonBlocking, hi);
+    }
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&r->ev_fir[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_aud[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&r->ev_h2d[i], cudaEventDisableTiming);
@@ -747,7 +816,9 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
     }
     if ((rc = r->d_carry[0].reserve(cs * 2)) || (rc = r->d_carry[1].reserve(cs * 2)) || (rc = r->d_state.reserve(64)) ||
         (rc = r->d_taps.reserve(T * 4)) || (rc = r->d_taps2.reserve(cfg->n_taps2 ? ((size_t)cfg->up * r->J + r->Jp + 16) * 4 : 4)) ||
-        (rc = r->d_dbuf.reserve(((size_t)r->h2 + 4096) * sizeof(float)))) {
+        (rc = r->d_dbuf[0].reserve(((size_t)r->h2 + 4096) * sizeof(float))) ||
+        (rc = r->d_dbuf[1].reserve(((size_t)r->h2 + 4096) * sizeof(float))) ||
+        (rc = r->d_dbuf[2].reserve(((size_t)r->h2 + 4096) * sizeof(float)))) {
         sdr_fmrx_free(r);
         return rc;
     }
@@ -783,6 +854,14 @@ void sdr_fmrx_free(sdr_fmrx *r) {
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
     if (r->copy_stream) cudaStreamSynchronize(r->copy_stream);
+    if (r->audio_stream) cudaStreamSynchronize(r->audio_stream);
+    for (int i = 0; i < 3; i++) {
+        r->d_dbuf[i].release();
+        if (r->ev_fir[i]) cudaEventDestroy(r->ev_fir[i]);
+        if (r->ev_aud[i]) cudaEventDestroy(r->ev_aud[i]);
+    }
+    if (r->ev_join) cudaEventDestroy(r->ev_join);
+    if (r->audio_stream) cudaStreamDestroy(r->audio_stream);
     for (int i = 0; i < 2; i++) {
         r->d_carry[i].release();
         r->d_x[i].release();
@@ -799,7 +878,6 @@ void sdr_fmrx_free(sdr_fmrx *r) {
     r->d_taps.release();
     r->d_taps2.release();
     r->d_state.release();
-    r->d_dbuf.release();
     r->d_tmp.release();
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
@@ -858,8 +936,9 @@ long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y
             SDR_CUDA_TRY(cudaMemcpyAsync(y_pairs + 2 * y_off, r->d_y[slot].p, pl.n_y * 8, cudaMemcpyDeviceToHost, r->stream));
         if (demod && pl.n_y)
             SDR_CUDA_TRY(cudaMemcpyAsync(demod + y_off, d_dem, pl.n_y * 4, cudaMemcpyDeviceToHost, r->stream));
-        if (pl.n_a)
-            SDR_CUDA_TRY(cudaMemcpyAsync(audio + a_off, r->d_audio[slot].p, pl.n_a * 4, cudaMemcpyDeviceToHost, r->stream));
+        if (pl.n_a)   // behind the kernel that produced it: the audio stream when there is a resample stage
+            SDR_CUDA_TRY(cudaMemcpyAsync(audio + a_off, r->d_audio[slot].p, pl.n_a * 4, cudaMemcpyDeviceToHost,
+                                         r->cfg.n_taps2 ? r->audio_stream : r->stream));
         SDR_CUDA_TRY(cudaEventRecord(r->ev_done[slot], r->stream));
         done += n;
         y_off += pl.n_y;
@@ -868,6 +947,7 @@ long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y
     }
     SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     SDR_CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->audio_stream));
     collect_timing(r);
     return (long)total.n_a;
 }
@@ -897,7 +977,6 @@ long sdr_fmrx_low_pass(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *
     r->last_launches = 0;
     SDR_CUDA_TRY(cudaMemcpyAsync(r->d_x[0].p, iq, n_samples * 2, cudaMemcpyHostToDevice, r->stream));
     if ((rc = launch_fir(r, r->d_x[0].as<uint8_t>(), n_samples, pl.r, pl.n_y, r->d_y[0].as<float2>(), nullptr))) return rc;
-    if ((rc = launch_carry_update(r, r->d_x[0].as<uint8_t>(), n_samples))) return rc;
     if (pl.n_y) SDR_CUDA_TRY(cudaMemcpyAsync(y_pairs, r->d_y[0].p, pl.n_y * 8, cudaMemcpyDeviceToHost, r->stream));
     SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     r->n_in += n_samples;
@@ -934,8 +1013,12 @@ long sdr_fmrx_resample(sdr_fmrx *r, const float *d, size_t n, float *out, size_t
     if (n_a > cap) return fail(SDR_E_CAP, "capacity %zu < %llu", cap, (unsigned long long)n_a);
     if (n == 0) return 0;
     if ((rc = ensure_dbuf(r, n)) || (rc = r->d_audio[0].reserve((n_a + 8) * 4))) return rc;
-    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_dbuf.as<float>() + r->h2, d, n * 4, cudaMemcpyHostToDevice, r->stream));
-    if ((rc = launch_resample(r, r->n_y, n, a0, n_a, r->d_audio[0].as<float>()))) return rc;
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->audio_stream));   // stage entry points are synchronous: one stream from here
+    const int cur = r->dcur, nxt = (cur + 1) % 3;
+    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_dbuf[cur].as<float>() + r->h2, d, n * 4, cudaMemcpyHostToDevice, r->stream));
+    if ((rc = launch_resample(r, r->d_dbuf[cur].as<float>(), r->n_y, n, a0, n_a, r->d_audio[0].as<float>(), r->stream))) return rc;
+    if ((rc = launch_hist_move(r, cur, nxt, n))) return rc;
+    r->dcur = nxt;
     if (n_a) SDR_CUDA_TRY(cudaMemcpyAsync(out, r->d_audio[0].p, n_a * 4, cudaMemcpyDeviceToHost, r->stream));
     SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     r->n_y += n;
@@ -948,6 +1031,7 @@ int sdr_fmrx_sync(sdr_fmrx *r) {
     int rc = use_device(r->device);
     if (rc) return rc;
     SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->audio_stream));
     collect_timing(r);
     return SDR_OK;
 }
@@ -956,6 +1040,7 @@ int sdr_fmrx_span_begin(sdr_fmrx *r) {
     if (!r) return fail(SDR_E_ARG, "null handle");
     int rc = use_device(r->device);
     if (rc) return rc;
+    if ((rc = join_audio(r))) return rc;   // the span starts when everything submitted before it is done
     SDR_CUDA_TRY(cudaEventRecord(r->ev_s[0], r->stream));
     return SDR_OK;
 }
@@ -964,6 +1049,7 @@ int sdr_fmrx_span_end(sdr_fmrx *r, float *ms) {
     if (!r || !ms) return fail(SDR_E_ARG, "null argument");
     int rc = use_device(r->device);
     if (rc) return rc;
+    if ((rc = join_audio(r))) return rc;   // ... and ends when the last audio kernel has finished
     SDR_CUDA_TRY(cudaEventRecord(r->ev_s[1], r->stream));
     SDR_CUDA_TRY(cudaEventSynchronize(r->ev_s[1]));
     SDR_CUDA_TRY(cudaEventElapsedTime(ms, r->ev_s[0], r->ev_s[1]));

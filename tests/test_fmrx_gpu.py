@@ -213,7 +213,7 @@ def test_device_resident_full_size_properties(S):
     assert g.process_dev(d_iq, n, d_a, na, d_demod=d_d) == na
     g.sync()
     ms, launches, spec = g.last_timing()
-    assert spec == 1 and ms[0] > 0 and launches == 4
+    assert spec == 1 and ms[0] > 0 and launches == 2      # fused convert+FIR+demod (carry and history folded in) + audio FIR
     audio, demod = d_a.download(np.float32, na), d_d.download(np.float32, ny)
     # (1) prefix parity against the oracle
     k = 300 * D
