@@ -487,6 +487,7 @@ struct sdr_chan {
     int bank_K = 0, bank_K1 = 0, bank_K2 = 0;
     std::vector<BankTab> bank_tabs;
     size_t smem_bank = 0;
+    H2DStager stager;                          // pageable caller buffers go through pinned pieces (common.cuh)
     DevBuf d_prev2;                            // bank path: the carried S[m-1] ping-pongs between d_prev and d_prev2
     int prev_cur = 0;
     std::vector<TapsU> taps_u;                 // one 16 KB parameter blob per 8 channels
@@ -865,6 +866,7 @@ void sdr_chan_free(sdr_chan *c) {
     c->d_taps.release();
     c->d_gt.release();
     c->d_fw.release();
+    c->stager.release();
     c->d_prev.release();
     c->d_prev2.release();
     c->d_x.release();
@@ -901,7 +903,7 @@ long sdr_chan_process(sdr_chan *c, const uint8_t *iq, size_t n_samples, float *y
     if ((rc = c->d_x.reserve(n_samples * 2 + 64)) || (need_y && (rc = c->d_y.reserve((size_t)c->C_pad * (n_out + 1) * 8))) ||
         (rc = c->d_d.reserve(C * (n_out + 1) * 4)))
         return rc;
-    SDR_CUDA_TRY(cudaMemcpyAsync(c->d_x.p, iq, n_samples * 2, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = c->stager.copy(c->d_x.p, iq, n_samples * 2, c->stream))) return rc;
     const size_t dcap = n_out ? n_out : 1;
     if ((rc = chan_run(c, c->d_x.as<uint8_t>(), n_samples, need_y ? c->d_y.as<float2>() : nullptr, c->d_d.as<float>(), dcap, n_out)))
         return rc;

@@ -91,6 +91,23 @@ struct PinBuf {
 
 constexpr size_t kDevRoom = 4096;   // head/tail room of sdr_dev_alloc()
 
+// Host -> device copy of caller memory that may be PAGEABLE (the drop-in caller hands over an ordinary Vec<u8>,
+// examples/simple_fm.rs:80,153).  cudaMemcpyAsync from pageable memory is staged by the driver on one CPU thread
+// (~10 GB/s, no overlap); here it goes through two pinned pieces filled by a small pool of memcpy threads, so the copy
+// engine moves piece p while the CPU fills piece p+1.  Pinned / registered sources take one plain cudaMemcpyAsync.
+// Like cudaMemcpyAsync from pageable memory, the call returns once `src` may be reused.
+struct H2DStager {
+    PinBuf piece[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    int next = 0;
+    int copy(void *d_dst, const void *h_src, size_t bytes, cudaStream_t stream);
+    void release();
+};
+bool host_ptr_is_pinned(const void *p);
+// memcpy split over the library's pool of copy threads (SDR_STAGE_THREADS, default min(8, cores / 2))
+void parallel_memcpy(void *dst, const void *src, size_t bytes);
+
 // ---- device-side PTX helpers (mbarrier, bulk async copy): ptx_helpers.cuh -------------------------
 
 

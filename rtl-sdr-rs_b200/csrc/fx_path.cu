@@ -463,6 +463,7 @@ struct sdr_fmrx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, audio_stream = nullptr;
     cudaEvent_t ev_fir[3]{}, ev_aud[3]{}, ev_join = nullptr;
     bool aud_used[3] = {false, false, false};
+    H2DStager stager;        // pageable caller buffers go through pinned pieces (common.cuh)
     static constexpr int kRing = 64;   // per-call kernel timings are harvested lazily from this ring
     cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_ring[kRing][4]{}, ev_s[2]{};
     cudaEvent_t *ev_t = ev_ring[0];
@@ -862,6 +863,7 @@ void sdr_fmrx_free(sdr_fmrx *r) {
     }
     if (r->ev_join) cudaEventDestroy(r->ev_join);
     if (r->audio_stream) cudaStreamDestroy(r->audio_stream);
+    r->stager.release();
     for (int i = 0; i < 2; i++) {
         r->d_carry[i].release();
         r->d_x[i].release();
@@ -925,7 +927,7 @@ long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y
         if (y_pairs && (rc = r->d_y[slot].reserve((chunk / r->cfg.decim + 8) * 8))) return rc;
         if (demod && (rc = r->d_tmp.reserve((chunk / r->cfg.decim + 8) * 4 * 2))) return rc;
         if (ci >= 2) SDR_CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_done[slot], 0));
-        SDR_CUDA_TRY(cudaMemcpyAsync(r->d_x[slot].p, iq + done * 2, n * 2, cudaMemcpyHostToDevice, r->copy_stream));
+        if ((rc = r->stager.copy(r->d_x[slot].p, iq + done * 2, n * 2, r->copy_stream))) return rc;
         SDR_CUDA_TRY(cudaEventRecord(r->ev_h2d[slot], r->copy_stream));
         SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_h2d[slot], 0));
         float *d_dem = demod ? r->d_tmp.as<float>() + (size_t)slot * (chunk / r->cfg.decim + 8) : nullptr;
@@ -975,7 +977,7 @@ long sdr_fmrx_low_pass(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *
     if (n_samples == 0) return 0;
     if ((rc = r->d_x[0].reserve(n_samples * 2 + 64)) || (rc = r->d_y[0].reserve((pl.n_y + 8) * 8))) return rc;
     r->last_launches = 0;
-    SDR_CUDA_TRY(cudaMemcpyAsync(r->d_x[0].p, iq, n_samples * 2, cudaMemcpyHostToDevice, r->stream));
+    if ((rc = r->stager.copy(r->d_x[0].p, iq, n_samples * 2, r->stream))) return rc;
     if ((rc = launch_fir(r, r->d_x[0].as<uint8_t>(), n_samples, pl.r, pl.n_y, r->d_y[0].as<float2>(), nullptr))) return rc;
     if (pl.n_y) SDR_CUDA_TRY(cudaMemcpyAsync(y_pairs, r->d_y[0].p, pl.n_y * 8, cudaMemcpyDeviceToHost, r->stream));
     SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));

@@ -1078,6 +1078,7 @@ struct sdr_demod {
     float last_ms = 0.f;
     uint32_t last_launches = 0;
     bool timing_valid = false;
+    H2DStager stager;          // pageable caller buffers go through pinned pieces (common.cuh)
     bool ring_open = false;    // a persistent ring owns the handle until sdr_ring_close()
     struct sdr_ring *ring = nullptr;   // that ring (sdr_demod_free closes it first)
 };
@@ -1420,6 +1421,7 @@ void sdr_demod_free(sdr_demod *d) {
         if (d->ev_h2d[i]) cudaEventDestroy(d->ev_h2d[i]);
         if (d->ev_done[i]) cudaEventDestroy(d->ev_done[i]);
     }
+    d->stager.release();
     d->d_state.release();
     d->d_a.release();
     d->d_b.release();
@@ -1518,8 +1520,7 @@ long sdr_demod_demodulate_batch(sdr_demod *d, const uint8_t *buf, size_t buf_len
         Plan pl = make_plan(d->cfg, p, q, S, nb);
         // the copy engine may not overwrite a slot until the kernel that read it has finished
         if (chunk >= 2) SDR_CUDA_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_done[slot], 0));
-        SDR_CUDA_TRY(cudaMemcpyAsync(d->d_in[slot].p, buf + done * buf_len, nb * buf_len, cudaMemcpyHostToDevice,
-                                     d->copy_stream));
+        if ((rc = d->stager.copy(d->d_in[slot].p, buf + done * buf_len, nb * buf_len, d->copy_stream))) return rc;
         SDR_CUDA_TRY(cudaEventRecord(d->ev_h2d[slot], d->copy_stream));
         SDR_CUDA_TRY(cudaStreamWaitEvent(d->stream, d->ev_h2d[slot], 0));
         if ((rc = launch_fused(d, d->d_in[slot].as<uint8_t>(), S, nb, p, q, pl, &dst[chunk & 1], &dst[(chunk + 1) & 1],

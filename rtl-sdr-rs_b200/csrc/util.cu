@@ -1,5 +1,9 @@
 // util.cu — error plumbing, device/pinned memory, synthetic IQ generator.
+#include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -201,6 +205,121 @@ void PinBuf::release() {
     if (p) host_free_or_park(p);
     p = nullptr;
     cap = 0;
+}
+
+// ---- pageable-source staging ------------------------------------------------------------------------------------------
+namespace {
+
+class CopyPool {
+public:
+    static CopyPool &get() {
+        static CopyPool *p = new CopyPool();   // leaked on purpose: worker threads must not be joined from a static destructor
+        return *p;
+    }
+    void run(char *dst, const char *src, size_t bytes) {
+        const size_t n = workers_.size() + 1;
+        if (n == 1 || bytes < (size_t(1) << 20)) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        const size_t part = ((bytes + n - 1) / n + 4095) & ~size_t(4095);
+        dst_ = dst, src_ = src, bytes_ = bytes, part_ = part;
+        pending_ = (int)workers_.size();
+        gen_++;
+        cv_.notify_all();
+        lk.unlock();
+        copy_part(0);   // the caller is worker 0
+        lk.lock();
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+private:
+    CopyPool() {
+        int n = 0;
+        if (const char *e = getenv("SDR_STAGE_THREADS")) n = atoi(e);
+        if (n <= 0) n = (int)std::min<unsigned>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 2));
+        for (int i = 1; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
+        for (auto &t : workers_) t.detach();
+    }
+    void copy_part(size_t i) {
+        const size_t lo = i * part_;
+        if (lo < bytes_) memcpy(dst_ + lo, src_ + lo, std::min(part_, bytes_ - lo));
+    }
+    void loop(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            lk.unlock();
+            copy_part((size_t)idx);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    char *dst_ = nullptr;
+    const char *src_ = nullptr;
+    size_t bytes_ = 0, part_ = 0;
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+};
+
+constexpr size_t kStagePiece = size_t(8) << 20;
+
+}  // namespace
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    static std::mutex one_at_a_time;   // the pool runs one job at a time; handles on different threads queue up here
+    std::lock_guard<std::mutex> lk(one_at_a_time);
+    CopyPool::get().run(static_cast<char *>(dst), static_cast<const char *>(src), bytes);
+}
+
+bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+int H2DStager::copy(void *d_dst, const void *h_src, size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return SDR_OK;
+    const char *env = getenv("SDR_STAGE_PAGEABLE");
+    if (host_ptr_is_pinned(h_src) || bytes < (size_t(1) << 20) || (env && atoi(env) == 0)) {
+        SDR_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
+        return SDR_OK;
+    }
+    for (size_t off = 0; off < bytes; off += kStagePiece) {
+        const int s = next;
+        next ^= 1;
+        const size_t n = std::min(kStagePiece, bytes - off);
+        int rc = piece[s].reserve(kStagePiece);
+        if (rc) return rc;
+        if (!ev[s]) SDR_CUDA_TRY(cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming));
+        if (used[s]) SDR_CUDA_TRY(cudaEventSynchronize(ev[s]));   // the copy engine is done with this piece
+        parallel_memcpy(piece[s].p, static_cast<const char *>(h_src) + off, n);
+        SDR_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, piece[s].p, n, cudaMemcpyHostToDevice, stream));
+        SDR_CUDA_TRY(cudaEventRecord(ev[s], stream));
+        used[s] = true;
+    }
+    return SDR_OK;
+}
+
+void H2DStager::release() {
+    for (int s = 0; s < 2; s++) {
+        if (ev[s]) {
+            cudaEventSynchronize(ev[s]);
+            cudaEventDestroy(ev[s]);
+            ev[s] = nullptr;
+        }
+        piece[s].release();
+        used[s] = false;
+    }
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
