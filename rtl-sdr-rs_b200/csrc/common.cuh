@@ -105,7 +105,7 @@ struct H2DStager {
     void release();
 };
 bool host_ptr_is_pinned(const void *p);
-// memcpy split over the library's pool of copy threads (SDR_STAGE_THREADS, default min(8, cores / 2))
+// memcpy split over the library's pool of copy threads (SDR_STAGE_THREADS, default min(12, 3/4 of the cores))
 void parallel_memcpy(void *dst, const void *src, size_t bytes);
 
 // ---- device-side PTX helpers (mbarrier, bulk async copy): ptx_helpers.cuh -------------------------

