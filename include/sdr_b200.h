@@ -216,6 +216,23 @@ long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]);
  * requirements, 0 = outside the specialised kernel's range (the generic kernel runs), < 0 = the picker chose a shape the
  * kernel would reject (a bug; sdr_last_error() says which requirement). */
 int sdr_rtc_pick_shape(uint32_t n_taps, uint32_t decim, int shape[4]);
+/* Diagnostic / build step, needs no GPU: compile the persistent-ring kernel of a run-time-specialised (n_taps, decim) shape
+ * exactly as sdr_fmrx_ring_open() would (it holds every load-phase variant of the FIR tile, so it takes several times as long
+ * as one FIR kernel); the cubin lands in the on-disk cache.  Returns its size, or a negative code. */
+long sdr_rtc_compile_ring(uint32_t n_taps, uint32_t decim);
+/* Persistent ring for the f32 receiver: the reader -> channel -> processor pair of examples/simple_fm.rs:55-60,108-128,
+ * 145-160 with ONE resident kernel behind it (same protocol as sdr_demod_ring_*: the producer acquires a pinned slot, fills
+ * it and commits it — one H2D copy plus a 4-byte doorbell, no kernel launch; the consumer collects the audio of the oldest
+ * buffer from host-mapped memory).  Output is bit-identical to one sdr_fmrx_process(buf_len / 2 samples) call per buffer.
+ * buf_len: bytes per buffer, a multiple of 16, holding at least the filter history and producing at least one audio sample
+ * (any USB-sized buffer does).  Needs a specialised FIR kernel (sdr_fmrx_kernel_kind() 1 or 2).  While the ring is open the
+ * handle's other stream entry points return SDR_E_STATE; close hands the stream position and history back to the handle. */
+typedef struct sdr_fmrx_ring sdr_fmrx_ring;
+int sdr_fmrx_ring_open(sdr_fmrx *r, size_t buf_len, uint32_t n_slots /* 2..64 */, sdr_fmrx_ring **out);
+int sdr_fmrx_ring_acquire(sdr_fmrx_ring *g, uint8_t **buf);              /* producer */
+int sdr_fmrx_ring_commit(sdr_fmrx_ring *g);                              /* producer: H2D copy + doorbell */
+long sdr_fmrx_ring_collect(sdr_fmrx_ring *g, float *audio, size_t cap);  /* consumer: audio of the oldest buffer */
+int sdr_fmrx_ring_close(sdr_fmrx_ring *g);
 int sdr_fmrx_span_begin(sdr_fmrx *r);
 int sdr_fmrx_span_end(sdr_fmrx *r, float *ms);
 /* Reposition a fresh stream at global sample index n (history = mid-scale): lets a rank that owns

@@ -31,7 +31,7 @@ from ._ffi import (  # noqa: F401
     shard_range,
 )
 from .demod import Demod, Ring  # noqa: F401
-from .fmrx import FmRx  # noqa: F401
+from .fmrx import FmRx, FmRing  # noqa: F401
 from .chan import Channeliser, Comm, bank_plan  # noqa: F401
 from .source import Source  # noqa: F401
 

@@ -113,6 +113,12 @@ SIGNATURES = {
     "sdr_fmrx_kernel_kind": (_i, [_vp, C.POINTER(C.c_char_p)]),
     "sdr_rtc_selftest": (_l, [C.c_uint32, C.c_uint32, C.POINTER(_i * 4)]),
     "sdr_rtc_pick_shape": (_i, [C.c_uint32, C.c_uint32, C.POINTER(_i * 4)]),
+    "sdr_rtc_compile_ring": (_l, [C.c_uint32, C.c_uint32]),
+    "sdr_fmrx_ring_open": (_i, [_vp, _sz, C.c_uint32, C.POINTER(_vp)]),
+    "sdr_fmrx_ring_acquire": (_i, [_vp, C.POINTER(_vp)]),
+    "sdr_fmrx_ring_commit": (_i, [_vp]),
+    "sdr_fmrx_ring_collect": (_l, [_vp, _vp, _sz]),
+    "sdr_fmrx_ring_close": (_i, [_vp]),
     "sdr_fmrx_span_begin": (_i, [_vp]),
     "sdr_fmrx_span_end": (_i, [_vp, C.POINTER(C.c_float)]),
     "sdr_fmrx_seek": (_i, [_vp, C.c_uint64]),

@@ -196,21 +196,23 @@ __device__ __forceinline__ void cvt_iq(uint32_t w, int half, const CvtConst &c, 
     asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(xi) : "h"((unsigned short)(pair >> 16)), "f"(c.bias));
 }
 
-template <int T, int D, int B, int NT, int WB, int PH, int PAD = 0>
-__global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_constant__ Taps<T> taps) {
+// One CTA tile of G::OUT outputs.  `blk` = tile index inside the call; `first_use` / `parity`: a persistent CTA (the ring
+// kernel below) re-arms the same mbarrier once per tile and flips its phase; PERSIST adds the trailing barrier that makes
+// the shared-memory tile reusable.
+template <int T, int D, int B, int NT, int WB, int PH, int PAD, bool PERSIST>
+__device__ __forceinline__ void fir_fast_tile(const FirArgs &a, const Taps<T> &taps, const long long blk, const bool last_blk,
+                                              const uint32_t parity, const bool first_use, uint64_t &bar, uint32_t &sh_soff) {
     using G = FastGeom<T, D, B, NT, WB, PAD>;
     constexpr int Q = G::Q, SPL = G::SPL;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t sh_soff;
     unsigned char *tile = smem;
     float2 *part = reinterpret_cast<float2 *>(smem + G::SM_TILE);
     float2 *ysm = reinterpret_cast<float2 *>(smem + G::SM_TILE + G::SM_PART);
 
     const int tid = threadIdx.x;
-    const long long out0 = (long long)blockIdx.x * G::OUT;          // first owned output (call-local)
+    const long long out0 = blk * G::OUT;          // first owned output (call-local)
     if (tid < (PAD ? 32 : 1)) {
-        if (tid == 0) {
+        if (tid == 0 && first_use) {
             mbar_init(&bar, 1);
             fence_barrier_init();
         }
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
         }
     }
     __syncthreads();
-    mbar_wait(&bar, 0);
+    mbar_wait(&bar, parity);
 
     // ---- convert once, accumulate per (block, lag) ----------------------------------------------
     // The thread's first sample sits PH samples into load unit (soff / WB) + tid * (B*D/SPL); with PAD every thread's
@@ -310,7 +312,192 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
         }
         if (i == a.n_out - 1) *a.last_y = y;
     }
-    if (a.carry_out && blockIdx.x == gridDim.x - 1) fold_carry_update(a, tid, NT);
+    if (a.carry_out && last_blk) fold_carry_update(a, tid, NT);
+    if (PERSIST) __syncthreads();   // the tile, the partial sums and ysm are rewritten by the next tile
+}
+
+template <int T, int D, int B, int NT, int WB, int PH, int PAD = 0>
+__global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_constant__ Taps<T> taps) {
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t sh_soff;
+    fir_fast_tile<T, D, B, NT, WB, PH, PAD, false>(a, taps, (long long)blockIdx.x, blockIdx.x == gridDim.x - 1, 0u, true, bar, sh_soff);
+}
+
+
+
+// =================================================================================================
+// Persistent ring for the f32 receiver: successive USB-sized buffers stream through ONE resident kernel
+// (reader -> channel -> processor of examples/simple_fm.rs:55-60,108-128,145-160; same protocol as k_demod_ring).
+//
+// The host copies buffer k into device slot k % m (m = n_slots + 1) and then, stream-ordered, writes the doorbell
+// seq_ready[k % n_slots] = k + 1.  Every CTA walks the buffers in order and takes FIR tiles blk = blockIdx.x, +gridDim.x ...
+// of that buffer — the same fir_fast_tile code as the one-shot kernel, so every output bit is the same.  No state hops
+// between buffers: the carried history of buffer k IS the tail of device slot k-1 (still intact: a device slot is
+// rewritten only after the buffer after it has been collected), and y[m-1] of a buffer's first output is recomputed from
+// it by the halo blocks.  The discriminator values go to a device-resident [history | new] buffer per slot (the FIR tiles of
+// buffer k also write the head of buffer k+1's); when the last FIR tile of a buffer has finished (a counter, then a
+// release-store of fir_gen) the audio tiles of that buffer run — the polyphase FIR a[i] = sum_j gp[phase][j] d[p_i - j]
+// with the same ascending-j fma chain as the one-shot audio kernels — straight into host-mapped memory; the CTA that
+// finishes the last one publishes seq_done[slot] = k + 1 there.  Host cost per buffer: two cudaMemcpyAsync enqueues.
+// =================================================================================================
+struct FxRingCtl {                 // device memory
+    unsigned int seq_ready[64];    // doorbells, written by the copy engine
+    unsigned int fir_cnt[72];      // FIR tiles finished, per device slot
+    unsigned int fir_gen[72];      // k + 1 once every FIR tile of buffer k has finished
+    unsigned int aud_cnt[72];      // audio tiles finished, per device slot
+    unsigned int stop;             // host sets 1 to retire the kernel
+};
+
+struct FxRingArgs {
+    FxRingCtl *ctl;
+    volatile unsigned int *seq_done;   // host-mapped [n_slots]
+    const uint8_t *d_in;               // device slots [m][slot_stride], each 16-B aligned
+    const uint8_t *carry0_end;         // one past the handle's carried samples (history of buffer 0)
+    float *dbuf;                       // [m][dbuf_stride]: h2 history values, then the buffer's discriminator values
+    float *h_out;                      // host-mapped audio slots [n_slots][out_stride]
+    const float *gp;                   // polyphase taps [L][J]
+    float2 *last_y;
+    unsigned long long S, n_in0, n_y0, slot_stride, dbuf_stride, out_stride;
+    unsigned int n_slots, m, D, L, M, J, h2, has_res;
+    float gain;
+};
+
+__device__ __forceinline__ unsigned int ring_ld_acquire(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ring_st_release(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int kRingAudioTile = 256;   // audio outputs per audio tile
+
+template <int T, int D, int B, int NT, int WB, int PAD = 0>
+__global__ void __launch_bounds__(NT) k_fmrx_ring(const FxRingArgs r, const __grid_constant__ Taps<T> taps) {
+    using G = FastGeom<T, D, B, NT, WB, PAD>;
+    __shared__ __align__(8) uint64_t bar;   // ONE mbarrier for every load-phase instantiation below: `uses` counts its phases
+    __shared__ uint32_t sh_soff;
+    __shared__ FirArgs sh_a;
+    __shared__ unsigned long long sh_a0, sh_p0;
+    __shared__ unsigned int sh_go, sh_ntiles, sh_natiles, sh_na, sh_phase, sh_ph0;
+    const int tid = threadIdx.x;
+    uint32_t uses = 0;
+    for (unsigned long long k = 0;; k++) {
+        const unsigned int hs = (unsigned int)(k % r.n_slots), ds = (unsigned int)(k % r.m);
+        if (tid == 0) {
+            unsigned int go = 2;
+            while (go == 2) {
+                if (ring_ld_acquire(&r.ctl->seq_ready[hs]) == (unsigned int)(k + 1)) go = 1;
+                else if (ring_ld_acquire(&r.ctl->stop))   // a doorbell rung just before close was written before stop
+                    go = ring_ld_acquire(&r.ctl->seq_ready[hs]) == (unsigned int)(k + 1) ? 1 : 0;
+                else __nanosleep(100);
+            }
+            sh_go = go;
+            if (go) {
+                // closed-form stream position of buffer k
+                const unsigned long long n0 = r.n_in0 + k * r.S;
+                const unsigned long long y0 = n0 / D, y1 = (n0 + r.S) / D;   // global FIR output range [y0, y1)
+                FirArgs a;
+                a.x = r.d_in + (size_t)ds * r.slot_stride;
+                a.carry_end = k ? r.d_in + (size_t)((k - 1) % r.m) * r.slot_stride + 2 * r.S : r.carry0_end;
+                a.n_samples = (long long)r.S;
+                a.n_out = (long long)(y1 - y0);
+                a.r = (uint32_t)(n0 - y0 * D);
+                a.gain = r.gain;
+                a.y_out = nullptr;
+                a.last_y = r.last_y;
+                a.carry_out = nullptr;
+                a.cs = 0;
+                a.h2 = (int)r.h2;
+                unsigned long long a0 = y0, a1 = y1;   // audio range; without a resample stage the audio IS d
+                if (r.has_res) {
+                    a0 = (y0 * r.L + r.M - 1) / r.M;
+                    a1 = (y1 * r.L + r.M - 1) / r.M;
+                    a.d_out = r.dbuf + (size_t)ds * r.dbuf_stride + r.h2;
+                    a.hist_out = r.dbuf + (size_t)((k + 1) % r.m) * r.dbuf_stride;
+                } else {
+                    a.d_out = r.h_out + (size_t)hs * r.out_stride;
+                    a.hist_out = nullptr;
+                }
+                sh_a = a;
+                sh_a0 = a0;
+                sh_na = (unsigned int)(a1 - a0);
+                sh_ntiles = (unsigned int)((a.n_out + G::OUT - 1) / G::OUT);
+                sh_natiles = r.has_res ? (sh_na + kRingAudioTile - 1) / kRingAudioTile : 0u;
+                // load phase of this buffer's tiles (fx_path.cu launch_fir): sample s0 = -(HB*D + r) inside its 16-byte line
+                const long long s0 = -((long long)G::HB * D + (long long)a.r);
+                sh_phase = (((uint32_t)((2 * s0) & 15)) % (uint32_t)WB) / 2u;
+            }
+        }
+        __syncthreads();
+        if (!sh_go) return;
+        const unsigned int n_tiles = sh_ntiles, n_atiles = sh_natiles;
+        // ---- FIR + discriminator tiles -------------------------------------------------------------------------------
+        for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const bool last = t == n_tiles - 1;
+            switch (sh_phase) {
+                case 0: fir_fast_tile<T, D, B, NT, WB, 0, PAD, true>(sh_a, taps, t, last, uses & 1, uses == 0, bar, sh_soff); break;
+                case 1: fir_fast_tile<T, D, B, NT, WB, 1, PAD, true>(sh_a, taps, t, last, uses & 1, uses == 0, bar, sh_soff); break;
+                case 2: fir_fast_tile<T, D, B, NT, WB, (WB == 8 ? 2 : 0), PAD, true>(sh_a, taps, t, last, uses & 1, uses == 0, bar, sh_soff); break;
+                default: fir_fast_tile<T, D, B, NT, WB, (WB == 8 ? 3 : 1), PAD, true>(sh_a, taps, t, last, uses & 1, uses == 0, bar, sh_soff); break;
+            }
+            uses++;
+            if (tid == 0) {   // (fir_fast_tile ended with a __syncthreads: every store of the tile has been issued)
+                if (!r.has_res) __threadfence_system();   // d went straight to host memory
+                __threadfence();
+                if (atomicAdd(&r.ctl->fir_cnt[ds], 1u) == n_tiles - 1) {
+                    r.ctl->fir_cnt[ds] = 0;
+                    ring_st_release(&r.ctl->fir_gen[ds], (unsigned int)(k + 1));
+                    if (!r.has_res) {
+                        __threadfence_system();
+                        r.seq_done[hs] = (unsigned int)(k + 1);
+                    }
+                }
+            }
+        }
+        // ---- audio tiles: wait for this buffer's (and, for the history head, the previous buffer's) FIR tiles ------------
+        for (unsigned int t = blockIdx.x; t < n_atiles; t += gridDim.x) {
+            if (tid == 0) {
+                while (ring_ld_acquire(&r.ctl->fir_gen[ds]) != (unsigned int)(k + 1)) __nanosleep(50);
+                if (k)
+                    while (ring_ld_acquire(&r.ctl->fir_gen[(k - 1) % r.m]) != (unsigned int)k) __nanosleep(50);
+                const unsigned long long t0 = (sh_a0 + (unsigned long long)t * kRingAudioTile) * r.M;
+                const unsigned long long p0 = t0 / r.L;
+                sh_p0 = p0;
+                sh_ph0 = (unsigned int)(t0 - p0 * r.L);
+            }
+            __syncthreads();
+            {
+                const unsigned long long n0 = r.n_in0 + k * r.S;
+                const unsigned long long y0 = n0 / D;
+                // dbuf index of d[p0]: history h2, then the buffer's values from global output y0
+                const float *dslot = r.dbuf + (size_t)ds * r.dbuf_stride;
+                const long long xbase = (long long)(sh_p0 - y0) + (long long)r.h2;
+                float *outp = r.h_out + (size_t)hs * r.out_stride + (size_t)t * kRingAudioTile;
+                const unsigned int n_here = sh_na - t * kRingAudioTile < (unsigned int)kRingAudioTile ? sh_na - t * kRingAudioTile : (unsigned int)kRingAudioTile;
+                for (unsigned int o = tid; o < n_here; o += NT) {
+                    const unsigned int trel = sh_ph0 + o * r.M;
+                    const unsigned int dp = trel / r.L, ph = trel - dp * r.L;
+                    const float *g = r.gp + (size_t)ph * r.J;
+                    const float *x = dslot + (xbase + dp);
+                    float acc = 0.f;
+                    for (unsigned int j = 0; j < r.J; j++) acc = fmaf(__ldg(g + j), __ldcg(x - j), acc);
+                    outp[o] = acc;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();   // audio stores reach host memory
+                if (atomicAdd(&r.ctl->aud_cnt[ds], 1u) == n_atiles - 1) {
+                    r.ctl->aud_cnt[ds] = 0;
+                    __threadfence_system();
+                    r.seq_done[hs] = (unsigned int)(k + 1);
+                }
+            }
+        }
+        __syncthreads();   // sh_a is rewritten for the next buffer
+    }
 }
 
 }  // namespace sdr

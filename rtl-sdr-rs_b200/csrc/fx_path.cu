@@ -17,11 +17,13 @@
 // Fallback for arbitrary (T,D): k_fir_generic — one warp per output, lanes stride the taps,
 // warp-shuffle reduction.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -273,6 +275,7 @@ struct FastVariant {
     int out_per_cta, hb, smem, nt, wb, b;
     void (*launch)(const FirArgs &, const float *taps, int phase, int grid, int smem, cudaStream_t);
     cudaError_t (*prepare)(int smem);
+    cudaError_t (*launch_ring)(const FxRingArgs &, const float *taps, int grid, int smem, cudaStream_t) = nullptr;
     const RtcModule *rtc = nullptr;   // run-time-compiled instance (launch/prepare unused): fns[PH], PH < wb / 2
     int pad = 0;                      // bytes of shared memory skipped after every thread's row (run-time instances)
 };
@@ -303,13 +306,24 @@ cudaError_t prepare_fast(int smem) {
     return e;
 }
 template <int T, int D, int B, int NT, int WB>
+cudaError_t launch_ring_fast(const FxRingArgs &a, const float *taps, int grid, int smem, cudaStream_t st) {
+    Taps<T> t;
+    memcpy(t.h, taps, sizeof(float) * T);
+    cudaError_t e = raise_dyn_smem(k_fmrx_ring<T, D, B, NT, WB>, (size_t)smem);
+    if (e != cudaSuccess) return e;
+    k_fmrx_ring<T, D, B, NT, WB><<<grid, NT, smem, st>>>(a, t);
+    return cudaGetLastError();
+}
+template <int T, int D, int B, int NT, int WB>
 FastVariant make_variant() {
     using G = FastGeom<T, D, B, NT, WB>;
     // the load-phase instantiations of this shape join the preload list (see KernelList in common.cuh)
     static const KernelList kl{(const void *)k_fir_fast<T, D, B, NT, WB, 0>, (const void *)k_fir_fast<T, D, B, NT, WB, 1>,
                                (const void *)k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 2 : 0)>,
-                               (const void *)k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 3 : 1)>};
-    return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, WB, B, &launch_fast<T, D, B, NT, WB>, &prepare_fast<T, D, B, NT, WB>};
+                               (const void *)k_fir_fast<T, D, B, NT, WB, (WB == 8 ? 3 : 1)>,
+                               (const void *)k_fmrx_ring<T, D, B, NT, WB>};
+    return FastVariant{T, D, G::OUT, G::HB, G::SMEM, NT, WB, B, &launch_fast<T, D, B, NT, WB>, &prepare_fast<T, D, B, NT, WB>,
+                       &launch_ring_fast<T, D, B, NT, WB>};
 }
 
 // Specialised (taps, decimation) shapes: BASELINE.json configs[1] (127, /75) and configs[2] (255, /100),
@@ -420,7 +434,7 @@ const FastVariant *rtc_variant(int device, uint32_t T, uint32_t D, int B, int NT
         if (why) *why = err_buf();
         return nullptr;
     }
-    FastVariant *v = new FastVariant{(int)T, (int)D, nblk - hb, hb, smem, NT, WB, B, nullptr, nullptr, mod, PAD};
+    FastVariant *v = new FastVariant{(int)T, (int)D, nblk - hb, hb, smem, NT, WB, B, nullptr, nullptr, nullptr, mod, PAD};
     cache[full] = v;
     return v;
 }
@@ -464,6 +478,7 @@ struct sdr_fmrx {
     cudaEvent_t ev_fir[3]{}, ev_aud[3]{}, ev_join = nullptr;
     bool aud_used[3] = {false, false, false};
     H2DStager stager;        // pageable caller buffers go through pinned pieces (common.cuh)
+    struct sdr_fmrx_ring *ring = nullptr;   // a persistent ring owns the handle until sdr_fmrx_ring_close()
     static constexpr int kRing = 64;   // per-call kernel timings are harvested lazily from this ring
     cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_ring[kRing][4]{}, ev_s[2]{};
     cudaEvent_t *ev_t = ev_ring[0];
@@ -496,6 +511,12 @@ int fx_reset_device_state(sdr_fmrx *r) {
 }
 
 inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// entry of every call that advances or rewinds the stream: not while a persistent ring owns the handle
+int fx_enter(sdr_fmrx *r) {
+    if (r->ring) return fail(SDR_E_STATE, "handle is owned by an open ring (sdr_fmrx_ring_close first)");
+    return use_device(r->device);
+}
 
 struct CallPlan {
     uint64_t n_y, n_a, a0;   // FIR outputs, audio outputs, first audio index
@@ -853,6 +874,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
 void sdr_fmrx_free(sdr_fmrx *r) {
     if (!r) return;
     cudaSetDevice(r->device);
+    if (r->ring) sdr_fmrx_ring_close(r->ring);   // retire a ring that is still open
     if (r->stream) cudaStreamSynchronize(r->stream);
     if (r->copy_stream) cudaStreamSynchronize(r->copy_stream);
     if (r->audio_stream) cudaStreamSynchronize(r->audio_stream);
@@ -888,7 +910,7 @@ void sdr_fmrx_free(sdr_fmrx *r) {
 
 int sdr_fmrx_reset(sdr_fmrx *r) {
     if (!r) return fail(SDR_E_ARG, "null handle");
-    int rc = use_device(r->device);
+    int rc = fx_enter(r);
     if (rc) return rc;
     return fx_reset_device_state(r);
 }
@@ -904,7 +926,7 @@ int sdr_fmrx_out_lens(const sdr_fmrx *r, size_t n_samples, size_t *n_y, size_t *
 long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y_pairs, size_t y_cap, float *demod,
                       size_t demod_cap, float *audio, size_t audio_cap) {
     if (!r || (!iq && n_samples)) return fail(SDR_E_ARG, "sdr_fmrx_process: null argument");
-    int rc = use_device(r->device);
+    int rc = fx_enter(r);
     if (rc) return rc;
     CallPlan total = plan_call(r, r->n_in, r->n_y, n_samples);
     if (y_pairs && total.n_y > y_cap) return fail(SDR_E_CAP, "y capacity %zu < %llu", y_cap, (unsigned long long)total.n_y);
@@ -958,7 +980,7 @@ long sdr_fmrx_process_dev(sdr_fmrx *r, const uint8_t *d_iq, size_t n_samples, fl
                           float *d_audio, size_t audio_cap) {
     if (!r || (!d_iq && n_samples)) return fail(SDR_E_ARG, "sdr_fmrx_process_dev: null argument");
     if (reinterpret_cast<uintptr_t>(d_iq) & 15) return fail(SDR_E_ARG, "device input must be 16-byte aligned (use sdr_dev_alloc)");
-    int rc = use_device(r->device);
+    int rc = fx_enter(r);
     if (rc) return rc;
     CallPlan pl = plan_call(r, r->n_in, r->n_y, n_samples);
     if (!d_audio && pl.n_a) return fail(SDR_E_ARG, "audio buffer required");
@@ -970,7 +992,7 @@ long sdr_fmrx_process_dev(sdr_fmrx *r, const uint8_t *d_iq, size_t n_samples, fl
 
 long sdr_fmrx_low_pass(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y_pairs, size_t cap_pairs) {
     if (!r || (!iq && n_samples) || !y_pairs) return fail(SDR_E_ARG, "sdr_fmrx_low_pass: null argument");
-    int rc = use_device(r->device);
+    int rc = fx_enter(r);
     if (rc) return rc;
     CallPlan pl = plan_call(r, r->n_in, r->n_y, n_samples);
     if (pl.n_y > cap_pairs) return fail(SDR_E_CAP, "capacity %zu < %llu pairs", cap_pairs, (unsigned long long)pl.n_y);
@@ -989,7 +1011,7 @@ long sdr_fmrx_low_pass(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *
 long sdr_fmrx_fm_demod(sdr_fmrx *r, const float *y_pairs, size_t n, float *out, size_t cap) {
     if (!r || (!y_pairs && n) || !out) return fail(SDR_E_ARG, "sdr_fmrx_fm_demod: null argument");
     if (n > cap) return fail(SDR_E_CAP, "capacity %zu < %zu", cap, n);
-    int rc = use_device(r->device);
+    int rc = fx_enter(r);
     if (rc) return rc;
     if (n == 0) return 0;
     if ((rc = r->d_y[0].reserve(n * 8)) || (rc = r->d_tmp.reserve(n * 4))) return rc;
@@ -1008,7 +1030,7 @@ long sdr_fmrx_fm_demod(sdr_fmrx *r, const float *y_pairs, size_t n, float *out, 
 long sdr_fmrx_resample(sdr_fmrx *r, const float *d, size_t n, float *out, size_t cap) {
     if (!r || (!d && n) || !out) return fail(SDR_E_ARG, "sdr_fmrx_resample: null argument");
     if (!r->cfg.n_taps2) return fail(SDR_E_STATE, "handle was created without a resample stage");
-    int rc = use_device(r->device);
+    int rc = fx_enter(r);
     if (rc) return rc;
     const uint64_t L = r->cfg.up, M = r->cfg.down;
     uint64_t a0 = ceil_div(r->n_y * L, M), n_a = ceil_div((r->n_y + n) * L, M) - a0;
@@ -1061,7 +1083,7 @@ int sdr_fmrx_span_end(sdr_fmrx *r, float *ms) {
 
 int sdr_fmrx_seek(sdr_fmrx *r, uint64_t global_sample_index) {
     if (!r) return fail(SDR_E_ARG, "null handle");
-    int rc = use_device(r->device);
+    int rc = fx_enter(r);
     if (rc) return rc;
     if ((rc = fx_reset_device_state(r))) return rc;
     r->n_in = global_sample_index;
@@ -1121,6 +1143,19 @@ long sdr_rtc_selftest(uint32_t n_taps, uint32_t decim, int shape[4]) {
     return (long)total;
 }
 
+long sdr_rtc_compile_ring(uint32_t n_taps, uint32_t decim) {
+    int B = 0, NT = 0, WB = 0, PAD = 0;
+    if (n_taps > 4096 || decim > 256 || !pick_fast_params((int)n_taps, (int)decim, &B, &NT, &WB, &PAD))
+        return fail(SDR_E_ARG, "(%u taps, /%u) is outside the block-owner kernel's range", n_taps, decim);
+    char name[160];
+    snprintf(name, sizeof name, "sdr::k_fmrx_ring<%u,%u,%d,%d,%d,%d>", n_taps, decim, B, NT, WB, PAD);
+    std::vector<std::vector<char>> cubins;
+    std::vector<std::string> lowered;
+    int rc = rtc_compile_cubins({name}, &cubins, &lowered, nullptr);
+    if (rc) return rc;
+    return (long)cubins[0].size();
+}
+
 int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, int reset) {
     if (!r) return fail(SDR_E_ARG, "null handle");
     int rc = use_device(r->device);
@@ -1133,6 +1168,269 @@ int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, in
         r->sum_ms[0] = r->sum_ms[1] = r->sum_ms[2] = 0.0;
         r->sum_calls = 0;
     }
+    return SDR_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Persistent ring of the f32 receiver (host side; kernel: k_fmrx_ring in fir_fast.cuh)
+// =================================================================================================
+struct sdr_fmrx_ring {
+    sdr_fmrx *r = nullptr;
+    size_t buf_len = 0, slot_stride = 0, out_stride = 0, dbuf_stride = 0;
+    uint64_t S = 0, n_in0 = 0, n_y0 = 0;
+    uint32_t n_slots = 0, m = 0;
+    uint8_t *h_in = nullptr;               // pinned [n_slots][buf_len]
+    DevBuf d_in, d_ctl, d_dbuf;
+    float *h_out = nullptr, *h_out_dev = nullptr;   // host-mapped audio slots
+    volatile unsigned int *h_seq_done = nullptr;
+    unsigned int *h_seq_done_dev = nullptr;
+    unsigned int *h_doorbell = nullptr;    // pinned [n_slots] + stop word at [64]
+    cudaStream_t ring_stream = nullptr, copy_stream = nullptr;
+    std::atomic<uint64_t> head{0}, tail{0};   // committed / collected buffers
+    bool acquired = false, launched = false;
+};
+
+namespace {
+
+void fx_ring_release(sdr_fmrx_ring *g) {
+    if (!g) return;
+    if (g->launched) ring_closed(g->r->device);
+    if (g->r && g->r->ring == g) g->r->ring = nullptr;
+    if (g->ring_stream) cudaStreamDestroy(g->ring_stream);
+    if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+    host_free_or_park(g->h_in);
+    host_free_or_park(g->h_out);
+    host_free_or_park((void *)g->h_seq_done);
+    host_free_or_park(g->h_doorbell);
+    g->d_in.release();
+    g->d_ctl.release();
+    g->d_dbuf.release();
+    delete g;
+}
+
+// audio range [a0, a1) of buffer k (global audio indices), closed form
+void fx_ring_audio_range(const sdr_fmrx_ring *g, uint64_t k, uint64_t *a0, uint64_t *a1) {
+    const sdr_fmrx *r = g->r;
+    const uint64_t D = r->cfg.decim, n0 = g->n_in0 + k * g->S, y0 = n0 / D, y1 = (n0 + g->S) / D;
+    if (r->cfg.n_taps2) {
+        *a0 = ceil_div(y0 * r->cfg.up, r->cfg.down);
+        *a1 = ceil_div(y1 * r->cfg.up, r->cfg.down);
+    } else {
+        *a0 = y0;
+        *a1 = y1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdr_fmrx_ring_open(sdr_fmrx *r, size_t buf_len, uint32_t n_slots, sdr_fmrx_ring **out) {
+    if (!r || !out) return fail(SDR_E_ARG, "sdr_fmrx_ring_open: null argument");
+    if (n_slots < 2 || n_slots > 64) return fail(SDR_E_ARG, "n_slots must be in [2, 64]");
+    if (buf_len == 0 || buf_len % 16) return fail(SDR_E_LEN, "buffer length %zu is not a positive multiple of 16 bytes", buf_len);
+    int rc = fx_enter(r);
+    if (rc) return rc;
+    if (!r->fast) return fail(SDR_E_STATE, "the ring runs the specialised FIR kernel; this (taps, decimation) shape has none (%s)", r->rtc_note.c_str());
+    const uint64_t S = buf_len / 2, D = r->cfg.decim, L = r->cfg.up, M = r->cfg.down;
+    const bool has_res = r->cfg.n_taps2 != 0;
+    if (S < (uint64_t)r->cs) return fail(SDR_E_LEN, "a ring buffer must hold at least the %d carried samples", r->cs);
+    if (S / D < (has_res ? (uint64_t)r->h2 : 1) || (has_res && (S / D) * L < M))
+        return fail(SDR_E_LEN, "a ring buffer must produce at least %d FIR outputs and one audio sample", has_res ? r->h2 : 1);
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    SDR_CUDA_TRY(cudaStreamSynchronize(r->audio_stream));
+    sdr_fmrx_ring *g = new sdr_fmrx_ring();
+    g->r = r;
+    g->buf_len = buf_len;
+    g->S = S;
+    g->n_slots = n_slots;
+    g->m = n_slots + 1;
+    g->slot_stride = buf_len;            // multiple of 16: every slot (and its end, the next buffer's carry) is aligned
+    g->n_in0 = r->n_in;
+    g->n_y0 = r->n_y;
+    const uint64_t max_y = S / D + 1;
+    g->dbuf_stride = (size_t)((r->h2 + max_y + 8 + 3) & ~3ull);
+    g->out_stride = (size_t)(((has_res ? ceil_div(max_y * L, M) + 1 : max_y) + 3) & ~3ull);
+    cudaError_t e = cudaHostAlloc((void **)&g->h_in, (size_t)n_slots * buf_len, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&g->h_out, (size_t)n_slots * g->out_stride * sizeof(float), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&g->h_out_dev, g->h_out, 0);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&g->h_seq_done, 64 * sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&g->h_seq_done_dev, (void *)g->h_seq_done, 0);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&g->h_doorbell, 72 * sizeof(unsigned int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->ring_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        fx_ring_release(g);
+        return fail(SDR_E_CUDA, "sdr_fmrx_ring_open: %s", cudaGetErrorString(e));
+    }
+    if ((rc = g->d_in.reserve((size_t)g->m * g->slot_stride + 64)) || (rc = g->d_ctl.reserve(sizeof(FxRingCtl))) ||
+        (rc = g->d_dbuf.reserve((size_t)g->m * g->dbuf_stride * sizeof(float)))) {
+        fx_ring_release(g);
+        return rc;
+    }
+    for (int i = 0; i < 64; i++) g->h_seq_done[i] = 0;
+    e = cudaMemsetAsync(g->d_ctl.p, 0, sizeof(FxRingCtl), g->copy_stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->d_dbuf.p, 0, (size_t)g->m * g->dbuf_stride * sizeof(float), g->copy_stream);
+    // the resampler history the handle carries becomes the head of buffer 0's discriminator slot
+    if (e == cudaSuccess && has_res)
+        e = cudaMemcpyAsync(g->d_dbuf.p, r->d_dbuf[r->dcur].p, (size_t)r->h2 * sizeof(float), cudaMemcpyDeviceToDevice, g->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->copy_stream);
+    if (e != cudaSuccess) {
+        fx_ring_release(g);
+        return fail(SDR_E_CUDA, "sdr_fmrx_ring_open: %s", cudaGetErrorString(e));
+    }
+    // nothing may be loaded lazily once a ring kernel is resident (see KernelList in common.cuh)
+    const FastVariant *v = r->fast;
+    const RtcModule *ring_mod = nullptr;
+    if (v->rtc) {
+        char key[112], name[160];
+        snprintf(key, sizeof key, "fmrx_ring<%d,%d,%d,%d,%d,%d>", v->T, v->D, v->b, v->nt, v->wb, v->pad);
+        snprintf(name, sizeof name, "sdr::k_fmrx_ring<%d,%d,%d,%d,%d,%d>", v->T, v->D, v->b, v->nt, v->wb, v->pad);
+        if ((rc = rtc_get_module(r->device, key, {name}, v->smem, &ring_mod))) {
+            fx_ring_release(g);
+            return rc;
+        }
+    }
+    if ((rc = preload_kernels())) {
+        fx_ring_release(g);
+        return rc;
+    }
+    FxRingArgs a{};
+    a.ctl = g->d_ctl.as<FxRingCtl>();
+    a.seq_done = g->h_seq_done_dev;
+    a.d_in = g->d_in.as<uint8_t>();
+    a.carry0_end = r->d_carry[r->carry_cur].as<uint8_t>() + (size_t)r->cs * 2;
+    a.dbuf = g->d_dbuf.as<float>();
+    a.h_out = g->h_out_dev;
+    a.gp = r->d_taps2.as<float>();
+    a.last_y = r->d_state.as<float2>();
+    a.S = S;
+    a.n_in0 = g->n_in0;
+    a.n_y0 = g->n_y0;
+    a.slot_stride = g->slot_stride;
+    a.dbuf_stride = g->dbuf_stride;
+    a.out_stride = g->out_stride;
+    a.n_slots = n_slots;
+    a.m = g->m;
+    a.D = (unsigned)D;
+    a.L = has_res ? (unsigned)L : 1u;
+    a.M = has_res ? (unsigned)M : 1u;
+    a.J = (unsigned)r->J;
+    a.h2 = (unsigned)r->h2;
+    a.has_res = has_res ? 1u : 0u;
+    a.gain = r->gain;
+    // one CTA per FIR tile of a buffer, at most one per SM: every CTA is resident (audio tiles wait for FIR tiles)
+    const uint64_t fir_tiles = ceil_div(max_y, (uint64_t)v->out_per_cta), aud_tiles = ceil_div(g->out_stride, (uint64_t)kRingAudioTile);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(std::max(fir_tiles, aud_tiles), (uint64_t)sm_count(r->device)));
+    if (v->rtc) {
+        void *params[2] = {&a, (void *)r->taps.data()};
+        rc = rtc_launch(ring_mod->fns[0], (unsigned)grid, (unsigned)v->nt, (unsigned)v->smem, g->ring_stream, params);
+        if (rc) {
+            fx_ring_release(g);
+            return rc;
+        }
+    } else {
+        e = v->launch_ring(a, r->taps.data(), grid, v->smem, g->ring_stream);
+        if (e != cudaSuccess) {
+            fx_ring_release(g);
+            return fail(SDR_E_CUDA, "sdr_fmrx_ring_open: launch failed: %s", cudaGetErrorString(e));
+        }
+    }
+    count_launch();
+    g->launched = true;
+    ring_opened(r->device);
+    r->ring = g;
+    *out = g;
+    return SDR_OK;
+}
+
+int sdr_fmrx_ring_acquire(sdr_fmrx_ring *g, uint8_t **buf) {
+    if (!g || !buf) return fail(SDR_E_ARG, "sdr_fmrx_ring_acquire: null argument");
+    if (g->acquired) return fail(SDR_E_STATE, "a slot is already acquired (commit it first)");
+    while (g->head.load() - g->tail.load() >= g->n_slots) std::this_thread::yield();   // ring full: wait for collect()
+    *buf = g->h_in + (size_t)(g->head.load() % g->n_slots) * g->buf_len;
+    g->acquired = true;
+    return SDR_OK;
+}
+
+int sdr_fmrx_ring_commit(sdr_fmrx_ring *g) {
+    if (!g) return fail(SDR_E_ARG, "null ring");
+    if (!g->acquired) return fail(SDR_E_STATE, "no slot acquired");
+    int rc = use_device(g->r->device);
+    if (rc) return rc;
+    const uint64_t k = g->head.load();
+    const uint32_t hs = (uint32_t)(k % g->n_slots), ds = (uint32_t)(k % g->m);
+    SDR_CUDA_TRY(cudaMemcpyAsync(g->d_in.as<uint8_t>() + (size_t)ds * g->slot_stride, g->h_in + (size_t)hs * g->buf_len, g->buf_len,
+                                 cudaMemcpyHostToDevice, g->copy_stream));
+    g->h_doorbell[hs] = (unsigned int)(k + 1);
+    SDR_CUDA_TRY(cudaMemcpyAsync(&g->d_ctl.as<FxRingCtl>()->seq_ready[hs], &g->h_doorbell[hs], sizeof(unsigned int),
+                                 cudaMemcpyHostToDevice, g->copy_stream));   // stream order: data first, then the doorbell
+    g->acquired = false;
+    g->head.store(k + 1);
+    return SDR_OK;
+}
+
+long sdr_fmrx_ring_collect(sdr_fmrx_ring *g, float *audio, size_t cap) {
+    if (!g || !audio) return fail(SDR_E_ARG, "sdr_fmrx_ring_collect: null argument");
+    const uint64_t k = g->tail.load();
+    if (k == g->head.load()) return fail(SDR_E_STATE, "nothing outstanding");
+    const uint32_t hs = (uint32_t)(k % g->n_slots);
+    uint64_t a0 = 0, a1 = 0;
+    fx_ring_audio_range(g, k, &a0, &a1);
+    const uint64_t na = a1 - a0;
+    if (na > cap) return fail(SDR_E_CAP, "output capacity %zu < %llu audio samples", cap, (unsigned long long)na);
+    uint64_t spins = 0;
+    while (g->h_seq_done[hs] != (unsigned int)(k + 1)) {
+        if ((++spins & 0xfff) == 0) {
+            cudaError_t e = cudaStreamQuery(g->ring_stream);
+            if (e != cudaErrorNotReady) {
+                (void)cudaGetLastError();
+                return fail(SDR_E_CUDA, "ring kernel is not running (%s)", cudaGetErrorString(e));
+            }
+            std::this_thread::yield();
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(audio, g->h_out + (size_t)hs * g->out_stride, na * sizeof(float));
+    g->tail.store(k + 1);
+    return (long)na;
+}
+
+int sdr_fmrx_ring_close(sdr_fmrx_ring *g) {
+    if (!g) return fail(SDR_E_ARG, "null ring");
+    sdr_fmrx *r = g->r;
+    int rc = use_device(r->device);
+    if (rc) return rc;
+    g->h_doorbell[64] = 1;
+    cudaError_t e = cudaMemcpyAsync(&g->d_ctl.as<FxRingCtl>()->stop, &g->h_doorbell[64], sizeof(unsigned int), cudaMemcpyHostToDevice,
+                                    g->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->ring_stream);   // every committed buffer is processed before stop is honoured
+    const uint64_t N = g->head.load();
+    if (e == cudaSuccess && N) {
+        // hand the stream back: position (closed form), the raw carry = tail of the last buffer's slot, the resampler
+        // history = head of the slot the next buffer would have used
+        const uint64_t D = r->cfg.decim;
+        const uint64_t n1 = g->n_in0 + N * g->S;
+        uint64_t a_dummy = 0, a1 = 0;
+        fx_ring_audio_range(g, N - 1, &a_dummy, &a1);
+        const uint8_t *last = g->d_in.as<uint8_t>() + (size_t)((N - 1) % g->m) * g->slot_stride;
+        e = cudaMemcpyAsync(r->d_carry[r->carry_cur].p, last + 2 * (g->S - (uint64_t)r->cs), (size_t)r->cs * 2, cudaMemcpyDeviceToDevice,
+                            g->copy_stream);
+        if (e == cudaSuccess && r->cfg.n_taps2)
+            e = cudaMemcpyAsync(r->d_dbuf[r->dcur].p, g->d_dbuf.as<float>() + (size_t)(N % g->m) * g->dbuf_stride,
+                                (size_t)r->h2 * sizeof(float), cudaMemcpyDeviceToDevice, g->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g->copy_stream);
+        if (e == cudaSuccess) {
+            r->n_in = n1;
+            r->n_y = n1 / D;
+            r->n_a = a1;
+        }
+    }
+    fx_ring_release(g);
+    if (e != cudaSuccess) return fail(SDR_E_CUDA, "sdr_fmrx_ring_close: %s", cudaGetErrorString(e));
     return SDR_OK;
 }
 

@@ -111,3 +111,39 @@ class FmRx:
         n = C.c_uint64(0)
         F.check(F.lib().sdr_fmrx_timing_totals(self._h, C.byref(sums), C.byref(n), int(reset)))
         return list(sums), n.value
+
+
+class FmRing:
+    """Persistent-kernel ring over an FmRx (sdr_fmrx_ring_*): buffers stream through one resident kernel."""
+
+    def __init__(self, rx: FmRx, buf_len: int, n_slots: int = 8):
+        self.rx, self.buf_len = rx, buf_len
+        h = C.c_void_p()
+        F.check(F.lib().sdr_fmrx_ring_open(rx._h, buf_len, n_slots, C.byref(h)))
+        self._h = h
+        self._cap = buf_len // 2 // max(rx.decim, 1) * max(rx.up, 1) // max(rx.down, 1) + 16
+
+    def submit(self, buf: np.ndarray):
+        """acquire the next pinned slot, copy `buf` into it, commit (H2D + doorbell, no kernel launch)."""
+        b = np.ascontiguousarray(buf, dtype=np.uint8)
+        assert b.size == self.buf_len
+        p = C.c_void_p()
+        F.check(F.lib().sdr_fmrx_ring_acquire(self._h, C.byref(p)))
+        C.memmove(p, b.ctypes.data, b.size)
+        F.check(F.lib().sdr_fmrx_ring_commit(self._h))
+
+    def collect(self) -> np.ndarray:
+        out = np.empty(self._cap, np.float32)
+        n = F.check(F.lib().sdr_fmrx_ring_collect(self._h, F.ptr(out), out.size))
+        return out[:n].copy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            h, self._h = self._h, None
+            F.check(F.lib().sdr_fmrx_ring_close(h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
