@@ -407,6 +407,49 @@ def per_buffer_bench(S, device: int, buf_len: int, n_bufs: int = 400) -> dict:
     return out
 
 
+def per_buffer_fx(S, device: int, w: dict, buf_len: int = 262144, n_bufs: int = 400) -> dict:
+    """The f32 receiver on the reference's call pattern (one 262144-byte host buffer at a time): one synchronous
+    sdr_fmrx_process per buffer, and the persistent ring (sdr_fmrx_ring_*: no launch per buffer)."""
+    taps, taps2 = taps_for(w)
+    src = S.Source.open_synth(SEED + 78)
+    bufs = np.empty((8, buf_len), np.uint8)
+    for b in bufs:
+        assert src.read_sync(b) == buf_len
+    src.close()
+    rx = S.FmRx(taps, w["D"], taps2, w["up"], w["down"], device=device)
+    for i in range(20):
+        rx.process(bufs[i % 8], want_y=False, want_demod=False)
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(n_bufs):
+        t1 = time.perf_counter()
+        rx.process(bufs[i % 8], want_y=False, want_demod=False)
+        lat.append(time.perf_counter() - t1)
+    sync_s = time.perf_counter() - t0
+    lat.sort()
+    out = {"buf_len": buf_len, "calls": n_bufs,
+           "sync_call": {"api": "sdr_fmrx_process", "us_per_call_median": round(lat[len(lat) // 2] * 1e6, 1),
+                         "us_per_call_p99": round(lat[int(len(lat) * 0.99)] * 1e6, 1),
+                         "msamples_per_s": round(n_bufs * (buf_len // 2) / sync_s / 1e6, 1)}}
+    slots = 8
+    ring = S.FmRing(rx, buf_len, slots)
+    for i in range(slots - 1):
+        ring.submit(bufs[i % 8])
+    t0 = time.perf_counter()
+    for i in range(n_bufs):
+        ring.collect()
+        ring.submit(bufs[i % 8])
+    ring_s = time.perf_counter() - t0
+    for i in range(slots - 1):
+        ring.collect()
+    ring.close()
+    rx.close()
+    out["ring"] = {"api": "sdr_fmrx_ring_acquire/commit/collect", "slots": slots,
+                   "us_per_buffer": round(ring_s / n_bufs * 1e6, 1),
+                   "msamples_per_s": round(n_bufs * (buf_len // 2) / ring_s / 1e6, 1)}
+    return out
+
+
 def chan_plan(w: dict, world: int, rank: int):
     """Channel plan of BASELINE.json configs[3]/[4].  One GPU: 64 channels at f_c = (c - 31.5) * 200 kHz
     (cfg4).  N GPUs: 64*N channels at f_c = (c - (64N-1)/2) * fs/(64N) (cfg5 is N = 8: (c - 255.5) * fs/512), 64 per
@@ -731,6 +774,8 @@ def main():
             if other == "cfg1" and not args.no_cpu_baseline and cx.rank == 0:
                 eo["cpu_baseline"] = cpu_legs_cfg1(wo)
             extra[other] = eo
+        if not args.no_e2e and cx.rank == 0 and w["name"] != "cfg1":
+            extra["per_buffer_f32"] = per_buffer_fx(S, cx.device, w)
         wc = workload_spec("chan")
         mc = measure_chan(cx, wc, d_in, max(3, x_steps // 2), 3, shard=False)
         extra["chan"] = {"workload": wc["desc"], "ms_per_step": mc["ms_per_step"], "input_msamples_per_s": mc["input_msamples_per_s"],

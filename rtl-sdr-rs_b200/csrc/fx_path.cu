@@ -1337,8 +1337,8 @@ int sdr_fmrx_ring_open(sdr_fmrx *r, size_t buf_len, uint32_t n_slots, sdr_fmrx_r
             fx_ring_release(g);
             return fail(SDR_E_CUDA, "sdr_fmrx_ring_open: launch failed: %s", cudaGetErrorString(e));
         }
+        count_launch();   // (rtc_launch counts its own)
     }
-    count_launch();
     g->launched = true;
     ring_opened(r->device);
     r->ring = g;
