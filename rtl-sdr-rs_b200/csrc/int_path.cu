@@ -90,8 +90,11 @@ __device__ __noinline__ int32_t d_fast_atan2_slow(int32_t y, int32_t x) {
 //     e = fma(f32|num|, rcp.approx(f32 den), -0.5)
 // carries an absolute error below 2^21 * (2^-23 [rcp] + 2^-24 [fma rounding]) = 0.375, so Q - 0.875 < e < Q - 0.125 and
 // trunc(e) (a negative e saturates to 0) is floor(Q) or floor(Q) - 1: ONE exact remainder test (`rem >= den`) repairs it.
-// BOUNDED = the caller guarantees |x| + |y| < 2^24 (true for every product of two D = 6 boxcar sums: <= 1536^2); then
-// den == 0 iff x == y == 0 (result 0, :384-386) and there is no out-of-line path at all.  Otherwise everything the
+// BOUNDED = the caller guarantees |x| + |y| < 2^30, so that nothing wraps BEFORE the shift (true for every product of two
+// boxcar sums up to downsample 128: 2 * (128 D)^2 <= 2^29); then den == 0 iff x == y == 0 (result 0, :384-386) and there
+// is no out-of-line path at all.  Beyond den = 2^24 the f32 image of den is rounded (relative 2^-24), but there
+// Q = |num| / den <= 2^31 / 2^24 = 128, so the estimate's absolute error is below 128 * 2^-22 and the same one-step repair
+// holds; the repair compares the exact 32-bit remainder (q * den <= |num| never wraps).  Otherwise everything the
 // estimate does not cover (den <= 0: x = y = 0 and the wrapped INT32_MIN cases; |den| >= 2^24) takes the slow form.
 template <bool BOUNDED>
 __device__ __forceinline__ int32_t d_fast_atan2_t(int32_t y, int32_t x) {
@@ -114,7 +117,8 @@ __device__ __forceinline__ int32_t d_fast_atan2_t(int32_t y, int32_t x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rn((uint32_t)den)));
     uint32_t q = __float2uint_rz(fmaf(fabsf(__int2float_rn(num)), r, -0.5f));
-    if ((q + 1u) * (uint32_t)den <= an) q++;   // (q+1)*den <= 2*an < 2^33 only when q+1 is the true quotient's successor: q*den <= an and den < 2^24, no wrap
+    // q is floor(Q) or floor(Q) - 1 (never more: q * den <= |num| < 2^32, so the remainder is exact in 32 bits)
+    if (an - q * (uint32_t)den >= (uint32_t)den) q++;
     const int32_t quo = num < 0 ? (int32_t)(0u - q) : (int32_t)q;
     const int32_t angle = (xpos ? pi4 : pi34) - quo;
     const int32_t res = y < 0 ? -angle : angle;
@@ -247,17 +251,24 @@ __device__ __noinline__ int2 lp_window_exact(const uint32_t *w32, int32_t off0, 
 // first window comes from the DT/2 words before its row: recomputed by every lane in the direct form, taken from the
 // neighbour lane by shuffle in the staged form (lane 0 recomputes it).  The KW results leave as one store.  Groups past the tile and the predecessor of window 0 produce
 // values nobody reads (dm[0] is either predecessor-only or repaired by the fix-up loop).
+constexpr int kMaxFusedDT = 32;
 template <int DT>
 struct PassGeom {   // windows per lane: the row must be whole 16-byte (even DT) / 8-byte (odd DT) chunks and fit in registers
     static constexpr bool ODD = (DT & 1) != 0;
-    static constexpr int KW = ODD ? 4 : (DT == 2 ? 8 : DT == 12 ? 2 : 4);
+    // even DT: the fewest windows whose bytes are whole 16-byte chunks (from 14 up; the hand-tuned counts below that)
+    static constexpr int KW = ODD ? 4 : DT >= 14 ? (DT % 8 == 0 ? 1 : DT % 4 == 0 ? 2 : 4) : (DT == 2 ? 8 : DT == 12 ? 2 : 4);
     static constexpr int ROW_WORDS = KW * DT / 2;
-    static_assert(DT >= 2 && DT <= 13, "register-resident pass: downsample 2..13");
+    // a lane recomputes the predecessor of its first window itself (direct form) only where that is a small share of
+    // its row; rows of one or two windows take it from the neighbour lane by shuffle
+    static constexpr bool RECOMPUTE_PRED = !ODD && DT != 8 && (DT <= 13 || KW >= 4);
+    static_assert(DT >= 2 && DT <= kMaxFusedDT, "register-resident pass: downsample 2..32");
     static_assert((ROW_WORDS * 4) % (ODD ? 8 : 16) == 0, "a lane's row is a whole number of load chunks");
-    // the bounded atan2 needs |x| + |y| <= (2 * 128 * DT)^2 < 2^24
-    static_assert(4ll * 128 * 128 * DT * DT < (1ll << 24), "products of two boxcar sums must stay below 2^24");
+    // the bounded atan2 needs |x| + |y| <= 2 * (128 * DT)^2 < 2^30
+    static_assert(2ll * 128 * 128 * DT * DT < (1ll << 30), "products of two boxcar sums must stay below 2^30");
 };
-constexpr bool has_fused_pass(int DT) { return DT >= 2 && DT <= 13; }
+constexpr bool has_fused_pass(int DT) { return DT >= 2 && DT <= kMaxFusedDT; }
+// windows per lane (PassGeom<DT>::KW) for the host's tile geometry
+constexpr int fused_pass_kw(int DT) { return (DT & 1) ? 4 : DT >= 14 ? (DT % 8 == 0 ? 1 : DT % 4 == 0 ? 2 : 4) : (DT == 2 ? 8 : DT == 12 ? 2 : 4); }
 
 template <int DT, int S, int NTH, bool GLOBAL>
 __device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const int32_t a0, const uint32_t ngroups, int16_t *dm) {
@@ -265,7 +276,7 @@ __device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const in
     constexpr int KW = PG::KW, HW = DT / 2, NCH = (PG::ROW_WORDS + S + 3) / 4;   // windows per lane, words per window, chunks
     constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u;   // phase-0 word: re [+1,0,0,-1], im [0,+1,+1,0]
     constexpr uint32_t CRE2 = 0x010000FFu, CIM2 = 0x00FFFF00u;   // phase-2 word: negated
-    if constexpr (GLOBAL && DT != 8) {   // DT = 8: the extra chunk costs registers the 40-register budget does not have (4.4 vs 4.1 TB/s)
+    if constexpr (GLOBAL && PG::RECOMPUTE_PRED) {   // (DT = 8: the extra chunk costs registers the 40-register budget does not have, 4.4 vs 4.1 TB/s)
         // direct form: every lane computes the predecessor of its first window itself from the chunk(s) before its row
         // (one more 128-bit load, DT more dp4a): no shuffle, no divergent lane-0 branch, no warp-uniform loop —
         // 0.428 -> 0.416 ms on cfg1
@@ -359,12 +370,16 @@ __device__ __forceinline__ void dn_pass_even(const unsigned char *tile, const in
             o[j] = (uint32_t)d_fast_atan2_t<true>(cim, cre);
         }
         if (g < ngroups) {
-            uint32_t pk[KW / 2];
+            if constexpr (KW == 1) {
+                dm[g] = (int16_t)(uint16_t)o[0];
+            } else {
+                uint32_t pk[KW / 2];
 #pragma unroll
-            for (int j = 0; j < KW / 2; j++) pk[j] = __byte_perm(o[2 * j], o[2 * j + 1], 0x5410);
-            if (KW == 2) *reinterpret_cast<uint32_t *>(dm + 2 * g) = pk[0];
-            if (KW == 4) *reinterpret_cast<uint2 *>(dm + 4 * g) = make_uint2(pk[0], pk[KW / 2 - 1]);
-            if (KW == 8) *reinterpret_cast<uint4 *>(dm + 8 * g) = make_uint4(pk[0], pk[KW / 8], pk[KW / 4], pk[KW / 2 - 1]);
+                for (int j = 0; j < KW / 2; j++) pk[j] = __byte_perm(o[2 * j], o[2 * j + 1], 0x5410);
+                if (KW == 2) *reinterpret_cast<uint32_t *>(dm + 2 * g) = pk[0];
+                if (KW == 4) *reinterpret_cast<uint2 *>(dm + 4 * g) = make_uint2(pk[0], pk[KW / 2 - 1]);
+                if (KW == 8) *reinterpret_cast<uint4 *>(dm + 8 * g) = make_uint4(pk[0], pk[KW / 8], pk[KW / 4], pk[KW / 2 - 1]);
+            }
         }
     }
 }
@@ -772,7 +787,13 @@ __global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedAr
 #ifndef SDR_INT_DIRECT_MINB
 #define SDR_INT_DIRECT_MINB 8
 #endif
-constexpr int direct_min_blocks(int DT) { return DT == 13 ? 4 : (DT == 10 || DT == 11) ? 5 : (DT == 8 || DT == 9) ? 6 : SDR_INT_DIRECT_MINB; }
+constexpr int direct_row_words(int DT) { return (DT & 1) ? 2 * DT : fused_pass_kw(DT) * DT / 2; }
+// from 14 up the register budget follows the row a lane holds (wide rows: fewer, fatter CTAs — the per-sample instruction
+// count falls with the downsample, so fewer warps keep the issue slots and the memory pipe busy)
+constexpr int direct_min_blocks(int DT) {
+    return DT >= 14 ? (direct_row_words(DT) <= 12 ? 5 : direct_row_words(DT) <= 20 ? 4 : direct_row_words(DT) <= 32 ? 3 : 2)
+                    : DT == 13 ? 4 : (DT == 10 || DT == 11) ? 5 : (DT == 8 || DT == 9) ? 6 : SDR_INT_DIRECT_MINB;
+}
 #ifndef SDR_INT_DIRECT_NTH
 #define SDR_INT_DIRECT_NTH 256   // threads per CTA of the direct kernel (128: 0.420 vs 0.426 ms on cfg1, 64 and 512 slower)
 #endif
@@ -986,7 +1007,7 @@ __global__ void k_fast_atan2_v(const int32_t *y, const int32_t *x, size_t n, int
     {
         // the BOUNDED form (used by the D = 6 pass) is exercised on its whole domain, the general one elsewhere
         const int64_t mag = llabs((long long)y[i]) + llabs((long long)x[i]);
-        out[i] = mag < (1ll << 24) ? d_fast_atan2_t<true>(y[i], x[i]) : d_fast_atan2(y[i], x[i]);
+        out[i] = mag < (1ll << 30) ? d_fast_atan2_t<true>(y[i], x[i]) : d_fast_atan2(y[i], x[i]);
     }
 }
 
@@ -1005,6 +1026,11 @@ static const KernelList kIntKernels{
     SDR_K(k_demod_direct<2>), SDR_K(k_demod_direct<3>), SDR_K(k_demod_direct<4>), SDR_K(k_demod_direct<5>),
     SDR_K(k_demod_direct<6>), SDR_K(k_demod_direct<7>), SDR_K(k_demod_direct<8>), SDR_K(k_demod_direct<9>),
     SDR_K(k_demod_direct<10>), SDR_K(k_demod_direct<11>), SDR_K(k_demod_direct<12>), SDR_K(k_demod_direct<13>),
+    SDR_K(k_demod_direct<14>), SDR_K(k_demod_direct<15>), SDR_K(k_demod_direct<16>), SDR_K(k_demod_direct<17>),
+    SDR_K(k_demod_direct<18>), SDR_K(k_demod_direct<19>), SDR_K(k_demod_direct<20>), SDR_K(k_demod_direct<21>),
+    SDR_K(k_demod_direct<22>), SDR_K(k_demod_direct<23>), SDR_K(k_demod_direct<24>), SDR_K(k_demod_direct<25>),
+    SDR_K(k_demod_direct<26>), SDR_K(k_demod_direct<27>), SDR_K(k_demod_direct<28>), SDR_K(k_demod_direct<29>),
+    SDR_K(k_demod_direct<30>), SDR_K(k_demod_direct<31>), SDR_K(k_demod_direct<32>),
     SDR_K(k_rotate_90), SDR_K(k_buf_to_complex), SDR_K(k_low_pass_complex), SDR_K(k_fm_demod), SDR_K(k_low_pass_real),
     SDR_K(k_fast_atan2_v), SDR_K(k_polar_v)};
 #undef SDR_K
@@ -1232,8 +1258,11 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     case DT_: k_demod_direct<DT_><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
         switch (d->cfg.downsample) {
             SDR_DIRECT_CASE(2) SDR_DIRECT_CASE(3) SDR_DIRECT_CASE(4) SDR_DIRECT_CASE(5) SDR_DIRECT_CASE(6) SDR_DIRECT_CASE(7)
-            SDR_DIRECT_CASE(8) SDR_DIRECT_CASE(9) SDR_DIRECT_CASE(10) SDR_DIRECT_CASE(11) SDR_DIRECT_CASE(12)
-            default: k_demod_direct<13><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
+            SDR_DIRECT_CASE(8) SDR_DIRECT_CASE(9) SDR_DIRECT_CASE(10) SDR_DIRECT_CASE(11) SDR_DIRECT_CASE(12) SDR_DIRECT_CASE(13)
+            SDR_DIRECT_CASE(14) SDR_DIRECT_CASE(15) SDR_DIRECT_CASE(16) SDR_DIRECT_CASE(17) SDR_DIRECT_CASE(18) SDR_DIRECT_CASE(19)
+            SDR_DIRECT_CASE(20) SDR_DIRECT_CASE(21) SDR_DIRECT_CASE(22) SDR_DIRECT_CASE(23) SDR_DIRECT_CASE(24) SDR_DIRECT_CASE(25)
+            SDR_DIRECT_CASE(26) SDR_DIRECT_CASE(27) SDR_DIRECT_CASE(28) SDR_DIRECT_CASE(29) SDR_DIRECT_CASE(30) SDR_DIRECT_CASE(31)
+            default: k_demod_direct<32><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
         }
 #undef SDR_DIRECT_CASE
     } else if (d->cfg.downsample == 6 && !(p0 & 1))
@@ -1374,7 +1403,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     {
         const char *ed = getenv("SDR_INT_DIRECT");
         if (has_fused_pass((int)D) && !(ed && atoi(ed) == 0)) {
-            const uint64_t kw = (D & 1) ? 4 : D == 2 ? 8 : D == 12 ? 2 : 4;   // PassGeom<D>::KW: windows per lane
+            const uint64_t kw = (uint64_t)fused_pass_kw((int)D);   // PassGeom<D>::KW: windows per lane
             for (int k = 0; k < 4; k++)
                 if (make_geom(D, fast, slow, ((kDirectNth * kw) << k) - 2, d->geo_direct[k], true) && d->geo_direct[k].smem_direct <= 48 * 1024)
                     d->n_direct = k + 1;

@@ -15,8 +15,8 @@ S.synth_fill_dev(d_in, 2 * n, 0xB2000001)
 BUF = 262144
 for D, fast, slow in ((6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48_000), (8, 125_000, 32_000), (10, 100_000, 32_000),
                       (12, 170_000, 32_000), (3, 334_000, 48_000), (5, 200_000, 32_000), (7, 143_000, 32_000), (9, 112_000, 32_000),
-                      (11, 100_000, 32_000), (13, 80_000, 32_000), (16, 150_000, 48_000), (21, 50_000, 32_000),
-                      (32, 32_000, 32_000)):
+                      (11, 100_000, 32_000), (13, 80_000, 32_000)) + tuple((d, 160_000, 32_000) for d in range(14, 33)) + (
+                      (40, 32_000, 32_000), (100, 48_000, 32_000)):
     cfg = S.DemodConfig(fast * D, fast, slow, D, 42)
     h = S.Demod(cfg)
     n_bufs = 2 * n // BUF
@@ -28,6 +28,8 @@ for D, fast, slow in ((6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48
         ms, _ = h.last_timing(); best = min(best, ms)
     print(f"int D={D:3d} {fast}->{slow}: {best:.3f} ms  {2.0 * n / best / 1e6:.0f} GB/s")
     d_out.free(); h.close()
+if len(sys.argv) > 1 and sys.argv[1] == "int":
+    sys.exit(0)
 for T, D in ((127, 75), (255, 100), (127, 50), (63, 25), (201, 64), (511, 100), (31, 10), (129, 16), (65, 32), (127, 48), (255, 96),
              (33, 8), (127, 40), (200, 3)):
     taps = channel_taps(T, D)

@@ -119,11 +119,14 @@ def test_fast_atan2_and_polar_vs_oracle(S):
     d = S.Demod()
     n = 200_000
     # mix of magnitudes: small, the wrap region (|4096*(x-|y|)| >= 2^31) and full-range i32
-    ys = [rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n), rng.integers(-2**31, 2**31, n), [0, 0, 5, -5, 1, -1, 7]]
-    xs = [rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n), rng.integers(-2**31, 2**31, n), [0, 3, 0, 0, 1, -1, -7]]
+    # (the register-resident pass uses the bounded divider on |x| + |y| < 2^30: +-2^28 pairs sweep that whole domain)
+    ys = [rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n), rng.integers(-2**31, 2**31, n), [0, 0, 5, -5, 1, -1, 7],
+          rng.integers(-2**28, 2**28, n), rng.integers(-2**25, 2**25, n)]
+    xs = [rng.integers(-800, 800, n), rng.integers(-900_000, 900_000, n), rng.integers(-2**31, 2**31, n), [0, 3, 0, 0, 1, -1, -7],
+          rng.integers(-2**28, 2**28, n), rng.integers(-2**25, 2**25, n)]
     # the divider's range boundaries: |x| + |y| at 1..3, 2^10, 2^19 (numerator wrap), 2^24 (f32-exact limit), 2^31
     for den in (1, 2, 3, 5, 1023, 1024, 1025, 2**19 - 1, 2**19, 2**19 + 1, 2**20 + 7, 2**24 - 2, 2**24 - 1, 2**24, 2**24 + 1,
-                2**25 + 3, 2**31 - 1, 2**31):
+                2**25 + 3, 2**26 - 1, 2**29 + 12345, 2**30 - 1, 2**30, 2**30 + 1, 2**31 - 1, 2**31):
         ax = np.unique(np.concatenate([rng.integers(0, den + 1, 4000), [0, 1, den // 2, den - 1, den],
                                        np.arange(min(den + 1, 600)), den - np.arange(min(den + 1, 600))])).astype(np.int64)
         ay = den - ax
@@ -254,6 +257,35 @@ def test_direct_kernel_every_tile_size(S, monkeypatch, D, fast, slow, passes):
     # and one whole-buffer call on the same handle continues the stream
     more = rng.integers(0, 256, 262144, dtype=np.uint8)
     assert np.array_equal(g.demodulate(more), o.demodulate(more))
+
+
+@pytest.mark.parametrize("D", range(14, 33))
+@pytest.mark.parametrize("passes", [1, 8])
+def test_direct_kernel_wide_downsamples(S, monkeypatch, D, passes):
+    """Downsample 14..32 (2.4 Msps capture at the example's 160 kHz is D = 15): the register-resident pass with rows of
+    one to four windows, the generalised bounded divider (|x| + |y| up to 2^26), saturated runs included."""
+    from sigutil import saturated_stream
+    monkeypatch.setenv("SDR_INT_DIRECT_PASSES", str(passes))
+    fast, slow = (160_000, 32_000) if D % 3 else (100_003, 31_999)
+    rng = np.random.default_rng(D * 10 + passes)
+    buf_len, n_bufs = 8 * 1531, 61
+    data = rng.integers(0, 256, buf_len * n_bufs, dtype=np.uint8)
+    data[buf_len * 20:buf_len * 30] = saturated_stream(rng, buf_len * 10)     # products of boxcar sums up to 2 * (128 D)^2
+    o = O.Demod(ocfg_of(D, fast, slow))
+    want = np.concatenate([o.demodulate(data[i * buf_len:(i + 1) * buf_len]) for i in range(n_bufs)])
+    g = S.Demod(cfg_of(S, D, fast, slow))
+    got = g.demodulate_batch(data, buf_len)
+    assert np.array_equal(got, want)
+    assert g.state() == o.state()
+    more = saturated_stream(rng, 262144)
+    assert np.array_equal(g.demodulate(more), o.demodulate(more))
+    assert g.state() == o.state()
+    # carried state set by hand, odd prev_index included (even D then takes the generic kernel)
+    st = dict(prev_index=D - 1, now_lpr=-70_000, prev_lpr_index=fast - 1, lp_now=(-700, 650), demod_pre=(-4000, 4096))
+    g.set_state(**st), o.set_state(**st)
+    assert np.array_equal(g.demodulate_batch(data[:buf_len * 9], buf_len), np.concatenate(
+        [o.demodulate(data[i * buf_len:(i + 1) * buf_len]) for i in range(9)]))
+    assert g.state() == o.state()
 
 
 @pytest.mark.parametrize("seed", range(8))
