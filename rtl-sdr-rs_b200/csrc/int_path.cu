@@ -470,6 +470,85 @@ __device__ __forceinline__ void dn_pass_odd(const unsigned char *tile, const int
     }
 }
 
+// ---- odd downsample from 15 up, STAGED form: the direct form's rows of two pairs (4 DT words per lane) no longer fit a
+// sensible register budget, and narrower global loads cost more L1 sector requests than the memory pipe has.  Here the
+// tile's bytes are in shared memory (one bulk copy) and a lane owns ONE pair of windows = DT words, read with 32-bit loads
+// at a lane stride of DT words — odd, hence bank-conflict free.  The first word of a lane's pair alternates between even
+// and odd word indices from lane to lane, so the rotate_90 phase of a word is not a compile-time constant: the dp4a sums
+// of the even-offset and the odd-offset words are kept apart (always with the phase-0 coefficients; the phase-2 ones are
+// their negation) and combined with the lane's sign afterwards.  E as in the direct form.
+constexpr bool has_staged_odd_pass(int DT) { return (DT & 1) && DT >= 15 && DT <= kMaxFusedDT; }
+
+template <int DT, int E, int NTH>
+__device__ __forceinline__ void dn_pass_odd_staged(const unsigned char *tile, const int32_t byte0, const uint32_t npairs,
+                                                   const int32_t last_w, int16_t *dm) {
+    constexpr int HW = (DT - 1) / 2;
+    constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u, LO = 0x0000FFFFu, HI = 0xFFFF0000u;
+    const int lane = threadIdx.x & 31;
+    // sums of one window: words [k0, k0 + HW] of the pair, the half-masked one first (B) or last (A)
+    auto window = [&](const uint32_t *v, const int k0, const bool is_b, const uint32_t fpar, int32_t &re, int32_t &im) {
+        int32_t r[2] = {0, 0}, i[2] = {0, 0};   // by parity of the word's offset inside the pair
+#pragma unroll
+        for (int k = 0; k <= HW; k++) {
+            const uint32_t m = (is_b ? k == 0 : k == HW) ? (is_b ? HI : LO) : 0xFFFFFFFFu;
+            r[(k0 + k) & 1] = dp4a_us(v[k0 + k], CRE0 & m, r[(k0 + k) & 1]);
+            i[(k0 + k) & 1] = dp4a_us(v[k0 + k], CIM0 & m, i[(k0 + k) & 1]);
+        }
+        // absolute word parity = fpar ^ offset parity: phase-0 words count +, phase-2 words -
+        const int32_t dr = r[0] - r[1], di = i[0] - i[1];
+        // start phase of the window: A starts on the first sample of word k0 (phase 0 or 2), B on the second sample of
+        // word k0 (phase 1 or 3)
+        const uint32_t wpar = (fpar ^ (uint32_t)k0) & 1u;
+        const int ph = is_b ? (wpar ? 3 : 1) : (wpar ? 2 : 0), pho = is_b ? (wpar ? 1 : 3) : (wpar ? 0 : 2);
+        (void)pho;
+        re = (fpar ? -dr : dr) + (wpar ? (is_b ? BoxK<DT>::re(3) : BoxK<DT>::re(2)) : (is_b ? BoxK<DT>::re(1) : BoxK<DT>::re(0)));
+        im = (fpar ? -di : di) + (wpar ? (is_b ? BoxK<DT>::im(3) : BoxK<DT>::im(2)) : (is_b ? BoxK<DT>::im(1) : BoxK<DT>::im(0)));
+        (void)ph;
+    };
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(tile + byte0);   // byte0 is a multiple of 4 (may be negative)
+    const uint32_t basepar = (uint32_t)(byte0 >> 2) & 1u;
+    for (uint32_t gb = threadIdx.x & ~31u; gb < npairs; gb += NTH) {
+        const uint32_t g = gb + lane;
+        const uint32_t gc = g < npairs ? g : npairs - 1;
+        const uint32_t *w = w0 + (size_t)DT * gc;
+        const uint32_t fpar = (basepar + gc) & 1u;   // DT is odd: the parity of the pair's first word alternates
+        uint32_t v[DT];
+#pragma unroll
+        for (int k = 0; k < DT; k++) v[k] = w[k];
+        int32_t re[2], im[2];
+        window(v, 0, false, fpar, re[0], im[0]);
+        window(v, HW, true, fpar, re[1], im[1]);
+        int32_t pre = __shfl_up_sync(0xffffffffu, re[1], 1), pim = __shfl_up_sync(0xffffffffu, im[1], 1);
+        if (lane == 0 && g > 0) {   // the B window of the pair before this one: its words HW .. DT-1
+            uint32_t pv[HW + 1];
+#pragma unroll
+            for (int k = 0; k <= HW; k++) pv[k] = w[k - DT + HW];
+            // (pv is indexed from 0, the window from offset HW of ITS pair: pass the pair parity that makes the word
+            // parities come out right — first word of that pair has parity fpar ^ 1, its word HW has (fpar ^ 1 ^ HW))
+            int32_t r[2] = {0, 0}, i[2] = {0, 0};
+#pragma unroll
+            for (int k = 0; k <= HW; k++) {
+                const uint32_t m = k == 0 ? HI : 0xFFFFFFFFu;
+                r[(HW + k) & 1] = dp4a_us(pv[k], CRE0 & m, r[(HW + k) & 1]);
+                i[(HW + k) & 1] = dp4a_us(pv[k], CIM0 & m, i[(HW + k) & 1]);
+            }
+            const uint32_t fp = fpar ^ 1u, wpar = (fp ^ (uint32_t)HW) & 1u;
+            const int32_t dr = r[0] - r[1], di = i[0] - i[1];
+            pre = (fp ? -dr : dr) + (wpar ? BoxK<DT>::re(3) : BoxK<DT>::re(1));
+            pim = (fp ? -di : di) + (wpar ? BoxK<DT>::im(3) : BoxK<DT>::im(1));
+        }
+        const int32_t wfirst = 2 * (int32_t)g - E;   // tile-relative index of the pair's A window
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            int32_t cre, cim;
+            d_cmul_conj(make_int2(re[j], im[j]), j ? make_int2(re[0], im[0]) : make_int2(pre, pim), cre, cim);
+            const int32_t o = d_fast_atan2_t<true>(cim, cre);
+            const int32_t wi = wfirst + j;
+            if (g < npairs && wi >= 0 && wi <= last_w) dm[wi] = (int16_t)(uint16_t)(uint32_t)o;
+        }
+    }
+}
+
 // ================================================================================================
 // Tile = EB consecutive audio outputs.  Shared pieces of the one-CTA-per-tile kernel and the persistent ring.
 // ================================================================================================
@@ -556,8 +635,15 @@ template <int DT, int NTH, bool GLOBAL>
 __device__ __forceinline__ void dn_pass(const unsigned char *tile, const TileInfo &ti, int16_t *dm, const int tid) {
     const int32_t off0 = ti.off0;
     const uint32_t nlp = ti.nlp;
-    if constexpr (PassGeom<DT>::ODD) {
-        static_assert(GLOBAL, "the odd-downsample pass exists in the direct form only");
+    if constexpr (PassGeom<DT>::ODD && !GLOBAL) {
+        static_assert(has_staged_odd_pass(DT), "staged odd-downsample pass: 15..31");
+        const int e = off0 & 1;                                   // window 0 starts on an odd sample: it is a B window
+        const int32_t byte0 = 2 * (off0 - e * DT);                // first byte of the pair that holds window 0
+        const uint32_t npairs = (nlp + (uint32_t)e + 1) / 2;
+        if (e) dn_pass_odd_staged<DT, 1, NTH>(tile, byte0, npairs, (int32_t)nlp - 1, dm);
+        else dn_pass_odd_staged<DT, 0, NTH>(tile, byte0, npairs, (int32_t)nlp - 1, dm);
+        return;
+    } else if constexpr (PassGeom<DT>::ODD) {
         const int e = off0 & 1;                                   // window 0 starts on an odd sample
         const int32_t byte0 = 2 * (off0 - e * DT);                // first byte of the pair that holds window 0
         const int32_t a0 = byte0 & ~7;
@@ -657,7 +743,9 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     __shared__ __align__(8) uint64_t bar;
     __shared__ TileInfo sh_ti;
 
-    unsigned char *tile_s = smem + (DT == 6 ? 16 : 0);   // D = 6: the aligned-chunk pass may read the 16 bytes before the tile
+    // D = 6: the aligned-chunk pass may read the 16 bytes before the tile; staged odd pass: the pair that holds window 0 may
+    // start up to 2*DT bytes before it (that half is computed from whatever is there and never stored)
+    unsigned char *tile_s = smem + (DT == 6 ? 16 : has_staged_odd_pass(DT) ? 128 : 0);
     int2 *lp = reinterpret_cast<int2 *>(smem + a.tile_cap);
     int16_t *dm = reinterpret_cast<int16_t *>(smem + (DIRECT ? 0 : a.dm_off));
     uint8_t *flag = smem + a.tile_cap + (((size_t)a.lp_cap * 10 + 15) & ~size_t(15));   // 16-byte aligned
@@ -695,7 +783,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
 
     int2 lastlp = make_int2(st.demod_pre_re, st.demod_pre_im);   // lp[nlp-1] for the carried state (last tile)
-    if constexpr (DT == 6 || DIRECT) {
+    if constexpr (DT == 6 || DIRECT || has_staged_odd_pass(DT)) {
         // ---- D = 6 (optimal_settings :189-190): boxcar + discriminator fused, no window array ---------------
         if (!DIRECT) mbar_wait(&bar, parity);
         dn_pass<DT, NTH, DIRECT>(tile, ti, dm, tid);
@@ -780,6 +868,11 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
 #endif
 template <int DT>
 __global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedArgs a) {
+    demod_tile<DT>(a, blockIdx.x, gridDim.x, 0, true);
+}
+// staged kernel of the odd downsamples from 15 up (dn_pass_odd_staged): a lane holds DT words
+template <int DT>
+__global__ void __launch_bounds__(256, DT <= 21 ? 4 : 3) k_demod_staged_odd(const FusedArgs a) {
     demod_tile<DT>(a, blockIdx.x, gridDim.x, 0, true);
 }
 // CTAs per SM the register allocation aims for: 8 (32 registers) while a lane's row is at most 16 words, fewer for
@@ -1023,6 +1116,9 @@ __global__ void k_polar_v(const int2 *a, const int2 *b, size_t n, int fast, OctT
 #define SDR_K(x) ((const void *)(x))
 static const KernelList kIntKernels{
     SDR_K(k_demod_fused<0>), SDR_K(k_demod_fused<6>), SDR_K(k_demod_ring<0>), SDR_K(k_demod_ring<6>),
+    SDR_K(k_demod_staged_odd<15>), SDR_K(k_demod_staged_odd<17>), SDR_K(k_demod_staged_odd<19>), SDR_K(k_demod_staged_odd<21>),
+    SDR_K(k_demod_staged_odd<23>), SDR_K(k_demod_staged_odd<25>), SDR_K(k_demod_staged_odd<27>), SDR_K(k_demod_staged_odd<29>),
+    SDR_K(k_demod_staged_odd<31>),
     SDR_K(k_demod_direct<2>), SDR_K(k_demod_direct<3>), SDR_K(k_demod_direct<4>), SDR_K(k_demod_direct<5>),
     SDR_K(k_demod_direct<6>), SDR_K(k_demod_direct<7>), SDR_K(k_demod_direct<8>), SDR_K(k_demod_direct<9>),
     SDR_K(k_demod_direct<10>), SDR_K(k_demod_direct<11>), SDR_K(k_demod_direct<12>), SDR_K(k_demod_direct<13>),
@@ -1064,8 +1160,8 @@ static bool make_geom(uint64_t D, uint64_t fast, uint64_t slow, uint64_t n_lp_ta
     const bool d6 = fused_layout;
     const uint64_t per = (fast + slow - 1) / slow;
     const uint64_t lp_cap = (EB * fast + slow - 1) / slow + per + 4;
-    // slack: 16-B pad in front (D = 6), bulk-copy rounding, chunk over-read
-    const uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 96;
+    // slack: pad in front (16 B for D = 6, 128 B for the staged odd pass), bulk-copy rounding, chunk over-read
+    const uint64_t tile_cap = ((2 * (lp_cap * D + D) + 15) & ~15ull) + 96 + (fused_layout ? 128 : 0);
     g.EB = (uint32_t)EB;
     g.lp_cap = (uint32_t)lp_cap;
     g.tile_cap = (uint32_t)tile_cap;
@@ -1094,6 +1190,8 @@ struct sdr_demod {
     OctTable oct{};
     Geom geo;                // staged-tile geometry of the handle's usual kernel (k_demod_fused<6> for D = 6, else <0>)
     Geom geo_gen;            // D = 6 only: geometry of the generic kernel, which takes the odd window starts
+    Geom geo_odd;            // odd D from 15 up: tiles of the staged register-resident pass (k_demod_staged_odd)
+    bool staged_odd = false;
     Geom geo_ring;           // the persistent ring's tiles (D = 6: SDR_RING_PASSES passes, default 1 — one USB buffer is
                              // only ~21845 windows, small tiles spread it over more CTAs)
     Geom geo_direct[4];      // direct kernel: tiles of 1, 2, 4, 8 passes (256 lanes x KW windows each); the launch picks by batch size
@@ -1232,7 +1330,7 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     // D = 6 with an even window start (every stream that was not given an odd prev_index by hand): direct kernel, with
     // the largest tile that still leaves `kDirectWaves` full waves of 8 CTAs per SM (SDR_INT_DIRECT_PASSES pins it)
     const bool odd_start_d6 = d->cfg.downsample == 6 && (p0 & 1);   // prev_index set by hand: generic kernel
-    const Geom *g = odd_start_d6 ? &d->geo_gen : &d->geo;
+    const Geom *g = odd_start_d6 ? &d->geo_gen : d->staged_odd ? &d->geo_odd : &d->geo;
     const bool direct = d->n_direct > 0 && ((d->cfg.downsample & 1) || !(p0 & 1));   // odd downsamples take any window start
     if (direct) {
         constexpr uint64_t kDirectWaves = 4;
@@ -1265,6 +1363,14 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
             default: k_demod_direct<32><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
         }
 #undef SDR_DIRECT_CASE
+    } else if (d->staged_odd) {
+#define SDR_ODD_CASE(DT_) \
+    case DT_: k_demod_staged_odd<DT_><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a); break;
+        switch (d->cfg.downsample) {
+            SDR_ODD_CASE(15) SDR_ODD_CASE(17) SDR_ODD_CASE(19) SDR_ODD_CASE(21) SDR_ODD_CASE(23) SDR_ODD_CASE(25) SDR_ODD_CASE(27)
+            SDR_ODD_CASE(29) SDR_ODD_CASE(31)
+        }
+#undef SDR_ODD_CASE
     } else if (d->cfg.downsample == 6 && !(p0 & 1))
         k_demod_fused<6><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a);
     else
@@ -1394,7 +1500,17 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
         if (rp < 1 || rp > 8) rp = 1;
         if (!make_geom(D, fast, slow, 1024ull * rp - 2, d->geo_ring, true)) d->geo_ring = d->geo;
     }
-    const size_t smem = std::max(std::max(d->geo.smem_staged, d->geo_gen.smem_staged), d->geo_ring.smem_staged);
+    {
+        const char *eo = getenv("SDR_INT_STAGED_ODD");
+        if (has_staged_odd_pass((int)D) && !(eo && atoi(eo) == 0)) {
+            const char *ep = getenv("SDR_INT_ODD_PASSES");
+            int op = ep ? atoi(ep) : (D <= 21 ? 2 : 1);   // 512 windows (one pair per lane) per pass
+            if (op < 1 || op > 8) op = 1;
+            d->staged_odd = make_geom(D, fast, slow, 512ull * op - 2, d->geo_odd, true);
+        }
+    }
+    const size_t smem = std::max(std::max(std::max(d->geo.smem_staged, d->geo_gen.smem_staged), d->geo_ring.smem_staged),
+                                 d->staged_odd ? d->geo_odd.smem_staged : 0);
     if (smem > 200 * 1024) {
         delete d;
         return fail(SDR_E_ARG, "downsample %u too large for the fused kernel's shared-memory tile", cfg->downsample);
@@ -1402,7 +1518,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     d->smem_bytes = smem;
     {
         const char *ed = getenv("SDR_INT_DIRECT");
-        if (has_fused_pass((int)D) && !(ed && atoi(ed) == 0)) {
+        if (has_fused_pass((int)D) && !d->staged_odd && !(ed && atoi(ed) == 0)) {
             const uint64_t kw = (uint64_t)fused_pass_kw((int)D);   // PassGeom<D>::KW: windows per lane
             for (int k = 0; k < 4; k++)
                 if (make_geom(D, fast, slow, ((kDirectNth * kw) << k) - 2, d->geo_direct[k], true) && d->geo_direct[k].smem_direct <= 48 * 1024)
@@ -1413,6 +1529,14 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     }
     cudaError_t e = raise_dyn_smem(k_demod_fused<0>, smem);
     if (e == cudaSuccess) e = raise_dyn_smem(k_demod_fused<6>, smem);
+    if (e == cudaSuccess && d->staged_odd) {
+#define SDR_ODD_CASE(DT_) case DT_: e = raise_dyn_smem(k_demod_staged_odd<DT_>, smem); break;
+        switch (D) {
+            SDR_ODD_CASE(15) SDR_ODD_CASE(17) SDR_ODD_CASE(19) SDR_ODD_CASE(21) SDR_ODD_CASE(23) SDR_ODD_CASE(25) SDR_ODD_CASE(27)
+            SDR_ODD_CASE(29) SDR_ODD_CASE(31)
+        }
+#undef SDR_ODD_CASE
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {

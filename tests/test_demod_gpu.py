@@ -262,6 +262,11 @@ def test_direct_kernel_every_tile_size(S, monkeypatch, D, fast, slow, passes):
 @pytest.mark.parametrize("D", range(14, 33))
 @pytest.mark.parametrize("passes", [1, 8])
 def test_direct_kernel_wide_downsamples(S, monkeypatch, D, passes):
+    # odd D from 15 up normally takes the staged one-pair-per-lane pass; passes == 8 pins the direct two-pair form instead
+    if D % 2 and passes == 8:
+        monkeypatch.setenv("SDR_INT_STAGED_ODD", "0")
+    elif D % 2:
+        monkeypatch.setenv("SDR_INT_ODD_PASSES", str(1 + D % 3))
     """Downsample 14..32 (2.4 Msps capture at the example's 160 kHz is D = 15): the register-resident pass with rows of
     one to four windows, the generalised bounded divider (|x| + |y| up to 2^26), saturated runs included."""
     from sigutil import saturated_stream
