@@ -3,8 +3,11 @@
 (1) time-sliced single-channel receiver: rank r owns slice r of ONE stream (sdr_fmrx_seek + halo warm-up);
     the concatenated per-rank outputs must equal a single-GPU run of the whole stream BIT FOR BIT.
 (2) channel-sharded channeliser: rank 0 generates the raw u8 slab, ONE ncclBroadcast (sdr_comm_bcast_u8)
-    delivers it to every rank, rank r channelises channels [8r, 8r+8); the gathered result must equal a
-    single-GPU run of all channels bit for bit."""
+    delivers it to every rank, rank r channelises channels [8r, 8r+8) with the direct-form kernel; the gathered
+    result must equal a single-GPU run of all channels bit for bit (the direct form treats channels independently).
+(3) the bench's plan: 64 channels per rank on the INTERLEAVED grid (rank r owns c = r mod world), which every rank runs
+    through the two-stage polyphase bank.  The bank's coefficient tables belong to a handle's own channel set, so the
+    reference is a single-GPU handle with the SAME set: bit for bit; and against the direct form: within 3e-6."""
 import json
 import os
 import sys
@@ -63,7 +66,9 @@ def main():
     uid = [S.Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     comm = S.Comm(local, rank, world, uid[0])
+    os.environ["SDR_CHAN_BANK"] = "0"      # (2) is the direct form on every handle; read when a handle is created
     ch = S.Channeliser(ctaps, Dc, fw_all[rank * C_per:(rank + 1) * C_per], device=local)
+    assert ch.kernel_kind()[0] == 1
     comm.bcast_u8(slab, 2 * n_c, 0)
     comm.chan_wait(ch)
     cap = n_c // Dc
@@ -72,6 +77,25 @@ def main():
     ch.sync(); comm.sync()
     cparts = [None] * world
     dist.all_gather_object(cparts, dict(rank=rank, d=d_cd.download(np.float32, C_per * cap).reshape(C_per, cap)[:, :m]))
+
+    # ---- (3) the interleaved 64-per-rank plan through the polyphase bank ----------------------------------
+    del os.environ["SDR_CHAN_BANK"]
+    Cb, Tb, Db = 64, 255, 100
+    cb_tot = Cb * world
+    n_b = Db * 800                                      # (the slab of (2) holds 81920 samples)
+    btaps = channel_taps(Tb, Db)
+
+    def plan(r):
+        offs = ((r + world * np.arange(Cb)) - (cb_tot - 1) / 2.0) / cb_tot
+        return (np.round(offs * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
+    chb = S.Channeliser(btaps, Db, plan(rank), device=local)
+    assert chb.kernel_kind()[0] == 2 and chb.kernel_kind()[1][0] == 64, chb.kernel_kind()
+    capb = n_b // Db
+    d_bd = S.DevBuffer(4 * Cb * capb, local)
+    mb = chb.process_dev(slab, n_b, d_bd, capb)          # the broadcast slab of (2), first n_b samples
+    chb.sync()
+    bparts = [None] * world
+    dist.all_gather_object(bparts, dict(rank=rank, d=d_bd.download(np.float32, Cb * capb).reshape(Cb, capb)[:, :mb]))
 
     if rank == 0:
         whole = S.DevBuffer(2 * total, 0)
@@ -89,6 +113,25 @@ def main():
         ref = d_all.download(np.float32, c_tot * cap).reshape(c_tot, cap)[:, :m1]
         cparts.sort(key=lambda p: p["rank"])
         ok &= bool(np.array_equal(np.concatenate([p["d"] for p in cparts], axis=0), ref))
+        bparts.sort(key=lambda p: p["rank"])
+        gain = 16384.0
+        for r in range(world):
+            same = S.Channeliser(btaps, Db, plan(r), device=0)
+            d_same = S.DevBuffer(4 * Cb * capb, 0)
+            ms = same.process_dev(slab, n_b, d_same, capb); same.sync()
+            ok &= bool(np.array_equal(d_same.download(np.float32, Cb * capb).reshape(Cb, capb)[:, :ms], bparts[r]["d"]))
+            os.environ["SDR_CHAN_BANK"] = "0"
+            direct = S.Channeliser(btaps, Db, plan(r), device=0)
+            del os.environ["SDR_CHAN_BANK"]
+            d_dir = S.DevBuffer(4 * Cb * capb, 0)
+            direct.process_dev(slab, n_b, d_dir, capb); direct.sync()
+            dd = d_dir.download(np.float32, Cb * capb).reshape(Cb, capb)[:, :ms] - bparts[r]["d"]
+            dd = (dd + gain) % (2 * gain) - gain              # on the circle (full scale = gain * pi / pi)
+            # uniform random bytes: every channel carries noise of comparable power, the discriminator is well conditioned
+            # almost everywhere; the few near-zero crossings are excluded by the median
+            ok &= bool(np.median(np.abs(dd)) < 3e-6 * gain * np.pi)
+            for b in (d_same, d_dir):
+                b.free()
         Path(os.environ["MULTIRANK_OUT"]).write_text(json.dumps({"ok": bool(ok), "world": world}))
     dist.barrier(device_ids=[local])
     dist.destroy_process_group()

@@ -1,8 +1,10 @@
 """Worker of tests/test_multirank_cpu.py: one rank of a world_size-2 gloo job on CPU.
 
-Exercises the N>1 HOST logic of the time-sliced stream (bench.py --gpus N) without a GPU:
-every rank cuts its slice with the C ABI's closed-form planner, the ORACLE stands in for the kernels
-(same arithmetic by the parity tests), and the slices must tile the single-stream result exactly."""
+Exercises the N>1 HOST logic without a GPU: (a) the time-sliced stream (bench.py --gpus N headline) — every
+rank cuts its slice with the C ABI's closed-form planner, the ORACLE stands in for the kernels (same arithmetic by the
+parity tests), and the slices must tile the single-stream result exactly; (b) north_star's channel partition — the raw
+slab exists on rank 0 only, ONE broadcast delivers it, rank r channelises the interleaved channel set c = r (mod world),
+for which sdr_chan_bank_plan() must find the rank's own uniform grid, and the gathered channels equal a single-rank run."""
 import json
 import os
 import sys
@@ -53,8 +55,36 @@ def main():
     nl, na_i, _ = S.demod_plan(dcfg, buf_len, b_hi - b_lo, st)
     t = torch.tensor([nl, na_i], dtype=torch.int64)
     dist.all_reduce(t)
+    # ---- north_star's partition: channels across ranks, ONE broadcast of the raw u8 slab, nothing else ---------------
+    # 16 channels per rank on the interleaved grid (rank r owns c = r mod world: its own channels sit on a uniform grid, so
+    # the library plans the polyphase bank for them); the slab is generated on rank 0 only and broadcast (gloo here, one
+    # ncclBroadcast on the GPUs); every rank channelises its share (oracle standing in for the kernel).
+    Cc, Tc, Dc, n_c = 16, 63, 20, 20 * 300 + 7
+    cc_tot = Cc * world
+    ctaps = channel_taps(Tc, Dc)
+
+    def plan(r):
+        offs = ((r + world * np.arange(Cc)) - (cc_tot - 1) / 2.0) / cc_tot
+        return (np.round(offs * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
+    slab = torch.from_numpy(O.synth_fill(2 * n_c, seed + 7).copy()) if rank == 0 else torch.zeros(2 * n_c, dtype=torch.uint8)
+    dist.broadcast(slab, src=0)
+    raw = slab.numpy()
+    bank = S.bank_plan(ctaps, Dc, plan(rank), want_tables=False)
+    yc, dc = O.channelise(raw, ctaps, Dc, plan(rank))
+    cgath = [None] * world
+    dist.all_gather_object(cgath, dict(rank=rank, fw=plan(rank), y=yc, d=dc, K=None if bank is None else int(bank[0][0])))
     ok = True
     if rank == 0:
+        # every channel of the full plan exactly once, each rank's set on a K = 16 grid, results equal to one rank doing all
+        cgath.sort(key=lambda g: g["rank"])
+        fw_full = (np.round(((np.arange(cc_tot) - (cc_tot - 1) / 2.0) / cc_tot) * 2.0 ** 32).astype(np.int64) % (1 << 32)).astype(np.uint32)
+        got_fw = np.concatenate([g["fw"] for g in cgath])
+        ok &= sorted(got_fw.tolist()) == sorted(fw_full.tolist())
+        ok &= all(g["K"] == Cc for g in cgath)
+        y_all, d_all = O.channelise(O.synth_fill(2 * n_c, seed + 7), ctaps, Dc, fw_full)
+        for g in cgath:
+            idx = g["rank"] + world * np.arange(Cc)
+            ok &= bool(np.array_equal(g["y"], y_all[idx]) and np.array_equal(g["d"], d_all[idx]))
         whole = O.synth_fill(2 * total, seed)
         yw, dw, aw = O.FxChain(taps, D, taps2, up, down).process(whole)
         gathered.sort(key=lambda g: g["rank"])
