@@ -105,21 +105,25 @@ def main():
         a1, d1 = S.DevBuffer(4 * na1, 0), S.DevBuffer(4 * ny1, 0)
         rx1.process_dev(whole, total, a1, na1, d_demod=d1); rx1.sync()
         parts.sort(key=lambda p: p["rank"])
-        ok &= bool(np.array_equal(np.concatenate([p["demod"] for p in parts]), d1.download(np.float32, ny1)))
-        ok &= bool(np.array_equal(np.concatenate([p["audio"] for p in parts]), a1.download(np.float32, na1)))
+        checks = {}
+        checks["slices_demod"] = bool(np.array_equal(np.concatenate([p["demod"] for p in parts]), d1.download(np.float32, ny1)))
+        checks["slices_audio"] = bool(np.array_equal(np.concatenate([p["audio"] for p in parts]), a1.download(np.float32, na1)))
+        os.environ["SDR_CHAN_BANK"] = "0"      # the reference of (2) is the direct form as well
         ch1 = S.Channeliser(ctaps, Dc, fw_all, device=0)
+        del os.environ["SDR_CHAN_BANK"]
+        assert ch1.kernel_kind()[0] == 1
         d_all = S.DevBuffer(4 * c_tot * cap, 0)
         m1 = ch1.process_dev(slab, n_c, d_all, cap); ch1.sync()
         ref = d_all.download(np.float32, c_tot * cap).reshape(c_tot, cap)[:, :m1]
         cparts.sort(key=lambda p: p["rank"])
-        ok &= bool(np.array_equal(np.concatenate([p["d"] for p in cparts], axis=0), ref))
+        checks["direct_shards"] = bool(np.array_equal(np.concatenate([p["d"] for p in cparts], axis=0), ref))
         bparts.sort(key=lambda p: p["rank"])
         gain = 16384.0
         for r in range(world):
             same = S.Channeliser(btaps, Db, plan(r), device=0)
             d_same = S.DevBuffer(4 * Cb * capb, 0)
             ms = same.process_dev(slab, n_b, d_same, capb); same.sync()
-            ok &= bool(np.array_equal(d_same.download(np.float32, Cb * capb).reshape(Cb, capb)[:, :ms], bparts[r]["d"]))
+            checks[f"bank_rank{r}_same_handle"] = bool(np.array_equal(d_same.download(np.float32, Cb * capb).reshape(Cb, capb)[:, :ms], bparts[r]["d"]))
             os.environ["SDR_CHAN_BANK"] = "0"
             direct = S.Channeliser(btaps, Db, plan(r), device=0)
             del os.environ["SDR_CHAN_BANK"]
@@ -129,9 +133,12 @@ def main():
             dd = (dd + gain) % (2 * gain) - gain              # on the circle (full scale = gain * pi / pi)
             # uniform random bytes: every channel carries noise of comparable power, the discriminator is well conditioned
             # almost everywhere; the few near-zero crossings are excluded by the median
-            ok &= bool(np.median(np.abs(dd)) < 3e-6 * gain * np.pi)
+            checks[f"bank_rank{r}_vs_direct"] = bool(np.median(np.abs(dd)) < 3e-6 * gain * np.pi)
             for b in (d_same, d_dir):
                 b.free()
+        ok = all(checks.values())
+        if not ok:
+            print("FAILED CHECKS:", {k: v for k, v in checks.items() if not v}, file=sys.stderr, flush=True)
         Path(os.environ["MULTIRANK_OUT"]).write_text(json.dumps({"ok": bool(ok), "world": world}))
     dist.barrier(device_ids=[local])
     dist.destroy_process_group()

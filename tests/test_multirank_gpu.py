@@ -27,5 +27,5 @@ def test_two_gpus_reproduce_one_gpu_bitwise(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "tests" / "multirank_gpu_worker.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0, "\n".join(ln for ln in (r.stdout + r.stderr).splitlines() if "NCCL INFO" not in ln)[-3000:]
     assert json.loads(out.read_text()) == {"ok": True, "world": 2}
