@@ -157,6 +157,26 @@ long sdr_fast_atan2(sdr_demod *d, const int32_t *y, const int32_t *x, size_t n, 
 long sdr_polar_discriminant(sdr_demod *d, const int32_t *a_pairs, const int32_t *b_pairs, size_t n,
                             int fast, int32_t *out);
 
+/* Optional audio post-stages after low_pass_real, ALL OFF BY DEFAULT: the reference computes
+ * `output_scale` (examples/simple_fm.rs:184,197-200) and never uses it, and has no de-emphasis, DC block or squelch — its
+ * output is the raw low_pass_real stream and so is the golden hash.  The stages restate what rtl_fm (the program the example
+ * was ported from) runs after its own low_pass_real, in its order and integer arithmetic (csrc/post.cu; "parity unpinned").
+ * One sdr_post_process() call = one block = the audio of one demodulate() call; state (de-emphasis and DC averages) is carried. */
+typedef struct {
+    uint32_t output_scale;    /* 0 or 1 = off; audio * scale, saturated to i16 */
+    uint32_t squelch_level;   /* 0 = off; a block is zeroed when rms((raw - 127.5) * 16) of its raw bytes is below the level */
+    uint32_t deemph_a;        /* 0 = off; rtl_fm deemph_filter constant, see sdr_post_deemph_a() */
+    uint32_t dc_block;        /* 0 = off, 1 = rtl_fm dc_block_filter */
+} sdr_post_config;
+typedef struct sdr_post sdr_post;
+/* round(1 / (1 - exp(-1 / (rate * tau)))): rate = audio rate in Hz, tau in microseconds (75 in the Americas, 50 elsewhere). */
+uint32_t sdr_post_deemph_a(uint32_t rate, double tau_us);
+int sdr_post_new(const sdr_post_config *cfg, int cuda_device, sdr_post **out);
+void sdr_post_free(sdr_post *p);
+/* In place on the caller's audio block (host memory).  raw / raw_len: the raw IQ bytes the block was demodulated from (only
+ * read when the squelch is on; may be NULL).  Returns n. */
+long sdr_post_process(sdr_post *p, int16_t *audio, size_t n, const uint8_t *raw, size_t raw_len);
+
 /* ============================================================================================
  * 2. f32 tap'd-FIR receiver (BASELINE.json configs 2-3; extension — no reference implementation,
  *    parity against the f64 oracle).  Stage names follow north_star: low_pass / fm_demod / resample.

@@ -365,6 +365,54 @@ long orc_demodulate_many_mt2(const orc_demod_config *cfg, const uint8_t *buf, si
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Optional audio post-stages (the reference has none — "parity unpinned"): rtl_fm's deemph_filter and
+ * dc_block_filter restated, plus this project's output_scale / raw-byte squelch (definitions in include/sdr_b200.h).   */
+void orc_post_init(orc_post *p, uint32_t output_scale, uint32_t squelch_level, uint32_t deemph_a, uint32_t dc_block) {
+    memset(p, 0, sizeof(*p));
+    p->output_scale = output_scale;
+    p->squelch_level = squelch_level;
+    p->deemph_a = deemph_a;
+    p->dc_block = dc_block;
+}
+
+void orc_post_process(orc_post *p, int16_t *x, size_t n, const uint8_t *raw, size_t raw_len) {
+    if (n == 0) return;
+    int gate_open = 1;
+    if (p->squelch_level && raw && raw_len) {
+        unsigned long long ss = 0;
+        for (size_t i = 0; i < raw_len; i++) {
+            int v = 2 * (int)raw[i] - 255;
+            ss += (unsigned long long)(v * v);
+        }
+        gate_open = (unsigned __int128)ss * 64u >= (unsigned __int128)p->squelch_level * p->squelch_level * raw_len;
+    }
+    const int scale = p->output_scale ? (int)p->output_scale : 1;
+    if (scale != 1 || !gate_open)
+        for (size_t i = 0; i < n; i++) {
+            int v = gate_open ? (int)x[i] * scale : 0;
+            x[i] = (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+        }
+    if (p->deemph_a) {   /* rtl_fm deemph_filter */
+        const int a = (int)p->deemph_a;
+        int avg = p->deemph_avg;
+        for (size_t i = 0; i < n; i++) {
+            int d = (int)x[i] - avg;
+            avg += d > 0 ? (d + a / 2) / a : (d - a / 2) / a;
+            x[i] = (int16_t)avg;
+        }
+        p->deemph_avg = avg;
+    }
+    if (p->dc_block) {   /* rtl_fm dc_block_filter */
+        long long sum = 0;
+        for (size_t i = 0; i < n; i++) sum += x[i];
+        int avg = (int)(sum / (long long)n);
+        avg = (avg + p->dc_avg * 9) / 10;
+        for (size_t i = 0; i < n; i++) x[i] = (int16_t)(uint16_t)(uint32_t)((int)x[i] - avg);
+        p->dc_avg = avg;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* f64 extension path (own definition — parity unpinned by the reference)               */
 
 static const double ORC_PI = 3.14159265358979323846264338327950288;

@@ -92,6 +92,15 @@ long orc_demodulate_many_mt(const orc_demod_config *cfg, const uint8_t *buf, siz
 long orc_demodulate_many_mt2(const orc_demod_config *cfg, const uint8_t *buf, size_t buf_len,
                              size_t n_bufs, int16_t *out, size_t out_cap, int threads, int fused);
 
+/* ---- optional audio post-stages (no reference implementation: rtl_fm's deemph_filter / dc_block_filter
+ * restated, output_scale and the raw-byte squelch as defined in include/sdr_b200.h) ------------------------------------ */
+typedef struct {
+    uint32_t output_scale, squelch_level, deemph_a, dc_block;
+    int32_t deemph_avg, dc_avg;
+} orc_post;
+void orc_post_init(orc_post *p, uint32_t output_scale, uint32_t squelch_level, uint32_t deemph_a, uint32_t dc_block);
+void orc_post_process(orc_post *p, int16_t *audio, size_t n, const uint8_t *raw, size_t raw_len);
+
 /* ---- f64 extension path ("parity unpinned" by the reference) ------------ */
 
 /* Streaming state of the f64 chain: raw-byte history for the FIR, last FIR output for the

@@ -18,6 +18,7 @@ from ._ffi import (  # noqa: F401
     RadioConfig,
     FmrxConfig,
     ChanConfig,
+    PostConfig,
     lib,
     device_count,
     device_info,
@@ -30,7 +31,7 @@ from ._ffi import (  # noqa: F401
     demod_plan,
     shard_range,
 )
-from .demod import Demod, Ring  # noqa: F401
+from .demod import Demod, Ring, AudioPost  # noqa: F401
 from .fmrx import FmRx, FmRing  # noqa: F401
 from .chan import Channeliser, Comm, bank_plan  # noqa: F401
 from .source import Source  # noqa: F401

@@ -48,6 +48,10 @@ class FmrxConfig(C.Structure):
                 ("up", C.c_uint32), ("down", C.c_uint32), ("gain", C.c_float)]
 
 
+class PostConfig(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("output_scale", "squelch_level", "deemph_a", "dc_block")]
+
+
 class ChanConfig(C.Structure):
     _fields_ = [("n_channels", C.c_uint32), ("n_taps", C.c_uint32), ("decim", C.c_uint32), ("gain", C.c_float)]
 
@@ -98,6 +102,10 @@ SIGNATURES = {
     "sdr_low_pass_real": (_l, [_vp, _vp, _sz, _vp, _sz]),
     "sdr_fast_atan2": (_l, [_vp, _vp, _vp, _sz, _vp]),
     "sdr_polar_discriminant": (_l, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "sdr_post_deemph_a": (C.c_uint32, [C.c_uint32, C.c_double]),
+    "sdr_post_new": (_i, [C.POINTER(PostConfig), _i, C.POINTER(_vp)]),
+    "sdr_post_free": (None, [_vp]),
+    "sdr_post_process": (_l, [_vp, _vp, _sz, _vp, _sz]),
     "sdr_fmrx_new": (_i, [C.POINTER(FmrxConfig), _vp, _vp, _i, C.POINTER(_vp)]),
     "sdr_fmrx_free": (None, [_vp]),
     "sdr_fmrx_reset": (_i, [_vp]),

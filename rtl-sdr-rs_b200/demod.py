@@ -182,3 +182,34 @@ class Ring:
             self.close()
         except Exception:
             pass
+
+
+class AudioPost:
+    """Optional post-stages after low_pass_real (sdr_post_*): output_scale, squelch, de-emphasis, DC block.  All off by default."""
+
+    def __init__(self, output_scale: int = 0, squelch_level: int = 0, deemph_a: int = 0, dc_block: bool = False, device: int = 0):
+        cfg = F.PostConfig(output_scale, squelch_level, deemph_a, int(dc_block))
+        h = C.c_void_p()
+        F.check(F.lib().sdr_post_new(C.byref(cfg), device, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def deemph_a(rate: int, tau_us: float = 75.0) -> int:
+        return int(F.lib().sdr_post_deemph_a(rate, tau_us))
+
+    def process(self, audio: np.ndarray, raw: np.ndarray | None = None) -> np.ndarray:
+        a = np.ascontiguousarray(audio, np.int16).copy()
+        r = np.ascontiguousarray(raw, np.uint8) if raw is not None else None
+        F.check(F.lib().sdr_post_process(self._h, F.ptr(a), a.size, F.ptr(r) if r is not None else None, r.size if r is not None else 0))
+        return a
+
+    def close(self):
+        if getattr(self, "_h", None):
+            F.lib().sdr_post_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

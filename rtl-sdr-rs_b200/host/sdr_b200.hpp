@@ -149,6 +149,21 @@ private:
     size_t buf_len_ = 0, out_cap_ = 0;
 };
 
+// Optional audio post-stages after low_pass_real (sdr_post_*): all off by default.
+class AudioPost {
+public:
+    explicit AudioPost(const sdr_post_config &cfg, int cuda_device = 0) { check(sdr_post_new(&cfg, cuda_device, &h_)); }
+    ~AudioPost() { sdr_post_free(h_); }
+    AudioPost(const AudioPost &) = delete;
+    AudioPost &operator=(const AudioPost &) = delete;
+    void process(std::vector<int16_t> &audio, const uint8_t *raw = nullptr, size_t raw_len = 0) {
+        check(sdr_post_process(h_, audio.data(), audio.size(), raw, raw_len));
+    }
+
+private:
+    sdr_post *h_ = nullptr;
+};
+
 // Buffer source with the read_sync contract of RtlSdr (src/lib.rs:153-155)
 class Source {
 public:

@@ -7,6 +7,8 @@
 //   ./simple_fm_b200 capture.bin | aplay -r 32000 -f S16_LE        (readme.md:13-18 pipes to `play`)
 //   ./simple_fm_b200 --synth 1000 > /dev/null                      (1000 seeded synthetic buffers)
 //   ./simple_fm_b200 --sync capture.bin                            (one sdr_demod_demodulate() per buffer)
+//   ./simple_fm_b200 --deemph 75 --dc-block capture.bin            (optional rtl_fm-style post-stages, off by default;
+//                                                                    also --scale N and, with --sync, --squelch LEVEL)
 //
 // Default mode is the persistent ring (sdr_demod_ring_*): the mpsc channel of :55 IS the ring of pinned slots —
 // the reader acquires a slot, read_sync()s straight into it and commits it (one H2D copy + a 4-byte doorbell, no
@@ -26,6 +28,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -128,6 +131,8 @@ struct Stats {
     }
 };
 
+static sdr::AudioPost *POST = nullptr;   // optional post-stages (null: the reference's output, untouched)
+
 static void emit(const std::vector<int16_t> &audio) {
     fwrite(audio.data(), sizeof(int16_t), audio.size(), stdout);     // output(), :430-438 (s16le on x86)
     fflush(stdout);
@@ -146,6 +151,7 @@ static void process_sync(sdr::Demod &demod, Channel &rx) {
         }
         const auto t0 = Clock::now();                                // :152
         std::vector<int16_t> result = demod.demodulate(buf);         // :153
+        if (POST) POST->process(result, buf.data(), buf.size());
         const std::chrono::duration<double> dt = Clock::now() - t0;
         st.total_time += dt;
         st.lat_us.push_back(dt.count() * 1e6);
@@ -171,6 +177,7 @@ static void process_ring(sdr::Ring &ring, Channel &rx) {
             rx.sent_at.pop_front();
         }
         ring.collect(result);                                        // spins on the buffer's completion word
+        if (POST) POST->process(result);
         st.lat_us.push_back(std::chrono::duration<double>(Clock::now() - sent_at).count() * 1e6);
         collected++;
         st.loop_count++;
@@ -188,15 +195,22 @@ int main(int argc, char **argv) {
     int device = 0;
     uint32_t slots = 8;
     bool sync_mode = false;
+    sdr_post_config post_cfg{};
+    double deemph_us = 0;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--synth") && i + 1 < argc) synth_bufs = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--slots") && i + 1 < argc) slots = (uint32_t)atoi(argv[++i]);
         else if (!strcmp(argv[i], "--sync")) sync_mode = true;
+        else if (!strcmp(argv[i], "--deemph") && i + 1 < argc) deemph_us = atof(argv[++i]);
+        else if (!strcmp(argv[i], "--dc-block")) post_cfg.dc_block = 1;
+        else if (!strcmp(argv[i], "--scale") && i + 1 < argc) post_cfg.output_scale = (uint32_t)atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--squelch") && i + 1 < argc) post_cfg.squelch_level = (uint32_t)atoi(argv[++i]);
         else path = argv[i];
     }
     if (!path && !synth_bufs) {
-        fprintf(stderr, "usage: %s <capture.bin> | --synth <n_buffers>  [--sync] [--slots N] [--device N]\n", argv[0]);
+        fprintf(stderr, "usage: %s <capture.bin> | --synth <n_buffers>  [--sync] [--slots N] [--device N]\n"
+                        "       optional post-stages (off by default): [--deemph <us>] [--dc-block] [--scale N] [--squelch LEVEL (--sync only)]\n", argv[0]);
         return 2;
     }
     try {
@@ -208,6 +222,14 @@ int main(int argc, char **argv) {
         sdr::Demod demod(settings.second, device);                                  // :137
         fprintf(stderr, "Oversampling input by: %ux\nOutput at %u Hz\nOutput scale: %u\n", demod.config.downsample,
                 demod.config.rate_in, demod.config.output_scale);                  // :138-140
+        std::unique_ptr<sdr::AudioPost> post;
+        if (deemph_us > 0) post_cfg.deemph_a = sdr_post_deemph_a(settings.second.rate_resample, deemph_us);
+        if (post_cfg.deemph_a || post_cfg.dc_block || post_cfg.output_scale > 1 || post_cfg.squelch_level) {
+            post.reset(new sdr::AudioPost(post_cfg, device));
+            POST = post.get();
+            fprintf(stderr, "Post-stages: scale %u, squelch %u, de-emphasis a = %u, DC block %u\n", post_cfg.output_scale,
+                    post_cfg.squelch_level, post_cfg.deemph_a, post_cfg.dc_block);
+        }
         Channel ch;
         auto guarded = [&](auto &&fn) {
             try {

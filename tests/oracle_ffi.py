@@ -42,6 +42,11 @@ class DemodState(C.Structure):
     ]
 
 
+class Post(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("output_scale", "squelch_level", "deemph_a", "dc_block")] + \
+               [("deemph_avg", C.c_int32), ("dc_avg", C.c_int32)]
+
+
 class Fx(C.Structure):
     _fields_ = [
         ("n_taps", C.c_uint32), ("decim", C.c_uint32),
@@ -107,6 +112,8 @@ def lib() -> C.CDLL:
     L.orc_demodulate_many_mt.restype = C.c_long
     L.orc_demodulate_many_mt2.argtypes = [C.POINTER(DemodConfig), u8p, sz, sz, i16p, sz, C.c_int, C.c_int]
     L.orc_demodulate_many_mt2.restype = C.c_long
+    L.orc_post_init.argtypes = [C.POINTER(Post)] + [C.c_uint32] * 4
+    L.orc_post_process.argtypes = [C.POINTER(Post), i16p, sz, u8p, sz]
     L.orc_fx_init.argtypes = [C.POINTER(Fx), f32p, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
     L.orc_fx_init.restype = C.c_int
     L.orc_fx_free.argtypes = [C.POINTER(Fx)]
@@ -211,6 +218,21 @@ class Demod:
         s = self.st
         return dict(prev_index=int(s.prev_index), now_lpr=s.now_lpr, prev_lpr_index=s.prev_lpr_index,
                     lp_now=(s.lp_now_re, s.lp_now_im), demod_pre=(s.demod_pre_re, s.demod_pre_im))
+
+
+class AudioPost:
+    """Oracle of the optional post-stages (orc_post_*)."""
+
+    def __init__(self, output_scale=0, squelch_level=0, deemph_a=0, dc_block=False):
+        self.s = Post()
+        lib().orc_post_init(C.byref(self.s), output_scale, squelch_level, deemph_a, int(dc_block))
+
+    def process(self, audio: np.ndarray, raw: np.ndarray | None = None) -> np.ndarray:
+        a = np.ascontiguousarray(audio, np.int16).copy()
+        r = np.ascontiguousarray(raw, np.uint8) if raw is not None else None
+        lib().orc_post_process(C.byref(self.s), _p(a, C.c_int16), a.size, _p(r, C.c_uint8) if r is not None else None,
+                               r.size if r is not None else 0)
+        return a
 
 
 def buf_to_complex(i16: np.ndarray) -> np.ndarray:

@@ -421,3 +421,22 @@ def test_device_resident_batch_and_size_independent_properties(S):
     assert n == (n_bufs * (BUF // 2) // 6) * 32_000 // 170_000
     for b in (d_in, d_in2, d_out):
         b.free()
+
+
+def test_optional_post_stages_match_the_oracle_and_default_to_off(S, golden_dir):
+    """output_scale / squelch / de-emphasis / DC block after low_pass_real.  Off by default (the golden audio is
+    untouched); each combination bit-exact against the oracle's restatement, state carried across blocks."""
+    head = np.fromfile(golden_dir / "capture_head.bin", np.uint8)
+    want = np.fromfile(golden_dir / "capture_head_audio.s16le", "<i2")
+    d = S.Demod()
+    audio = [d.demodulate(head[c * BUF:(c + 1) * BUF]) for c in range(4)]
+    off = S.AudioPost()
+    assert np.array_equal(np.concatenate([off.process(a, head[c * BUF:(c + 1) * BUF]) for c, a in enumerate(audio)]), want)
+    a75 = S.AudioPost.deemph_a(32000, 75.0)
+    assert a75 == 3 and S.AudioPost.deemph_a(32000, 50.0) == 2
+    rng = np.random.default_rng(3)
+    for scale, level, a, dc in ((5, 0, 0, False), (0, 0, a75, False), (0, 0, 0, True), (2, 300, 3, True), (0, 4000, 0, False)):
+        g, o = S.AudioPost(scale, level, a, dc), O.AudioPost(scale, level, a, dc)
+        for c, blk in enumerate(audio + [rng.integers(-30000, 30000, 5000).astype(np.int16)]):
+            raw = head[c * BUF:(c + 1) * BUF] if c < 4 else np.full(4096, 127, np.uint8)
+            assert np.array_equal(g.process(blk, raw), o.process(blk, raw)), (scale, level, a, dc, c)

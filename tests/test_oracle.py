@@ -238,3 +238,40 @@ def test_synth_fill_is_offset_consistent():
     b = O.synth_fill(1000, 0xB2000001, byte_offset=1234)
     assert np.array_equal(a[1234:2234], b)
     assert 100 < a.mean() < 155 and len(np.unique(a)) > 200
+
+
+def test_post_stages_against_a_numpy_restatement():
+    """SURVEY §8f-4 stages (no reference implementation; rtl_fm's deemph_filter / dc_block_filter restated): the C oracle
+    against an independent numpy/python restatement, several blocks with carried state."""
+    rng = np.random.default_rng(84)
+    a75 = int(round(1.0 / (1.0 - np.exp(-1.0 / (32000 * 75e-6)))))
+    assert a75 == 3            # 32 kHz audio, 75 us
+    for scale, level, a, dc in ((0, 0, 0, False), (5, 0, 0, False), (0, 0, a75, False), (0, 0, 0, True), (3, 400, 7, True), (42, 0, 2, True)):
+        o = O.AudioPost(scale, level, a, dc)
+        avg = dc_avg = 0
+        for blk in range(5):
+            x = rng.integers(-20000, 20000, 4112 + blk).astype(np.int16)
+            raw = rng.integers(0, 256, 4096, dtype=np.uint8) if blk % 2 == 0 else np.full(4096, 128, np.uint8)   # loud / silent
+            want = x.astype(np.int64)
+            if level:
+                dev = 2 * raw.astype(np.int64) - 255
+                if int((dev * dev).sum()) * 64 < level * level * raw.size:
+                    want[:] = 0
+            if scale > 1:
+                want = np.clip(want * scale, -32768, 32767)
+            if a:
+                out = np.empty_like(want)
+                for i, v in enumerate(want.tolist()):
+                    d = v - avg
+                    q = (abs(d) + a // 2) // a if d != 0 else 0      # C: (d + a/2) / a for d > 0, (d - a/2) / a otherwise, truncating
+                    avg += q if d > 0 else -q
+                    out[i] = avg
+                want = out
+            if dc:
+                m = int(want.sum())
+                m = abs(m) // want.size * (1 if m >= 0 else -1)       # truncating division
+                t = m + dc_avg * 9
+                dc_avg = abs(t) // 10 * (1 if t >= 0 else -1)
+                want = ((want - dc_avg + 32768) % 65536) - 32768
+            got = o.process(x, raw)
+            assert np.array_equal(got, want.astype(np.int16)), (scale, level, a, dc, blk)

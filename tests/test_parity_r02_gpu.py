@@ -192,6 +192,20 @@ def test_streaming_shell_binary_on_full_capture(golden_dir):
     print("\n" + "\n".join(lat))
 
 
+def test_streaming_shell_post_stages(golden_dir):
+    """--deemph / --dc-block / --scale after low_pass_real: the shell's output equals the oracle's post-stages applied to the
+    golden audio block by block (blocks = the per-buffer audio counts 4112 / 4113 of the capture)."""
+    import oracle_ffi as O
+    head = np.fromfile(golden_dir / "capture_head.bin", np.uint8)
+    o, post = O.Demod(), O.AudioPost(2, 0, 3, True)
+    want = np.concatenate([post.process(o.demodulate(head[c * BUF:(c + 1) * BUF])) for c in range(4)])
+    for mode in ([], ["--sync"]):
+        rc, out, err = _shell([*mode, "--deemph", "75", "--dc-block", "--scale", "2", str(golden_dir / "capture_head.bin")])
+        assert rc == 0, err
+        assert np.array_equal(np.frombuffer(out, "<i2"), want), mode
+        assert "Post-stages" in err
+
+
 def test_streaming_shell_reports_errors_in_its_exit_status(tmp_path):
     rc, _, err = _shell([str(tmp_path / "does_not_exist.bin")])
     assert rc == 1 and "error" in err.lower()
