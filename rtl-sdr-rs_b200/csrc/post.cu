@@ -11,7 +11,7 @@
 //
 // De-emphasis is a nonlinear (integer-rounded) recurrence, so it runs as one sequential thread — at audio rate that is a
 // few thousand samples per 128 ms buffer (~60 us); the other stages are one small parallel kernel.  "Parity unpinned":
-// the oracle restates the same definitions (oracle/sdr_oracle.c orc_post_*), checked against numpy in tests/test_oracle.py.
+// the test suite checks them against an independent CPU restatement of the same definitions.
 #include <cmath>
 
 #include "common.cuh"
