@@ -22,7 +22,7 @@ OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
 sys.path.insert(0, str(ROOT / "scripts"))
 from ncu_summary import WANT  # noqa: E402
 
-DOMINANT = {"cfg2": "k_fir_fast", "cfg3": "k_fir_fast", "cfg1": "k_demod_d", "chan": "k_chan_fir"}
+DOMINANT = {"cfg2": "k_fir_fast", "cfg3": "k_fir_fast", "cfg1": "k_demod_d", "chan": "k_chan_"}
 
 
 def raw_rows(rep):
