@@ -162,6 +162,12 @@ class Ctx:
         self.rank, self.local_rank, self.world = dist_env()
         self.dist = None
         if self.world > 1:
+            # NCCL's broadcast kernel shares the SMs with the FMA-bound channeliser (multi_gpu leg): 16 CTAs move a 64 MiB
+            # slab at 320 GB/s (8 ranks) to 520 GB/s (2 ranks), about the channeliser's own pace, where the default 32 CTAs
+            # cost it more than they gain (ms per 2^28-sample step at N = 2: 32 CTAs 1.87, 16: 1.76, 8: 2.34; at N = 8
+            # exposed broadcast time 0.92 ms with 32 CTAs, 0.23 ms with 16).  NCCL reads the variable once per process, at its
+            # first initialisation — so it is set here, before torch creates its communicator.
+            os.environ.setdefault("NCCL_MAX_CTAS", "16")
             import torch
             import torch.distributed as dist
             torch.cuda.set_device(self.local_rank)
@@ -500,9 +506,6 @@ def measure_chan(cx: Ctx, w: dict, d_in, steps: int, warmup: int, shard: bool) -
     d_dem = S.DevBuffer(4 * C * cap, cx.device)
     comm = None
     if shard and world > 1:
-        # NCCL's broadcast kernel shares the SMs with the FMA-bound channeliser: 16 CTAs move a 64 MiB slab at ~520 GB/s,
-        # enough to stay under the channeliser (measured at N = 2, ms per step: 32 CTAs (default) 1.87, 16: 1.76, 8: 2.34)
-        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         uid = [S.Comm.unique_id() if cx.rank == 0 else None]
         cx.dist.broadcast_object_list(uid, src=0)
         comm = S.Comm(cx.device, cx.rank, world, uid[0])
@@ -788,7 +791,7 @@ def main():
         if cx.world > 1:
             # north_star's multi-GPU design: the channel shard with the NCCL slab broadcast.  Ranks other than 0 hold
             # whatever their time slice left in d_in; every slab is overwritten by the broadcast before it is read.
-            multi = measure_chan(cx, wc, d_in, max(3, x_steps // 2), 3, shard=True)
+            multi = measure_chan(cx, wc, d_in, 10, 5, shard=True)
             multi["single_gpu_ms_per_step"] = mc["ms_per_step"]
             multi["efficiency_vs_one_gpu_same_run"] = round(mc["ms_per_step"] / multi["ms_per_step"], 4)
 
