@@ -148,10 +148,6 @@ class Ring:
     """Persistent-kernel ring over a Demod (sdr_demod_ring_*): buffers stream through one resident kernel."""
 
     def __init__(self, demod: Demod, buf_len: int, n_slots: int = 8):
-        # While the ring kernel is resident, anything that device-synchronises (cudaFree of a handle that the
-        # garbage collector finalises, an allocation) would wait for it forever: finalise garbage first.
-        import gc
-        gc.collect()
         self.demod, self.buf_len = demod, buf_len
         h = C.c_void_p()
         F.check(F.lib().sdr_demod_ring_open(demod._h, buf_len, n_slots, C.byref(h)))
