@@ -200,6 +200,79 @@ __global__ void __launch_bounds__(kFirThreads) k_fir_real_r8(const float *dbuf, 
     }
 }
 
+// L = M = 1, packed form.  Two consecutive outputs share every sample with taps one apart:
+//   out[n] += g[j] * x[n-j],   out[n+1] += g[j+1] * x[n-j]
+// so ONE packed FFMA2 does both with the sample as the scalar-broadcast operand and the tap PAIR (g[j], g[j+1]) as the
+// vector operand — no register-pair alignment problem (the reason a window-pair formulation needs the window twice).
+// The overlapping tap pairs P[k] = (G[k], G[k+1]), G[0] = 0, G[k] = g[k-1], are a kernel parameter (uniform loads).  Per
+// 16 outputs x 16 taps: 128 FFMA2 + 8 LDS.128 + 16 uniform loads instead of 256 FFMA + 12 LDS.  Each output is still the
+// ascending-tap fma chain of k_fir_real_r8 / k_resample_poly / the ring's audio tiles (the extra first and last products
+// have a zero tap), so all of them agree bit for bit.
+constexpr int kFirPMaxJ = 2048;
+struct TapsP {
+    float2 p[kFirPMaxJ];
+};
+__global__ void __launch_bounds__(kFirThreads) k_fir_real_p2(const float *dbuf, int h2, int Jp, long long n_out, long long n_valid,
+                                                             float *out, const __grid_constant__ TapsP taps) {
+    extern __shared__ __align__(16) float fsm[];
+    float4 *win4 = reinterpret_cast<float4 *>(fsm);   // window only (same padded chunk layout as k_fir_real_r8)
+    float *win = fsm;
+    const long long o0 = (long long)blockIdx.x * kFirOblk;
+    const long long gbase = (long long)h2 + o0 - Jp;
+    const int n_chunks = (kFirOblk + Jp) / 4;
+    if ((gbase & 3) == 0 && gbase >= 0 && gbase + kFirOblk + Jp <= n_valid) {
+        const float4 *src = reinterpret_cast<const float4 *>(dbuf + gbase);
+        for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) win4[c + (c >> 3)] = src[c];
+    } else {
+        for (int idx = threadIdx.x; idx < kFirOblk + Jp; idx += blockDim.x) {
+            long long gi = gbase + idx;
+            win[idx + (idx >> 5) * 4] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
+        }
+    }
+    __syncthreads();
+    unsigned long long acc[kFirR / 2];
+#pragma unroll
+    for (int q = 0; q < kFirR / 2; q++) acc[q] = 0ull;
+    const int t0 = threadIdx.x * kFirR;
+    for (int k0 = 0; k0 < Jp; k0 += kFirTC) {
+        // pair q (outputs t0 + 2q, + 1), tap pair k = k0 + kk: sample win[Jp + t0 + 2q + 1 - k] = w[17 + 2q - kk]
+        float w[kFirR + kFirTC];
+        const int c0 = (Jp + t0 - k0 - kFirTC) >> 2;
+#pragma unroll
+        for (int c = 0; c < (kFirR + kFirTC) / 4; c++) {
+            float4 v = win4[(c0 + c) + ((c0 + c) >> 3)];
+            w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int kk = 0; kk < kFirTC; kk++) {
+            const float2 pk = taps.p[k0 + kk];
+            const unsigned long long pp = pack_f32x2(pk.x, pk.y);
+#pragma unroll
+            for (int q = 0; q < kFirR / 2; q++) {
+                const float sm = w[kFirTC + 1 + 2 * q - kk];
+                const unsigned long long ss = pack_f32x2(sm, sm);
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[q]) : "l"(ss), "l"(pp));
+            }
+        }
+    }
+    float a[kFirR];
+#pragma unroll
+    for (int q = 0; q < kFirR / 2; q++) {
+        const float2 v = unpack_f32x2(acc[q]);
+        a[2 * q] = v.x, a[2 * q + 1] = v.y;
+    }
+    float *dst = out + o0 + t0;
+    if (o0 + t0 + kFirR <= n_out && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int c = 0; c < kFirR / 4; c++)
+            reinterpret_cast<float4 *>(dst)[c] = make_float4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < kFirR; r++)
+            if (o0 + t0 + r < n_out) dst[r] = a[r];
+    }
+}
+
 // Generic rational L/M: one output per thread, polyphase taps in shared memory (row stride Js = J|1 so the
 // L phases of a warp hit different banks), the d window of a 256-output tile staged once, 32-bit index
 // math relative to a per-tile 64-bit base computed by one thread.
@@ -258,7 +331,7 @@ __global__ void __launch_bounds__(256) k_resample_poly(const float *dbuf, int h2
 }
 
 static const KernelList kFxKernels{(const void *)k_fir_generic, (const void *)k_update_carry, (const void *)k_hist_move,
-                                   (const void *)k_fm_demod_f32, (const void *)k_store_prev, (const void *)k_fir_real_r8,
+                                   (const void *)k_fm_demod_f32, (const void *)k_store_prev, (const void *)k_fir_real_r8, (const void *)k_fir_real_p2,
                                    (const void *)k_resample_poly};
 
 }  // namespace sdr
@@ -479,6 +552,8 @@ struct sdr_fmrx {
     bool aud_used[3] = {false, false, false};
     H2DStager stager;        // pageable caller buffers go through pinned pieces (common.cuh)
     struct sdr_fmrx_ring *ring = nullptr;   // a persistent ring owns the handle until sdr_fmrx_ring_close()
+    TapsP *taps_p = nullptr;   // L = M = 1: overlapping tap pairs of k_fir_real_p2 (null: k_fir_real_r8)
+    int Jpp = 0;               // taps of that kernel: J + 1 rounded up to 16
     static constexpr int kRing = 64;   // per-call kernel timings are harvested lazily from this ring
     cudaEvent_t ev_h2d[2]{}, ev_done[2]{}, ev_ring[kRing][4]{}, ev_s[2]{};
     cudaEvent_t *ev_t = ev_ring[0];
@@ -637,8 +712,12 @@ int launch_resample(sdr_fmrx *r, const float *dbuf, uint64_t P0, uint64_t n_new,
         uint64_t blocks = ceil_div(n_a, (uint64_t)kFirOblk);
         if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
         size_t sm = fir_real_smem(r->Jp);
-        k_fir_real_r8<<<(int)blocks, kFirThreads, sm, st>>>(dbuf, r->h2, r->d_taps2.as<float>(), r->Jp, (long long)n_a,
-                                                            (long long)(r->h2 + n_new), d_audio);
+        if (r->taps_p)
+            k_fir_real_p2<<<(int)blocks, kFirThreads, fir_real_smem(r->Jpp), st>>>(dbuf, r->h2, r->Jpp, (long long)n_a,
+                                                                                  (long long)(r->h2 + n_new), d_audio, *r->taps_p);
+        else
+            k_fir_real_r8<<<(int)blocks, kFirThreads, sm, st>>>(dbuf, r->h2, r->d_taps2.as<float>(), r->Jp, (long long)n_a,
+                                                                (long long)(r->h2 + n_new), d_audio);
         SDR_LAUNCH_CHECK();
         r->last_launches++;
     } else if (n_a) {
@@ -858,6 +937,18 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         size_t sm = fir_real_smem(r->Jp);
         if (e == cudaSuccess && sm > 48 * 1024)
             e = raise_dyn_smem(k_fir_real_r8, sm);
+        // packed audio FIR (L = M = 1): tap pairs P[k] = (G[k], G[k+1]), G[0] = 0, G[k] = g[k-1]
+        const char *ep = getenv("SDR_FIR_AUDIO_P2");
+        if (cfg->up == 1 && cfg->down == 1 && !(ep && atoi(ep) == 0)) {
+            const int Jpp = (int)((cfg->n_taps2 + 1 + 15) & ~15u);
+            if (Jpp <= kFirPMaxJ && Jpp <= r->h2) {
+                r->taps_p = new TapsP();
+                r->Jpp = Jpp;
+                auto G = [&](int k) { return (k >= 1 && k <= (int)cfg->n_taps2) ? taps2[k - 1] : 0.f; };
+                for (int k = 0; k < kFirPMaxJ; k++) r->taps_p->p[k] = k < Jpp ? make_float2(G(k), G(k + 1)) : make_float2(0.f, 0.f);
+                if (e == cudaSuccess && fir_real_smem(Jpp) > 48 * 1024) e = raise_dyn_smem(k_fir_real_p2, fir_real_smem(Jpp));
+            }
+        }
     }
     if (e != cudaSuccess) {
         sdr_fmrx_free(r);
@@ -886,6 +977,7 @@ void sdr_fmrx_free(sdr_fmrx *r) {
     if (r->ev_join) cudaEventDestroy(r->ev_join);
     if (r->audio_stream) cudaStreamDestroy(r->audio_stream);
     r->stager.release();
+    delete r->taps_p;
     for (int i = 0; i < 2; i++) {
         r->d_carry[i].release();
         r->d_x[i].release();
