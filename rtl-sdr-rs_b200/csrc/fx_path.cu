@@ -550,6 +550,7 @@ struct sdr_fmrx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, audio_stream = nullptr;
     cudaEvent_t ev_fir[3]{}, ev_aud[3]{}, ev_join = nullptr;
     bool aud_used[3] = {false, false, false};
+    bool audio_serial = false;
     H2DStager stager;        // pageable caller buffers go through pinned pieces (common.cuh)
     struct sdr_fmrx_ring *ring = nullptr;   // a persistent ring owns the handle until sdr_fmrx_ring_close()
     TapsP *taps_p = nullptr;   // L = M = 1: overlapping tap pairs of k_fir_real_p2 (null: k_fir_real_r8)
@@ -792,7 +793,8 @@ int run_chunk(sdr_fmrx *r, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d
     float *d_target = has_res ? dnew : (d_audio ? d_audio : dnew);
     // this call writes the body of `cur` and the head of `nxt`; the last reader of either is the audio kernel of the
     // call two back (buffer index nxt), which runs on the other stream
-    if (has_res && r->aud_used[nxt]) SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_aud[nxt], 0));
+    cudaStream_t ast = r->audio_serial ? r->stream : r->audio_stream;
+    if (has_res && r->aud_used[nxt] && !r->audio_serial) SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_aud[nxt], 0));
     if (timed) {
         next_timing_slot(r);
         SDR_CUDA_TRY(cudaEventRecord(r->ev_t[0], r->stream));
@@ -802,13 +804,17 @@ int run_chunk(sdr_fmrx *r, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d
     if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[1], r->stream));
     if (has_res) {
         if (!fold_hist && (rc = launch_hist_move(r, cur, nxt, pl.n_y))) return rc;
-        SDR_CUDA_TRY(cudaEventRecord(r->ev_fir[cur], r->stream));
-        SDR_CUDA_TRY(cudaStreamWaitEvent(r->audio_stream, r->ev_fir[cur], 0));
-        if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], r->audio_stream));
-        if ((rc = launch_resample(r, r->d_dbuf[cur].as<float>(), r->n_y, pl.n_y, pl.a0, pl.n_a, d_audio, r->audio_stream))) return rc;
-        if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[3], r->audio_stream));
-        SDR_CUDA_TRY(cudaEventRecord(r->ev_aud[cur], r->audio_stream));
-        r->aud_used[cur] = true;
+        if (!r->audio_serial) {
+            SDR_CUDA_TRY(cudaEventRecord(r->ev_fir[cur], r->stream));
+            SDR_CUDA_TRY(cudaStreamWaitEvent(ast, r->ev_fir[cur], 0));
+        }
+        if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], ast));
+        if ((rc = launch_resample(r, r->d_dbuf[cur].as<float>(), r->n_y, pl.n_y, pl.a0, pl.n_a, d_audio, ast))) return rc;
+        if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[3], ast));
+        if (!r->audio_serial) {
+            SDR_CUDA_TRY(cudaEventRecord(r->ev_aud[cur], ast));
+            r->aud_used[cur] = true;
+        }
         r->dcur = nxt;
     } else if (timed) {
         SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], r->stream));
@@ -896,7 +902,11 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         // placed as soon as FIR CTAs retire
         int lo = 0, hi = 0;
         e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&r->audio_stream, cudaStreamNonBlocking, hi);
+        // SDR_FMRX_AUDIO_STREAM: "serial" = the audio kernel follows the FIR kernel on the main stream, "low" = own stream
+        // at the lowest priority, default = own stream at the highest priority (A/B runs)
+        const char *ea = getenv("SDR_FMRX_AUDIO_STREAM");
+        r->audio_serial = ea && !strcmp(ea, "serial");
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&r->audio_stream, cudaStreamNonBlocking, (ea && !strcmp(ea, "low")) ? lo : hi);
     }
     for (int i = 0; i < 3 && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&r->ev_fir[i], cudaEventDisableTiming);
@@ -1054,7 +1064,7 @@ long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y
             SDR_CUDA_TRY(cudaMemcpyAsync(demod + y_off, d_dem, pl.n_y * 4, cudaMemcpyDeviceToHost, r->stream));
         if (pl.n_a)   // behind the kernel that produced it: the audio stream when there is a resample stage
             SDR_CUDA_TRY(cudaMemcpyAsync(audio + a_off, r->d_audio[slot].p, pl.n_a * 4, cudaMemcpyDeviceToHost,
-                                         r->cfg.n_taps2 ? r->audio_stream : r->stream));
+                                         (r->cfg.n_taps2 && !r->audio_serial) ? r->audio_stream : r->stream));
         SDR_CUDA_TRY(cudaEventRecord(r->ev_done[slot], r->stream));
         done += n;
         y_off += pl.n_y;

@@ -200,3 +200,38 @@ def test_bank_device_resident_slab(S):
     assert np.array_equal(np.concatenate([first, second], axis=1), host)
     ms, launches = ch.last_timing()
     assert launches == 2 and ms > 0          # one bank launch + the carry update
+
+
+@pytest.mark.parametrize("plan", ["cfg4", "cfg5-interleaved", "non-uniform"])
+def test_channeliser_against_a_numpy_expectation_computed_here(S, plan):
+    """Not through oracle/: the direct definition restated with numpy/scipy in f64 — mix by the 32-bit-phase NCO, FIR, decimate,
+    discriminate — for a handful of channels of each plan (bank kernel for the two uniform plans, direct form for the third)."""
+    from scipy.signal import lfilter
+    from sigutil import rel_err
+    fs, C, T, D = 20e6, 64, 255, 100
+    taps = channel_taps(T, D)
+    if plan == "cfg4":
+        fw = freq_words((np.arange(C) - 31.5) * 200e3, fs)
+    elif plan == "cfg5-interleaved":
+        fw = freq_words(((5 + 8 * np.arange(C)) - 255.5) * (fs / 512), fs)
+    else:
+        fw = freq_words(np.sort(np.random.default_rng(9).uniform(-9e6, 9e6, C)), fs)
+    n = D * 500 + 11
+    iq = fm_test_signal(n, fs=fs, f_c=1.3e6, f_dev=60e3)
+    ch = S.Channeliser(taps, D, fw)
+    assert ch.kernel_kind()[0] == (1 if plan == "non-uniform" else 2)
+    y, d = ch.process(iq)
+    x = (iq[0::2].astype(np.float64) - 127.0) + 1j * (iq[1::2].astype(np.float64) - 127.0)
+    nn = np.arange(n, dtype=np.uint64)
+    worst = 0.0
+    for c in (0, 1, 17, 40, 63):
+        theta = 2.0 * np.pi * ((np.uint64(fw[c]) * nn) % np.uint64(1 << 32)).astype(np.float64) / 2.0 ** 32
+        yc = lfilter(taps.astype(np.float64), [1.0], x * np.exp(-1j * theta))[D - 1::D]
+        want = np.stack([yc.real, yc.imag], axis=1)
+        assert_close(y[c], want, what=f"{plan} ch{c} vs numpy")
+        worst = max(worst, rel_err(y[c], want))
+        z = yc * np.conj(np.concatenate([[0.0], yc[:-1]]))
+        dc = GAIN * np.arctan2(z.imag, z.real)
+        dc[z == 0] = 0.0
+        assert_demod_propagated(d[c], want, dc, GAIN, what=f"{plan} demod ch{c} vs numpy")
+    assert worst <= 1e-5, worst
