@@ -486,7 +486,7 @@ struct sdr_chan {
     bool use_bank = false;
     int bank_K = 0, bank_K1 = 0, bank_K2 = 0;
     std::vector<BankTab> bank_tabs;
-    size_t smem_bank = 0;
+    size_t smem_bank = 0, smem_bank_tile = 0;
     H2DStager stager;                          // pageable caller buffers go through pinned pieces (common.cuh)
     DevBuf d_prev2;                            // bank path: the carried S[m-1] ping-pongs between d_prev and d_prev2
     int prev_cur = 0;
@@ -568,6 +568,7 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
             b.NJ = ((int)c->cfg.n_taps + b.K1 - 1) / b.K1;
             b.Tp = b.K1 * b.NJ;
             b.eoff = (b.Tp * c->bank_K2 + 1) & ~1;
+            b.esm_off = (int)c->smem_bank_tile;
             b.gain = c->gain;
             const uint64_t tiles = (n_out + (kBankThreads - 1) - 1) / (kBankThreads - 1);
             if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
@@ -778,7 +779,8 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
             // the halo lane of the first tile reaches back D + r + Tp - 1 samples before the call (r < D, Tp < T + K1)
             const size_t Tp = (size_t)bp.K1 * ((cfg->n_taps + bp.K1 - 1) / bp.K1);
             c->cs = (int)((Tp + 2 * (size_t)D + 16 + 7) & ~size_t(7));
-            c->smem_bank = (((size_t)kBankThreads * D + Tp + 16) * 2 + 15 + 32) & ~size_t(15);
+            c->smem_bank_tile = (((size_t)kBankThreads * D + Tp + 16) * 2 + 15 + 32) & ~size_t(15);
+            c->smem_bank = c->smem_bank_tile + (SDR_BANK_E_SMEM ? (size_t)bp.K1 * kBankCH * 8 : 0);
             if (c->smem_bank > 200 * 1024) c->use_bank = false;
         }
     }

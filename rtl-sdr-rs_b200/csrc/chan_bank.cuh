@@ -35,6 +35,9 @@ namespace sdr {
 #ifndef SDR_BANK_UNROLL
 #define SDR_BANK_UNROLL 4
 #endif
+#ifndef SDR_BANK_E_SMEM
+#define SDR_BANK_E_SMEM 0   // 1: stage-2 coefficients from shared memory (broadcast LDS.128) instead of uniform loads (A/B)
+#endif
 constexpr int kBankUnroll = SDR_BANK_UNROLL;
 constexpr int kBankThreads = SDR_BANK_NT;   // lanes per CTA (one output time each; lane 0 is the predecessor halo)
 constexpr int kBankCH = 64;            // channels per launch (packed accumulators held in registers)
@@ -60,6 +63,7 @@ struct BankArgs {
     uint32_t r, n0_lo;
     int ch0, n_ch, Tp, D, K1, NJ;   // Tp = K1 * NJ: taps after zero padding
     int eoff;                       // first E entry (host-computed: keeps the index arithmetic on the uniform datapath)
+    int esm_off;                    // SDR_BANK_E_SMEM builds: byte offset of the E copy in dynamic shared memory
     float gain;
 };
 
@@ -154,6 +158,12 @@ __global__ void __launch_bounds__(kBankThreads, SDR_BANK_MINB) k_chan_bank(const
 
     const int K1 = K1T ? K1T : a.K1, NJ = NJT ? NJT : a.NJ;
     const int eoff = a.eoff;
+#if SDR_BANK_E_SMEM
+    // E[r1][c] behind the raw tile (a.esm_off bytes into the dynamic shared memory, 16-byte aligned)
+    float2 *esm = reinterpret_cast<float2 *>(smem + a.esm_off);
+    for (int i = tid; i < K1 * CH; i += NT) esm[i] = tab.v[eoff + i];
+    __syncthreads();
+#endif
     int gidx = 0, eidx = eoff;
 #pragma unroll 1
     for (int r1 = 0; r1 < K1; r1++) {
@@ -198,8 +208,13 @@ __global__ void __launch_bounds__(kBankThreads, SDR_BANK_MINB) k_chan_bank(const
 #pragma unroll
         for (int c0 = 0; c0 < CH; c0 += 8) {
             float4 e4[4];
+#if SDR_BANK_E_SMEM
+#pragma unroll
+            for (int q = 0; q < 4; q++) e4[q] = *reinterpret_cast<const float4 *>(&esm[(eidx - eoff) + c0 + 2 * q]);
+#else
 #pragma unroll
             for (int q = 0; q < 4; q++) e4[q] = *reinterpret_cast<const float4 *>(&tab.v[eidx + c0 + 2 * q]);
+#endif
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 bk_fma2(Y[c0 + 2 * q], e4[q].x, a2[(c0 + 2 * q) % K2]);

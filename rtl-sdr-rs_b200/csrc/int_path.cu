@@ -478,6 +478,10 @@ __device__ __forceinline__ void dn_pass_odd(const unsigned char *tile, const int
 // of the even-offset and the odd-offset words are kept apart (always with the phase-0 coefficients; the phase-2 ones are
 // their negation) and combined with the lane's sign afterwards.  E as in the direct form.
 constexpr bool has_staged_odd_pass(int DT) { return (DT & 1) && DT >= 15 && DT <= kMaxFusedDT; }
+// ... and the even downsamples with an odd number of words per window (14, 18, 22, 26, 30): in the direct form their rows
+// are four windows (28-60 words); staged, a lane owns ONE window = DT/2 words at an odd (conflict-free) lane stride.
+constexpr bool has_staged_even_pass(int DT) { return DT % 4 == 2 && DT >= 14 && DT <= kMaxFusedDT; }
+constexpr bool has_staged_pass(int DT) { return has_staged_odd_pass(DT) || has_staged_even_pass(DT); }
 
 template <int DT, int E, int NTH>
 __device__ __forceinline__ void dn_pass_odd_staged(const unsigned char *tile, const int32_t byte0, const uint32_t npairs,
@@ -546,6 +550,43 @@ __device__ __forceinline__ void dn_pass_odd_staged(const unsigned char *tile, co
             const int32_t wi = wfirst + j;
             if (g < npairs && wi >= 0 && wi <= last_w) dm[wi] = (int16_t)(uint16_t)(uint32_t)o;
         }
+    }
+}
+
+// Even downsample with DT/2 odd, even window start: one window (DT/2 whole words) per lane, same sign-split sums.
+template <int DT, int NTH>
+__device__ __forceinline__ void dn_pass_even_staged(const unsigned char *tile, const int32_t byte0, const uint32_t nwin, int16_t *dm) {
+    constexpr int HW = DT / 2;
+    constexpr uint32_t CRE0 = 0xFF000001u, CIM0 = 0x00010100u;
+    static_assert(HW & 1, "an odd number of words per window (conflict-free lane stride)");
+    const int lane = threadIdx.x & 31;
+    auto window = [&](const uint32_t *w, const uint32_t fpar, int32_t &re, int32_t &im) {
+        int32_t r[2] = {0, 0}, i[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < HW; k++) {
+            const uint32_t v = w[k];
+            r[k & 1] = dp4a_us(v, CRE0, r[k & 1]);
+            i[k & 1] = dp4a_us(v, CIM0, i[k & 1]);
+        }
+        const int32_t dr = r[0] - r[1], di = i[0] - i[1];
+        re = (fpar ? -dr : dr) + (fpar ? BoxK<DT>::re(2) : BoxK<DT>::re(0));
+        im = (fpar ? -di : di) + (fpar ? BoxK<DT>::im(2) : BoxK<DT>::im(0));
+    };
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(tile + byte0);   // byte0: first byte of window 0, a multiple of 4
+    const uint32_t basepar = (uint32_t)(byte0 >> 2) & 1u;
+    for (uint32_t gb = threadIdx.x & ~31u; gb < nwin; gb += NTH) {
+        const uint32_t g = gb + lane;
+        const uint32_t gc = g < nwin ? g : nwin - 1;
+        const uint32_t *w = w0 + (size_t)HW * gc;
+        const uint32_t fpar = (basepar + gc) & 1u;   // HW is odd: the parity of the window's first word alternates
+        int32_t re, im;
+        window(w, fpar, re, im);
+        int32_t pre = __shfl_up_sync(0xffffffffu, re, 1), pim = __shfl_up_sync(0xffffffffu, im, 1);
+        if (lane == 0 && g > 0) window(w - HW, fpar ^ 1u, pre, pim);   // the window before this warp's first
+        int32_t cre, cim;
+        d_cmul_conj(make_int2(re, im), make_int2(pre, pim), cre, cim);
+        const int32_t o = d_fast_atan2_t<true>(cim, cre);
+        if (g < nwin) dm[g] = (int16_t)(uint16_t)(uint32_t)o;
     }
 }
 
@@ -656,6 +697,10 @@ __device__ __forceinline__ void dn_pass(const unsigned char *tile, const TileInf
         default: dn_pass_odd<DT, 1, 1, NTH>(tile, a0, ngroups, last_w, dm); break;
         }
         return;
+    } else if constexpr (!GLOBAL && has_staged_even_pass(DT)) {
+        // even window starts only (the host sends an odd one to the generic kernel)
+        dn_pass_even_staged<DT, NTH>(tile, 2 * off0, nlp, dm);
+        return;
     } else {
         // even downsample: the host launches this form for even window starts only (an odd one needs an odd prev_index
         // set by hand, sdr_demod_set_state, and takes the generic three-phase kernel)
@@ -745,7 +790,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
 
     // D = 6: the aligned-chunk pass may read the 16 bytes before the tile; staged odd pass: the pair that holds window 0 may
     // start up to 2*DT bytes before it (that half is computed from whatever is there and never stored)
-    unsigned char *tile_s = smem + (DT == 6 ? 16 : has_staged_odd_pass(DT) ? 128 : 0);
+    unsigned char *tile_s = smem + (DT == 6 ? 16 : has_staged_pass(DT) ? 128 : 0);
     int2 *lp = reinterpret_cast<int2 *>(smem + a.tile_cap);
     int16_t *dm = reinterpret_cast<int16_t *>(smem + (DIRECT ? 0 : a.dm_off));
     uint8_t *flag = smem + a.tile_cap + (((size_t)a.lp_cap * 10 + 15) & ~size_t(15));   // 16-byte aligned
@@ -783,7 +828,7 @@ __device__ __forceinline__ void demod_tile(const FusedArgs &a, const uint32_t ti
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tile);
 
     int2 lastlp = make_int2(st.demod_pre_re, st.demod_pre_im);   // lp[nlp-1] for the carried state (last tile)
-    if constexpr (DT == 6 || DIRECT || has_staged_odd_pass(DT)) {
+    if constexpr (DT == 6 || DIRECT || has_staged_pass(DT)) {
         // ---- D = 6 (optimal_settings :189-190): boxcar + discriminator fused, no window array ---------------
         if (!DIRECT) mbar_wait(&bar, parity);
         dn_pass<DT, NTH, DIRECT>(tile, ti, dm, tid);
@@ -872,7 +917,7 @@ __global__ void __launch_bounds__(256, SDR_INT_MINB) k_demod_fused(const FusedAr
 }
 // staged kernel of the odd downsamples from 15 up (dn_pass_odd_staged): a lane holds DT words
 template <int DT>
-__global__ void __launch_bounds__(256, DT <= 21 ? 4 : 3) k_demod_staged_odd(const FusedArgs a) {
+__global__ void __launch_bounds__(256, DT <= 21 || !(DT & 1) ? 4 : 3) k_demod_staged_odd(const FusedArgs a) {
     demod_tile<DT>(a, blockIdx.x, gridDim.x, 0, true);
 }
 // CTAs per SM the register allocation aims for: 8 (32 registers) while a lane's row is at most 16 words, fewer for
@@ -1118,7 +1163,8 @@ static const KernelList kIntKernels{
     SDR_K(k_demod_fused<0>), SDR_K(k_demod_fused<6>), SDR_K(k_demod_ring<0>), SDR_K(k_demod_ring<6>),
     SDR_K(k_demod_staged_odd<15>), SDR_K(k_demod_staged_odd<17>), SDR_K(k_demod_staged_odd<19>), SDR_K(k_demod_staged_odd<21>),
     SDR_K(k_demod_staged_odd<23>), SDR_K(k_demod_staged_odd<25>), SDR_K(k_demod_staged_odd<27>), SDR_K(k_demod_staged_odd<29>),
-    SDR_K(k_demod_staged_odd<31>),
+    SDR_K(k_demod_staged_odd<31>), SDR_K(k_demod_staged_odd<14>), SDR_K(k_demod_staged_odd<18>), SDR_K(k_demod_staged_odd<22>),
+    SDR_K(k_demod_staged_odd<26>), SDR_K(k_demod_staged_odd<30>),
     SDR_K(k_demod_direct<2>), SDR_K(k_demod_direct<3>), SDR_K(k_demod_direct<4>), SDR_K(k_demod_direct<5>),
     SDR_K(k_demod_direct<6>), SDR_K(k_demod_direct<7>), SDR_K(k_demod_direct<8>), SDR_K(k_demod_direct<9>),
     SDR_K(k_demod_direct<10>), SDR_K(k_demod_direct<11>), SDR_K(k_demod_direct<12>), SDR_K(k_demod_direct<13>),
@@ -1330,7 +1376,8 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
     // D = 6 with an even window start (every stream that was not given an odd prev_index by hand): direct kernel, with
     // the largest tile that still leaves `kDirectWaves` full waves of 8 CTAs per SM (SDR_INT_DIRECT_PASSES pins it)
     const bool odd_start_d6 = d->cfg.downsample == 6 && (p0 & 1);   // prev_index set by hand: generic kernel
-    const Geom *g = odd_start_d6 ? &d->geo_gen : d->staged_odd ? &d->geo_odd : &d->geo;
+    const bool staged = d->staged_odd && ((d->cfg.downsample & 1) || !(p0 & 1));   // even D: even window starts only
+    const Geom *g = odd_start_d6 ? &d->geo_gen : staged ? &d->geo_odd : &d->geo;
     const bool direct = d->n_direct > 0 && ((d->cfg.downsample & 1) || !(p0 & 1));   // odd downsamples take any window start
     if (direct) {
         constexpr uint64_t kDirectWaves = 4;
@@ -1363,12 +1410,12 @@ int launch_fused(sdr_demod *d, const uint8_t *d_in, uint64_t S, uint64_t n_calls
             default: k_demod_direct<32><<<(unsigned)blocks, kDirectNth, g->smem_direct, d->stream>>>(a); break;
         }
 #undef SDR_DIRECT_CASE
-    } else if (d->staged_odd) {
+    } else if (staged) {
 #define SDR_ODD_CASE(DT_) \
     case DT_: k_demod_staged_odd<DT_><<<(unsigned)blocks, 256, d->smem_bytes, d->stream>>>(a); break;
         switch (d->cfg.downsample) {
             SDR_ODD_CASE(15) SDR_ODD_CASE(17) SDR_ODD_CASE(19) SDR_ODD_CASE(21) SDR_ODD_CASE(23) SDR_ODD_CASE(25) SDR_ODD_CASE(27)
-            SDR_ODD_CASE(29) SDR_ODD_CASE(31)
+            SDR_ODD_CASE(29) SDR_ODD_CASE(31) SDR_ODD_CASE(14) SDR_ODD_CASE(18) SDR_ODD_CASE(22) SDR_ODD_CASE(26) SDR_ODD_CASE(30)
         }
 #undef SDR_ODD_CASE
     } else if (d->cfg.downsample == 6 && !(p0 & 1))
@@ -1502,9 +1549,9 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
     }
     {
         const char *eo = getenv("SDR_INT_STAGED_ODD");
-        if (has_staged_odd_pass((int)D) && !(eo && atoi(eo) == 0)) {
+        if (has_staged_pass((int)D) && !(eo && atoi(eo) == 0)) {
             const char *ep = getenv("SDR_INT_ODD_PASSES");
-            int op = ep ? atoi(ep) : 3;   // 512 windows (one pair per lane) per pass; measured D = 15 / 21 / 31: 3.2 / 4.1 / 4.4 TB/s
+            int op = ep ? atoi(ep) : ((D & 1) ? 3 : 6);   // odd: 512 windows per pass (one pair per lane); even: 256 (one window)   // 512 windows (one pair per lane) per pass; measured D = 15 / 21 / 31: 3.2 / 4.1 / 4.4 TB/s
                                           // with 1 pass, 5.1 / 5.4 / 5.3 with 3, 5.0 / 4.7 / 3.6 with 4
             if (op < 1 || op > 8) op = 1;
             d->staged_odd = make_geom(D, fast, slow, 512ull * op - 2, d->geo_odd, true);
@@ -1534,7 +1581,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
 #define SDR_ODD_CASE(DT_) case DT_: e = raise_dyn_smem(k_demod_staged_odd<DT_>, smem); break;
         switch (D) {
             SDR_ODD_CASE(15) SDR_ODD_CASE(17) SDR_ODD_CASE(19) SDR_ODD_CASE(21) SDR_ODD_CASE(23) SDR_ODD_CASE(25) SDR_ODD_CASE(27)
-            SDR_ODD_CASE(29) SDR_ODD_CASE(31)
+            SDR_ODD_CASE(29) SDR_ODD_CASE(31) SDR_ODD_CASE(14) SDR_ODD_CASE(18) SDR_ODD_CASE(22) SDR_ODD_CASE(26) SDR_ODD_CASE(30)
         }
 #undef SDR_ODD_CASE
     }
