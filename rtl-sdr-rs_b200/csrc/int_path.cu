@@ -1551,7 +1551,7 @@ int sdr_demod_new(const sdr_demod_config *cfg, int cuda_device, sdr_demod **out)
         const char *eo = getenv("SDR_INT_STAGED_ODD");
         if (has_staged_pass((int)D) && !(eo && atoi(eo) == 0)) {
             const char *ep = getenv("SDR_INT_ODD_PASSES");
-            int op = ep ? atoi(ep) : ((D & 1) ? 3 : 6);   // odd: 512 windows per pass (one pair per lane); even: 256 (one window)   // 512 windows (one pair per lane) per pass; measured D = 15 / 21 / 31: 3.2 / 4.1 / 4.4 TB/s
+            int op = ep ? atoi(ep) : 3;   // odd: 512 windows per pass (one pair per lane); even: 256 (one window per lane)   // 512 windows (one pair per lane) per pass; measured D = 15 / 21 / 31: 3.2 / 4.1 / 4.4 TB/s
                                           // with 1 pass, 5.1 / 5.4 / 5.3 with 3, 5.0 / 4.7 / 3.6 with 4
             if (op < 1 || op > 8) op = 1;
             d->staged_odd = make_geom(D, fast, slow, 512ull * op - 2, d->geo_odd, true);
