@@ -520,6 +520,7 @@ void fx_touch_variants() { (void)find_variant(0, 0); }
 namespace {
 
 constexpr size_t kFxChunkSamples = size_t(16) << 20;   // 32 MiB of IQ per pipelined chunk (host API)
+constexpr size_t kFxSmallCallBytes = size_t(1) << 20;  // calls up to 1 MiB take the one-stream path
 
 }  // namespace
 
@@ -783,7 +784,7 @@ void next_timing_slot(sdr_fmrx *r) {
 // One chunk, everything resident.  d_demod / d_y optional; d_audio required when the chain has a tail.  The audio stage
 // (if any) is enqueued on the audio stream; `audio_done` (optional) is recorded behind it there.
 int run_chunk(sdr_fmrx *r, const uint8_t *d_x, size_t n, float2 *d_y, float *d_demod, float *d_audio,
-              const CallPlan &pl, bool timed) {
+              const CallPlan &pl, bool timed, bool serial_audio = false) {
     int rc;
     const bool has_res = r->cfg.n_taps2 != 0;
     if ((rc = ensure_dbuf(r, pl.n_y))) return rc;
@@ -793,8 +794,18 @@ int run_chunk(sdr_fmrx *r, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d
     float *d_target = has_res ? dnew : (d_audio ? d_audio : dnew);
     // this call writes the body of `cur` and the head of `nxt`; the last reader of either is the audio kernel of the
     // call two back (buffer index nxt), which runs on the other stream
-    cudaStream_t ast = r->audio_serial ? r->stream : r->audio_stream;
-    if (has_res && r->aud_used[nxt] && !r->audio_serial) SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_aud[nxt], 0));
+    // serial: the audio kernel follows the FIR kernel on the main stream (small synchronous calls: one stream, one wait;
+    // SDR_FMRX_AUDIO_STREAM=serial pins it for A/B runs)
+    const bool serial = serial_audio || r->audio_serial;
+    cudaStream_t ast = serial ? r->stream : r->audio_stream;
+    if (has_res && r->aud_used[nxt]) {
+        SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_aud[nxt], 0));
+        r->aud_used[nxt] = false;
+    }
+    if (has_res && serial && r->aud_used[cur]) {   // this buffer's last reader was an overlapped audio kernel three calls back
+        SDR_CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_aud[cur], 0));
+        r->aud_used[cur] = false;
+    }
     if (timed) {
         next_timing_slot(r);
         SDR_CUDA_TRY(cudaEventRecord(r->ev_t[0], r->stream));
@@ -804,14 +815,14 @@ int run_chunk(sdr_fmrx *r, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d
     if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[1], r->stream));
     if (has_res) {
         if (!fold_hist && (rc = launch_hist_move(r, cur, nxt, pl.n_y))) return rc;
-        if (!r->audio_serial) {
+        if (!serial) {
             SDR_CUDA_TRY(cudaEventRecord(r->ev_fir[cur], r->stream));
             SDR_CUDA_TRY(cudaStreamWaitEvent(ast, r->ev_fir[cur], 0));
         }
         if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[2], ast));
         if ((rc = launch_resample(r, r->d_dbuf[cur].as<float>(), r->n_y, pl.n_y, pl.a0, pl.n_a, d_audio, ast))) return rc;
         if (timed) SDR_CUDA_TRY(cudaEventRecord(r->ev_t[3], ast));
-        if (!r->audio_serial) {
+        if (!serial) {
             SDR_CUDA_TRY(cudaEventRecord(r->ev_aud[cur], ast));
             r->aud_used[cur] = true;
         }
@@ -1036,6 +1047,24 @@ long sdr_fmrx_process(sdr_fmrx *r, const uint8_t *iq, size_t n_samples, float *y
     if (!audio && total.n_a) return fail(SDR_E_ARG, "audio buffer required");
     if (total.n_a > audio_cap) return fail(SDR_E_CAP, "audio capacity %zu < %llu", audio_cap, (unsigned long long)total.n_a);
     r->last_launches = 0;
+    if (n_samples * 2 <= kFxSmallCallBytes && !getenv("SDR_FMRX_NO_SMALL_PATH")) {
+        // one USB-sized buffer per call (the reference's call pattern, examples/simple_fm.rs:80,153): everything on ONE
+        // stream — copy in, FIR+demod, audio stage, copies out, one wait
+        const size_t max_y = n_samples / r->cfg.decim + 8;
+        if ((rc = r->d_x[0].reserve(kFxSmallCallBytes + 64)) || (rc = r->d_audio[0].reserve((total.n_a + 8) * 4)) ||
+            (y_pairs && (rc = r->d_y[0].reserve(max_y * 8))) || (demod && (rc = r->d_tmp.reserve(max_y * 4))))
+            return rc;
+        SDR_CUDA_TRY(cudaMemcpyAsync(r->d_x[0].p, iq, n_samples * 2, cudaMemcpyHostToDevice, r->stream));
+        if ((rc = run_chunk(r, r->d_x[0].as<uint8_t>(), n_samples, y_pairs ? r->d_y[0].as<float2>() : nullptr,
+                            demod ? r->d_tmp.as<float>() : nullptr, r->d_audio[0].as<float>(), total, true, true)))
+            return rc;
+        if (y_pairs && total.n_y) SDR_CUDA_TRY(cudaMemcpyAsync(y_pairs, r->d_y[0].p, total.n_y * 8, cudaMemcpyDeviceToHost, r->stream));
+        if (demod && total.n_y) SDR_CUDA_TRY(cudaMemcpyAsync(demod, r->d_tmp.p, total.n_y * 4, cudaMemcpyDeviceToHost, r->stream));
+        if (total.n_a) SDR_CUDA_TRY(cudaMemcpyAsync(audio, r->d_audio[0].p, total.n_a * 4, cudaMemcpyDeviceToHost, r->stream));
+        SDR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+        collect_timing(r);
+        return (long)total.n_a;
+    }
     // chunk on a multiple of 8 samples so that every chunk starts 16-byte aligned in the caller's buffer
     const size_t chunk = kFxChunkSamples;
     size_t done = 0, y_off = 0, a_off = 0;
