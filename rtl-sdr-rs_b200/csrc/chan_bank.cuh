@@ -67,27 +67,6 @@ struct BankArgs {
     float gain;
 };
 
-// atan2 for the fused discriminator: minimax odd polynomial of degree 15 on [0, 1] (max error 1.2e-7 rad in f32) after
-// the usual octant reduction; ~20 instructions instead of atan2f's ~40.  Not both arguments zero.
-__device__ __forceinline__ float bank_atan2(float y, float x) {
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float q = __fdividef(mn, mx);
-    const float s = q * q;
-    float p = -0.004054520279169083f;
-    p = fmaf(p, s, 0.021862786263227463f);
-    p = fmaf(p, s, -0.0559120811522007f);
-    p = fmaf(p, s, 0.09642180055379868f);
-    p = fmaf(p, s, -0.13908623158931732f);
-    p = fmaf(p, s, 0.19946564733982086f);
-    p = fmaf(p, s, -0.33329859375953674f);
-    p = fmaf(p, s, 0.9999993443489075f);
-    p *= q;
-    if (ay > ax) p = 1.57079632679489662f - p;
-    if (x < 0.f) p = 3.14159265358979324f - p;
-    return copysignf(p, y);
-}
-
 __device__ __forceinline__ unsigned long long bk_pack(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -254,7 +233,7 @@ __global__ void __launch_bounds__(kBankThreads, SDR_BANK_MINB) k_chan_bank(const
         if (first_of_call) pv = pin[c];
         const float cre = fmaf(s.x, pv.x, s.y * pv.y);        // Re(S conj P)
         const float cim = fmaf(s.y, pv.x, -(s.x * pv.y));     // Im(S conj P)
-        float t = bank_atan2(cim, cre) - tab.v[phib + c].x;
+        float t = poly_atan2(cim, cre) - tab.v[phib + c].x;
         t -= t > 3.14159265358979324f ? 6.28318530717958648f : 0.f;
         t += t <= -3.14159265358979324f ? 6.28318530717958648f : 0.f;
         // zero predecessor (stream start): 0 by definition (the polynomial's 0/0 is discarded here)

@@ -69,4 +69,25 @@ __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc
         : "memory");
 }
 
+// atan2 for the f32 discriminators: minimax odd polynomial of degree 15 on [0, 1] (max error 1.2e-7 rad in f32) after the
+// usual octant reduction; ~20 instructions instead of atan2f's ~40.  Not both arguments zero.
+__device__ __forceinline__ float poly_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float q = __fdividef(mn, mx);
+    const float s = q * q;
+    float p = -0.004054520279169083f;
+    p = fmaf(p, s, 0.021862786263227463f);
+    p = fmaf(p, s, -0.0559120811522007f);
+    p = fmaf(p, s, 0.09642180055379868f);
+    p = fmaf(p, s, -0.13908623158931732f);
+    p = fmaf(p, s, 0.19946564733982086f);
+    p = fmaf(p, s, -0.33329859375953674f);
+    p = fmaf(p, s, 0.9999993443489075f);
+    p *= q;
+    if (ay > ax) p = 1.57079632679489662f - p;
+    if (x < 0.f) p = 3.14159265358979324f - p;
+    return copysignf(p, y);
+}
+
 }  // namespace sdr
