@@ -743,6 +743,16 @@ def main():
 
     m = measure_stream(cx, w, d_in, args.steps, args.warmup, sample_clocks=True)
     value = cx.world * n / (m["ms_per_step"] * 1e-3) / 1e6               # whole-job Msamples/s
+    alone = None
+    if w["name"] != "cfg1":
+        # In the timed region the audio kernel of step k runs UNDER the fused kernel of step k+1 (own stream), so the fused
+        # kernel's event-bracketed time includes that contention.  The same kernel with the audio stage serialised behind it
+        # (a handle created with SDR_FMRX_AUDIO_STREAM=serial), measured after the timed region:
+        os.environ["SDR_FMRX_AUDIO_STREAM"] = "serial"
+        try:
+            alone = measure_stream(cx, w, d_in, max(5, min(args.steps, 10)), 3)
+        finally:
+            del os.environ["SDR_FMRX_AUDIO_STREAM"]
     e2e = None if args.no_e2e else measure_e2e(cx, w, args.steps)
 
     # ---- everything below runs AFTER the headline's timed region --------------------------------------------------
@@ -810,6 +820,12 @@ def main():
         "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic", "config": cfg,
         "roofline": roofline_of(w, m), "clocks": m["clocks"], "e2e": e2e, "gpu_launches": int(m["launches"]),
     }
+    if alone is not None:
+        ra = roofline_of(w, alone)
+        line["roofline"]["kernel_alone"] = {
+            "kernel_ms": ra["kernel_ms"], "achieved": ra["achieved"], "frac": ra["frac"], "step_ms_serialised": round(alone["ms_per_step"], 4),
+            "note": "same kernel, audio stage serialised behind it instead of overlapped with the next step (measured in this run, "
+                    "after the timed region): the kernel itself streams at this rate; overlapping costs it time but shortens the step"}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w)
         if w["name"] == "cfg1":
