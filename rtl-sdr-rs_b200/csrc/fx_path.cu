@@ -217,59 +217,63 @@ __global__ void __launch_bounds__(kFirThreads) k_fir_real_p2(const float *dbuf, 
     extern __shared__ __align__(16) float fsm[];
     float4 *win4 = reinterpret_cast<float4 *>(fsm);   // window only (same padded chunk layout as k_fir_real_r8)
     float *win = fsm;
-    const long long o0 = (long long)blockIdx.x * kFirOblk;
-    const long long gbase = (long long)h2 + o0 - Jp;
     const int n_chunks = (kFirOblk + Jp) / 4;
-    if ((gbase & 3) == 0 && gbase >= 0 && gbase + kFirOblk + Jp <= n_valid) {
-        const float4 *src = reinterpret_cast<const float4 *>(dbuf + gbase);
-        for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) win4[c + (c >> 3)] = src[c];
-    } else {
-        for (int idx = threadIdx.x; idx < kFirOblk + Jp; idx += blockDim.x) {
-            long long gi = gbase + idx;
-            win[idx + (idx >> 5) * 4] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
-        }
-    }
-    __syncthreads();
-    unsigned long long acc[kFirR / 2];
-#pragma unroll
-    for (int q = 0; q < kFirR / 2; q++) acc[q] = 0ull;
     const int t0 = threadIdx.x * kFirR;
-    for (int k0 = 0; k0 < Jp; k0 += kFirTC) {
-        // pair q (outputs t0 + 2q, + 1), tap pair k = k0 + kk: sample win[Jp + t0 + 2q + 1 - k] = w[17 + 2q - kk]
-        float w[kFirR + kFirTC];
-        const int c0 = (Jp + t0 - k0 - kFirTC) >> 2;
-#pragma unroll
-        for (int c = 0; c < (kFirR + kFirTC) / 4; c++) {
-            float4 v = win4[(c0 + c) + ((c0 + c) >> 3)];
-            w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
-        }
-#pragma unroll
-        for (int kk = 0; kk < kFirTC; kk++) {
-            const float2 pk = taps.p[k0 + kk];
-            const unsigned long long pp = pack_f32x2(pk.x, pk.y);
-#pragma unroll
-            for (int q = 0; q < kFirR / 2; q++) {
-                const float sm = w[kFirTC + 1 + 2 * q - kk];
-                const unsigned long long ss = pack_f32x2(sm, sm);
-                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[q]) : "l"(ss), "l"(pp));
+    // grid-stride over tiles: the launch caps the CTAs per SM so that this kernel trickles along UNDER the next call's
+    // fused FIR kernel instead of flooding the SMs for its whole duration (fx_path.cu, launch_resample)
+    for (long long o0 = (long long)blockIdx.x * kFirOblk; o0 < n_out; o0 += (long long)gridDim.x * kFirOblk) {
+        const long long gbase = (long long)h2 + o0 - Jp;
+        if ((gbase & 3) == 0 && gbase >= 0 && gbase + kFirOblk + Jp <= n_valid) {
+            const float4 *src = reinterpret_cast<const float4 *>(dbuf + gbase);
+            for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) win4[c + (c >> 3)] = src[c];
+        } else {
+            for (int idx = threadIdx.x; idx < kFirOblk + Jp; idx += blockDim.x) {
+                long long gi = gbase + idx;
+                win[idx + (idx >> 5) * 4] = (gi >= 0 && gi < n_valid) ? dbuf[gi] : 0.f;
             }
         }
-    }
-    float a[kFirR];
+        __syncthreads();
+        unsigned long long acc[kFirR / 2];
 #pragma unroll
-    for (int q = 0; q < kFirR / 2; q++) {
-        const float2 v = unpack_f32x2(acc[q]);
-        a[2 * q] = v.x, a[2 * q + 1] = v.y;
-    }
-    float *dst = out + o0 + t0;
-    if (o0 + t0 + kFirR <= n_out && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int q = 0; q < kFirR / 2; q++) acc[q] = 0ull;
+        for (int k0 = 0; k0 < Jp; k0 += kFirTC) {
+            // pair q (outputs t0 + 2q, + 1), tap pair k = k0 + kk: sample win[Jp + t0 + 2q + 1 - k] = w[17 + 2q - kk]
+            float w[kFirR + kFirTC];
+            const int c0 = (Jp + t0 - k0 - kFirTC) >> 2;
 #pragma unroll
-        for (int c = 0; c < kFirR / 4; c++)
-            reinterpret_cast<float4 *>(dst)[c] = make_float4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
-    } else {
+            for (int c = 0; c < (kFirR + kFirTC) / 4; c++) {
+                float4 v = win4[(c0 + c) + ((c0 + c) >> 3)];
+                w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
+            }
 #pragma unroll
-        for (int r = 0; r < kFirR; r++)
-            if (o0 + t0 + r < n_out) dst[r] = a[r];
+            for (int kk = 0; kk < kFirTC; kk++) {
+                const float2 pk = taps.p[k0 + kk];
+                const unsigned long long pp = pack_f32x2(pk.x, pk.y);
+#pragma unroll
+                for (int q = 0; q < kFirR / 2; q++) {
+                    const float sm = w[kFirTC + 1 + 2 * q - kk];
+                    const unsigned long long ss = pack_f32x2(sm, sm);
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[q]) : "l"(ss), "l"(pp));
+                }
+            }
+        }
+        float a[kFirR];
+#pragma unroll
+        for (int q = 0; q < kFirR / 2; q++) {
+            const float2 v = unpack_f32x2(acc[q]);
+            a[2 * q] = v.x, a[2 * q + 1] = v.y;
+        }
+        float *dst = out + o0 + t0;
+        if (o0 + t0 + kFirR <= n_out && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int c = 0; c < kFirR / 4; c++)
+                reinterpret_cast<float4 *>(dst)[c] = make_float4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kFirR; r++)
+                if (o0 + t0 + r < n_out) dst[r] = a[r];
+        }
+        __syncthreads();   // the window is rewritten by the next tile
     }
 }
 
@@ -552,6 +556,7 @@ struct sdr_fmrx {
     cudaEvent_t ev_fir[3]{}, ev_aud[3]{}, ev_join = nullptr;
     bool aud_used[3] = {false, false, false};
     bool audio_serial = false;
+    int audio_ctas_per_sm = 2;   // resident CTAs per SM of an audio kernel that runs under a fused FIR kernel
     H2DStager stager;        // pageable caller buffers go through pinned pieces (common.cuh)
     struct sdr_fmrx_ring *ring = nullptr;   // a persistent ring owns the handle until sdr_fmrx_ring_close()
     TapsP *taps_p = nullptr;   // L = M = 1: overlapping tap pairs of k_fir_real_p2 (null: k_fir_real_r8)
@@ -714,16 +719,20 @@ int launch_resample(sdr_fmrx *r, const float *dbuf, uint64_t P0, uint64_t n_new,
         uint64_t blocks = ceil_div(n_a, (uint64_t)kFirOblk);
         if (blocks > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
         size_t sm = fir_real_smem(r->Jp);
-        if (r->taps_p)
-            k_fir_real_p2<<<(int)blocks, kFirThreads, fir_real_smem(r->Jpp), st>>>(dbuf, r->h2, r->Jpp, (long long)n_a,
-                                                                                  (long long)(r->h2 + n_new), d_audio, *r->taps_p);
+        if (r->taps_p) {
+            // on its own stream the kernel runs under the next call's fused kernel: cap its CTAs per SM (SDR_FMRX_AUDIO_CTAS)
+            const uint64_t cap = st == r->audio_stream ? (uint64_t)sm_count(r->device) * r->audio_ctas_per_sm : blocks;
+            k_fir_real_p2<<<(int)std::min(blocks, std::max<uint64_t>(cap, 1)), kFirThreads, fir_real_smem(r->Jpp), st>>>(
+                dbuf, r->h2, r->Jpp, (long long)n_a, (long long)(r->h2 + n_new), d_audio, *r->taps_p);
+        }
         else
             k_fir_real_r8<<<(int)blocks, kFirThreads, sm, st>>>(dbuf, r->h2, r->d_taps2.as<float>(), r->Jp, (long long)n_a,
                                                                 (long long)(r->h2 + n_new), d_audio);
         SDR_LAUNCH_CHECK();
         r->last_launches++;
     } else if (n_a) {
-        int blocks = (int)std::min<uint64_t>(ceil_div(n_a, 256), (uint64_t)sm_count(r->device) * 16);
+        int blocks = (int)std::min<uint64_t>(ceil_div(n_a, 256),
+                                             (uint64_t)sm_count(r->device) * (st == r->audio_stream ? 2 * r->audio_ctas_per_sm : 16));
         size_t tb = (((size_t)r->cfg.up * (r->J | 1) + 3) & ~size_t(3)) * sizeof(float);
         int in_smem = tb <= 32 * 1024;
         // window of d one 256-output tile touches; staged in shared memory when it is small
@@ -917,6 +926,7 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
         // at the lowest priority, default = own stream at the highest priority (A/B runs)
         const char *ea = getenv("SDR_FMRX_AUDIO_STREAM");
         r->audio_serial = ea && !strcmp(ea, "serial");
+        if (const char *ec = getenv("SDR_FMRX_AUDIO_CTAS")) r->audio_ctas_per_sm = std::max(1, atoi(ec));
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&r->audio_stream, cudaStreamNonBlocking, (ea && !strcmp(ea, "low")) ? lo : hi);
     }
     for (int i = 0; i < 3 && e == cudaSuccess; i++) {
