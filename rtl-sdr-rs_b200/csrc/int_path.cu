@@ -744,6 +744,32 @@ __device__ __forceinline__ void resample_tile(const FusedArgs &a, const IntState
         }
         return;
     }
+    if (a.div_slow.shift != 0xffffffffu && a.div_audio.shift != 0xffffffffu && rb < slow && (uint32_t)a.div <= 64u) {
+        // any other ratio without an unusual carried prev_lpr_index: every window holds floor(fast/slow) = a.div samples
+        // or one more — a tile-uniform count of plain loads and ONE predicated one, no per-load compare, no special
+        // cases in the two magic divisions.  (|sum| <= 65 * 32768 except where the carried now_lpr is added.)
+        const uint32_t mg = a.div_slow.magic, sh = a.div_slow.shift, base = (uint32_t)a.div;
+        for (uint32_t t = tid; t < ne; t += nthreads) {
+            const uint32_t n0 = t * fast - rb + slow - 1;
+            const uint32_t r0 = t ? __umulhi(n0, mg) >> sh : 0u;
+            const uint32_t r1 = __umulhi(n0 + fast, mg) >> sh;
+            const int16_t *dp = dm + dbase + r0;
+            int32_t sum = 0;
+            for (uint32_t j = 0; j < base; j++) sum += (int32_t)dp[j];
+            if (r1 - r0 > base) sum += (int32_t)dp[base];
+            uint32_t mag, qm;
+            if (e0zero && t == 0) {   // the carried partial sum can be anything
+                sum = wadd(sum, st.now_lpr);
+                mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
+                qm = mag >> 31 ? (uint32_t)((int64_t)mag / a.div) : udiv(mag, a.div_audio);
+            } else {
+                mag = sum < 0 ? (uint32_t)0 - (uint32_t)sum : (uint32_t)sum;
+                qm = __umulhi(mag, a.div_audio.magic) >> a.div_audio.shift;
+            }
+            outp[t] = (int16_t)(uint16_t)(sum < 0 ? (uint32_t)0 - qm : qm);
+        }
+        return;
+    }
     for (uint32_t t = tid; t < ne; t += nthreads) {
         const uint32_t r0 = t ? udiv(t * fast - rb + slow - 1, a.div_slow) : 0u;
         const uint32_t r1 = udiv((t + 1) * fast - rb + slow - 1, a.div_slow);

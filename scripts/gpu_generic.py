@@ -17,6 +17,8 @@ for D, fast, slow in ((6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48
                       (12, 170_000, 32_000), (3, 334_000, 48_000), (5, 200_000, 32_000), (7, 143_000, 32_000), (9, 112_000, 32_000),
                       (11, 100_000, 32_000), (13, 80_000, 32_000)) + tuple((d, 160_000, 32_000) for d in range(14, 33)) + (
                       (40, 32_000, 32_000), (100, 48_000, 32_000)):
+    if len(sys.argv) > 2 and str(D) not in sys.argv[2:]:
+        continue
     cfg = S.DemodConfig(fast * D, fast, slow, D, 42)
     h = S.Demod(cfg)
     n_bufs = 2 * n // BUF
