@@ -123,6 +123,36 @@ __device__ __forceinline__ uint32_t load_tile_rows(unsigned char *tile, const Fi
     return soff;
 }
 
+// Same padded layout, short rows: every thread of the CTA moves 16-byte pieces with cp.async (LDGSTS) and then lets the
+// mbarrier count its own copies (cp.async.mbarrier.arrive.noinc: the barrier is initialised with NT arrivals and no byte
+// count).  Every piece lies wholly in the carry or wholly in the call input (carry_bytes is a multiple of 16).
+template <int ROW, int PAD, int NT>
+__device__ __forceinline__ uint32_t load_tile_rows_async(unsigned char *tile, const FirArgs &a, long long s0, long long s1,
+                                                         uint64_t *bar, const int tid) {
+    static_assert(ROW % 16 == 0 && PAD % 16 == 0, "16-byte pieces");
+    const uint32_t soff = (uint32_t)((2 * s0) & 15);
+    long long x_lo = s0 > 0 ? s0 : 0;
+    uint32_t carry_bytes = 0, x_bytes = 0;
+    if (s0 < 0) {
+        long long c_hi = s1 < 0 ? s1 : 0;
+        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
+    }
+    long long b_lo = 0;
+    if (s1 > 0) {
+        b_lo = (2 * x_lo) & ~15ll;
+        x_bytes = (uint32_t)(((2 * s1 + 15) & ~15ll) - b_lo);
+    }
+    const uint32_t total = carry_bytes + x_bytes;
+    const unsigned char *csrc = a.carry_end + 2 * s0 - soff;
+    const unsigned char *xsrc = a.x + b_lo - carry_bytes;
+    for (uint32_t f = (uint32_t)tid * 16u; f < total; f += (uint32_t)NT * 16u) {
+        const uint32_t row = f / ROW;
+        cp_async_16(tile + f + row * PAD, (f < carry_bytes ? csrc : xsrc) + f);
+    }
+    cp_async_mbar_arrive_noinc(bar);
+    return soff;
+}
+
 // =================================================================================================
 // Specialised kernel
 // =================================================================================================
@@ -133,6 +163,13 @@ __host__ __device__ constexpr int fast_pick_hb(int Q, int NBLK, int D, int SPL) 
     while (((NBLK - hb) * D) % SPL != 0) hb++;
     return hb;
 }
+// partial sums are stored [block][lag] with this row length: an even lag count from 4 up gets one unused slot, so that
+// the combine (lane stride = one row) and the per-thread stores stop colliding on the same banks
+__host__ __device__ constexpr int fast_qp(int Q) { return (Q >= 4 && Q % 2 == 0) ? Q + 1 : Q; }
+// rows of a padded tile (PAD != 0) shorter than this are staged with 16-byte cp.async by ALL threads instead of one bulk
+// copy per row issued by warp 0 (a 32-byte row per bulk copy serialises the whole CTA behind one warp)
+constexpr int kRowsAsyncBelow = 256;
+
 template <int T, int D, int B, int NT, int WB, int PAD = 0>
 struct FastGeom {
     static constexpr int Q = (T + D - 1) / D;           // lags: outputs a sample contributes to
@@ -143,7 +180,9 @@ struct FastGeom {
     static constexpr int TILE_BYTES = NBLK * D * 2;
     static constexpr int ROW = B * D * 2;                // bytes one thread owns
     static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32 + (NT + 1) * PAD;
-    static constexpr int SM_PART = NBLK * Q * 8;        // float2 partial per (block, lag)
+    static constexpr int QP = fast_qp(Q);               // row length of the partial-sum array
+    static constexpr int SM_PART = NBLK * QP * 8;       // float2 partial per (block, lag)
+    static constexpr bool ROWS_ASYNC = PAD != 0 && ROW < kRowsAsyncBelow;
     static constexpr int SM_Y = NBLK * 8;
     static constexpr int SMEM = SM_TILE + SM_PART + SM_Y;
     static_assert(WB == 4 || WB == 8, "LDS.32 or LDS.64");
@@ -214,12 +253,25 @@ __device__ __forceinline__ void fir_fast_tile(const FirArgs &a, const Taps<T> &t
 
     const int tid = threadIdx.x;
     const long long out0 = blk * G::OUT;          // first owned output (call-local)
-    if (tid < (PAD ? 32 : 1)) {
+    // tile = blocks [out0 - HB, out0 - HB + NBLK); block b covers samples [b*D - r, (b+1)*D - r)
+    if constexpr (G::ROWS_ASYNC) {
+        if (first_use) {   // CTA-uniform
+            if (tid == 0) {
+                mbar_init(&bar, NT);
+                fence_barrier_init();
+            }
+            __syncthreads();
+        }
+        const long long s0 = (out0 - G::HB) * D - (long long)a.r;
+        const long long last_out = out0 + G::OUT < a.n_out ? out0 + G::OUT : a.n_out;   // exclusive
+        const long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
+        const uint32_t so = load_tile_rows_async<G::ROW, PAD, NT>(tile, a, s0, s1, &bar, tid);
+        if (tid == 0) sh_soff = so;
+    } else if (tid < (PAD ? 32 : 1)) {
         if (tid == 0 && first_use) {
             mbar_init(&bar, 1);
             fence_barrier_init();
         }
-        // tile = blocks [out0 - HB, out0 - HB + NBLK); block b covers samples [b*D - r, (b+1)*D - r)
         long long s0 = (out0 - G::HB) * D - (long long)a.r;
         long long last_out = out0 + G::OUT < a.n_out ? out0 + G::OUT : a.n_out;   // exclusive
         long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
@@ -279,7 +331,7 @@ __device__ __forceinline__ void fir_fast_tile(const FirArgs &a, const Taps<T> &t
 #pragma unroll
     for (int b = 0; b < B; b++)
 #pragma unroll
-        for (int q = 0; q < Q; q++) part[(tid * B + b) * Q + q] = unpack_f32x2(acc[b][q]);
+        for (int q = 0; q < Q; q++) part[(tid * B + b) * G::QP + q] = unpack_f32x2(acc[b][q]);
     __syncthreads();
 
     // ---- combine partials oldest block first: y[g] = P[g-Q+1][Q-1] + ... + P[g][0] -----------------
@@ -290,7 +342,7 @@ __device__ __forceinline__ void fir_fast_tile(const FirArgs &a, const Taps<T> &t
         if (g >= Q - 1) {
 #pragma unroll
             for (int q = Q - 1; q >= 0; q--) {
-                float2 p = part[(g - q) * Q + q];
+                float2 p = part[(g - q) * G::QP + q];
                 yr += p.x;
                 yi += p.y;
             }

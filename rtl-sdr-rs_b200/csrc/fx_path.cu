@@ -474,7 +474,7 @@ bool pick_fast_params(int T, int D, int *Bo, int *NTo, int *WBo, int *PADo) {
     int pick = 0;
     for (int NT = 32; NT <= 512; NT += 32) {
         const int nblk = NT * B, hb = fast_pick_hb(Q, nblk, D, spl);
-        const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)(NT + 1) * PAD + (long)nblk * Q * 8 + (long)nblk * 8;
+        const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)(NT + 1) * PAD + (long)nblk * fast_qp(Q) * 8 + (long)nblk * 8;
         if (nblk - hb <= hb) continue;
         if (smem > 56 * 1024) break;
         pick = NT;
@@ -503,7 +503,7 @@ const FastVariant *rtc_variant(int device, uint32_t T, uint32_t D, int B, int NT
     if (it != cache.end()) return it->second;
     const int Q = ((int)T + (int)D - 1) / (int)D, spl = WB / 2, nblk = NT * B;
     const int hb = fast_pick_hb(Q, nblk, (int)D, spl);
-    const int smem = ((nblk * (int)D * 2 + 15) / 16) * 16 + 32 + (NT + 1) * PAD + nblk * Q * 8 + nblk * 8;
+    const int smem = ((nblk * (int)D * 2 + 15) / 16) * 16 + 32 + (NT + 1) * PAD + nblk * fast_qp(Q) * 8 + nblk * 8;
     std::vector<std::string> names;
     for (int ph = 0; ph < spl; ph++) names.push_back(fast_name_expr((int)T, (int)D, B, NT, WB, ph, PAD));
     const RtcModule *mod = nullptr;
@@ -1255,7 +1255,7 @@ int sdr_rtc_pick_shape(uint32_t n_taps, uint32_t decim, int shape[4]) {
     // the kernel's own compile-time requirements (FastGeom's static_asserts), re-stated on the host
     const int T = (int)n_taps, D = (int)decim, Q = (T + D - 1) / D, spl = WB / 2, nblk = NT * B;
     const int hb = fast_pick_hb(Q, nblk, D, spl), row = B * D * 2;
-    const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)(NT + 1) * PAD + (long)nblk * Q * 8 + (long)nblk * 8;
+    const long smem = (((long)nblk * D * 2 + 15) / 16) * 16 + 32 + (long)(NT + 1) * PAD + (long)nblk * fast_qp(Q) * 8 + (long)nblk * 8;
     if (WB != 4 && WB != 8) return fail(SDR_E_STATE, "picked load width %d", WB);
     if ((B * D) % spl) return fail(SDR_E_STATE, "thread span %d is not a whole number of %d-sample loads", B * D, spl);
     if (nblk - hb <= hb) return fail(SDR_E_STATE, "tile of %d blocks is all halo (%d)", nblk, hb);

@@ -57,6 +57,15 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// 16-byte asynchronous copy global -> shared by one thread (SASS LDGSTS), bypassing L1
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+// the mbarrier receives one arrival from this thread when all of its cp.async issued so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // same, with an L2 evict-first policy: the IQ stream is read exactly once
 __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, uint32_t bytes,
                                                 uint64_t *bar) {

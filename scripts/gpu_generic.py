@@ -17,6 +17,8 @@ for D, fast, slow in ((6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48
                       (12, 170_000, 32_000), (3, 334_000, 48_000), (5, 200_000, 32_000), (7, 143_000, 32_000), (9, 112_000, 32_000),
                       (11, 100_000, 32_000), (13, 80_000, 32_000)) + tuple((d, 160_000, 32_000) for d in range(14, 33)) + (
                       (40, 32_000, 32_000), (100, 48_000, 32_000)):
+    if len(sys.argv) > 1 and sys.argv[1] == "f32":
+        break
     if len(sys.argv) > 2 and str(D) not in sys.argv[2:]:
         continue
     cfg = S.DemodConfig(fast * D, fast, slow, D, 42)
@@ -32,7 +34,8 @@ for D, fast, slow in ((6, 170_000, 32_000), (2, 96_000, 48_000), (4, 250_000, 48
     d_out.free(); h.close()
 if len(sys.argv) > 1 and sys.argv[1] == "int":
     sys.exit(0)
-for T, D in ((127, 75), (255, 100), (127, 50), (63, 25), (201, 64), (511, 100), (31, 10), (129, 16), (65, 32), (127, 48), (255, 96),
+F32_SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] if len(sys.argv) > 2 and sys.argv[1] == "f32" else None
+for T, D in F32_SHAPES or ((127, 75), (255, 100), (127, 50), (63, 25), (201, 64), (511, 100), (31, 10), (129, 16), (65, 32), (127, 48), (255, 96),
              (33, 8), (127, 40), (200, 3)):
     taps = channel_taps(T, D)
     h = S.FmRx(taps, D, None, 1, 1)
