@@ -87,45 +87,12 @@ __device__ __forceinline__ uint32_t load_tile(unsigned char *tile, const FirArgs
     return soff;
 }
 
-// Same tile, staged ROW bytes at a time with PAD bytes of shared memory skipped after every row (a row = the bytes one
-// thread owns): when ROW is a multiple of 128 every thread's loads would otherwise hit the same bank.  Executed by
-// warp 0: lane 0 posts the byte count, then the 32 lanes issue the row copies (one or two per row: a row may straddle
-// the carry / call-input boundary).  ROW and every piece are multiples of 16 bytes.
-template <int ROW, int PAD>
-__device__ __forceinline__ uint32_t load_tile_rows(unsigned char *tile, const FirArgs &a, long long s0, long long s1,
-                                                   uint64_t *bar, const int lane) {
-    static_assert(ROW % 16 == 0 && PAD % 16 == 0, "bulk copies move 16-byte multiples");
-    const uint32_t soff = (uint32_t)((2 * s0) & 15);
-    long long x_lo = s0 > 0 ? s0 : 0;
-    uint32_t carry_bytes = 0, x_bytes = 0;
-    if (s0 < 0) {
-        long long c_hi = s1 < 0 ? s1 : 0;
-        carry_bytes = (uint32_t)((2 * (c_hi - s0) + soff + 15) & ~15ll);
-    }
-    long long b_lo = 0;
-    if (s1 > 0) {
-        b_lo = (2 * x_lo) & ~15ll;
-        x_bytes = (uint32_t)(((2 * s1 + 15) & ~15ll) - b_lo);
-    }
-    const uint32_t total = carry_bytes + x_bytes;
-    if (lane == 0) mbar_arrive_expect_tx(bar, total);
-    __syncwarp();
-    // flat tile byte f lives in the carry for f < carry_bytes, in x after that (the two parts abut, see load_tile)
-    const unsigned char *csrc = a.carry_end + 2 * s0 - soff;
-    const unsigned char *xsrc = a.x + b_lo;
-    for (uint32_t f = (uint32_t)lane * ROW; f < total; f += 32u * ROW) {
-        const uint32_t end = f + ROW < total ? f + ROW : total;
-        unsigned char *dst = tile + (size_t)(f / ROW) * (ROW + PAD);
-        const uint32_t cut = carry_bytes < f ? f : (carry_bytes < end ? carry_bytes : end);   // [f, cut) carry, [cut, end) x
-        if (cut > f) bulk_g2s(dst, csrc + f, cut - f, bar);
-        if (end > cut) bulk_g2s_stream(dst + (cut - f), xsrc + (cut - carry_bytes), end - cut, bar);
-    }
-    return soff;
-}
-
-// Same padded layout, short rows: every thread of the CTA moves 16-byte pieces with cp.async (LDGSTS) and then lets the
-// mbarrier count its own copies (cp.async.mbarrier.arrive.noinc: the barrier is initialised with NT arrivals and no byte
-// count).  Every piece lies wholly in the carry or wholly in the call input (carry_bytes is a multiple of 16).
+// Same tile with PAD bytes of shared memory skipped after every ROW bytes (a row = the bytes one thread owns): when ROW is a
+// multiple of 128 every thread's loads would otherwise hit the same bank.  Every thread of the CTA moves 16-byte pieces
+// with cp.async (LDGSTS) and then lets the mbarrier count its own copies (cp.async.mbarrier.arrive.noinc: the barrier is
+// initialised with NT arrivals and no byte count).  ROW and carry_bytes are multiples of 16, so every piece lies wholly in
+// one row and wholly in the carry or in the call input.  (Round 1 issued one bulk copy per row from warp 0: with 32-byte
+// rows the whole CTA waited behind 288 serialised copies — (129,/16) 0.65 -> 1.92 TB/s, (201,/64) 3.2 -> 4.2.)
 template <int ROW, int PAD, int NT>
 __device__ __forceinline__ uint32_t load_tile_rows_async(unsigned char *tile, const FirArgs &a, long long s0, long long s1,
                                                          uint64_t *bar, const int tid) {
@@ -166,9 +133,6 @@ __host__ __device__ constexpr int fast_pick_hb(int Q, int NBLK, int D, int SPL) 
 // partial sums are stored [block][lag] with this row length: an even lag count from 4 up gets one unused slot, so that
 // the combine (lane stride = one row) and the per-thread stores stop colliding on the same banks
 __host__ __device__ constexpr int fast_qp(int Q) { return (Q >= 4 && Q % 2 == 0) ? Q + 1 : Q; }
-// rows of a padded tile (PAD != 0) shorter than this are staged with 16-byte cp.async by ALL threads instead of one bulk
-// copy per row issued by warp 0 (a 32-byte row per bulk copy serialises the whole CTA behind one warp)
-constexpr int kRowsAsyncBelow = 256;
 
 template <int T, int D, int B, int NT, int WB, int PAD = 0>
 struct FastGeom {
@@ -182,7 +146,7 @@ struct FastGeom {
     static constexpr int SM_TILE = ((TILE_BYTES + 15) / 16) * 16 + 32 + (NT + 1) * PAD;
     static constexpr int QP = fast_qp(Q);               // row length of the partial-sum array
     static constexpr int SM_PART = NBLK * QP * 8;       // float2 partial per (block, lag)
-    static constexpr bool ROWS_ASYNC = PAD != 0 && ROW < kRowsAsyncBelow;
+    static constexpr bool ROWS_ASYNC = PAD != 0;        // padded tiles are staged by cp.async from every thread
     static constexpr int SM_Y = NBLK * 8;
     static constexpr int SMEM = SM_TILE + SM_PART + SM_Y;
     static_assert(WB == 4 || WB == 8, "LDS.32 or LDS.64");
@@ -267,21 +231,15 @@ __device__ __forceinline__ void fir_fast_tile(const FirArgs &a, const Taps<T> &t
         const long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
         const uint32_t so = load_tile_rows_async<G::ROW, PAD, NT>(tile, a, s0, s1, &bar, tid);
         if (tid == 0) sh_soff = so;
-    } else if (tid < (PAD ? 32 : 1)) {
-        if (tid == 0 && first_use) {
+    } else if (tid == 0) {
+        if (first_use) {
             mbar_init(&bar, 1);
             fence_barrier_init();
         }
         long long s0 = (out0 - G::HB) * D - (long long)a.r;
         long long last_out = out0 + G::OUT < a.n_out ? out0 + G::OUT : a.n_out;   // exclusive
         long long s1 = last_out * D - (long long)a.r;                              // end of the last needed block
-        if constexpr (PAD != 0) {
-            __syncwarp();
-            const uint32_t so = load_tile_rows<G::ROW, PAD>(tile, a, s0, s1, &bar, tid);
-            if (tid == 0) sh_soff = so;
-        } else {
-            sh_soff = load_tile(tile, a, s0, s1, &bar);
-        }
+        sh_soff = load_tile(tile, a, s0, s1, &bar);
     }
     __syncthreads();
     mbar_wait(&bar, parity);
