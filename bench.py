@@ -288,10 +288,11 @@ def roofline_of(w: dict, m: dict) -> dict:
                     f"{achieved / 7700.0:.3f}"}
 
 
-def measure_e2e(cx: Ctx, w: dict, steps: int, pageable: bool = False) -> dict:
+def measure_e2e(cx: Ctx, w: dict, steps: int, pageable: bool = False, registered: bool = False) -> dict:
     """The same metric through the public C-ABI call with HOST buffers: H2D of the input and D2H of the audio inside the
     timed region, every step.  pageable=False: pinned host memory (sdr_host_alloc); True: an ordinary heap array, which is
-    what a drop-in caller's Vec<u8> is (examples/simple_fm.rs:80,153)."""
+    what a drop-in caller's Vec<u8> is (examples/simple_fm.rs:80,153); registered=True: the same heap array, page-locked
+    once with sdr_host_register before the timed region (what a caller with a long-lived buffer would do)."""
     S = cx.S
     from rtl_sdr_rs_b200 import _ffi as F
     n_e = 1 << 27
@@ -304,6 +305,8 @@ def measure_e2e(cx: Ctx, w: dict, steps: int, pageable: bool = False) -> dict:
         in_arr = np.empty(2 * n_e, np.uint8)
         in_arr[:] = hb.array
         hb.free()
+        if registered:
+            S.host_register(in_arr)
     in_ptr = F.ptr(in_arr)
     e_steps = max(3, min(steps, 10))
     if w["name"] == "cfg1":
@@ -336,13 +339,16 @@ def measure_e2e(cx: Ctx, w: dict, steps: int, pageable: bool = False) -> dict:
     he.close()
     if not pageable:
         hb.free()
+    elif registered:
+        S.host_unregister(in_arr)
     if out_h:
         out_h.free()
     return {"value": round(cx.world * n_e * e_steps / e_s / 1e6, 2), "unit": "Msamples/s",
             "h2d_bytes_per_step": 2 * n_e, "d2h_bytes_per_step": int(n_out_e) * (2 if w["name"] == "cfg1" else 4),
             "steps": e_steps, "samples_per_step": n_e,
             "api": "sdr_demod_demodulate_batch" if w["name"] == "cfg1" else "sdr_fmrx_process",
-            "host_memory": "pageable (ordinary heap array, like the caller's Vec<u8>)" if pageable else "pinned (sdr_host_alloc)",
+            "host_memory": ("caller-owned heap array page-locked once with sdr_host_register" if registered else
+                            "pageable (ordinary heap array, like the caller's Vec<u8>)") if pageable else "pinned (sdr_host_alloc)",
             "note": "host input -> chunked H2D overlapped with the kernels -> D2H of the audio, per step"}
 
 
@@ -766,6 +772,9 @@ def main():
             e2e_page = measure_e2e(cx, w, args.steps, pageable=True)
             e2e["pageable"] = {k: e2e_page[k] for k in ("value", "unit", "host_memory")}
             e2e["pageable"]["fraction_of_pinned"] = round(e2e_page["value"] / e2e["value"], 3)
+            e2e_reg = measure_e2e(cx, w, args.steps, pageable=True, registered=True)
+            e2e["registered"] = {k: e2e_reg[k] for k in ("value", "unit", "host_memory")}
+            e2e["registered"]["fraction_of_pinned"] = round(e2e_reg["value"] / e2e["value"], 3)
             e2e["h2d_ceiling"] = h2d
             e2e["fraction_of_h2d_ceiling"] = round(e2e["value"] / h2d["msamples_per_s"], 3)
         for other in ("cfg1", "cfg3", "cfg2"):

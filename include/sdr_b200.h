@@ -56,6 +56,13 @@ void *sdr_dev_alloc(int device, size_t bytes);          /* 256-B aligned, 4 KiB 
 void sdr_dev_free(int device, void *p);
 void *sdr_host_alloc(size_t bytes);                     /* pinned host memory */
 void sdr_host_free(void *p);
+/* Page-lock / release a buffer the CALLER owns (the reader's long-lived `Box<[u8; DEFAULT_BUF_LENGTH]>`,
+ * examples/simple_fm.rs:114, or a batch Vec<u8>): calls given a pointer inside a registered buffer copy by DMA straight
+ * from it, as from sdr_host_alloc memory, instead of through the pageable staging.  Registering costs about as much as
+ * touching every page once; do it once per buffer, not per call, and unregister before freeing the memory.
+ * Registering twice / unregistering an unknown pointer is SDR_OK.  SDR_E_STATE while a persistent ring is open. */
+int sdr_host_register(void *p, size_t bytes);
+int sdr_host_unregister(void *p);
 int sdr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
 int sdr_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
 int sdr_dev_memset(int device, void *dst, int value, size_t bytes);

@@ -26,6 +26,8 @@ from ._ffi import (  # noqa: F401
     optimal_settings,
     DevBuffer,
     HostBuffer,
+    host_register,
+    host_unregister,
     synth_fill_dev,
     fmrx_plan,
     demod_plan,

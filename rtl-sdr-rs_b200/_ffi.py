@@ -72,6 +72,8 @@ SIGNATURES = {
     "sdr_dev_free": (None, [_i, _vp]),
     "sdr_host_alloc": (_vp, [_sz]),
     "sdr_host_free": (None, [_vp]),
+    "sdr_host_register": (_i, [_vp, _sz]),
+    "sdr_host_unregister": (_i, [_vp]),
     "sdr_memcpy_h2d": (_i, [_i, _vp, _vp, _sz]),
     "sdr_memcpy_d2h": (_i, [_i, _vp, _vp, _sz]),
     "sdr_dev_memset": (_i, [_i, _vp, _i, _sz]),
@@ -255,6 +257,15 @@ class DevBuffer:
             self.free()
         except Exception:
             pass
+
+
+def host_register(arr: np.ndarray) -> None:
+    """Page-lock a numpy array the caller owns (sdr_host_register): later calls DMA straight from it."""
+    check(lib().sdr_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes))
+
+
+def host_unregister(arr: np.ndarray) -> None:
+    check(lib().sdr_host_unregister(C.c_void_p(arr.ctypes.data)))
 
 
 class HostBuffer:

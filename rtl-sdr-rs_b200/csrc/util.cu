@@ -431,6 +431,30 @@ void *sdr_host_alloc(size_t bytes) {
     return p;
 }
 void sdr_host_free(void *p) { host_free_or_park(p); }
+// Page-lock a buffer the caller owns (a long-lived Vec<u8> / Box<[u8; N]>): every call that is handed a pointer inside it
+// afterwards copies by DMA straight from it, like memory from sdr_host_alloc, instead of through the staging pieces.
+int sdr_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return fail(SDR_E_ARG, "null / empty buffer");
+    if (ring_is_open(-1)) return fail(SDR_E_STATE, "a persistent ring is open on this process: register buffers before opening it");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        (void)cudaGetLastError();
+        return SDR_OK;
+    }
+    if (e != cudaSuccess) return fail(SDR_E_CUDA, "cudaHostRegister(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return SDR_OK;
+}
+int sdr_host_unregister(void *p) {
+    if (!p) return SDR_OK;
+    if (ring_is_open(-1)) return fail(SDR_E_STATE, "a persistent ring is open on this process: close it before unregistering");
+    cudaError_t e = cudaHostUnregister(p);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        (void)cudaGetLastError();
+        return SDR_OK;
+    }
+    if (e != cudaSuccess) return fail(SDR_E_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SDR_OK;
+}
 int sdr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes) {
     int rc = use_device(device);
     if (rc) return rc;

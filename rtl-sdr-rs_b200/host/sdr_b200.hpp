@@ -34,6 +34,19 @@ using RadioConfig = sdr_radio_config;   // :173-176
 constexpr uint32_t FREQUENCY = 94'900'000, SAMPLE_RATE = 170'000, RATE_RESAMPLE = 32'000;   // :25-27
 constexpr size_t DEFAULT_BUF_LENGTH = SDR_DEFAULT_BUF_LENGTH;                                 // src/lib.rs:25
 
+// A caller-owned buffer page-locked for the lifetime of this object (sdr_host_register): calls that are handed a pointer
+// inside it copy by DMA straight from it.  The reader's long-lived Box<[u8; DEFAULT_BUF_LENGTH]> (:114) is the use case.
+class Registered {
+  public:
+    Registered(void *p, size_t bytes) : p_(p) { check(sdr_host_register(p, bytes)); }
+    ~Registered() { sdr_host_unregister(p_); }
+    Registered(const Registered &) = delete;
+    Registered &operator=(const Registered &) = delete;
+
+  private:
+    void *p_;
+};
+
 // optimal_settings(freq, rate) -> (RadioConfig, DemodConfig), :189-214
 inline std::pair<RadioConfig, DemodConfig> optimal_settings(uint32_t freq = FREQUENCY, uint32_t rate = SAMPLE_RATE) {
     RadioConfig r{};
