@@ -247,6 +247,10 @@ int sdr_rtc_pick_shape(uint32_t n_taps, uint32_t decim, int shape[4]);
  * exactly as sdr_fmrx_ring_open() would (it holds every load-phase variant of the FIR tile, so it takes several times as long
  * as one FIR kernel); the cubin lands in the on-disk cache.  Returns its size, or a negative code. */
 long sdr_rtc_compile_ring(uint32_t n_taps, uint32_t decim);
+/* Same for the output-owner FIR kernel (k_fir_slide: shapes with more than 16 lags per sample, T <= 640, decim <= 64, and the
+ * decimations up to 4): shape[2] = {outputs per thread, threads per CTA}.  Returns the cubin size, or a negative code
+ * (SDR_E_ARG: the shape is outside that kernel's range and sdr_fmrx_new() would run the generic kernel). */
+long sdr_rtc_compile_slide(uint32_t n_taps, uint32_t decim, int shape[2]);
 /* Persistent ring for the f32 receiver: the reader -> channel -> processor pair of examples/simple_fm.rs:55-60,108-128,
  * 145-160 with ONE resident kernel behind it (same protocol as sdr_demod_ring_*: the producer acquires a pinned slot, fills
  * it and commits it — one H2D copy plus a 4-byte doorbell, no kernel launch; the consumer collects the audio of the oldest

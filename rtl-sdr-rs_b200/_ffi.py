@@ -124,6 +124,7 @@ SIGNATURES = {
     "sdr_rtc_selftest": (_l, [C.c_uint32, C.c_uint32, C.POINTER(_i * 4)]),
     "sdr_rtc_pick_shape": (_i, [C.c_uint32, C.c_uint32, C.POINTER(_i * 4)]),
     "sdr_rtc_compile_ring": (_l, [C.c_uint32, C.c_uint32]),
+    "sdr_rtc_compile_slide": (_l, [C.c_uint32, C.c_uint32, C.POINTER(_i)]),
     "sdr_fmrx_ring_open": (_i, [_vp, _sz, C.c_uint32, C.POINTER(_vp)]),
     "sdr_fmrx_ring_acquire": (_i, [_vp, C.POINTER(_vp)]),
     "sdr_fmrx_ring_commit": (_i, [_vp]),

@@ -346,6 +346,106 @@ __global__ void __launch_bounds__(NT) k_fir_fast(const FirArgs a, const __grid_c
 
 
 // =================================================================================================
+// "Output-owner" kernel for the shapes the block-owner form serves badly or not at all: many lags per sample (more than 16:
+// T > 16 D) or a very small decimation, where one thread's few samples cannot amortise the per-thread partial-sum traffic.
+// Every sample of the CTA tile is converted ONCE into a packed (re, im) f32 tile in shared memory; a thread then owns R
+// consecutive outputs and slides over its (R-1) D + T samples: one LDS.64 per sample feeds up to R FFMA2 (tap = uniform
+// register from the __grid_constant__ parameter, compile-time index).  Per-output sum order: oldest sample first, fixed,
+// so results do not depend on how the stream is tiled or chunked.  The float2 tile skips one slot after every R D samples
+// when R D is even: the lane stride in 8-byte units is odd, LDS.64 is conflict-free.  Local output 0 of a CTA is the
+// predecessor of its first owned output (discriminator), recomputed.
+// =================================================================================================
+template <int T, int D, int R, int NT>
+struct SlideGeom {
+    static constexpr int NOUT = NT * R;               // outputs computed per CTA
+    static constexpr int OPC = NOUT - 1;              // outputs owned per CTA
+    static constexpr int NS = T + (NOUT - 1) * D;     // samples in the tile
+    static constexpr int RD = R * D;
+    static constexpr int PADF = (RD % 2 == 0) ? 1 : 0;
+    static constexpr int W = (R - 1) * D + T;         // samples one thread reads
+    static constexpr int SM_RAW = ((NS * 2 + 15) / 16) * 16 + 32;
+    static constexpr int NF = NS + (NS / RD + 1) * PADF;
+    static constexpr int SM_F = NF * 8;
+    static constexpr int SMEM = SM_RAW + SM_F + NOUT * 8;
+    static_assert(NT % 32 == 0 && R >= 1, "whole warps");
+};
+__host__ __device__ constexpr int slide_smem(int T, int D, int R, int NT) {
+    const int nout = NT * R, ns = T + (nout - 1) * D, rd = R * D, padf = (rd % 2 == 0) ? 1 : 0;
+    return ((ns * 2 + 15) / 16) * 16 + 32 + (ns + (ns / rd + 1) * padf) * 8 + nout * 8;
+}
+
+template <int T, int D, int R, int NT>
+__global__ void __launch_bounds__(NT) k_fir_slide(const FirArgs a, const __grid_constant__ Taps<T> taps) {
+    using G = SlideGeom<T, D, R, NT>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t sh_soff;
+    unsigned char *raw = smem;
+    unsigned long long *xf = reinterpret_cast<unsigned long long *>(smem + G::SM_RAW);
+    float2 *ysm = reinterpret_cast<float2 *>(smem + G::SM_RAW + G::SM_F);
+    const int tid = threadIdx.x;
+    const long long out0 = (long long)blockIdx.x * G::OPC;
+    const long long left = a.n_out - out0;
+    const int n_here = left < G::OPC ? (int)left : G::OPC;   // owned outputs that exist; local output l is out0 - 1 + l
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        const long long s0 = out0 * D - (long long)a.r - T;   // oldest sample of local output 0
+        const long long s1 = (out0 + n_here) * D - (long long)a.r;
+        sh_soff = load_tile(raw, a, s0, s1, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    // ---- convert every sample once ------------------------------------------------------------------
+    const uint16_t *t16 = reinterpret_cast<const uint16_t *>(raw + sh_soff);
+    const CvtConst cb = cvt_consts();
+    const int ns = T + n_here * D;   // samples that exist in this tile
+    for (int i = tid; i < G::NS; i += NT) {
+        float xr = 0.f, xi = 0.f;
+        if (i < ns) cvt_iq(t16[i], 0, cb, xr, xi);
+        xf[i + (i / G::RD) * G::PADF] = pack_f32x2(xr, xi);
+    }
+    __syncthreads();
+
+    // ---- R outputs per thread, sliding over the window ------------------------------------------------
+    unsigned long long acc[R];
+#pragma unroll
+    for (int rr = 0; rr < R; rr++) acc[rr] = 0ull;
+    const unsigned long long *xw = xf + tid * (G::RD + G::PADF);
+#pragma unroll
+    for (int j = 0; j < G::W; j++) {
+        const unsigned long long x2 = xw[j + (j / G::RD) * G::PADF];
+#pragma unroll
+        for (int rr = 0; rr < R; rr++) {
+            const int k = T - 1 - (j - rr * D);   // output rr of this thread starts rr * D samples later
+            if (k >= 0 && k < T) fma_f32x2(acc[rr], taps.h[k], x2);
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; rr++) ysm[tid * R + rr] = unpack_f32x2(acc[rr]);
+    __syncthreads();
+
+    // ---- discriminator + stores (32-bit indices relative to the tile, as in fir_fast_tile) ---------------------------
+    const long long hfrom = left - a.h2;                       // tile-relative index of the first history value
+    const int hoff = (a.hist_out == nullptr || hfrom >= G::OPC) ? G::OPC : (hfrom < 0 ? 0 : (int)hfrom);
+    float2 *yp = a.y_out ? a.y_out + out0 : nullptr;
+    float *dp = a.d_out ? a.d_out + out0 : nullptr;
+    const bool last_cta = blockIdx.x == gridDim.x - 1;
+    for (int o = tid; o < n_here; o += NT) {
+        const float2 y = ysm[o + 1];
+        if (yp) yp[o] = y;
+        if (dp) {
+            const float dv = discriminate(y, ysm[o], a.gain);
+            dp[o] = dv;
+            if (o >= hoff) a.hist_out[o - (int)hfrom] = dv;
+        }
+        if (last_cta && o == n_here - 1) *a.last_y = y;
+    }
+    if (a.carry_out && blockIdx.x == gridDim.x - 1) fold_carry_update(a, tid, NT);
+}
+
+// =================================================================================================
 // Persistent ring for the f32 receiver: successive USB-sized buffers stream through ONE resident kernel
 // (reader -> channel -> processor of examples/simple_fm.rs:55-60,108-128,145-160; same protocol as k_demod_ring).
 //

@@ -516,6 +516,54 @@ const FastVariant *rtc_variant(int device, uint32_t T, uint32_t D, int B, int NT
     return v;
 }
 
+
+// ---- output-owner kernel (k_fir_slide, fir_fast.cuh): shapes the block-owner form cannot take (more than 16 lags per
+// sample, unrolled body too large) and, measured, the very small decimations ---------------------------------------
+// shapes that HAVE a block-owner instance but run faster on the output-owner kernel (measured)
+bool prefer_slide(int T, int D) {
+    // decimations up to 4 with 8 or more lags per sample: (31,/2) 0.75 vs 0.36 TB/s, (63,/4) 0.85 vs 0.58, (8,/1) 0.63 vs 0.30;
+    // with few lags the block-owner form stays ahead ((15,/4) 1.6 vs 1.1), and from /5 up it always is ((129,/16) 1.9 vs 1.0)
+    return D <= 4 && (T + D - 1) / D >= 8;
+}
+struct SlideVariant {
+    int T, D, R, nt, smem, opc;
+    const RtcModule *rtc;
+};
+// R outputs per thread: an unrolled body of about 768 FFMA2 at most (ptxas time), a tile of at most 72 KB
+bool pick_slide_params(int T, int D, int *Ro, int *NTo) {
+    if (T < 1 || D < 1 || T > 640 || D > 64) return false;
+    int R = std::max(1, std::min(8, 768 / T));
+    for (;;) {
+        for (int NT : {128, 64, 32})
+            if (slide_smem(T, D, R, NT) <= 72 * 1024) {
+                *Ro = R, *NTo = NT;
+                return true;
+            }
+        if (R == 1) return false;
+        R--;
+    }
+}
+const SlideVariant *rtc_slide_variant(int device, uint32_t T, uint32_t D, int R, int NT, std::string *why) {
+    static std::mutex mu;
+    static std::map<std::string, SlideVariant *> cache;
+    char key[96], name[128];
+    snprintf(key, sizeof key, "fir_slide<%u,%u,%d,%d>", T, D, R, NT);
+    snprintf(name, sizeof name, "sdr::k_fir_slide<%u,%u,%d,%d>", T, D, R, NT);
+    std::lock_guard<std::mutex> lk(mu);
+    const std::string full = std::to_string(device) + "|" + key;
+    auto it = cache.find(full);
+    if (it != cache.end()) return it->second;
+    const int smem = slide_smem((int)T, (int)D, R, NT);
+    const RtcModule *mod = nullptr;
+    if (rtc_get_module(device, key, {std::string(name)}, smem, &mod)) {
+        if (why) *why = err_buf();
+        return nullptr;
+    }
+    SlideVariant *v = new SlideVariant{(int)T, (int)D, R, NT, smem, NT * R - 1, mod};
+    cache[full] = v;
+    return v;
+}
+
 }  // namespace
 namespace sdr {
 // the shape table is a function-local static: make sure it exists (and has listed its kernels) before a preload
@@ -534,7 +582,8 @@ struct sdr_fmrx {
     std::vector<float> taps, taps2;
     float gain = 0.f;
     const FastVariant *fast = nullptr;
-    int kernel_kind = 0;     // 0 generic (k_fir_generic), 1 pre-compiled k_fir_fast, 2 run-time-compiled k_fir_fast
+    int kernel_kind = 0;     // 0 generic (k_fir_generic), 1 pre-compiled k_fir_fast, 2 run-time-compiled k_fir_fast, 3 run-time-compiled k_fir_slide
+    const struct SlideVariant *slide = nullptr;
     std::string rtc_note;    // why run-time compilation was not used, when it was wanted
     // generic geometry
     int gen_opc = 0;
@@ -681,6 +730,16 @@ int launch_fir(sdr_fmrx *r, const uint8_t *d_x, size_t n, uint32_t rphase, uint6
             return SDR_OK;
         }
         v->launch(a, r->taps.data(), phase, (int)grid, v->smem, r->stream);
+    } else if (r->slide) {
+        const SlideVariant *v = r->slide;
+        uint64_t grid = ceil_div(n_out, (uint64_t)v->opc);
+        if (grid > 0x7fffffffull) return fail(SDR_E_ARG, "call too large for one launch");
+        void *params[2] = {&a, (void *)r->taps.data()};   // (FirArgs, Taps<T>) by value
+        int rc = rtc_launch(v->rtc->fns[0], (unsigned)grid, (unsigned)v->nt, (unsigned)v->smem, r->stream, params);
+        if (rc) return rc;
+        r->last_launches++;
+        r->carry_cur ^= 1;
+        return SDR_OK;
     } else {
         GenArgs g{};
         g.f = a;
@@ -888,6 +947,17 @@ int sdr_fmrx_new(const sdr_fmrx_config *cfg, const float *taps, const float *tap
             if (v) r->fast = v, r->kernel_kind = 2;
         } else if (!r->fast && !off) {
             r->rtc_note = "shape outside the block-owner kernel's range (decim > 256, more than 16 lags per sample, or an unrolled body of more than 640 tap-samples)";
+        }
+        // output-owner kernel: where the block-owner form has no instance, and (SDR_FIR_SLIDE=1) wherever it exists
+        const char *es = getenv("SDR_FIR_SLIDE");
+        const bool slide_force = es && atoi(es) == 1, slide_off = es && !strcmp(es, "0");
+        int R = 0, SNT = 0;
+        if (!off && !slide_off && (slide_force || r->kernel_kind == 0 || prefer_slide((int)cfg->n_taps, (int)cfg->decim)) &&
+            r->kernel_kind != 1 && pick_slide_params((int)cfg->n_taps, (int)cfg->decim, &R, &SNT)) {
+            std::string why;
+            const SlideVariant *sv = rtc_slide_variant(cuda_device, cfg->n_taps, cfg->decim, R, SNT, &why);
+            if (sv) r->slide = sv, r->fast = nullptr, r->kernel_kind = 3, r->rtc_note.clear();
+            else if (r->kernel_kind == 0) r->rtc_note = why;
         }
     }
     const uint64_t T = cfg->n_taps, D = cfg->decim;
@@ -1238,7 +1308,7 @@ int sdr_fmrx_last_timing(const sdr_fmrx *r, float ms[3], uint32_t *n_launches, i
     if (ms)
         for (int i = 0; i < 3; i++) ms[i] = r->last_ms[i];
     if (n_launches) *n_launches = r->last_launches;
-    if (specialised) *specialised = r->fast ? 1 : 0;
+    if (specialised) *specialised = (r->fast || r->slide) ? 1 : 0;
     return SDR_OK;
 }
 
@@ -1290,6 +1360,20 @@ long sdr_rtc_compile_ring(uint32_t n_taps, uint32_t decim) {
         return fail(SDR_E_ARG, "(%u taps, /%u) is outside the block-owner kernel's range", n_taps, decim);
     char name[160];
     snprintf(name, sizeof name, "sdr::k_fmrx_ring<%u,%u,%d,%d,%d,%d>", n_taps, decim, B, NT, WB, PAD);
+    std::vector<std::vector<char>> cubins;
+    std::vector<std::string> lowered;
+    int rc = rtc_compile_cubins({name}, &cubins, &lowered, nullptr);
+    if (rc) return rc;
+    return (long)cubins[0].size();
+}
+
+long sdr_rtc_compile_slide(uint32_t n_taps, uint32_t decim, int shape[2]) {
+    int R = 0, NT = 0;
+    if (!pick_slide_params((int)n_taps, (int)decim, &R, &NT))
+        return fail(SDR_E_ARG, "(%u taps, /%u) is outside the output-owner kernel's range", n_taps, decim);
+    if (shape) shape[0] = R, shape[1] = NT;
+    char name[160];
+    snprintf(name, sizeof name, "sdr::k_fir_slide<%u,%u,%d,%d>", n_taps, decim, R, NT);
     std::vector<std::vector<char>> cubins;
     std::vector<std::string> lowered;
     int rc = rtc_compile_cubins({name}, &cubins, &lowered, nullptr);

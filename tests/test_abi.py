@@ -205,3 +205,20 @@ def test_rtc_shape_picker_only_picks_shapes_the_kernel_accepts(S):
             else:
                 outside += 1
     assert picked > 1500 and outside > 300, (picked, outside)
+
+
+def test_rtc_compiles_the_output_owner_kernel_without_a_gpu():
+    """k_fir_slide (csrc/fir_fast.cuh): the shapes the block-owner kernel cannot take compile through NVRTC with no device;
+    shapes outside BOTH unrolled kernels are refused (sdr_fmrx_new() then runs k_fir_generic)."""
+    import ctypes as C
+    sdrpkg.load()
+    from rtl_sdr_rs_b200 import _ffi as F
+    L = F.lib()
+    sh = (C.c_int * 2)()
+    n = L.sdr_rtc_compile_slide(31, 2, sh)
+    assert n > 10_000, L.sdr_last_error()
+    assert sh[0] == 8 and sh[1] == 128          # 8 outputs per thread, 128 threads
+    n = L.sdr_rtc_compile_slide(200, 3, sh)
+    assert n > 10_000 and sh[0] == 3            # 768 / 200 outputs per thread
+    assert L.sdr_rtc_compile_slide(1001, 250, sh) == -1
+    assert L.sdr_rtc_compile_slide(300, 301, sh) == -1

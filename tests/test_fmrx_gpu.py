@@ -29,10 +29,12 @@ def ragged_cuts(n, rng, pieces):
     return [0, *cuts.tolist(), n]
 
 
-SHAPES = [  # (T, D, kernel kind: 1 = pre-compiled k_fir_fast, 2 = k_fir_fast compiled by NVRTC for the shape, 0 = generic)
+SHAPES = [  # (T, D, kernel kind: 1 = pre-compiled k_fir_fast, 2 = k_fir_fast compiled by NVRTC for the shape,
+           #  3 = k_fir_slide (output-owner kernel, NVRTC): more than 16 lags per sample, or a decimation up to 4 with 8+ lags; 0 = generic)
     (127, 75, 1), (255, 100, 1), (6, 6, 1),
-    (63, 20, 2), (31, 7, 2), (1, 1, 2), (5, 64, 2), (127, 50, 2), (201, 64, 2), (33, 125, 2), (129, 16, 2), (65, 32, 2),
-    (200, 3, 0), (300, 301, 0), (1001, 250, 0),   # > 16 lags per sample / decim > 256 / unrolled body too large: generic kernel
+    (63, 20, 2), (31, 7, 2), (1, 1, 2), (7, 3, 2), (5, 64, 2), (127, 50, 2), (201, 64, 2), (33, 125, 2), (129, 16, 2), (65, 32, 2),
+    (200, 3, 3), (65, 4, 3), (31, 2, 3), (255, 8, 3), (16, 1, 3),
+    (300, 301, 0), (1001, 250, 0),   # decim > 256 / too many taps for either unrolled kernel: generic kernel
 ]
 
 
@@ -95,7 +97,7 @@ def test_rtc_instance_is_bit_identical_to_the_precompiled_one(S, monkeypatch, T,
         assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), (lo, hi)
 
 
-@pytest.mark.parametrize("T,D", [(127, 75), (255, 100), (63, 20)])
+@pytest.mark.parametrize("T,D", [(127, 75), (255, 100), (63, 20), (129, 16), (65, 4), (200, 3)])
 def test_streaming_is_bitwise_chunk_invariant(S, T, D):
     """Fixed-order partial sums: how the stream is cut into calls must not change a single bit."""
     rng = np.random.default_rng(T)
@@ -122,7 +124,7 @@ def test_boxcar_taps_equal_the_pinned_integer_path(S):
         assert np.array_equal(y, lp.astype(np.float32))
 
 
-@pytest.mark.parametrize("T,D,fs", [(127, 75, 2.4e6), (255, 100, 20e6), (63, 20, 1.0e6)])
+@pytest.mark.parametrize("T,D,fs", [(127, 75, 2.4e6), (255, 100, 20e6), (63, 20, 1.0e6), (65, 4, 1.0e6), (200, 3, 1.0e6)])
 def test_fused_chain_on_fm_parity_signal(S, T, D, fs):
     """SURVEY §8d parity set: FM test signal, 75 kHz deviation, 1 kHz tone, N(0, 8^2) noise."""
     n = 1 << 20
