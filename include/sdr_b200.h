@@ -229,7 +229,9 @@ int sdr_fmrx_last_timing(const sdr_fmrx *r, float ms[3], uint32_t *n_launches, i
 int sdr_fmrx_timing_totals(sdr_fmrx *r, double sums_ms[3], uint64_t *n_calls, int reset);
 /* Which convert+FIR(+demod) kernel the handle runs: 0 = generic (one warp per output), 1 = pre-compiled
  * k_fir_fast (the BASELINE.json shapes), 2 = k_fir_fast compiled at sdr_fmrx_new() time for this (n_taps, decim)
- * by NVRTC (same source as the pre-compiled instances, bit-identical arithmetic).  When 0 and a specialised kernel
+ * by NVRTC (same source as the pre-compiled instances, bit-identical arithmetic), 3 = k_fir_slide, the output-owner kernel
+ * compiled by NVRTC for shapes with more than 16 taps per decimation step (n_taps <= 640, decim <= 64) and for decimations
+ * up to 4 with 8 or more (SDR_FIR_SLIDE=0 / 1: never / wherever it exists).  When 0 and a specialised kernel
  * was wanted, *note (optional, valid until the handle is freed) says why it could not be had.
  * SDR_FIR_RTC=0 in the environment disables run-time compilation. */
 int sdr_fmrx_kernel_kind(const sdr_fmrx *r, const char **note);
