@@ -460,10 +460,12 @@ void build_bank_tab(const sdr_chan_config &cfg, const float *taps, const uint32_
             }
         }
     idx = (idx + 1) & ~size_t(1);   // E starts on an even entry (16-byte aligned pairs)
+    // E[r1][c] = e^{j 2 pi c r1 / K}, stored per channel pair as (re c, re c+1), (im c, im c+1) — see stage 2 of k_chan_bank
     for (uint32_t r1 = 0; r1 < K1; r1++)
-        for (uint32_t c = 0; c < (uint32_t)kBankCH; c++) {
-            const double ph = PI2 * (double)(((uint64_t)c * r1) % K) / K;
-            tab.v[idx++] = make_float2((float)std::cos(ph), (float)std::sin(ph));
+        for (uint32_t c = 0; c < (uint32_t)kBankCH; c += 2) {
+            const double ph0 = PI2 * (double)(((uint64_t)c * r1) % K) / K, ph1 = PI2 * (double)(((uint64_t)(c + 1) * r1) % K) / K;
+            tab.v[idx++] = make_float2((float)std::cos(ph0), (float)std::cos(ph1));
+            tab.v[idx++] = make_float2((float)std::sin(ph0), (float)std::sin(ph1));
         }
     for (uint32_t c = 0; c < (uint32_t)kBankCH; c++) {
         const uint32_t ch = g * kBankCH + c;
@@ -568,7 +570,6 @@ int chan_run(sdr_chan *c, const uint8_t *d_x, size_t n, float2 *d_y, float *d_d,
             b.NJ = ((int)c->cfg.n_taps + b.K1 - 1) / b.K1;
             b.Tp = b.K1 * b.NJ;
             b.eoff = (b.Tp * c->bank_K2 + 1) & ~1;
-            b.esm_off = (int)c->smem_bank_tile;
             b.gain = c->gain;
             const uint64_t tiles = (n_out + (kBankThreads - 1) - 1) / (kBankThreads - 1);
             if (tiles > 0x7fffffffull) return fail(SDR_E_ARG, "call too large");
@@ -780,7 +781,7 @@ int sdr_chan_new(const sdr_chan_config *cfg, const float *taps, const uint32_t *
             const size_t Tp = (size_t)bp.K1 * ((cfg->n_taps + bp.K1 - 1) / bp.K1);
             c->cs = (int)((Tp + 2 * (size_t)D + 16 + 7) & ~size_t(7));
             c->smem_bank_tile = (((size_t)kBankThreads * D + Tp + 16) * 2 + 15 + 32) & ~size_t(15);
-            c->smem_bank = c->smem_bank_tile + (SDR_BANK_E_SMEM ? (size_t)bp.K1 * kBankCH * 8 : 0);
+            c->smem_bank = c->smem_bank_tile;
             if (c->smem_bank > 200 * 1024) c->use_bank = false;
         }
     }

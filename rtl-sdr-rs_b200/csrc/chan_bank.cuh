@@ -35,9 +35,6 @@ namespace sdr {
 #ifndef SDR_BANK_UNROLL
 #define SDR_BANK_UNROLL 4
 #endif
-#ifndef SDR_BANK_E_SMEM
-#define SDR_BANK_E_SMEM 0   // 1: stage-2 coefficients from shared memory (broadcast LDS.128) instead of uniform loads (A/B)
-#endif
 constexpr int kBankUnroll = SDR_BANK_UNROLL;
 constexpr int kBankThreads = SDR_BANK_NT;   // lanes per CTA (one output time each; lane 0 is the predecessor halo)
 constexpr int kBankCH = 64;            // channels per launch (packed accumulators held in registers)
@@ -46,7 +43,7 @@ constexpr int kBankMaxK2 = 8;
 
 // Every residue r1 gets the same number of taps NJ = ceil(T / K1): the filter is zero-padded to Tp = K1*NJ taps.
 // [0, Tp*K2): G, sub-filter taps in the order they are consumed: for r1, for j (k = r1 + j*K1), for b2
-// [eoff = Tp*K2 rounded up to even, eoff + K1*64): E[r1][c];   [.., + 64): (phi_c, 0)
+// [eoff = Tp*K2 rounded up to even, eoff + K1*64): E[r1][c], per channel pair (re c, re c+1), (im c, im c+1);   [.., + 64): (phi_c, 0)
 struct BankTab {
     float2 v[kBankTabEntries];
 };
@@ -63,7 +60,6 @@ struct BankArgs {
     uint32_t r, n0_lo;
     int ch0, n_ch, Tp, D, K1, NJ;   // Tp = K1 * NJ: taps after zero padding
     int eoff;                       // first E entry (host-computed: keeps the index arithmetic on the uniform datapath)
-    int esm_off;                    // SDR_BANK_E_SMEM builds: byte offset of the E copy in dynamic shared memory
     float gain;
 };
 
@@ -137,12 +133,6 @@ __global__ void __launch_bounds__(kBankThreads, SDR_BANK_MINB) k_chan_bank(const
 
     const int K1 = K1T ? K1T : a.K1, NJ = NJT ? NJT : a.NJ;
     const int eoff = a.eoff;
-#if SDR_BANK_E_SMEM
-    // E[r1][c] behind the raw tile (a.esm_off bytes into the dynamic shared memory, 16-byte aligned)
-    float2 *esm = reinterpret_cast<float2 *>(smem + a.esm_off);
-    for (int i = tid; i < K1 * CH; i += NT) esm[i] = tab.v[eoff + i];
-    __syncthreads();
-#endif
     int gidx = 0, eidx = eoff;
 #pragma unroll 1
     for (int r1 = 0; r1 < K1; r1++) {
@@ -184,24 +174,24 @@ __global__ void __launch_bounds__(kBankThreads, SDR_BANK_MINB) k_chan_bank(const
         // ---- stage 2: every channel adds E[c][r1] * A[r1][c mod K2] ---------------------------------------------------
         // eight channels at a time: four 16-byte uniform loads (two coefficients each), then the eight real-part FMAs,
         // then the eight imaginary-part FMAs — the two FMAs into one accumulator are never back to back
+        // E rows are stored per channel PAIR as (re c, re c+1), (im c, im c+1): the two halves of every 64-bit uniform load
+        // are consumed together (by two independent accumulators), so the load lands in the register pair the FMAs read.
+        // With (re, im) pairs the halves had different lifetimes and two of three loads cost two UMOVs on top: the loop body
+        // went from 601 to 479 instructions for (K2, K1, NJ) = (5, 20, 13).  The two FMAs into one accumulator are never
+        // back to back.
 #pragma unroll
-        for (int c0 = 0; c0 < CH; c0 += 8) {
-            float4 e4[4];
-#if SDR_BANK_E_SMEM
+        for (int c0 = 0; c0 < CH; c0 += 4) {
+            float4 e4[2];
 #pragma unroll
-            for (int q = 0; q < 4; q++) e4[q] = *reinterpret_cast<const float4 *>(&esm[(eidx - eoff) + c0 + 2 * q]);
-#else
+            for (int q = 0; q < 2; q++) e4[q] = *reinterpret_cast<const float4 *>(&tab.v[eidx + c0 + 2 * q]);
 #pragma unroll
-            for (int q = 0; q < 4; q++) e4[q] = *reinterpret_cast<const float4 *>(&tab.v[eidx + c0 + 2 * q]);
-#endif
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 2; q++) {
                 bk_fma2(Y[c0 + 2 * q], e4[q].x, a2[(c0 + 2 * q) % K2]);
-                bk_fma2(Y[c0 + 2 * q + 1], e4[q].z, a2[(c0 + 2 * q + 1) % K2]);
+                bk_fma2(Y[c0 + 2 * q + 1], e4[q].y, a2[(c0 + 2 * q + 1) % K2]);
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                bk_fma2(Y[c0 + 2 * q], e4[q].y, a2r[(c0 + 2 * q) % K2]);
+            for (int q = 0; q < 2; q++) {
+                bk_fma2(Y[c0 + 2 * q], e4[q].z, a2r[(c0 + 2 * q) % K2]);
                 bk_fma2(Y[c0 + 2 * q + 1], e4[q].w, a2r[(c0 + 2 * q + 1) % K2]);
             }
         }

@@ -45,7 +45,9 @@ def bank_model(iq, taps, D, fw, plan, tabs):
                     A[b] += v[gidx + b] * xs
                 gidx += K2
             for c in range(CH):
-                S[c] += v[eidx + c] * A[c % K2]
+                # E is stored per channel pair: entry (re c, re c+1), then entry (im c, im c+1)
+                pair = tabs[g, eidx + (c & ~1):eidx + (c & ~1) + 2].astype(np.float64)
+                S[c] += (pair[0, c & 1] + 1j * pair[1, c & 1]) * A[c % K2]
             eidx += CH
         phi = tabs[g, eoff + K1 * CH:eoff + K1 * CH + CH, 0].astype(np.float64)
         nm = (np.arange(M, dtype=np.uint64) + 1) * D - 1
