@@ -120,10 +120,22 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def n_samples(self) -> int:
+        try:
+            return sum(1 for line in Path(self.path).read_text().splitlines() if line.count(",") >= 8)
+        except Exception:
+            return 0
+
+    def wait_first(self, timeout: float = 5.0) -> None:
+        """Block until nvidia-smi has printed its first sample: its start-up (NVML initialisation over every GPU of the
+        box) takes driver locks and stalls kernel launches for milliseconds — it must be over BEFORE the timed region."""
+        t0 = time.perf_counter()
+        while self.proc is not None and self.n_samples() < 1 and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()          # exact PID we started
         try:
             self.proc.wait(timeout=5)
@@ -232,27 +244,44 @@ def measure_stream(cx: Ctx, w: dict, d_in, steps: int, warmup: int, sample_clock
         cx.barrier()
         h.sync()
 
+    # the clock sampler starts BEFORE the warm-up and is given time to print its first sample: a nvidia-smi process that
+    # starts inside a timed region of a few milliseconds stalls the launches of that region (measured on the 8-GPU box:
+    # 0.60 instead of 0.35 ms per step).  It then samples every 100 ms through warm-up, timed region and the load tail below.
+    sampler = ClockSampler(cx.device) if (sample_clocks and cx.rank == 0) else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first()
     for _ in range(warmup):
         step()
     barrier()
     if w["name"] != "cfg1":
         h.timing_totals(reset=True)
     launches0 = S.kernel_launch_count()
-    sampler = ClockSampler(cx.device) if (sample_clocks and cx.rank == 0) else None
-    if sampler:
-        sampler.start()
     barrier()
     h.span_begin()
     for _ in range(steps):
         step()
     total_ms = h.span_end()          # records the closing event and waits for it
     barrier()
-    clocks = sampler.stop() if sampler else None
     launches = S.kernel_launch_count() - launches0
+    if w["name"] != "cfg1":
+        sums, calls = h.timing_totals()
+    if sample_clocks:
+        # load tail (untimed, every rank, same step): the timed region lasts a few milliseconds, the sampler's period is
+        # 100 ms — keep the identical load running until it has taken three more samples (at most 0.6 s)
+        have = cx.sum_over_ranks(sampler.n_samples() if sampler else 0)
+        t_end = time.perf_counter() + 0.6
+        while True:
+            for _ in range(20):
+                step()
+            h.sync()
+            now = cx.sum_over_ranks(sampler.n_samples() if sampler else 0)
+            if cx.sum_over_ranks(int(now >= have + 3 or time.perf_counter() > t_end)) > 0:
+                break
+    clocks = sampler.stop() if sampler else None
     if w["name"] == "cfg1":
         kern_ms = total_ms / steps
     else:
-        sums, calls = h.timing_totals()
         kern_ms = sums[0] / max(calls, 1)
     total_ms, kern_ms = cx.max_over_ranks(total_ms, kern_ms)
     launches = cx.sum_over_ranks(launches)
@@ -698,7 +727,10 @@ def run_chan(args, w):
     sampler = ClockSampler(cx.device) if cx.rank == 0 else None
     if sampler:
         sampler.start()
+        sampler.wait_first()          # nvidia-smi's start-up must not overlap the timed region
     m = measure_chan(cx, w, d_in, args.steps, max(args.warmup, 3), shard=cx.world > 1)
+    if sampler:
+        time.sleep(0.15)
     clocks = sampler.stop() if sampler else None
     if cx.rank == 0:
         line = {"metric": "channel-Msamples/s (input Msamples/s x channels) through the channeliser", "workload": "chan",
