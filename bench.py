@@ -747,6 +747,17 @@ def run_chan(args, w):
     return 0
 
 
+def guarded(errors: dict, name: str, fn, *a, **kw):
+    """Run one of the legs that FOLLOW the headline's timed region; a failure there is recorded in the line
+    (`extra_errors`) and must not cost the headline number."""
+    try:
+        return fn(*a, **kw)
+    except Exception as e:   # noqa: BLE001 — reported, not swallowed
+        errors[name] = f"{type(e).__name__}: {e}"[:400]
+        print(f"bench.py: leg '{name}' failed: {errors[name]}", file=sys.stderr)
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -781,17 +792,17 @@ def main():
 
     m = measure_stream(cx, w, d_in, args.steps, args.warmup, sample_clocks=True)
     value = cx.world * n / (m["ms_per_step"] * 1e-3) / 1e6               # whole-job Msamples/s
-    alone = None
+    alone, errors = None, {}
     if w["name"] != "cfg1":
         # In the timed region the audio kernel of step k runs UNDER the fused kernel of step k+1 (own stream), so the fused
         # kernel's event-bracketed time includes that contention.  The same kernel with the audio stage serialised behind it
         # (a handle created with SDR_FMRX_AUDIO_STREAM=serial), measured after the timed region:
         os.environ["SDR_FMRX_AUDIO_STREAM"] = "serial"
         try:
-            alone = measure_stream(cx, w, d_in, max(5, min(args.steps, 10)), 3)
+            alone = guarded(errors, "kernel_alone", measure_stream, cx, w, d_in, max(5, min(args.steps, 10)), 3)
         finally:
             del os.environ["SDR_FMRX_AUDIO_STREAM"]
-    e2e = None if args.no_e2e else measure_e2e(cx, w, args.steps)
+    e2e = None if args.no_e2e else guarded(errors, "e2e", measure_e2e, cx, w, args.steps)
 
     # ---- everything below runs AFTER the headline's timed region --------------------------------------------------
     extra, multi = None, None
@@ -799,21 +810,26 @@ def main():
     if not args.no_extra and full_size:
         extra = {}
         x_steps = max(5, min(args.steps, 10))
-        h2d = measure_h2d_ceiling(cx)
+        h2d = guarded(errors, "h2d_ceiling", measure_h2d_ceiling, cx)
         if e2e is not None:
-            e2e_page = measure_e2e(cx, w, args.steps, pageable=True)
-            e2e["pageable"] = {k: e2e_page[k] for k in ("value", "unit", "host_memory")}
-            e2e["pageable"]["fraction_of_pinned"] = round(e2e_page["value"] / e2e["value"], 3)
-            e2e_reg = measure_e2e(cx, w, args.steps, pageable=True, registered=True)
-            e2e["registered"] = {k: e2e_reg[k] for k in ("value", "unit", "host_memory")}
-            e2e["registered"]["fraction_of_pinned"] = round(e2e_reg["value"] / e2e["value"], 3)
-            e2e["h2d_ceiling"] = h2d
-            e2e["fraction_of_h2d_ceiling"] = round(e2e["value"] / h2d["msamples_per_s"], 3)
+            e2e_page = guarded(errors, "e2e.pageable", measure_e2e, cx, w, args.steps, pageable=True)
+            if e2e_page:
+                e2e["pageable"] = {k: e2e_page[k] for k in ("value", "unit", "host_memory")}
+                e2e["pageable"]["fraction_of_pinned"] = round(e2e_page["value"] / e2e["value"], 3)
+            e2e_reg = guarded(errors, "e2e.registered", measure_e2e, cx, w, args.steps, pageable=True, registered=True)
+            if e2e_reg:
+                e2e["registered"] = {k: e2e_reg[k] for k in ("value", "unit", "host_memory")}
+                e2e["registered"]["fraction_of_pinned"] = round(e2e_reg["value"] / e2e["value"], 3)
+            if h2d:
+                e2e["h2d_ceiling"] = h2d
+                e2e["fraction_of_h2d_ceiling"] = round(e2e["value"] / h2d["msamples_per_s"], 3)
         for other in ("cfg1", "cfg3", "cfg2"):
             if other == w["name"]:
                 continue
             wo = workload_spec(other)
-            mo = measure_stream(cx, wo, d_in, x_steps, 3)
+            mo = guarded(errors, f"extra.{other}", measure_stream, cx, wo, d_in, x_steps, 3)
+            if mo is None:
+                continue
             ro = roofline_of(wo, mo)
             eo = {"workload": wo["desc"], "ms_per_step": round(mo["ms_per_step"], 4),
                   "msamples_per_s": round(cx.world * wo["n"] / (mo["ms_per_step"] * 1e-3) / 1e6, 1), "steps": x_steps,
@@ -821,34 +837,38 @@ def main():
                   "roofline": {k: ro[k] for k in ("achieved", "peak", "unit", "frac", "kernel", "kernel_ms", "alg_bytes_per_sample",
                                                   "kernel_share_of_step", "whole_step_frac", "traffic")}}
             if other == "cfg1" and not args.no_e2e:
-                e1 = measure_e2e(cx, wo, x_steps)
-                e1p = measure_e2e(cx, wo, x_steps, pageable=True)
-                eo["e2e"] = {"value": e1["value"], "unit": "Msamples/s", "api": e1["api"], "host_memory": e1["host_memory"],
-                             "h2d_bytes_per_step": e1["h2d_bytes_per_step"], "d2h_bytes_per_step": e1["d2h_bytes_per_step"],
-                             "pageable_value": e1p["value"], "fraction_of_h2d_ceiling": round(e1["value"] / h2d["msamples_per_s"], 3)}
+                e1 = guarded(errors, "extra.cfg1.e2e", measure_e2e, cx, wo, x_steps)
+                e1p = guarded(errors, "extra.cfg1.e2e.pageable", measure_e2e, cx, wo, x_steps, pageable=True)
+                if e1:
+                    eo["e2e"] = {"value": e1["value"], "unit": "Msamples/s", "api": e1["api"], "host_memory": e1["host_memory"],
+                                 "h2d_bytes_per_step": e1["h2d_bytes_per_step"], "d2h_bytes_per_step": e1["d2h_bytes_per_step"],
+                                 "pageable_value": e1p["value"] if e1p else None,
+                                 "fraction_of_h2d_ceiling": round(e1["value"] / h2d["msamples_per_s"], 3) if h2d else None}
                 if cx.rank == 0:
-                    eo["per_buffer"] = per_buffer_bench(S, cx.device, wo["buf_len"])
+                    eo["per_buffer"] = guarded(errors, "extra.cfg1.per_buffer", per_buffer_bench, S, cx.device, wo["buf_len"])
             if other == "cfg1" and not args.no_cpu_baseline and cx.rank == 0:
-                eo["cpu_baseline"] = cpu_legs_cfg1(wo)
+                eo["cpu_baseline"] = guarded(errors, "extra.cfg1.cpu_baseline", cpu_legs_cfg1, wo)
             extra[other] = eo
         if not args.no_e2e and cx.rank == 0 and w["name"] != "cfg1":
-            extra["per_buffer_f32"] = per_buffer_fx(S, cx.device, w)
+            extra["per_buffer_f32"] = guarded(errors, "extra.per_buffer_f32", per_buffer_fx, S, cx.device, w)
         wc = workload_spec("chan")
-        mc = measure_chan(cx, wc, d_in, max(3, x_steps // 2), 3, shard=False)
-        extra["chan"] = {"workload": wc["desc"], "ms_per_step": mc["ms_per_step"], "input_msamples_per_s": mc["input_msamples_per_s"],
-                         "channel_msamples_per_s": mc["channel_msamples_per_s"], "gpu_launches": mc["gpu_launches"],
-                         "channel_plan": mc["channel_plan"],
-                         "roofline": chan_roofline(wc, cx.info, mc["kernel_ms_per_slab"], (m["clocks"] or {}).get("sm_mhz"), mc["kernel"])}
+        mc = guarded(errors, "extra.chan", measure_chan, cx, wc, d_in, max(3, x_steps // 2), 3, shard=False)
+        if mc:
+            extra["chan"] = {"workload": wc["desc"], "ms_per_step": mc["ms_per_step"], "input_msamples_per_s": mc["input_msamples_per_s"],
+                             "channel_msamples_per_s": mc["channel_msamples_per_s"], "gpu_launches": mc["gpu_launches"],
+                             "channel_plan": mc["channel_plan"],
+                             "roofline": chan_roofline(wc, cx.info, mc["kernel_ms_per_slab"], (m["clocks"] or {}).get("sm_mhz"), mc["kernel"])}
         if cx.world > 1:
             # north_star's multi-GPU design: the channel shard with the NCCL slab broadcast.  Ranks other than 0 hold
             # whatever their time slice left in d_in; every slab is overwritten by the broadcast before it is read.
-            multi = measure_chan(cx, wc, d_in, 10, 5, shard=True)
-            multi["single_gpu_ms_per_step"] = mc["ms_per_step"]
-            multi["efficiency_vs_one_gpu_same_run"] = round(mc["ms_per_step"] / multi["ms_per_step"], 4)
+            multi = guarded(errors, "multi_gpu", measure_chan, cx, wc, d_in, 10, 5, shard=True)
+            if multi and mc:
+                multi["single_gpu_ms_per_step"] = mc["ms_per_step"]
+                multi["efficiency_vs_one_gpu_same_run"] = round(mc["ms_per_step"] / multi["ms_per_step"], 4)
 
     if w["name"] == "cfg1" and not args.no_e2e and cx.rank == 0 and (args.no_extra or not full_size):
         extra = extra or {}
-        extra["per_buffer"] = per_buffer_bench(S, cx.device, w["buf_len"])
+        extra["per_buffer"] = guarded(errors, "extra.per_buffer", per_buffer_bench, S, cx.device, w["buf_len"])
 
     if cx.rank != 0:
         cx.close()
@@ -868,13 +888,15 @@ def main():
             "note": "same kernel, audio stage serialised behind it instead of overlapped with the next step (measured in this run, "
                     "after the timed region): the kernel itself streams at this rate; overlapping costs it time but shortens the step"}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(w)
+        line["cpu_baseline"] = guarded(errors, "cpu_baseline", cpu_baseline, w)
         if w["name"] == "cfg1":
-            line["cpu_baseline_legs"] = cpu_legs_cfg1(w)
+            line["cpu_baseline_legs"] = guarded(errors, "cpu_baseline_legs", cpu_legs_cfg1, w)
     if extra:
         line["extra"] = extra
     if multi:
         line["multi_gpu"] = multi
+    if errors:
+        line["extra_errors"] = errors
     print(json.dumps(line))
     cx.close()
     return 0
