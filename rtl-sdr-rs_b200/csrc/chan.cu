@@ -1073,7 +1073,16 @@ int sdr_comm_init(int cuda_device, int rank, int world, const uint8_t id[SDR_NCC
         delete c;
         return nccl_fail("ncclCommInitRank", r);
     }
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    // The broadcast kernel's few CTAs must be placed as soon as an SM has room: at equal priority a kernel that arrives
+    // while the channeliser's grid is being dispatched gets only that grid's tail, and whether broadcast(s+1) or
+    // channeliser(s) arrives first depends on how far the host thread runs ahead (three 8-GPU sessions: 1.8-2.4 ms per
+    // step).  Highest priority makes the overlap independent of the arrival order.  SDR_COMM_PRIO=0: default priority.
+    int prio_lo = 0, prio_hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const char *ep = getenv("SDR_COMM_PRIO");
+    if (e == cudaSuccess)
+        e = (ep && atoi(ep) == 0) ? cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)
+                                  : cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_chan, cudaEventDisableTiming);
     if (e != cudaSuccess) {
